@@ -1,0 +1,254 @@
+# -*- coding: utf-8 -*-
+"""Generate the golden fixtures in tests/golden/ from the UNMODIFIED reference.
+
+Runs only in the authoring container (needs /root/reference); the fixtures it writes
+are committed and are what pins the oracle (and the CUDA path) on machines without the
+reference.  The reference is imported through the stub packages in oracle/ref_stubs/
+(stand-ins for the absent `torchmetrics` / `nicr_scene_analysis_datasets`, no arithmetic).
+
+    python tests/golden/make_golden.py
+
+Every fixture stores the inputs and the reference's outputs; python dict outputs are
+stored as JSON strings.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference/src')
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'ref_stubs'))
+os.environ.setdefault('OMP_NUM_THREADS', '1')
+
+from nicr_mt_scene_analysis.metric import MeanIntersectionOverUnion  # noqa: E402
+from nicr_mt_scene_analysis.metric.pq import compare_and_accumulate  # noqa: E402
+from nicr_mt_scene_analysis.model.postprocessing import get_postprocessing_class  # noqa: E402
+from nicr_mt_scene_analysis.utils.panoptic_merge import deeplab_merge_batch  # noqa: E402
+
+from nicr_mt_scene_analysis_b200 import testing  # noqa: E402
+
+
+def jdump(obj):
+    return np.array(json.dumps(obj))
+
+
+def dicts_to_json(list_of_dicts):
+    return jdump([{str(k): v for k, v in d.items()} for d in list_of_dicts])
+
+
+def meta_to_json(meta):
+    return jdump([{str(k): {kk: (list(vv) if isinstance(vv, tuple) else vv)
+                            for kk, vv in v.items()} for k, v in d.items()} for d in meta])
+
+
+def run_postprocess(name, B, C, H, W, K, seed, quantize, with_orientation=True, top_k=64,
+                    ks=3, thr=0.1, apply_fg=False, normalized=True, dist_thr=None,
+                    compute_scores=False):
+    data = testing.make_batch(B, C, H, W, K, seed=seed, with_orientation=with_orientation,
+                              quantize=quantize)
+    if not normalized:      # offsets in pixels
+        data['offset'][:, 0] *= H
+        data['offset'][:, 1] *= W
+    is_thing = testing.default_is_thing(C)
+    has_ori = tuple(bool(t and (c % 4 == 1)) for c, t in enumerate(is_thing))
+    sem = get_postprocessing_class('semantic')()
+    ins = get_postprocessing_class('instance', heatmap_threshold=thr,
+                                   heatmap_nms_kernel_size=ks, top_k_instances=top_k,
+                                   heatmap_apply_foreground_mask=apply_fg,
+                                   normalized_offset=normalized,
+                                   offset_distance_threshold=dist_thr)()
+    pan = get_postprocessing_class('panoptic', semantic_postprocessing=sem,
+                                   instance_postprocessing=ins,
+                                   semantic_classes_is_thing=is_thing,
+                                   semantic_class_has_orientation=has_ori,
+                                   normalized_offset=normalized,
+                                   compute_scores=compute_scores)()
+    inst_out = (data['heat'], data['offset']) + ((data['orientation'],) if with_orientation else ())
+    batch = testing.make_batch_dict(B, H, W)
+    r = pan.postprocess(((data['logits'], inst_out), (None, None)), batch, is_training=False)
+    out = {
+        'logits': data['logits'].numpy(), 'heat': data['heat'].numpy(),
+        'offset': data['offset'].numpy(),
+        'is_thing': np.array(is_thing), 'has_orientation': np.array(has_ori),
+        'cfg': jdump(dict(top_k=top_k, ks=ks, thr=thr, apply_fg=apply_fg, normalized=normalized,
+                          dist_thr=dist_thr, compute_scores=compute_scores)),
+        'semantic_segmentation_idx': r['semantic_segmentation_idx'].numpy().astype(np.uint8),
+        'semantic_segmentation_score': r['semantic_segmentation_score'].numpy(),
+        'panoptic_foreground_mask': r['panoptic_foreground_mask'].numpy(),
+        'panoptic_segmentation_deeplab': r['panoptic_segmentation_deeplab'].numpy(),
+        'panoptic_segmentation_deeplab_semantic_idx':
+            r['panoptic_segmentation_deeplab_semantic_idx'].numpy().astype(np.uint8),
+        'panoptic_segmentation_deeplab_instance_idx':
+            r['panoptic_segmentation_deeplab_instance_idx'].numpy(),
+        'ids': dicts_to_json(r['panoptic_segmentation_deeplab_ids']),
+        'meta': meta_to_json(r['panoptic_segmentation_deeplab_instance_meta']),
+    }
+    if with_orientation:
+        out['orientation'] = data['orientation'].numpy()
+        out['orientations'] = dicts_to_json(r['orientations_panoptic_segmentation_deeplab_instance'])
+    if compute_scores:
+        for k in ('semantic_score', 'instance_score', 'panoptic_score'):
+            out[k] = r[f'panoptic_segmentation_deeplab_{k}'].numpy()
+    # centres as the instance post-processing itself reports them
+    fg = r['panoptic_foreground_mask']
+    cmask, clist = ins._get_instance_centers(data['heat'], fg)
+    out['center_mask'] = cmask.numpy()
+    out['centers'] = jdump([c.tolist() for c in clist])
+    np.savez_compressed(os.path.join(HERE, f'post_{name}.npz'), **out)
+    print(name, 'centres/frame', [len(c) for c in clist],
+          'instances', [len(d) for d in r['panoptic_segmentation_deeplab_ids']])
+
+
+def run_centers():
+    """tie-heavy heat-maps straight into _get_instance_centers (instance.py:78-168)."""
+    g = torch.Generator().manual_seed(7)
+    H, W = 40, 52
+    cases = []
+    for ks, k, thr, q in ((3, 7, 0.1, 8.0), (5, 4, 0.3, 4.0), (3, 64, 0.1, 1024.0),
+                          (1, 5, 0.5, 8.0), (3, 3, -0.5, 2.0), (7, 2, 0.05, 16.0)):
+        heat = torch.rand(3, 1, H, W, generator=g)
+        heat = torch.round(heat * q) / q
+        if thr < 0:
+            heat[:, :, 0, 0] = 0.0           # the (0,0) corner case
+            heat[1] = -heat[1]
+        fgm = torch.rand(3, H, W, generator=g) > 0.3
+        for apply_fg in (False, True):
+            post = get_postprocessing_class('instance', heatmap_threshold=thr,
+                                            heatmap_nms_kernel_size=ks, top_k_instances=k,
+                                            heatmap_apply_foreground_mask=apply_fg)()
+            cmask, clist = post._get_instance_centers(heat.clone(), fgm)
+            cases.append(dict(ks=ks, k=k, thr=thr, apply_fg=apply_fg, heat=heat.numpy().tolist(),
+                              fg=fgm.numpy().astype(int).tolist(),
+                              mask=cmask.numpy().astype(int).tolist(),
+                              centers=[c.tolist() for c in clist]))
+            print('centers', ks, k, thr, apply_fg, [len(c) for c in clist])
+    np.savez_compressed(os.path.join(HERE, 'centers.npz'), cases=jdump(cases))
+
+
+def blocky(g, B, H, W, n_values, block):
+    low = torch.randint(0, n_values, (B, (H + block - 1) // block, (W + block - 1) // block),
+                        generator=g)
+    return low.repeat_interleave(block, 1).repeat_interleave(block, 2)[:, :H, :W].contiguous()
+
+
+def run_merge():
+    """deeplab_merge_batch as a stand-alone API (panoptic_merge.py:18-40, 172-225), with
+    void (0) in the semantic map and a foreground mask that disagrees with it."""
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 4, 48, 64
+    sem = blocky(g, B, H, W, 7, 8)                       # 0 = void, 1..6
+    # sprinkle noise so majority votes have close calls / exact ties
+    noise = torch.randint(0, 7, (B, H, W), generator=g)
+    sem = torch.where(torch.rand(B, H, W, generator=g) < 0.3, noise, sem)
+    ins = blocky(g, B, H, W, 9, 12).to(torch.uint8)
+    fg = blocky(g, B, H, W, 4, 6) > 0
+    thing_ids = np.array([2, 3, 5])
+    L = 1 << 16
+    pan, ids = deeplab_merge_batch(sem, ins, fg, L, thing_ids, 0)
+    pan2, ids2 = deeplab_merge_batch(sem, ins, fg, 1000, thing_ids, 3)
+    np.savez_compressed(os.path.join(HERE, 'merge.npz'), sem=sem.numpy(), ins=ins.numpy(),
+                        fg=fg.numpy(), thing_ids=thing_ids, L=L, pan=pan.numpy(),
+                        ids=dicts_to_json(ids), pan_L1000_void3=pan2.numpy(),
+                        ids_L1000_void3=dicts_to_json(ids2))
+    print('merge', [len(d) for d in ids])
+
+
+def run_pq():
+    """compare_and_accumulate on random blocky panoptic maps (pq.py:60-179)."""
+    g = torch.Generator().manual_seed(13)
+    B, H, W = 6, 64, 80
+    L, OFF, NC = 1 << 16, 256 ** 3, 7
+    cat_t = blocky(g, B, H, W, NC, 16)
+    inst_t = blocky(g, B, H, W, 3, 8)
+    cat_p = torch.where(torch.rand(B, H, W, generator=g) < 0.15,
+                        blocky(g, B, H, W, NC, 16), cat_t)
+    inst_p = torch.roll(inst_t, 2, dims=-1)
+    is_thing = torch.tensor([False, True, False, True, True, False, True])
+    tgt = cat_t * L + torch.where(is_thing[cat_t], inst_t + 1, torch.zeros_like(inst_t))
+    tgt = torch.where((cat_t == 0) & (inst_t == 2), torch.full_like(tgt, 5), tgt)  # ignored w/ id>0
+    pred = cat_p * L + torch.where(is_thing[cat_p], inst_p + 1, torch.zeros_like(inst_p))
+    res = {'iou': [], 'tp': [], 'fn': [], 'fp': [], 'matches': []}
+    for b in range(B):
+        iou, tp, fn, fp, m = compare_and_accumulate(pred[b], tgt[b], NC, 0, L, OFF, 0)
+        res['iou'].append(iou.numpy().copy()); res['tp'].append(tp.numpy().copy())
+        res['fn'].append(fn.numpy().copy()); res['fp'].append(fp.numpy().copy())
+        res['matches'].append(sorted([list(x) for x in m]))
+    state = [torch.zeros(NC, dtype=torch.float64) for _ in range(4)]
+    for b in range(B):      # PanopticQuality.update accumulation order  pq.py:298-303
+        for s, k in zip(state, ('iou', 'tp', 'fn', 'fp')):
+            s += torch.from_numpy(res[k][b])
+    np.savez_compressed(
+        os.path.join(HERE, 'pq.npz'), pred=pred.numpy(), target=tgt.numpy(),
+        is_thing=is_thing.numpy(), L=L, offset=OFF, num_categories=NC,
+        iou=np.stack(res['iou']), tp=np.stack(res['tp']), fn=np.stack(res['fn']),
+        fp=np.stack(res['fp']), matches=jdump(res['matches']),
+        state=np.stack([s.numpy() for s in state]))
+    print('pq tp', np.stack(res['tp']).sum(0), 'fp', np.stack(res['fp']).sum(0),
+          'fn', np.stack(res['fn']).sum(0))
+
+
+def run_miou():
+    """MeanIntersectionOverUnion.update / compute (miou.py:44-94)."""
+    g = torch.Generator().manual_seed(17)
+    out = {}
+    for n in (6, 41, 200):
+        m0 = MeanIntersectionOverUnion(n_classes=n, ignore_first_class=False)
+        m1 = MeanIntersectionOverUnion(n_classes=n, ignore_first_class=True)
+        preds, tgts = [], []
+        for _ in range(2):
+            t = torch.randint(0, n - 1, (3, 32, 40), generator=g)     # last class never in GT
+            p = torch.where(torch.rand(3, 32, 40, generator=g) < 0.7, t,
+                            torch.randint(0, n, (3, 32, 40), generator=g))
+            m0.update(p, t.to(torch.uint8) if n <= 255 else t)
+            m1.update(p, t)
+            preds.append(p); tgts.append(t)
+        miou0, ious0 = m0.compute(return_ious=True)
+        miou1, ious1 = m1.compute(return_ious=True)
+        out[f'pred_{n}'] = torch.stack(preds).numpy()
+        out[f'target_{n}'] = torch.stack(tgts).numpy()
+        out[f'confmat_{n}'] = m0.confmat.numpy()
+        out[f'miou0_{n}'] = miou0.numpy(); out[f'ious0_{n}'] = ious0.numpy()
+        out[f'miou1_{n}'] = miou1.numpy(); out[f'ious1_{n}'] = ious1.numpy()
+    np.savez_compressed(os.path.join(HERE, 'miou.npz'), **out)
+    print('miou ok')
+
+
+def run_orientation():
+    """_get_instance_orientation stand-alone with a GT-style int32 instance map and
+    foreground masks / None (instance.py:270-319)."""
+    g = torch.Generator().manual_seed(19)
+    B, H, W = 3, 40, 56
+    seg = blocky(g, B, H, W, 6, 10).to(torch.int32)
+    seg[seg == 5] = 300                                   # ids beyond uint8
+    ang = torch.rand(B, H, W, generator=g) * 0.5 + seg.float()
+    ori = torch.stack((torch.cos(ang), torch.sin(ang)), 1).contiguous()
+    mask = blocky(g, B, H, W, 3, 7) > 0
+    post = get_postprocessing_class('instance')()
+    r_mask = post._get_instance_orientation(ori, seg, mask)
+    r_none = post._get_instance_orientation(ori, seg, None)
+    np.savez_compressed(os.path.join(HERE, 'orientation.npz'), ori=ori.numpy(), seg=seg.numpy(),
+                        mask=mask.numpy(), with_mask=dicts_to_json(r_mask),
+                        without_mask=dicts_to_json(r_none))
+    print('orientation', [len(d) for d in r_mask])
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(1)
+    run_postprocess('q10', B=3, C=8, H=96, W=128, K=5, seed=1, quantize='q10')
+    run_postprocess('tie', B=3, C=6, H=96, W=128, K=6, seed=2, quantize='tie', top_k=3)
+    run_postprocess('odd', B=2, C=5, H=75, W=91, K=4, seed=3, quantize='q10', ks=5,
+                    apply_fg=True, dist_thr=20, top_k=8)
+    run_postprocess('pixel_offsets', B=2, C=7, H=64, W=80, K=4, seed=4, quantize='q10',
+                    normalized=False, with_orientation=False)
+    run_postprocess('scores', B=2, C=6, H=64, W=96, K=4, seed=5, quantize='q10',
+                    compute_scores=True)
+    run_centers()
+    run_merge()
+    run_pq()
+    run_miou()
+    run_orientation()
