@@ -1,0 +1,233 @@
+/*
+ * nicr_panoptic_b200.h -- C ABI of libnicr_panoptic_b200.so
+ *
+ * B200 (sm_100a) implementation of the dense panoptic post-processing and
+ * evaluation hot path of TUI-NICR/nicr-multitask-scene-analysis v0.3.0.
+ * Reference citations are relative to src/nicr_mt_scene_analysis/ of that repo.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name starts with `h_`
+ *    (host pointer, read synchronously before the call returns);
+ *  - dense tensors are contiguous NCHW / (B,H,W); P = H*W;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *    the calls never synchronise;
+ *  - return value: NPB_OK or a negative NPB_ERR_* for errors detectable on the
+ *    host (bad arguments, launch failure).  Data-dependent errors (too many
+ *    centres, table overflow, class id out of range ...) are reported through
+ *    the `status` device words (one int32 per frame or per call, see each
+ *    function), using the same NPB_ERR_* codes;
+ *  - `status` words must be zero (NPB_OK) on entry; errors are merged with atomicMin so
+ *    several calls may share one status buffer;
+ *  - no function allocates device memory: scratch is passed in as `workspace`
+ *    (size from the matching *_workspace_bytes function, 256-byte aligned).
+ *
+ * Per-instance tables use a fixed row length NPB_MAX_INST = 256 (instance ids
+ * are uint8 in the reference, model/postprocessing/instance.py:236; id 0 = no
+ * instance, so at most 255 centres per frame are representable).
+ */
+#ifndef NICR_PANOPTIC_B200_H
+#define NICR_PANOPTIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPB_MAX_INST 256
+
+#define NPB_OK 0
+#define NPB_ERR_ARG (-1)               /* invalid argument / unsupported size            */
+#define NPB_ERR_TOO_MANY_CENTERS (-2)  /* > 255 centres in a frame (uint8 ids would wrap) */
+#define NPB_ERR_ZERO_DIVISION (-3)     /* PQ: union == 0 (reference raises ZeroDivisionError) */
+#define NPB_ERR_CATEGORY_RANGE (-4)    /* class / category id outside [0, n)              */
+#define NPB_ERR_CAPACITY (-5)          /* a fixed-capacity table overflowed               */
+#define NPB_ERR_CUDA (-6)              /* CUDA launch error (see npb_last_cuda_error)     */
+
+/* integer dtypes accepted where the reference accepts "any int tensor" */
+#define NPB_U8 0
+#define NPB_I16 1
+#define NPB_I32 2
+#define NPB_I64 3
+#define NPB_BOOL 4
+
+int npb_abi_version(void);
+const char *npb_error_string(int code);
+const char *npb_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------
+ * Semantic arg-max.
+ * Replaces: model/postprocessing/semantic.py:52-53  (softmax(dim=1); max(dim=1)).
+ * sem_out[b][p]   = first index of the maximal logit (== reference arg-max of the
+ *                   soft-max, see DESIGN.md "soft-max caveat"), uint8, 0..C-1
+ * score_out[b][p] = soft-max probability of that class (nullable)
+ * ------------------------------------------------------------------------- */
+int npb_semantic_argmax(const float *logits, int B, int C, int H, int W,
+                        uint8_t *sem_out, float *score_out, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Class-set mask: mask_out[i] = h_class_lut[sem[i]] (uint8 0/1), N = number of pixels.
+ * Replaces: torch.isin(semantic_idx, thing_class_ids), model/postprocessing/panoptic.py:123-127
+ *           (and :296-300 for the orientation classes).
+ * ------------------------------------------------------------------------- */
+int npb_thing_mask(const uint8_t *sem, int64_t N, int C, const uint8_t *h_class_lut,
+                   uint8_t *mask_out, void *stream);
+
+/* out[i] = (int64) in[i] + add : the reference's int64 index maps (semantic.py:53 idx,
+ * panoptic.py:160 `pan // L`) from the compact uint8 maps the kernels produce. */
+int npb_widen_u8(const uint8_t *in, int64_t N, int64_t add, int64_t *out, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Instance-centre detection: threshold, k x k NMS (first maximum wins), top-k value,
+ * raster ordered centre list.
+ * Replaces: InstancePostprocessing._get_instance_centers,
+ *           model/postprocessing/instance.py:78-168.
+ * heat (B,1,H,W) f32.  fg (B,H,W) u8 is only read when apply_fg_mask != 0
+ * (instance.py:142-143).  Outputs:
+ *   centers_yx [B][256][2] int32 (y, x) in raster order, n_centers [B],
+ *   center_score [B][256] f32 = heat[y][x] (instance.py:264), status [B].
+ * ------------------------------------------------------------------------- */
+size_t npb_instance_centers_workspace_bytes(int B, int H, int W, int nms_kernel_size);
+int npb_instance_centers(const float *heat, int B, int H, int W, float threshold,
+                         int nms_kernel_size, int top_k, const uint8_t *fg, int apply_fg_mask,
+                         void *workspace, int32_t *centers_yx, int32_t *n_centers,
+                         float *center_score, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Offset grouping (+ fused semantic arg-max, class votes and orientation sums).
+ * Replaces: InstancePostprocessing._get_instance_segmentation (instance.py:170-268),
+ *           the thing mask of PanopticPostprocessing (panoptic.py:118-128), the
+ *           offset de-normalisation (panoptic.py:105-111 / instance.py:361-367), the
+ *           per-instance histogram half of deeplab_merge (utils/panoptic_merge.py:194-199)
+ *           and the sums of _get_instance_orientation (instance.py:301-310).
+ * Exactly one of {logits, sem_in, fg_in} selects where "foreground" comes from:
+ *   logits (B,C,H,W) f32 : arg-max here (sem_out (B,H,W) u8 is written), fg = h_thing_lut[class]
+ *   sem_in (B,H,W) u8    : classes given,                                 fg = h_thing_lut[class]
+ *   fg_in  (B,H,W) u8    : foreground mask given, no classes (C must be 1)
+ * offset (B,2,H,W) f32 (ch0 = y, ch1 = x); orientation (B,2,H,W) f32 or NULL.
+ * Outputs: inst_out (B,H,W) u8 (centre index + 1, 0 = none),
+ *   vote_hist [B][256][C] u32 (pixels of instance i with class c; zeroed by the call),
+ *   ori_sum  [B][256][2] f64 (sum cos, sum sin per instance; NULL iff orientation NULL).
+ * ------------------------------------------------------------------------- */
+int npb_group_pixels(const float *logits, const uint8_t *sem_in, const uint8_t *fg_in,
+                     const float *offset, const float *orientation, int B, int C, int H, int W,
+                     const uint8_t *h_thing_lut, const int32_t *centers_yx,
+                     const int32_t *n_centers, int normalized_offset, int use_distance_threshold,
+                     float distance_threshold, uint8_t *sem_out, uint8_t *inst_out,
+                     uint32_t *vote_hist, double *ori_sum, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Per-frame instance table: majority class (smallest class on ties), per-class running
+ * instance number in ascending instance id, panoptic id, area, mean orientation.
+ * Replaces: the loop of deeplab_merge_semantic_and_instance,
+ *           utils/panoptic_merge.py:192-210, the area bincount instance.py:253 and
+ *           atan2 of instance.py:313 / utils/_orientation.py:39-42.
+ * class_offset is added to the histogram column to obtain the panoptic class
+ * (1 for network classes without void, 0 when the votes already include void);
+ * an instance whose panoptic class is 0 is skipped (panoptic_merge.py:201-202).
+ * Outputs (rows of 256, row 0 unused):
+ *   inst_class  i32 : panoptic class of the instance, -1 = no pixel / skipped
+ *   inst_pan_id i64 : class * L + running number, `void_label` if skipped
+ *   inst_area   i32 ; inst_angle f32 (NaN when the class has no orientation or ori_sum NULL)
+ * ------------------------------------------------------------------------- */
+int npb_finalize_instances(const uint32_t *vote_hist, const double *ori_sum,
+                           const int32_t *n_centers, int B, int C, int class_offset,
+                           int64_t max_instances_per_category, int64_t void_label,
+                           const uint8_t *h_orientation_lut, int32_t *inst_class,
+                           int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle,
+                           void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Panoptic id map.
+ * Replaces: the masked assignments of utils/panoptic_merge.py:210, 213-223 and
+ *           `pan // L` of panoptic.py:160.
+ *   inst > 0            -> inst_pan_id[inst]
+ *   inst == 0, stuff c  -> (c + 1) * L
+ *   inst == 0, thing c  -> 0 (void)
+ * sem (B,H,W) u8 network classes, inst (B,H,W) u8; pan_out (B,H,W) i64;
+ * pan_sem_out (B,H,W) u8 = pan // L (nullable; needs inst_class from npb_finalize_instances).
+ * ------------------------------------------------------------------------- */
+int npb_write_panoptic(const uint8_t *sem, const uint8_t *inst, const int64_t *inst_pan_id,
+                       const int32_t *inst_class, int B, int C, int H, int W,
+                       const uint8_t *h_thing_lut,
+                       int64_t max_instances_per_category, int64_t *pan_out,
+                       uint8_t *pan_sem_out, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Whole post-processing of a batch in one call (centres -> grouping -> table -> ids).
+ * Replaces: PanopticPostprocessing._postprocess_inference, panoptic.py:77-167, 294-314.
+ * Same arguments as the stage functions above; `status` [B] collects stage errors.
+ * ------------------------------------------------------------------------- */
+size_t npb_panoptic_forward_workspace_bytes(int B, int C, int H, int W, int nms_kernel_size);
+int npb_panoptic_forward(const float *logits, const float *heat, const float *offset,
+                         const float *orientation, int B, int C, int H, int W,
+                         const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
+                         float threshold, int nms_kernel_size, int top_k, int apply_fg_mask,
+                         int normalized_offset, int use_distance_threshold,
+                         float distance_threshold, int64_t max_instances_per_category,
+                         void *workspace, uint8_t *sem_out, uint8_t *inst_out, int64_t *pan_out,
+                         uint8_t *pan_sem_out, int32_t *centers_yx, int32_t *n_centers,
+                         float *center_score, int32_t *inst_class, int64_t *inst_pan_id,
+                         int32_t *inst_area, float *inst_angle, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Stand-alone deeplab merge for arbitrary semantic / instance / foreground maps.
+ * Replaces: deeplab_merge_batch, utils/panoptic_merge.py:18-40, 172-225.
+ * sem (B,P) int64 in [0, n_classes) (0 = void), ins (B,P) u8, fg (B,P) u8.
+ * h_thing_lut [n_classes].  Outputs as npb_finalize_instances + pan_out (B,P) i64.
+ * workspace: npb_deeplab_merge_workspace_bytes.  status [1].
+ * ------------------------------------------------------------------------- */
+size_t npb_deeplab_merge_workspace_bytes(int B, int n_classes);
+int npb_deeplab_merge(const int64_t *sem, const uint8_t *ins, const uint8_t *fg, int B, int64_t P,
+                      int n_classes, int64_t max_instances_per_category,
+                      const uint8_t *h_thing_lut, int64_t void_label, void *workspace,
+                      int64_t *pan_out, int32_t *inst_class, int64_t *inst_pan_id,
+                      int32_t *inst_area, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Stand-alone per-instance orientation for arbitrary instance maps.
+ * Replaces: InstancePostprocessing._get_instance_orientation, instance.py:270-319.
+ * orientation (B,2,P) f32, seg (B,P) of dtype seg_dtype (NPB_U8 / NPB_I32 / NPB_I64),
+ * mask (B,P) u8 or NULL.  ids must lie in [0, max_id].
+ * Outputs: count [B][max_id+1] i32 (pixels of the id inside the mask),
+ *          angle [B][max_id+1] f32, sums [B][max_id+1][2] f64 (zeroed by the call).
+ * ------------------------------------------------------------------------- */
+int npb_instance_orientation(const float *orientation, const void *seg, int seg_dtype,
+                             const uint8_t *mask, int B, int64_t P, int max_id, int32_t *count,
+                             float *angle, double *sums, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * mIoU confusion matrix:  confmat[target][pred] += 1  (int64, accumulated in place).
+ * Replaces: MeanIntersectionOverUnion.update, metric/miou.py:44-56.
+ * status [1] : NPB_ERR_CATEGORY_RANGE if a value lies outside [0, n_classes).
+ * ------------------------------------------------------------------------- */
+int npb_confmat_update(const void *preds, int preds_dtype, const void *target, int target_dtype,
+                       int64_t N, int n_classes, int64_t *confmat, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * PQ segment matching + accumulation for a batch of frames (and, fused, the mIoU
+ * confusion matrix of `pred // L` against a semantic target when confmat != NULL).
+ * Replaces: compare_and_accumulate metric/pq.py:60-179 and the accumulation of
+ *           PanopticQuality.update pq.py:298-303 (frames are added in frame order, the
+ *           IoU sums of one frame in ascending (target*offset + pred) order, so the float64
+ *           states are bit-identical to the reference's);
+ *           with confmat: MeanIntersectionOverUnion.update of task_helper/panoptic.py:123-126.
+ * pred, target (B,P) int64 panoptic ids (>= 0).  sem_target (B,P) u8 or NULL.
+ * State (accumulated in place): iou/tp/fn/fp [num_categories] f64, confmat [n][n] i64.
+ * Per-frame outputs (nullable): frame_stats [B][4][num_categories] f64,
+ *   matches [B][match_cap][2] i64 (gt_id, pred_id), n_matches [B].
+ * status [B]: NPB_ERR_ZERO_DIVISION / _CATEGORY_RANGE / _CAPACITY per frame.
+ * ------------------------------------------------------------------------- */
+size_t npb_pq_update_workspace_bytes(int B, int num_categories);
+int npb_pq_update(const int64_t *pred, const int64_t *target, const uint8_t *sem_target, int B,
+                  int64_t P, int num_categories, int64_t ignored_label,
+                  int64_t max_instances_per_category, int64_t offset, int64_t void_segment_id,
+                  void *workspace, double *iou, double *tp, double *fn, double *fp,
+                  int64_t *confmat, int confmat_n, double *frame_stats, int64_t *matches,
+                  int match_cap, int32_t *n_matches, int32_t *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NICR_PANOPTIC_B200_H */

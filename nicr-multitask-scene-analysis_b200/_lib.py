@@ -1,0 +1,145 @@
+# -*- coding: utf-8 -*-
+"""ctypes binding of libnicr_panoptic_b200.so (include/nicr_panoptic_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing, or a tensor does not
+live on a CUDA device, the call raises.  Torch is used for device memory and streams only.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
+                    c_void_p)
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libnicr_panoptic_b200.so')
+
+MAX_INST = 256
+
+OK = 0
+ERR_ARG, ERR_TOO_MANY_CENTERS, ERR_ZERO_DIVISION, ERR_CATEGORY_RANGE, ERR_CAPACITY, ERR_CUDA = \
+    -1, -2, -3, -4, -5, -6
+
+U8, I16, I32, I64, BOOL = 0, 1, 2, 3, 4
+_DTYPE_CODES = {torch.uint8: U8, torch.int16: I16, torch.int32: I32, torch.int64: I64,
+                torch.bool: BOOL}
+
+_P = c_void_p
+_SIGNATURES = {
+    'npb_abi_version': (c_int, []),
+    'npb_error_string': (c_char_p, [c_int]),
+    'npb_last_cuda_error': (c_char_p, []),
+    'npb_semantic_argmax': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    'npb_thing_mask': (c_int, [_P, c_int64, c_int, _P, _P, _P]),
+    'npb_widen_u8': (c_int, [_P, c_int64, c_int64, _P, _P]),
+    'npb_instance_centers_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'npb_instance_centers': (c_int, [_P, c_int, c_int, c_int, c_float, c_int, c_int, _P, c_int,
+                                     _P, _P, _P, _P, _P, _P]),
+    'npb_group_pixels': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,
+                                 c_int, c_int, c_float, _P, _P, _P, _P, _P]),
+    'npb_finalize_instances': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, _P, _P,
+                                       _P, _P, _P, _P]),
+    'npb_write_panoptic': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P,
+                                   _P, _P]),
+    'npb_panoptic_forward_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'npb_panoptic_forward': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_float,
+                                     c_int, c_int, c_int, c_int, c_int, c_float, c_int64, _P, _P,
+                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'npb_deeplab_merge_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'npb_deeplab_merge': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int64, _P, c_int64, _P, _P,
+                                  _P, _P, _P, _P, _P]),
+    'npb_instance_orientation': (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P,
+                                         _P, _P]),
+    'npb_confmat_update': (c_int, [_P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P]),
+    'npb_pq_update_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'npb_pq_update': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int64, c_int64, c_int64,
+                              c_int64, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class NpbError(RuntimeError):
+    """Error reported by libnicr_panoptic_b200 (host return code or device status word)."""
+
+    def __init__(self, code: int, where: str = ''):
+        self.code = int(code)
+        msg = lib().npb_error_string(self.code).decode()
+        if self.code == ERR_CUDA:
+            msg += ': ' + lib().npb_last_cuda_error().decode()
+        super().__init__(f'{where}: {msg} (code {self.code})' if where else
+                         f'{msg} (code {self.code})')
+
+
+def lib():
+    """Load the shared library once.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python __graft_entry__.py build` '
+                '(nvcc, sm_100a).  There is no CPU / PyTorch fallback for this path.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name)     # AttributeError if the ABI lost a symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(code: int, where: str = '') -> None:
+    if code != OK:
+        raise NpbError(code, where)
+
+
+def raise_for_status(status, where: str = '') -> None:
+    """`status`: iterable of int status words already on the host."""
+    worst = min((int(s) for s in status), default=0)
+    if worst == ERR_ZERO_DIVISION:
+        # the reference's `intersection_area / union` raises exactly this (metric/pq.py:145)
+        raise ZeroDivisionError('division by zero')
+    if worst != OK:
+        raise NpbError(worst, where)
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype: Optional[torch.dtype] = None,
+                 ndim: Optional[int] = None) -> torch.Tensor:
+    """Validate a tensor handed to a kernel: CUDA, (dtype), (ndim); returns it contiguous."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name}: expected a torch.Tensor, got {type(t).__name__}')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name}: expected a CUDA tensor (this implementation has no CPU '
+                           f'path); got device {t.device}')
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f'{name}: expected dtype {dtype}, got {t.dtype}')
+    if ndim is not None and t.ndim != ndim:
+        raise ValueError(f'{name}: expected {ndim} dims, got shape {tuple(t.shape)}')
+    return t.contiguous()
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPE_CODES[t.dtype]
+    except KeyError:
+        raise TypeError(f'unsupported integer dtype {t.dtype}') from None
+
+
+def host_lut(flags: Sequence[bool], n: int):
+    """bool sequence -> ctypes uint8 array (host look-up table argument `h_*_lut`)."""
+    arr = (ctypes.c_uint8 * max(n, 1))()
+    for i, f in enumerate(flags):
+        if i < n and f:
+            arr[i] = 1
+    return arr

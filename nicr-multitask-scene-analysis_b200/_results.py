@@ -1,0 +1,164 @@
+# -*- coding: utf-8 -*-
+"""Containers for post-processing results.
+
+`ResultDict` is a plain `dict` whose values may be *deferred*: a few entries of the
+reference's result dict are expensive, rarely read copies of information the kernels keep
+in compact form (e.g. the (B,C,H,W) soft-max scores, int64 twins of uint8 maps).  They are
+present as keys (so `k in result`, `result.keys()` behave like the reference's dict) and are
+materialised by the owning kernel call on first access.
+
+`InstanceTables` holds the per-instance tables of a batch after their single device->host
+copy and turns them into the python dicts / lists of the reference API.
+"""
+from typing import Any, Callable, Dict, List
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class _Deferred:
+    __slots__ = ('fn',)
+
+    def __init__(self, fn: Callable[[], Any]):
+        self.fn = fn
+
+
+class ResultDict(dict):
+    def defer(self, key: str, fn: Callable[[], Any]) -> None:
+        dict.__setitem__(self, key, _Deferred(fn))
+
+    def alias(self, key: str, source: str) -> None:
+        """`key` resolves to whatever `source` resolves to (identity full-res twins)."""
+        dict.__setitem__(self, key, _Deferred(lambda: self[source]))
+
+    def _resolve(self, key, value):
+        if isinstance(value, _Deferred):
+            value = value.fn()
+            dict.__setitem__(self, key, value)
+        return value
+
+    def __getitem__(self, key):
+        return self._resolve(key, dict.__getitem__(self, key))
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def pop(self, key, *default):
+        if key in self:
+            value = self[key]
+            dict.__delitem__(self, key)
+            return value
+        if default:
+            return default[0]
+        raise KeyError(key)
+
+    def items(self):
+        return [(k, self[k]) for k in list(dict.keys(self))]
+
+    def values(self):
+        return [self[k] for k in list(dict.keys(self))]
+
+    def is_deferred(self, key: str) -> bool:
+        return isinstance(dict.__getitem__(self, key), _Deferred)
+
+    def materialize(self) -> 'ResultDict':
+        for k in list(dict.keys(self)):
+            self[k]
+        return self
+
+
+class InstanceTables:
+    """Per-instance tables of one batch (rows of `_lib.MAX_INST`, row 0 unused).
+
+    One packed device buffer -> one asynchronous copy into pinned host memory; `wait()`
+    blocks on the copy, checks the per-frame status words and exposes numpy views.
+    """
+
+    FIELDS = (('status', np.int32, 1), ('n_centers', np.int32, 1),
+              ('centers_yx', np.int32, 2 * _lib.MAX_INST), ('center_score', np.float32, _lib.MAX_INST),
+              ('inst_class', np.int32, _lib.MAX_INST), ('inst_area', np.int32, _lib.MAX_INST),
+              ('inst_angle', np.float32, _lib.MAX_INST), ('inst_pan_id', np.int64, _lib.MAX_INST))
+
+    def __init__(self, batch_size: int, device: torch.device):
+        self.B = batch_size
+        self.device = device
+        self._offsets = {}
+        off = 0
+        # int64 field first-aligned: lay fields out in descending alignment
+        for name, dt, per_frame in sorted(self.FIELDS, key=lambda f: -np.dtype(f[1]).itemsize):
+            nbytes = np.dtype(dt).itemsize * per_frame * batch_size
+            self._offsets[name] = (off, nbytes, dt, per_frame)
+            off += (nbytes + 15) // 16 * 16
+        self.nbytes = off
+        self.dev = torch.zeros(off, dtype=torch.uint8, device=device)
+        self._host = None
+        self._event = None
+        self._np = None
+        self._where = 'panoptic post-processing'
+
+    def dptr(self, name: str):
+        off, _, _, _ = self._offsets[name]
+        import ctypes
+        return ctypes.c_void_p(self.dev.data_ptr() + off)
+
+    def dview(self, name: str) -> torch.Tensor:
+        off, nbytes, dt, per_frame = self._offsets[name]
+        tdt = {np.int32: torch.int32, np.float32: torch.float32, np.int64: torch.int64}[dt]
+        v = self.dev[off:off + nbytes].view(tdt)
+        return v.view(self.B, per_frame) if per_frame > 1 else v
+
+    def start_download(self) -> None:
+        self._host = torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=True)
+        self._host.copy_(self.dev, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(self.device))
+
+    def wait(self) -> 'InstanceTables':
+        if self._np is None:
+            if self._event is None:
+                self.start_download()
+            self._event.synchronize()
+            raw = self._host.numpy()
+            self._np = {}
+            for name, (off, nbytes, dt, per_frame) in self._offsets.items():
+                a = raw[off:off + nbytes].view(dt)
+                self._np[name] = a.reshape(self.B, per_frame) if per_frame > 1 else a
+            _lib.raise_for_status(self._np['status'], self._where)
+        return self
+
+    def __getitem__(self, name: str) -> np.ndarray:
+        return self.wait()._np[name]
+
+    # ---- python structures of the reference API ------------------------------------------
+    def centers_list(self) -> List[torch.Tensor]:
+        """instance.py:163-166: list of (n, 2) int32 tensors (y, x), raster order."""
+        n = self['n_centers']
+        c = self['centers_yx'].reshape(self.B, _lib.MAX_INST, 2)
+        return [torch.from_numpy(c[b, :n[b]].copy()) for b in range(self.B)]
+
+    def meta(self) -> List[Dict[int, Dict[str, Any]]]:
+        """instance.py:253-266: {id: {'center_yx', 'area', 'score'}} for every centre."""
+        n = self['n_centers']
+        c = self['centers_yx'].reshape(self.B, _lib.MAX_INST, 2).tolist()
+        area = self['inst_area'].tolist()
+        score = self['center_score'].tolist()
+        return [{i + 1: {'center_yx': (c[b][i][0], c[b][i][1]), 'area': area[b][i + 1],
+                         'score': score[b][i]} for i in range(n[b])} for b in range(self.B)]
+
+    def panoptic_ids(self) -> List[Dict[int, int]]:
+        """panoptic_merge.py:209: {panoptic id: raw instance id}, ascending instance id."""
+        n = self['n_centers']
+        cls = self['inst_class']
+        pan = self['inst_pan_id']
+        return [{int(pan[b, i]): i for i in range(1, n[b] + 1) if cls[b, i] >= 0}
+                for b in range(self.B)]
+
+    def orientations(self) -> List[Dict[int, float]]:
+        """instance.py:301-317: {raw instance id: angle} for instances whose panoptic class
+        carries an orientation (angle is NaN-free there by construction)."""
+        n = self['n_centers']
+        ang = self['inst_angle']
+        return [{i: float(ang[b, i]) for i in range(1, n[b] + 1) if not np.isnan(ang[b, i])}
+                for b in range(self.B)]

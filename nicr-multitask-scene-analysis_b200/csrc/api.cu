@@ -1,0 +1,106 @@
+// api.cu -- C-ABI glue: error strings, launch-error bookkeeping, the one-call pipeline
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace npb {
+
+static thread_local char g_last_cuda_error[256] = "";
+
+int record_launch(const char *what)
+{
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return NPB_OK;
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
+    return NPB_ERR_CUDA;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace npb
+
+using namespace npb;
+
+extern "C" int npb_abi_version(void) { return 1; }
+
+extern "C" const char *npb_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" const char *npb_error_string(int code)
+{
+    switch (code) {
+        case NPB_OK: return "ok";
+        case NPB_ERR_ARG: return "invalid argument";
+        case NPB_ERR_TOO_MANY_CENTERS: return "more than 255 instance centres in a frame";
+        case NPB_ERR_ZERO_DIVISION: return "division by zero (union of segments is empty)";
+        case NPB_ERR_CATEGORY_RANGE: return "class / category id out of range";
+        case NPB_ERR_CAPACITY: return "fixed-capacity table overflowed";
+        case NPB_ERR_CUDA: return "CUDA error";
+        default: return "unknown error";
+    }
+}
+
+// workspace layout of npb_panoptic_forward: [centres scratch | vote_hist | ori_sum]
+extern "C" size_t npb_panoptic_forward_workspace_bytes(int B, int C, int H, int W,
+                                                       int nms_kernel_size)
+{
+    size_t bytes = align256(npb_instance_centers_workspace_bytes(B, H, W, nms_kernel_size));
+    bytes += align256((size_t)B * kMaxInst * C * sizeof(uint32_t));
+    bytes += align256((size_t)B * kMaxInst * 2 * sizeof(double));
+    return bytes;
+}
+
+extern "C" int npb_panoptic_forward(
+    const float *logits, const float *heat, const float *offset, const float *orientation, int B,
+    int C, int H, int W, const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
+    float threshold, int nms_kernel_size, int top_k, int apply_fg_mask, int normalized_offset,
+    int use_distance_threshold, float distance_threshold, int64_t max_instances_per_category,
+    void *workspace, uint8_t *sem_out, uint8_t *inst_out, int64_t *pan_out, uint8_t *pan_sem_out,
+    int32_t *centers_yx, int32_t *n_centers, float *center_score, int32_t *inst_class,
+    int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle, int32_t *status, void *stream)
+{
+    if (!logits || !heat || !offset || !workspace || !sem_out || !inst_out || !pan_out ||
+        !centers_yx || !n_centers || !center_score || !inst_class || !inst_pan_id || !inst_area ||
+        !status || !h_thing_lut)
+        return NPB_ERR_ARG;
+    if (C < 1 || C > 255) return NPB_ERR_ARG;
+    if (orientation && (!inst_angle || !h_orientation_lut)) return NPB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    void *ws_centers = ws;
+    ws += align256(npb_instance_centers_workspace_bytes(B, H, W, nms_kernel_size));
+    uint32_t *vote_hist = (uint32_t *)ws;
+    ws += align256((size_t)B * kMaxInst * C * sizeof(uint32_t));
+    double *ori_sum = orientation ? (double *)ws : nullptr;
+
+    cudaMemsetAsync(status, 0, (size_t)B * sizeof(int32_t), s);
+    int rc;
+    const uint8_t *fg = nullptr;
+    const float *group_logits = logits;
+    const uint8_t *group_sem = nullptr;
+    if (apply_fg_mask) {
+        // the centre mask needs the thing mask first (instance.py:142-143): run the arg-max
+        // as its own pass and reuse inst_out as the temporary foreground map
+        rc = npb_semantic_argmax(logits, B, C, H, W, sem_out, nullptr, stream);
+        if (rc != NPB_OK) return rc;
+        rc = npb_thing_mask(sem_out, (int64_t)B * H * W, C, h_thing_lut, inst_out, stream);
+        if (rc != NPB_OK) return rc;
+        fg = inst_out;
+        group_logits = nullptr;
+        group_sem = sem_out;
+    }
+    rc = npb_instance_centers(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
+                              ws_centers, centers_yx, n_centers, center_score, status, stream);
+    if (rc != NPB_OK) return rc;
+    rc = npb_group_pixels(group_logits, group_sem, nullptr, offset, orientation, B, C, H, W,
+                          h_thing_lut, centers_yx, n_centers, normalized_offset,
+                          use_distance_threshold, distance_threshold, sem_out, inst_out, vote_hist,
+                          ori_sum, stream);
+    if (rc != NPB_OK) return rc;
+    rc = npb_finalize_instances(vote_hist, ori_sum, n_centers, B, C, 1, max_instances_per_category,
+                                0, h_orientation_lut, inst_class, inst_pan_id, inst_area,
+                                inst_angle, stream);
+    if (rc != NPB_OK) return rc;
+    return npb_write_panoptic(sem_out, inst_out, inst_pan_id, inst_class, B, C, H, W, h_thing_lut,
+                              max_instances_per_category, pan_out, pan_sem_out, stream);
+}

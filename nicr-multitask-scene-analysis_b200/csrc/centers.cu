@@ -1,0 +1,231 @@
+// centers.cu -- instance-centre detection (heat-map threshold + k x k NMS + top-k)
+//
+// Replaces InstancePostprocessing._get_instance_centers
+// (reference: model/postprocessing/instance.py:78-168).  Semantics kept bit-exactly:
+//   :86-88   h = (x > thr) ? x : -1                       (strict >)
+//   :97-109  VALID k x k max-pool, ATen keeps the FIRST maximum in row-major window order
+//   :123-129 a pixel survives iff it is that first maximum of its own window
+//            => strictly greater than the window entries before it, >= those after it;
+//            the border ring of width r = (k-1)/2 never survives, except that pixel (0,0)
+//            survives when its thresholded value is exactly 0.0 (zero padding quirk)
+//   :133,147-149  kth = max(k-th largest of the post-NMS map, 0)
+//   :152-166 centres = pixels >= kth (ties can give more than k), raster order
+// Only survivors with value >= 0 can ever be selected, so only those are materialised
+// ("candidates"); everything else is equivalent to the -1 fill.
+//
+// Kernel 1 (nms_candidates_kernel): shared-memory halo tiles, warp-aggregated append.
+// Kernel 2 (select_centers_kernel): one CTA per frame, exact radix select of the k-th
+//   largest value over the candidate list, compaction, rank sort by pixel index.
+#include "common.cuh"
+
+namespace npb {
+
+constexpr int kTileW = 64;
+constexpr int kTileH = 16;
+constexpr int kNmsThreads = 256;
+constexpr int kSelThreads = 1024;
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, int r,
+                      uint2 *__restrict__ cand, int cap, int32_t *__restrict__ cand_cnt)
+{
+    extern __shared__ float tile[];  // (kTileH + 2r) x (kTileW + 2r)
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+    const int pitch = kTileW + 2 * r, rows = kTileH + 2 * r;
+    const size_t P = (size_t)H * W;
+    const float *hb = heat + (size_t)b * P;
+
+    for (int i = threadIdx.x; i < rows * pitch; i += kNmsThreads) {
+        const int ty = i / pitch, tx = i - ty * pitch;
+        const int y = y0 - r + ty, x = x0 - r + tx;
+        float v = -1.0f;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            v = __ldg(hb + (size_t)y * W + x);
+            v = (v > thr) ? v : -1.0f;
+        }
+        tile[i] = v;
+    }
+    __syncthreads();
+
+    const int tx = threadIdx.x & (kTileW - 1);
+    const int ty0 = threadIdx.x / kTileW;  // 0..3
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < kTileH / (kNmsThreads / kTileW); ++j) {
+        const int ty = ty0 + j * (kNmsThreads / kTileW);
+        const int y = y0 + ty, x = x0 + tx;
+        bool surv = false;
+        float v = -1.0f;
+        if (y < H && x < W) {
+            if (y >= r && y < H - r && x >= r && x < W - r) {
+                v = tile[(ty + r) * pitch + tx + r];
+                if (v >= 0.0f) {
+                    surv = true;
+                    for (int dy = -r; dy <= r; ++dy) {
+                        const float *row = tile + (ty + r + dy) * pitch + tx + r;
+                        for (int dx = -r; dx <= r; ++dx) {
+                            const float w = row[dx];
+                            const bool before = (dy < 0) || (dy == 0 && dx < 0);
+                            // entries before self must be strictly smaller, the rest <= self
+                            if (before ? !(v > w) : (w > v)) surv = false;
+                        }
+                    }
+                }
+            } else if (r > 0 && y == 0 && x == 0) {
+                v = tile[r * pitch + r];
+                surv = (v == 0.0f);
+            }
+        }
+        const unsigned m = __ballot_sync(kFullMask, surv);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(cand_cnt + b, __popc(m));
+            base = __shfl_sync(kFullMask, base, leader);
+            if (surv) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                // v + 0.0f canonicalises -0.0 so that the bit pattern orders like the value
+                if (slot < cap)
+                    cand[(size_t)b * cap + slot] =
+                        make_uint2(__float_as_uint(v + 0.0f), (unsigned)(y * W + x));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_centers_kernel(const uint2 *__restrict__ cand, int cap,
+                      const int32_t *__restrict__ cand_cnt, const float *__restrict__ heat,
+                      const uint8_t *__restrict__ fg, int H, int W, int top_k,
+                      int32_t *__restrict__ centers_yx, int32_t *__restrict__ n_centers,
+                      float *__restrict__ center_score, int32_t *__restrict__ status)
+{
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_remaining;
+    __shared__ int s_n;
+    __shared__ unsigned s_idx[kMaxInst];
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const size_t P = (size_t)H * W;
+    const uint2 *cb = cand + (size_t)b * cap;
+    int S = cand_cnt[b];
+    if (S > cap) {  // cannot happen (cap is the independent-set bound); be loud if it does
+        if (tid == 0) set_status(status + b, NPB_ERR_CAPACITY);
+        S = cap;
+    }
+
+    // exact k-th largest candidate value: 4 passes of an 8-bit radix select on the f32 bits
+    // (all candidate values are >= +0.0, so the unsigned bit pattern is order preserving)
+    unsigned kth_bits = 0u;
+    if (S > top_k) {
+        unsigned prefix = 0u, mask = 0u;
+        if (tid == 0) s_remaining = (unsigned)top_k;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) hist[tid] = 0u;
+            __syncthreads();
+            for (int i = tid; i < S; i += kSelThreads) {
+                const unsigned bits = cb[i].x;
+                if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned rem = s_remaining;
+                int d = 255;
+                for (; d > 0; --d) {
+                    if (hist[d] >= rem) break;
+                    rem -= hist[d];
+                }
+                s_prefix = prefix | ((unsigned)d << shift);
+                s_remaining = rem;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            mask |= 0xFFu << shift;
+        }
+        kth_bits = prefix;
+    }
+
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const uint8_t *fgb = fg ? fg + (size_t)b * P : nullptr;
+    for (int i = tid; i < S; i += kSelThreads) {
+        const uint2 c = cb[i];
+        if (c.x >= kth_bits && (!fgb || fgb[c.y])) {
+            const int slot = atomicAdd(&s_n, 1);
+            if (slot < kMaxInst) s_idx[slot] = c.y;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n > kMaxInst - 1) {
+        if (tid == 0) {
+            set_status(status + b, NPB_ERR_TOO_MANY_CENTERS);
+            n_centers[b] = 0;
+        }
+        return;
+    }
+    if (tid < n) {  // rank sort by flat pixel index = raster (y, x) order of nonzero()
+        const unsigned my = s_idx[tid];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (s_idx[j] < my);
+        const int y = (int)(my / (unsigned)W), x = (int)(my - (unsigned)y * (unsigned)W);
+        int32_t *o = centers_yx + ((size_t)b * kMaxInst + rank) * 2;
+        o[0] = y;
+        o[1] = x;
+        center_score[(size_t)b * kMaxInst + rank] = heat[(size_t)b * P + my];
+    }
+    if (tid == 0) n_centers[b] = n;
+}
+
+static int cand_capacity(int H, int W, int ks)
+{
+    if (ks <= 1) return H * W;
+    return ((H + 1) / 2) * ((W + 1) / 2) + 1;  // survivors are pairwise non-adjacent
+}
+
+}  // namespace npb
+
+using namespace npb;
+
+extern "C" size_t npb_instance_centers_workspace_bytes(int B, int H, int W, int nms_kernel_size)
+{
+    const size_t cap = (size_t)cand_capacity(H, W, nms_kernel_size);
+    size_t bytes = (size_t)B * cap * sizeof(uint2);
+    bytes = (bytes + 255) & ~(size_t)255;
+    bytes += ((size_t)B * sizeof(int32_t) + 255) & ~(size_t)255;
+    return bytes;
+}
+
+extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, float threshold,
+                                    int nms_kernel_size, int top_k, const uint8_t *fg,
+                                    int apply_fg_mask, void *workspace, int32_t *centers_yx,
+                                    int32_t *n_centers, float *center_score, int32_t *status,
+                                    void *stream)
+{
+    if (!heat || !workspace || !centers_yx || !n_centers || !center_score || !status)
+        return NPB_ERR_ARG;
+    if (B < 1 || H < 1 || W < 1 || (nms_kernel_size & 1) == 0 || nms_kernel_size < 1 ||
+        nms_kernel_size > 31)
+        return NPB_ERR_ARG;
+    if (top_k < 1 || (long long)top_k > (long long)H * W) return NPB_ERR_ARG;  // torch.topk raises
+    if ((long long)H * W >= (1ll << 31)) return NPB_ERR_ARG;
+    if (apply_fg_mask && !fg) return NPB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int r = (nms_kernel_size - 1) / 2;
+    const int cap = cand_capacity(H, W, nms_kernel_size);
+    uint2 *cand = (uint2 *)workspace;
+    size_t off = ((size_t)B * cap * sizeof(uint2) + 255) & ~(size_t)255;
+    int32_t *cand_cnt = (int32_t *)((char *)workspace + off);
+
+    cudaMemsetAsync(cand_cnt, 0, (size_t)B * sizeof(int32_t), s);
+    dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, B);
+    const size_t smem = (size_t)(kTileH + 2 * r) * (kTileW + 2 * r) * sizeof(float);
+    nms_candidates_kernel<<<grid, kNmsThreads, smem, s>>>(heat, H, W, threshold, r, cand, cap,
+                                                          cand_cnt);
+    select_centers_kernel<<<B, kSelThreads, 0, s>>>(cand, cap, cand_cnt, heat,
+                                                    apply_fg_mask ? fg : nullptr, H, W, top_k,
+                                                    centers_yx, n_centers, center_score, status);
+    return record_launch("npb_instance_centers");
+}

@@ -1,0 +1,52 @@
+// common.cuh -- shared device helpers for libnicr_panoptic_b200 (sm_100a only)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nicr_panoptic_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libnicr_panoptic_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace npb {
+
+constexpr int kMaxInst = NPB_MAX_INST;  // row length of every per-instance table
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// 256-bit class set passed by value in kernel parameters (classes are uint8)
+struct ClassSet {
+    uint32_t w[8];
+    __host__ __device__ bool has(int c) const { return (w[(c >> 5) & 7] >> (c & 31)) & 1u; }
+};
+
+inline ClassSet make_class_set(const uint8_t *h_lut, int n)
+{
+    ClassSet s;
+    for (int i = 0; i < 8; ++i) s.w[i] = 0;
+    if (h_lut)
+        for (int c = 0; c < n && c < 256; ++c)
+            if (h_lut[c]) s.w[c >> 5] |= (1u << (c & 31));
+    return s;
+}
+
+// record the first (most negative wins is irrelevant: any) error of a frame / call
+__device__ __forceinline__ void set_status(int32_t *status, int code)
+{
+    if (status) atomicMin(status, code);
+}
+
+// streaming (read-once) loads: keep them out of L1, mark evict-first in L2
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream_f1(const float *p) { return __ldcs(p); }
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+
+int record_launch(const char *what);  // api.cu: cudaGetLastError -> NPB_ERR_CUDA
+
+}  // namespace npb

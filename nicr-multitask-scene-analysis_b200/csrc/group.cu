@@ -1,0 +1,309 @@
+// group.cu -- fused semantic arg-max + offset grouping + class votes + orientation sums
+//
+// One streaming pass over the decoder outputs of a batch.  Per pixel (4 consecutive pixels
+// per thread, 128-bit loads):
+//   1. arg-max over the C logit planes (first maximal index)      semantic.py:52-53
+//   2. foreground = class is a thing                              panoptic.py:118-128
+//   3. loc = (y, x) + offset * (H, W)   (one f32 mul, one f32 add) panoptic.py:105-111,
+//                                                                  instance.py:194
+//   4. nearest centre: argmin_i sqrtf(fmaf(dx,dx,dy*dy)), first index on ties
+//                                                                  instance.py:223-236
+//   5. optional distance threshold                                 instance.py:246-247
+//   6. votes hist[instance][class] += 1 and sum(cos), sum(sin) per instance
+//                                      panoptic_merge.py:194-199, instance.py:301-310
+// The centre list of the frame (<= 255 (y, x) pairs) is staged in shared memory.
+//
+// Exactness of step 4: the reference compares the SQRT'ed f32
+// distances.  sqrtf is monotone, so a later centre can only win if its squared distance is
+// smaller; it is accepted without a square root when it is smaller by more than 2^-20
+// relative (then the rounded roots differ for sure) and otherwise the two IEEE sqrtf values
+// are compared -- identical decisions to the reference at ~5 flops per (pixel, centre).
+//
+// Votes and sums are warp-aggregated: pixels of a warp almost always share (instance,
+// class), so a warp issues one RED per distinct key instead of one per pixel.
+#include "common.cuh"
+
+namespace npb {
+
+constexpr int kGroupThreads = 256;
+
+enum SemSource { kFromLogits = 0, kFromSemMap = 1, kFromFgMask = 2 };
+
+struct GroupParams {
+    const float *logits;
+    const uint8_t *sem_in;
+    const uint8_t *fg_in;
+    const float *offset;
+    const float *orientation;
+    const int32_t *centers_yx;
+    const int32_t *n_centers;
+    uint8_t *sem_out;
+    uint8_t *inst_out;
+    uint32_t *vote_hist;
+    double *ori_sum;
+    int C, H, W, P;
+    float fH, fW;
+    int normalized, use_thr;
+    float dist_thr;
+    ClassSet thing;
+};
+
+template <int VEC>
+struct PixVec;
+template <>
+struct PixVec<4> {
+    using F = float4;
+    __device__ static void loadf(const float *p, float (&v)[4], bool stream)
+    {
+        const float4 t = stream ? ld_stream_f4((const float4 *)p) : *(const float4 *)p;
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ static void loadb(const uint8_t *p, int (&v)[4])
+    {
+        const uint32_t t = *(const uint32_t *)p;
+        v[0] = t & 255u; v[1] = (t >> 8) & 255u; v[2] = (t >> 16) & 255u; v[3] = t >> 24;
+    }
+    __device__ static void storeb(uint8_t *p, const int (&v)[4])
+    {
+        *(uint32_t *)p = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) |
+                         ((uint32_t)v[3] << 24);
+    }
+};
+template <>
+struct PixVec<1> {
+    __device__ static void loadf(const float *p, float (&v)[1], bool stream)
+    {
+        v[0] = stream ? ld_stream_f1(p) : *p;
+    }
+    __device__ static void loadb(const uint8_t *p, int (&v)[1]) { v[0] = *p; }
+    __device__ static void storeb(uint8_t *p, const int (&v)[1]) { *p = (uint8_t)v[0]; }
+};
+
+template <int VEC, int MODE, bool ORI>
+__global__ void __launch_bounds__(kGroupThreads) group_pixels_kernel(const GroupParams prm)
+{
+    __shared__ float2 s_centers[kMaxInst];
+
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int P = prm.P, W = prm.W, C = prm.C;
+    const int n = prm.n_centers[b];
+    for (int i = tid; i < n; i += kGroupThreads) {
+        const int32_t *c = prm.centers_yx + ((size_t)b * kMaxInst + i) * 2;
+        s_centers[i] = make_float2((float)c[0], (float)c[1]);
+    }
+    __syncthreads();
+
+    const int p0 = (blockIdx.x * kGroupThreads + tid) * VEC;
+    const bool active = p0 < P;  // P % VEC == 0 is guaranteed by the launcher
+    const size_t fb = (size_t)b * P + p0;
+
+    // ---- 1. semantic class ------------------------------------------------------------
+    int cls[VEC];
+    bool fg[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { cls[j] = 0; fg[j] = false; }
+    if (active) {
+        if (MODE == kFromLogits) {
+            const float *lp = prm.logits + (size_t)b * C * P + p0;
+            float best[VEC];
+            PixVec<VEC>::loadf(lp, best, true);
+#pragma unroll 8
+            for (int c = 1; c < C; ++c) {
+                float v[VEC];
+                PixVec<VEC>::loadf(lp + (size_t)c * P, v, true);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if (v[j] > best[j]) { best[j] = v[j]; cls[j] = c; }
+            }
+            PixVec<VEC>::storeb(prm.sem_out + fb, cls);
+        } else if (MODE == kFromSemMap) {
+            PixVec<VEC>::loadb(prm.sem_in + fb, cls);
+        }
+        if (MODE == kFromFgMask) {
+            int m[VEC];
+            PixVec<VEC>::loadb(prm.fg_in + fb, m);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) fg[j] = (m[j] != 0);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) fg[j] = prm.thing.has(cls[j]);
+        }
+    }
+
+    // ---- 2. nearest centre ------------------------------------------------------------
+    int inst[VEC];
+    bool any_fg = false;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { inst[j] = 0; any_fg |= fg[j]; }
+
+    if (any_fg && n > 0) {
+        float oy[VEC], ox[VEC];
+        PixVec<VEC>::loadf(prm.offset + (size_t)b * 2 * P + p0, oy, true);
+        PixVec<VEC>::loadf(prm.offset + (size_t)b * 2 * P + P + p0, ox, true);
+        float ly[VEC], lx[VEC];
+        int y = p0 / W, x = p0 - y * W;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float dy = oy[j], dx = ox[j];
+            if (prm.normalized) { dy = __fmul_rn(dy, prm.fH); dx = __fmul_rn(dx, prm.fW); }
+            ly[j] = __fadd_rn((float)y, dy);
+            lx[j] = __fadd_rn((float)x, dx);
+            if (++x == W) { x = 0; ++y; }
+        }
+        float sbest[VEC];
+        int ibest[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { sbest[j] = __int_as_float(0x7f800000); ibest[j] = 0; }
+        const float kSafe = 0.99999905f;  // 1 - 2^-20
+        for (int i = 0; i < n; ++i) {
+            const float2 c = s_centers[i];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float d0 = __fsub_rn(c.x, ly[j]);
+                const float d1 = __fsub_rn(c.y, lx[j]);
+                const float s = __fmaf_rn(d1, d1, __fmul_rn(d0, d0));
+                if (s < sbest[j]) {
+                    if (s < __fmul_rn(sbest[j], kSafe) || __fsqrt_rn(s) < __fsqrt_rn(sbest[j])) {
+                        sbest[j] = s;
+                        ibest[j] = i;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (fg[j]) {
+                inst[j] = ibest[j] + 1;
+                if (prm.use_thr && __fsqrt_rn(sbest[j]) > prm.dist_thr) inst[j] = 0;
+            }
+        }
+    }
+    if (active) PixVec<VEC>::storeb(prm.inst_out + fb, inst);
+
+    // ---- 3. votes + orientation sums (warp aggregated) ----------------------------------
+    int key[VEC];
+    bool any_inst = false;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        key[j] = inst[j] > 0 ? (inst[j] << 8) | (MODE == kFromFgMask ? 0 : cls[j]) : -1;
+        any_inst |= (inst[j] > 0);
+    }
+    if (!__any_sync(kFullMask, any_inst)) return;
+
+    float oc[VEC], os[VEC];
+    if (ORI) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { oc[j] = 0.0f; os[j] = 0.0f; }
+        if (any_inst) {
+            PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + p0, oc, true);
+            PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + P + p0, os, true);
+        }
+    }
+    const int CH = (MODE == kFromFgMask) ? 1 : C;
+    uint32_t *hist = prm.vote_hist + (size_t)b * kMaxInst * CH;
+    double *osum = ORI ? prm.ori_sum + (size_t)b * kMaxInst * 2 : nullptr;
+
+    unsigned pending = 0u;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) pending |= (key[j] >= 0 ? 1u : 0u) << j;
+    while (true) {
+        const unsigned has = __ballot_sync(kFullMask, pending != 0u);
+        if (!has) break;
+        const int leader = __ffs(has) - 1;
+        int mine = -1;
+#pragma unroll
+        for (int j = VEC - 1; j >= 0; --j)
+            if ((pending >> j) & 1u) mine = key[j];
+        const int cur = __shfl_sync(kFullMask, mine, leader);
+        int cnt = 0;
+        float sc = 0.0f, ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (((pending >> j) & 1u) && key[j] == cur) {
+                ++cnt;
+                if (ORI) { sc += oc[j]; ss += os[j]; }
+                pending &= ~(1u << j);
+            }
+        }
+        cnt = __reduce_add_sync(kFullMask, cnt);
+        if (ORI) { sc = warp_sum(sc); ss = warp_sum(ss); }
+        if (lane == 0) {
+            const int ii = cur >> 8, cc = cur & 255;
+            atomicAdd(hist + (size_t)ii * CH + cc, (uint32_t)cnt);
+            if (ORI) {
+                atomicAdd(osum + 2 * ii, (double)sc);
+                atomicAdd(osum + 2 * ii + 1, (double)ss);
+            }
+        }
+    }
+}
+
+template <int VEC, int MODE>
+static void launch_group(const GroupParams &prm, int B, bool ori, cudaStream_t s)
+{
+    dim3 grid((prm.P / VEC + kGroupThreads - 1) / kGroupThreads, B);
+    if (ori)
+        group_pixels_kernel<VEC, MODE, true><<<grid, kGroupThreads, 0, s>>>(prm);
+    else
+        group_pixels_kernel<VEC, MODE, false><<<grid, kGroupThreads, 0, s>>>(prm);
+}
+
+}  // namespace npb
+
+using namespace npb;
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+extern "C" int npb_group_pixels(const float *logits, const uint8_t *sem_in, const uint8_t *fg_in,
+                                const float *offset, const float *orientation, int B, int C,
+                                int H, int W, const uint8_t *h_thing_lut,
+                                const int32_t *centers_yx, const int32_t *n_centers,
+                                int normalized_offset, int use_distance_threshold,
+                                float distance_threshold, uint8_t *sem_out, uint8_t *inst_out,
+                                uint32_t *vote_hist, double *ori_sum, void *stream)
+{
+    const int n_src = (logits != nullptr) + (sem_in != nullptr) + (fg_in != nullptr);
+    if (n_src != 1 || !offset || !centers_yx || !n_centers || !inst_out || !vote_hist)
+        return NPB_ERR_ARG;
+    if (B < 1 || B > 65535 || C < 1 || C > 256 || H < 1 || W < 1) return NPB_ERR_ARG;
+    if ((long long)H * W >= (1ll << 30)) return NPB_ERR_ARG;
+    if (logits && !sem_out) return NPB_ERR_ARG;
+    if (!fg_in && !h_thing_lut) return NPB_ERR_ARG;
+    if (fg_in && C != 1) return NPB_ERR_ARG;
+    if ((orientation != nullptr) != (ori_sum != nullptr)) return NPB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    GroupParams prm;
+    prm.logits = logits; prm.sem_in = sem_in; prm.fg_in = fg_in;
+    prm.offset = offset; prm.orientation = orientation;
+    prm.centers_yx = centers_yx; prm.n_centers = n_centers;
+    prm.sem_out = sem_out; prm.inst_out = inst_out;
+    prm.vote_hist = vote_hist; prm.ori_sum = ori_sum;
+    prm.C = C; prm.H = H; prm.W = W; prm.P = H * W;
+    prm.fH = (float)H; prm.fW = (float)W;
+    prm.normalized = normalized_offset; prm.use_thr = use_distance_threshold;
+    prm.dist_thr = distance_threshold;
+    prm.thing = make_class_set(h_thing_lut, fg_in ? 0 : C);
+
+    const int CH = fg_in ? 1 : C;
+    cudaMemsetAsync(vote_hist, 0, (size_t)B * kMaxInst * CH * sizeof(uint32_t), s);
+    if (ori_sum) cudaMemsetAsync(ori_sum, 0, (size_t)B * kMaxInst * 2 * sizeof(double), s);
+
+    const bool vec4 = (prm.P % 4 == 0) && W >= 4 && aligned16(logits) && aligned16(offset) &&
+                      aligned16(orientation) && (((uintptr_t)sem_in | (uintptr_t)fg_in |
+                                                  (uintptr_t)sem_out | (uintptr_t)inst_out) & 3u) == 0;
+    const bool ori = orientation != nullptr;
+    if (logits) {
+        if (vec4) launch_group<4, kFromLogits>(prm, B, ori, s);
+        else launch_group<1, kFromLogits>(prm, B, ori, s);
+    } else if (sem_in) {
+        if (vec4) launch_group<4, kFromSemMap>(prm, B, ori, s);
+        else launch_group<1, kFromSemMap>(prm, B, ori, s);
+    } else {
+        if (vec4) launch_group<4, kFromFgMask>(prm, B, ori, s);
+        else launch_group<1, kFromFgMask>(prm, B, ori, s);
+    }
+    return record_launch("npb_group_pixels");
+}

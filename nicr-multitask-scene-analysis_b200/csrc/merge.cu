@@ -1,0 +1,267 @@
+// merge.cu -- per-frame instance table + panoptic id map (the "deeplab merge")
+//
+// Replaces deeplab_merge_semantic_and_instance (reference: utils/panoptic_merge.py:172-225):
+//   :192-210  instances in ascending id: class = torch.mode(sem[mask]) (smallest value on
+//             ties), skip class 0, running number per class, pan id = class * L + number
+//   :213-223  every non-thing, non-void class: pan[(sem == c) & (ins == 0)] = c * L
+// plus the meta areas (instance.py:253) and the orientation angle (instance.py:313,
+// utils/_orientation.py:39-42).  The per-pixel histogram half lives in group.cu (fused path)
+// or in merge_votes_kernel below (stand-alone API).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace npb {
+
+// one CTA per frame, thread i <-> raw instance id i
+__global__ void __launch_bounds__(kMaxInst)
+finalize_instances_kernel(const uint32_t *__restrict__ vote_hist,
+                          const double *__restrict__ ori_sum,
+                          const int32_t *__restrict__ n_centers, int C, int class_offset,
+                          long long L, long long void_label, ClassSet orient,
+                          int32_t *__restrict__ inst_class, int64_t *__restrict__ inst_pan_id,
+                          int32_t *__restrict__ inst_area, float *__restrict__ inst_angle)
+{
+    __shared__ int s_cls[kMaxInst];
+    const int b = blockIdx.x, i = threadIdx.x;
+    const int n = n_centers ? n_centers[b] : kMaxInst - 1;
+    const uint32_t *row = vote_hist + ((size_t)b * kMaxInst + i) * C;
+
+    int cls = -1;
+    uint32_t best = 0, area = 0;
+    if (i >= 1 && i <= n) {
+        for (int c = 0; c < C; ++c) {
+            const uint32_t h = row[c];
+            area += h;
+            if (h > best) { best = h; cls = c; }  // strict > : smallest class wins ties
+        }
+    }
+    int pcls = (cls >= 0) ? cls + class_offset : -1;
+    if (pcls == 0) pcls = -1;  // majority is void -> instance dropped (panoptic_merge.py:201)
+    s_cls[i] = pcls;
+    __syncthreads();
+    int number = 1;
+    if (pcls >= 0)
+        for (int j = 1; j < i; ++j) number += (s_cls[j] == pcls);
+
+    const size_t o = (size_t)b * kMaxInst + i;
+    inst_class[o] = pcls;
+    inst_pan_id[o] = (pcls >= 0) ? (long long)pcls * L + number : void_label;
+    inst_area[o] = (int32_t)area;
+    float ang = nanf("");
+    if (ori_sum && pcls >= 0 && orient.has(pcls)) {
+        const double sc = ori_sum[2 * o], ss = ori_sum[2 * o + 1];
+        // the reference forms f32 sums and calls atan2 on them (instance.py:310-313)
+        ang = (float)atan2((double)(float)ss, (double)(float)sc);
+    }
+    if (inst_angle) inst_angle[o] = ang;
+}
+
+// 4 pixels per thread: 32-bit loads of the two uint8 maps, two 128-bit stores of int64 ids
+template <int VEC>
+__global__ void __launch_bounds__(256)
+write_panoptic_kernel(const uint8_t *__restrict__ sem, const uint8_t *__restrict__ inst,
+                      const int64_t *__restrict__ inst_pan_id,
+                      const int32_t *__restrict__ inst_class, int P, long long L,
+                      ClassSet thing, int64_t *__restrict__ pan_out,
+                      uint8_t *__restrict__ pan_sem_out)
+{
+    __shared__ long long s_pan[kMaxInst];
+    __shared__ int s_cls[kMaxInst];
+    const int b = blockIdx.y;
+    s_pan[threadIdx.x] = inst_pan_id[(size_t)b * kMaxInst + threadIdx.x];
+    if (pan_sem_out) {
+        const int c = inst_class[(size_t)b * kMaxInst + threadIdx.x];
+        s_cls[threadIdx.x] = c < 0 ? 0 : c;  // dropped instance -> void
+    }
+    __syncthreads();
+    const int p0 = (blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (p0 >= P) return;
+    const size_t fb = (size_t)b * P + p0;
+    uint32_t sw, iw;
+    if (VEC == 4) {
+        sw = *(const uint32_t *)(sem + fb);
+        iw = *(const uint32_t *)(inst + fb);
+    } else {
+        sw = sem[fb];
+        iw = inst[fb];
+    }
+    long long out[VEC];
+    uint32_t psw = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int c = (sw >> (8 * j)) & 255, ii = (iw >> (8 * j)) & 255;
+        long long v;
+        int pc;  // panoptic class = v / L without the 64-bit division
+        if (ii > 0) {
+            v = s_pan[ii];
+            pc = pan_sem_out ? s_cls[ii] : 0;
+        } else {
+            pc = thing.has(c) ? 0 : c + 1;
+            v = (long long)pc * L;
+        }
+        out[j] = v;
+        psw |= (uint32_t)pc << (8 * j);
+    }
+    if (VEC == 4) {
+        longlong2 *o = (longlong2 *)(pan_out + fb);
+        o[0] = make_longlong2(out[0], out[1]);
+        o[1] = make_longlong2(out[2], out[3]);
+        if (pan_sem_out) *(uint32_t *)(pan_sem_out + fb) = psw;
+    } else {
+        pan_out[fb] = out[0];
+        if (pan_sem_out) pan_sem_out[fb] = (uint8_t)psw;
+    }
+}
+
+// ---- stand-alone merge: arbitrary semantic / instance / foreground maps -----------------
+__global__ void __launch_bounds__(256)
+merge_votes_kernel(const int64_t *__restrict__ sem, const uint8_t *__restrict__ ins,
+                   const uint8_t *__restrict__ fg, long long P, int n_classes,
+                   uint32_t *__restrict__ vote_hist, int32_t *__restrict__ status)
+{
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    uint32_t *hist = vote_hist + (size_t)b * kMaxInst * n_classes;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < ((P + 31) / 32) * 32;
+         p += (long long)gridDim.x * 256) {
+        int key = -1;
+        if (p < P) {
+            const size_t q = (size_t)b * P + p;
+            const long long c = sem[q];
+            if (c < 0 || c >= n_classes) {
+                set_status(status, NPB_ERR_CATEGORY_RANGE);
+            } else if (ins[q] > 0 && fg[q]) {
+                key = ((int)ins[q]) * n_classes + (int)c;
+            }
+        }
+        // warp aggregation over equal keys
+        unsigned pending = __ballot_sync(kFullMask, key >= 0);
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const int cur = __shfl_sync(kFullMask, key, leader);
+            const unsigned same = __ballot_sync(kFullMask, key == cur);
+            if (lane == leader) atomicAdd(hist + cur, (uint32_t)__popc(same));
+            pending &= ~same;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+merge_write_kernel(const int64_t *__restrict__ sem, const uint8_t *__restrict__ ins,
+                   const uint8_t *__restrict__ fg, const int64_t *__restrict__ inst_pan_id,
+                   long long P, int n_classes, long long L, long long void_label,
+                   const uint8_t *__restrict__ thing_lut, int64_t *__restrict__ pan_out)
+{
+    __shared__ long long s_pan[kMaxInst];
+    const int b = blockIdx.y;
+    s_pan[threadIdx.x] = inst_pan_id[(size_t)b * kMaxInst + threadIdx.x];
+    __syncthreads();
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P;
+         p += (long long)gridDim.x * 256) {
+        const size_t q = (size_t)b * P + p;
+        const long long c = sem[q];
+        const int ii = ins[q];
+        long long v = void_label;
+        if (ii > 0) {
+            if (fg[q]) v = s_pan[ii];
+        } else if (c > 0 && c < n_classes && !thing_lut[c]) {
+            v = c * L;
+        }
+        pan_out[q] = v;
+    }
+}
+
+}  // namespace npb
+
+using namespace npb;
+
+extern "C" int npb_finalize_instances(const uint32_t *vote_hist, const double *ori_sum,
+                                      const int32_t *n_centers, int B, int C, int class_offset,
+                                      int64_t max_instances_per_category, int64_t void_label,
+                                      const uint8_t *h_orientation_lut, int32_t *inst_class,
+                                      int64_t *inst_pan_id, int32_t *inst_area,
+                                      float *inst_angle, void *stream)
+{
+    if (!vote_hist || !inst_class || !inst_pan_id || !inst_area) return NPB_ERR_ARG;
+    if (B < 1 || C < 1 || C > 65536 || max_instances_per_category < 1) return NPB_ERR_ARG;
+    // the orientation set is indexed by PANOPTIC class (network class + class_offset)
+    uint8_t lut[256] = {0};
+    if (h_orientation_lut)
+        for (int c = 0; c < C && c + class_offset < 256; ++c)
+            if (c + class_offset >= 0) lut[c + class_offset] = h_orientation_lut[c];
+    const ClassSet orient = make_class_set(lut, 256);
+    finalize_instances_kernel<<<B, kMaxInst, 0, (cudaStream_t)stream>>>(
+        vote_hist, ori_sum, n_centers, C, class_offset, (long long)max_instances_per_category,
+        (long long)void_label, orient, inst_class, inst_pan_id, inst_area, inst_angle);
+    return record_launch("npb_finalize_instances");
+}
+
+extern "C" int npb_write_panoptic(const uint8_t *sem, const uint8_t *inst,
+                                  const int64_t *inst_pan_id, const int32_t *inst_class, int B,
+                                  int C, int H, int W,
+                                  const uint8_t *h_thing_lut, int64_t max_instances_per_category,
+                                  int64_t *pan_out, uint8_t *pan_sem_out, void *stream)
+{
+    if (!sem || !inst || !inst_pan_id || !pan_out || !h_thing_lut) return NPB_ERR_ARG;
+    if (pan_sem_out && !inst_class) return NPB_ERR_ARG;
+    if (B < 1 || B > 65535 || C < 1 || C > 255 || max_instances_per_category < 1)
+        return NPB_ERR_ARG;
+    if ((long long)H * W >= (1ll << 30)) return NPB_ERR_ARG;
+    const int P = H * W;
+    const ClassSet thing = make_class_set(h_thing_lut, C);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec4 = (P % 4 == 0) &&
+                      (((uintptr_t)sem | (uintptr_t)inst | (uintptr_t)pan_sem_out) & 3u) == 0 &&
+                      ((uintptr_t)pan_out & 15u) == 0;
+    if (vec4) {
+        dim3 grid((P / 4 + 255) / 256, B);
+        write_panoptic_kernel<4><<<grid, 256, 0, s>>>(sem, inst, inst_pan_id, inst_class, P,
+                                                      (long long)max_instances_per_category,
+                                                      thing, pan_out, pan_sem_out);
+    } else {
+        dim3 grid((P + 255) / 256, B);
+        write_panoptic_kernel<1><<<grid, 256, 0, s>>>(sem, inst, inst_pan_id, inst_class, P,
+                                                      (long long)max_instances_per_category,
+                                                      thing, pan_out, pan_sem_out);
+    }
+    return record_launch("npb_write_panoptic");
+}
+
+extern "C" size_t npb_deeplab_merge_workspace_bytes(int B, int n_classes)
+{
+    size_t bytes = (size_t)B * kMaxInst * n_classes * sizeof(uint32_t);
+    bytes = (bytes + 255) & ~(size_t)255;
+    bytes += ((size_t)n_classes + 255) & ~(size_t)255;  // device copy of the thing lut
+    return bytes;
+}
+
+extern "C" int npb_deeplab_merge(const int64_t *sem, const uint8_t *ins, const uint8_t *fg, int B,
+                                 int64_t P, int n_classes, int64_t max_instances_per_category,
+                                 const uint8_t *h_thing_lut, int64_t void_label, void *workspace,
+                                 int64_t *pan_out, int32_t *inst_class, int64_t *inst_pan_id,
+                                 int32_t *inst_area, int32_t *status, void *stream)
+{
+    if (!sem || !ins || !fg || !workspace || !pan_out || !inst_class || !inst_pan_id ||
+        !inst_area || !status || !h_thing_lut)
+        return NPB_ERR_ARG;
+    if (B < 1 || B > 65535 || P < 1 || n_classes < 1 || n_classes > 65536) return NPB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t *hist = (uint32_t *)workspace;
+    const size_t hist_bytes = (size_t)B * kMaxInst * n_classes * sizeof(uint32_t);
+    uint8_t *d_lut = (uint8_t *)workspace + ((hist_bytes + 255) & ~(size_t)255);
+    cudaMemsetAsync(hist, 0, hist_bytes, s);
+    // pageable host source: the copy is staged before the call returns
+    cudaMemcpyAsync(d_lut, h_thing_lut, (size_t)n_classes, cudaMemcpyHostToDevice, s);
+    const int bx = (int)((P + 256 * 8 - 1) / (256 * 8));
+    dim3 grid(bx < 1 ? 1 : bx, B);
+    merge_votes_kernel<<<grid, 256, 0, s>>>(sem, ins, fg, (long long)P, n_classes, hist, status);
+    const ClassSet none = make_class_set(nullptr, 0);
+    finalize_instances_kernel<<<B, kMaxInst, 0, s>>>(
+        hist, nullptr, nullptr, n_classes, 0, (long long)max_instances_per_category,
+        (long long)void_label, none, inst_class, inst_pan_id, inst_area, nullptr);
+    merge_write_kernel<<<grid, 256, 0, s>>>(sem, ins, fg, inst_pan_id, (long long)P, n_classes,
+                                            (long long)max_instances_per_category,
+                                            (long long)void_label, d_lut, pan_out);
+    return record_launch("npb_deeplab_merge");
+}

@@ -1,0 +1,87 @@
+// semantic.cu -- stand-alone semantic arg-max (+ optional soft-max score of the winner)
+//
+// Replaces SemanticPostprocessing._postprocess_inference's softmax + max
+// (reference: model/postprocessing/semantic.py:52-53).  One streaming pass over the C logit
+// planes; the score uses an online soft-max (running max + rescaled running sum) so the
+// logits are read exactly once:  score = exp(max - max) / sum_c exp(x_c - max) = 1 / sum.
+#include "common.cuh"
+
+namespace npb {
+
+template <int VEC, bool SCORE>
+__global__ void __launch_bounds__(256)
+semantic_argmax_kernel(const float *__restrict__ logits, int C, int P,
+                       uint8_t *__restrict__ sem_out, float *__restrict__ score_out)
+{
+    const int b = blockIdx.y;
+    const int p0 = (blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (p0 >= P) return;
+    const float *lp = logits + (size_t)b * C * P + p0;
+    float best[VEC], sum[VEC];
+    int cls[VEC];
+    if (VEC == 4) {
+        const float4 t = ld_stream_f4((const float4 *)lp);
+        best[0] = t.x; best[1 % VEC] = t.y; best[2 % VEC] = t.z; best[3 % VEC] = t.w;
+    } else {
+        best[0] = ld_stream_f1(lp);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { cls[j] = 0; sum[j] = 1.0f; }
+#pragma unroll 8
+    for (int c = 1; c < C; ++c) {
+        float v[VEC];
+        if (VEC == 4) {
+            const float4 t = ld_stream_f4((const float4 *)(lp + (size_t)c * P));
+            v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+        } else {
+            v[0] = ld_stream_f1(lp + (size_t)c * P);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (v[j] > best[j]) {
+                if (SCORE) sum[j] = sum[j] * __expf(best[j] - v[j]) + 1.0f;
+                best[j] = v[j];
+                cls[j] = c;
+            } else if (SCORE) {
+                sum[j] += __expf(v[j] - best[j]);
+            }
+        }
+    }
+    const size_t fb = (size_t)b * P + p0;
+    if (VEC == 4) {
+        *(uint32_t *)(sem_out + fb) = (uint32_t)cls[0] | ((uint32_t)cls[1 % VEC] << 8) |
+                                      ((uint32_t)cls[2 % VEC] << 16) | ((uint32_t)cls[3 % VEC] << 24);
+        if (SCORE)
+            *(float4 *)(score_out + fb) = make_float4(1.0f / sum[0], 1.0f / sum[1 % VEC],
+                                                      1.0f / sum[2 % VEC], 1.0f / sum[3 % VEC]);
+    } else {
+        sem_out[fb] = (uint8_t)cls[0];
+        if (SCORE) score_out[fb] = 1.0f / sum[0];
+    }
+}
+
+}  // namespace npb
+
+using namespace npb;
+
+extern "C" int npb_semantic_argmax(const float *logits, int B, int C, int H, int W,
+                                   uint8_t *sem_out, float *score_out, void *stream)
+{
+    if (!logits || !sem_out) return NPB_ERR_ARG;
+    if (B < 1 || B > 65535 || C < 1 || C > 256 || H < 1 || W < 1) return NPB_ERR_ARG;
+    if ((long long)H * W >= (1ll << 30)) return NPB_ERR_ARG;
+    const int P = H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec4 = (P % 4 == 0) && (((uintptr_t)logits | (uintptr_t)score_out) & 15u) == 0 &&
+                      ((uintptr_t)sem_out & 3u) == 0;
+    if (vec4) {
+        dim3 grid((P / 4 + 255) / 256, B);
+        if (score_out) semantic_argmax_kernel<4, true><<<grid, 256, 0, s>>>(logits, C, P, sem_out, score_out);
+        else semantic_argmax_kernel<4, false><<<grid, 256, 0, s>>>(logits, C, P, sem_out, score_out);
+    } else {
+        dim3 grid((P + 255) / 256, B);
+        if (score_out) semantic_argmax_kernel<1, true><<<grid, 256, 0, s>>>(logits, C, P, sem_out, score_out);
+        else semantic_argmax_kernel<1, false><<<grid, 256, 0, s>>>(logits, C, P, sem_out, score_out);
+    }
+    return record_launch("npb_semantic_argmax");
+}

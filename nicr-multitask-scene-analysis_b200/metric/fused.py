@@ -1,0 +1,47 @@
+# -*- coding: utf-8 -*-
+"""One-pass evaluation: PQ and the mIoU confusion matrix from a single read of the
+predicted panoptic map.
+
+The reference's validation step (task_helper/panoptic.py:104-126) calls
+`PanopticQualityWithOrientationMAE.update(pred, target)` and then
+`MeanIntersectionOverUnion.update(pred // max_instances, semantic_target)`: the prediction
+is read twice and `pred // L` is materialised as an int64 tensor in between.
+`PanopticEvaluation.update` feeds both metric objects from one launch of `npb_pq_update`
+(17 bytes per pixel: int64 prediction, int64 panoptic target, uint8 semantic target); the
+states it leaves in the two metric objects are identical to those of the two separate calls.
+"""
+from typing import Optional
+
+import torch
+
+from .miou import MeanIntersectionOverUnion
+from .pq import PanopticQuality
+
+
+class PanopticEvaluation:
+    def __init__(self, pq: PanopticQuality, miou: MeanIntersectionOverUnion):
+        assert miou._n_classes <= 256
+        self.pq = pq
+        self.miou = miou
+
+    def update(self, panoptic_preds: torch.Tensor, panoptic_targets: torch.Tensor,
+               semantic_targets: torch.Tensor, want_matches: bool = False):
+        """(B,H,W) int64, (B,H,W) int64, (B,H,W) uint8.  Returns (matches, n_matches) device
+        tensors when `want_matches` (for the MAAE loop), else None."""
+        if semantic_targets.dtype != torch.uint8:
+            semantic_targets = semantic_targets.to(torch.uint8)
+        matches, n_matches, _ = self.pq._launch(
+            panoptic_preds, panoptic_targets, sem_target=semantic_targets,
+            confmat=self.miou.confmat, want_matches=want_matches)
+        return (matches, n_matches) if want_matches else None
+
+    def reset(self) -> None:
+        self.pq.reset()
+        self.miou.reset()
+
+    def compute(self, suffix: str = ''):
+        out = self.pq.compute(suffix=suffix)
+        miou, ious = self.miou.compute(return_ious=True)
+        out[f'semantic{suffix}_miou'] = miou
+        out[f'semantic{suffix}_ious_per_class'] = ious
+        return out

@@ -1,0 +1,185 @@
+# -*- coding: utf-8 -*-
+"""Panoptic quality on the GPU (API of metric/pq.py:60-361).
+
+`update` is one call of `npb_pq_update` (csrc/eval.cu): a streaming pixel pass building a
+per-frame (gt segment, pred segment) contingency table, a per-frame matcher and an ordered
+accumulation -- it replaces the reference's process pool + three `torch.unique` sorts per
+frame.  The float64 states are bit-identical to the reference's (same summation orders).
+`compute` mirrors pq.py:304-361 on the rank-summed states.
+"""
+from ctypes import c_int, c_int64
+from typing import Dict, List, Optional, Set, Tuple, Union
+
+import torch
+
+from .. import _lib
+from ._state import MetricState
+
+_EPSILON = 1e-10
+MATCH_CAP = 1024        # matched (gt, pred) pairs kept per frame
+
+
+def _safe_divide(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """x / y, 0 where |y| < 1e-10 (pq.py:182-187)."""
+    return torch.where(torch.abs(y) < _EPSILON, torch.zeros_like(x), x / y)
+
+
+class _PQKernel:
+    """Workspace + launch helper shared by PanopticQuality and compare_and_accumulate."""
+
+    @staticmethod
+    def run(pred: torch.Tensor, target: torch.Tensor, num_categories: int, ignored_label: int,
+            max_instances_per_category: int, offset: int, void_segment_id: int,
+            iou, tp, fn, fp, sem_target: Optional[torch.Tensor] = None,
+            confmat: Optional[torch.Tensor] = None, want_matches: bool = False,
+            want_frame_stats: bool = False):
+        dev = iou.device
+        if not dev.type == 'cuda':
+            raise RuntimeError('PanopticQuality.update needs its states on a CUDA device')
+        pred = _lib.require_cuda(pred.to(dev).to(torch.int64), 'preds', ndim=3)
+        target = _lib.require_cuda(target.to(dev).to(torch.int64), 'targets', ndim=3)
+        assert target.shape == pred.shape
+        B = pred.shape[0]
+        P = pred.shape[1] * pred.shape[2]
+        L = _lib.lib()
+        ws = torch.empty(L.npb_pq_update_workspace_bytes(B, num_categories), dtype=torch.uint8,
+                         device=dev)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        matches = n_matches = frame_stats = None
+        if want_matches:
+            matches = torch.empty((B, MATCH_CAP, 2), dtype=torch.int64, device=dev)
+            n_matches = torch.zeros(B, dtype=torch.int32, device=dev)
+        if want_frame_stats:
+            frame_stats = torch.empty((B, 4, num_categories), dtype=torch.float64, device=dev)
+        n_cm = 0
+        if confmat is not None:
+            sem_target = _lib.require_cuda(sem_target.to(dev), 'semantic target', torch.uint8, 3)
+            n_cm = confmat.shape[0]
+        _lib.check(L.npb_pq_update(
+            _lib.ptr(pred), _lib.ptr(target), _lib.ptr(sem_target), c_int(B), c_int64(P),
+            c_int(num_categories), c_int64(ignored_label), c_int64(max_instances_per_category),
+            c_int64(offset), c_int64(void_segment_id), _lib.ptr(ws), _lib.ptr(iou), _lib.ptr(tp),
+            _lib.ptr(fn), _lib.ptr(fp), _lib.ptr(confmat), c_int(n_cm), _lib.ptr(frame_stats),
+            _lib.ptr(matches), c_int(MATCH_CAP), _lib.ptr(n_matches), _lib.ptr(status),
+            _lib.stream_ptr(dev)), 'npb_pq_update')
+        return status, matches, n_matches, frame_stats
+
+
+def compare_and_accumulate(
+    pred: torch.Tensor,
+    target: torch.Tensor,
+    num_categories: int,
+    ignored_label: int,
+    max_instances_per_category,
+    offset: int,
+    void_segment_id: int
+) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, Set[Tuple[int, int]]]:
+    """One frame (H,W): returns (iou, tp, fn, fp) float64 [num_categories] (CPU) and the set
+    of matched (gt_segment_id, pred_segment_id) pairs -- pq.py:60-179."""
+    if not pred.is_cuda:
+        raise RuntimeError('compare_and_accumulate: expected CUDA tensors (no CPU path)')
+    dev = pred.device
+    state = [torch.zeros(num_categories, dtype=torch.float64, device=dev) for _ in range(4)]
+    status, matches, n_matches, _ = _PQKernel.run(
+        pred[None], target[None], num_categories, ignored_label, max_instances_per_category,
+        offset, void_segment_id, *state, want_matches=True)
+    _lib.raise_for_status(status.cpu().tolist(), 'compare_and_accumulate')
+    n = int(n_matches[0].item())
+    pairs = {(int(g), int(p)) for g, p in matches[0, :n].cpu().tolist()}
+    iou, tp, fn, fp = (s.cpu() for s in state)
+    return iou, tp, fn, fp, pairs
+
+
+class PanopticQuality(MetricState):
+    def __init__(
+        self,
+        num_categories: int,
+        ignored_label: int,
+        max_instances_per_category: int,
+        offset: int,
+        is_thing: Union[torch.Tensor, List[bool]],
+        num_workers=None,          # accepted for API parity; there is no process pool
+        device=None
+    ) -> None:
+        super().__init__(device)
+        self.num_categories = num_categories
+        self.ignored_label = ignored_label
+        self.max_instances_per_category = max_instances_per_category
+        self.offset = offset
+        self.is_thing = torch.as_tensor(is_thing).to(torch.bool).cpu()
+        self.is_stuff = torch.logical_not(self.is_thing)
+        assert len(self.is_thing) == self.num_categories
+        # one void segment with instance id 0 (pq.py:220-222)
+        self.void_segment_id = self.ignored_label * self.max_instances_per_category
+        for name in ('iou_per_class', 'tp_per_class', 'fn_per_class', 'fp_per_class'):
+            self.add_state(name, torch.zeros(num_categories, dtype=torch.float64),
+                           dist_reduce_fx='sum')
+        self._pending_status: List[torch.Tensor] = []
+
+    # ---- update --------------------------------------------------------------------------
+    def _launch(self, preds, targets, **kw):
+        assert preds.ndim == 3
+        assert targets.shape == preds.shape
+        status, matches, n_matches, frame_stats = _PQKernel.run(
+            preds, targets, self.num_categories, self.ignored_label,
+            self.max_instances_per_category, self.offset, self.void_segment_id,
+            self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class, **kw)
+        self._pending_status.append(status)
+        return matches, n_matches, frame_stats
+
+    def update(self, preds: torch.Tensor, targets: torch.Tensor) -> None:
+        """preds, targets: (B,H,W) panoptic ids (class * max_instances + instance).
+        Asynchronous; data-dependent errors surface at `compute()` / `check_status()`."""
+        self._launch(preds, targets)
+
+    def check_status(self) -> None:
+        pending, self._pending_status = self._pending_status, []
+        for status in pending:
+            _lib.raise_for_status(status.cpu().tolist(), type(self).__name__ + '.update')
+
+    def reset(self) -> None:
+        super().reset()
+        self._pending_status = []
+
+    # ---- compute (pq.py:254-361) -----------------------------------------------------------
+    @staticmethod
+    def _valid(counts: torch.Tensor, ignored_label: int) -> torch.Tensor:
+        valid = counts != 0
+        if 0 <= ignored_label < len(valid):
+            valid[ignored_label] = False
+        return valid
+
+    def _host_states(self) -> Dict[str, torch.Tensor]:
+        self.check_status()
+        return {k: v.cpu() for k, v in self.synced_states().items()}
+
+    def result_per_category(self, states: Optional[Dict[str, torch.Tensor]] = None) -> Dict:
+        s = states if states is not None else self._host_states()
+        sq = _safe_divide(s['iou_per_class'], s['tp_per_class'])
+        rq = _safe_divide(s['tp_per_class'], s['tp_per_class'] + 0.5 * s['fn_per_class'] +
+                          0.5 * s['fp_per_class'])
+        return {'sq_per_class': sq, 'rq_per_class': rq, 'pq_per_class': torch.multiply(sq, rq)}
+
+    def compute(self, suffix: str = '') -> Dict:
+        s = self._host_states()
+        results = self.result_per_category(s)
+        tp, fn, fp = s['tp_per_class'], s['fn_per_class'], s['fp_per_class']
+        valid = self._valid(tp + fn + fp, self.ignored_label)        # panopticapi convention
+        valid_gt = self._valid(tp + fn, self.ignored_label)          # categories with GT only
+        subsets = {
+            f'all{suffix}': valid,
+            f'things{suffix}': valid & self.is_thing,
+            f'stuff{suffix}': valid & self.is_stuff,
+            f'all_with_gt{suffix}': valid_gt,
+            f'things_with_gt{suffix}': valid_gt & self.is_thing,
+            f'stuff_with_gt{suffix}': valid_gt & self.is_stuff,
+        }
+        for name, sel in subsets.items():
+            if torch.any(sel):
+                for q in ('pq', 'sq', 'rq'):
+                    results[f'{name}_{q}'] = torch.mean(results[f'{q}_per_class'][sel])
+                results[f'{name}_num_categories'] = torch.sum(sel.int())
+            else:
+                for q in ('pq', 'sq', 'rq', 'num_categories'):
+                    results[f'{name}_{q}'] = torch.tensor(0)
+        return results

@@ -1,0 +1,217 @@
+# -*- coding: utf-8 -*-
+"""Panoptic post-processing on the GPU (API of model/postprocessing/panoptic.py:23-316).
+
+`_postprocess_inference` issues ONE C-ABI call, `npb_panoptic_forward`, which enqueues
+    centre NMS/top-k  ->  fused arg-max + offset grouping + votes + orientation sums
+    ->  per-frame instance table  ->  panoptic id map
+on the current CUDA stream, followed by one asynchronous device->host copy of the packed
+per-instance tables from which the python dicts of the reference API are built.
+
+Differences to the reference that a caller can observe (all documented in DESIGN.md):
+  * dense outputs stay on the CUDA device (the reference moves the panoptic outputs to the
+    CPU, panoptic.py:143-152); `.cpu()` in the callers keeps working;
+  * a few bulky, rarely read entries are deferred (see _results.ResultDict);
+  * more than 255 centres in a frame raise instead of silently wrapping uint8 ids.
+Extra keyword arguments (accepted through **kwargs like the reference's):
+  * `async_results=True`: do not block on the table download; the dict / list entries are
+    built on first access.
+"""
+from ctypes import c_float, c_int, c_int64
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from ... import _lib
+from ..._results import InstanceTables, ResultDict
+from ...utils.fullres import fullres_key, valid_region_and_fullres_shape
+from ._base import DensePostprocessingBase
+from .instance import InstancePostprocessing
+from .semantic import SemanticPostprocessing, widen_u8
+
+
+class PanopticPostprocessing(DensePostprocessingBase):
+    def __init__(
+        self,
+        semantic_postprocessing: SemanticPostprocessing,
+        instance_postprocessing: InstancePostprocessing,
+        semantic_classes_is_thing: Tuple[bool],
+        semantic_class_has_orientation: Tuple[bool],
+        normalized_offset: bool = True,
+        compute_scores: bool = False,
+        **kwargs
+    ) -> None:
+        super().__init__()
+        self._semantic_postprocessing = semantic_postprocessing
+        self._instance_postprocessing = instance_postprocessing
+        # both tuples are WITHOUT void (network classes); panoptic labels are class + 1
+        self._is_thing = tuple(bool(t) for t in semantic_classes_is_thing)
+        self._has_orientation = tuple(bool(t) for t in semantic_class_has_orientation)
+        self._thing_class_ids = np.where(self._is_thing)[0]
+        self._thing_ids_panoptic = self._thing_class_ids + 1
+        self._orientation_ids = np.where(self._has_orientation)[0] + 1
+        self._normalized_offset = normalized_offset
+        self._compute_scores = compute_scores
+        self._max_instances_per_category = 1 << 16
+        self._async_results = bool(kwargs.get('async_results', False))
+
+    @property
+    def max_instances_per_category(self):
+        return self._max_instances_per_category
+
+    def _postprocess_training(self, data, batch):
+        (s_output, i_output), (s_side_outputs, i_side_outputs) = data
+        r_sem = self._semantic_postprocessing._postprocess_training((s_output, s_side_outputs), batch)
+        r_ins = self._instance_postprocessing._postprocess_training((i_output, i_side_outputs), batch)
+        return {**r_sem, **r_ins}
+
+    # ------------------------------------------------------------------ fused kernel chain
+    def _forward_kernels(self, logits, heat, offset, orientation):
+        post = self._instance_postprocessing
+        logits = _lib.require_cuda(logits, 'semantic logits', torch.float32, 4)
+        dev = logits.device
+        heat = _lib.require_cuda(heat, 'center_heatmap', torch.float32, 4)
+        offset = _lib.require_cuda(offset, 'center_offset', torch.float32, 4)
+        if orientation is not None:
+            orientation = _lib.require_cuda(orientation, 'orientation', torch.float32, 4)
+        B, C, H, W = logits.shape
+        if len(self._is_thing) != C:
+            raise ValueError(f'semantic_classes_is_thing has {len(self._is_thing)} entries, the '
+                             f'logits have {C} classes')
+        if heat.shape != (B, 1, H, W) or offset.shape != (B, 2, H, W):
+            raise ValueError('instance outputs do not match the semantic logits in shape')
+        L = _lib.lib()
+        ks = post._heatmap_nms_kernel_size
+        ws = torch.empty(L.npb_panoptic_forward_workspace_bytes(B, C, H, W, ks),
+                         dtype=torch.uint8, device=dev)
+        sem = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        inst = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        pan = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+        pan_sem = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        tables = InstanceTables(B, dev)
+        use_thr = post._offset_distance_threshold is not None
+        _lib.check(L.npb_panoptic_forward(
+            _lib.ptr(logits), _lib.ptr(heat), _lib.ptr(offset), _lib.ptr(orientation),
+            c_int(B), c_int(C), c_int(H), c_int(W),
+            _lib.host_lut(self._is_thing, C), _lib.host_lut(self._has_orientation, C),
+            c_float(post._heatmap_threshold), c_int(ks), c_int(post._top_k_instances),
+            c_int(int(post._heatmap_apply_foreground_mask)), c_int(int(self._normalized_offset)),
+            c_int(int(use_thr)), c_float(float(post._offset_distance_threshold) if use_thr else 0.0),
+            c_int64(self._max_instances_per_category), _lib.ptr(ws), _lib.ptr(sem), _lib.ptr(inst),
+            _lib.ptr(pan), _lib.ptr(pan_sem), tables.dptr('centers_yx'), tables.dptr('n_centers'),
+            tables.dptr('center_score'), tables.dptr('inst_class'), tables.dptr('inst_pan_id'),
+            tables.dptr('inst_area'), tables.dptr('inst_angle'), tables.dptr('status'),
+            _lib.stream_ptr(dev)), 'npb_panoptic_forward')
+        tables.start_download()
+        return sem, inst, pan, pan_sem, tables
+
+    def _thing_mask(self, sem_u8: torch.Tensor) -> torch.Tensor:
+        """panoptic.py:123-127 `isin(semantic idx, thing ids)` -> bool (B,H,W)."""
+        out = torch.empty(sem_u8.shape, dtype=torch.uint8, device=sem_u8.device)
+        C = len(self._is_thing)
+        _lib.check(_lib.lib().npb_thing_mask(
+            _lib.ptr(sem_u8), c_int64(sem_u8.numel()), c_int(C), _lib.host_lut(self._is_thing, C),
+            _lib.ptr(out), _lib.stream_ptr(sem_u8.device)), 'npb_thing_mask')
+        return out.view(torch.bool)
+
+    def _postprocess_inference(self, data, batch):
+        (s_output, i_output), (s_side_outputs, i_side_outputs) = data
+        with_orientation = (3 == len(i_output))
+        center_heatmap, center_offset = i_output[0], i_output[1]
+        orientation = i_output[2] if with_orientation else None
+
+        sem, inst, pan, pan_sem, tables = self._forward_kernels(
+            s_output, center_heatmap, center_offset, orientation)
+
+        # semantic + instance entries (panoptic.py:86-94); the class map is shared
+        r = ResultDict(semantic_output=s_output, semantic_side_outputs=s_side_outputs)
+        self._semantic_postprocessing._fill_inference_entries(r, s_output, batch, sem_u8=sem)
+        r.update(self._instance_postprocessing._postprocess_inference((i_output, i_side_outputs),
+                                                                     batch))
+
+        # panoptic entries (panoptic.py:128-167)
+        r.defer('panoptic_foreground_mask', lambda: self._thing_mask(sem))
+        r['panoptic_segmentation_deeplab'] = pan
+        r['_panoptic_segmentation_deeplab_semantic_idx_u8'] = pan_sem
+        r.defer('panoptic_segmentation_deeplab_semantic_idx', lambda: widen_u8(pan_sem))
+        r['panoptic_segmentation_deeplab_instance_idx'] = inst
+        r['_panoptic_instance_tables'] = tables
+        if self._async_results:
+            r.defer('panoptic_segmentation_deeplab_ids', tables.panoptic_ids)
+            r.defer('panoptic_segmentation_deeplab_instance_meta', lambda: self._meta(r, tables))
+        else:
+            r['panoptic_segmentation_deeplab_ids'] = tables.panoptic_ids()
+            r['panoptic_segmentation_deeplab_instance_meta'] = tables.meta()
+
+        if self._compute_scores:
+            self._add_scores(r, s_output, pan, pan_sem, tables)
+
+        # full resolution (panoptic.py:242-291)
+        crop, shape = valid_region_and_fullres_shape(batch, 'instance')
+        dense = ['panoptic_segmentation_deeplab', 'panoptic_segmentation_deeplab_instance_idx',
+                 'panoptic_segmentation_deeplab_semantic_idx']
+        if self._compute_scores:
+            dense += [f'panoptic_segmentation_deeplab_{k}_score'
+                      for k in ('semantic', 'instance', 'panoptic')]
+        identity = self._is_identity_resize((pan.shape[-2], pan.shape[-1]), crop, shape)
+        for key in dense:
+            if identity:
+                r.alias(fullres_key(key), key)
+            else:
+                r.defer(fullres_key(key),
+                        lambda key=key: self._crop_to_valid_region_and_resize_prediction(
+                            r[key], crop, shape, mode='nearest'))
+
+        # orientation (panoptic.py:294-314)
+        if with_orientation:
+            if self._async_results:
+                r.defer('orientations_panoptic_segmentation_deeplab_instance', tables.orientations)
+            else:
+                orientations = tables.orientations()
+                r['orientations_panoptic_segmentation_deeplab_instance'] = orientations
+                for meta_b, ori_b in zip(r['panoptic_segmentation_deeplab_instance_meta'],
+                                         orientations):
+                    for id_, entry in meta_b.items():
+                        entry['orientation'] = ori_b.get(id_, float('nan'))
+        return r
+
+    @staticmethod
+    def _meta(r: ResultDict, tables: InstanceTables):
+        meta = tables.meta()
+        if 'orientations_panoptic_segmentation_deeplab_instance' in r:
+            for meta_b, ori_b in zip(meta, tables.orientations()):
+                for id_, entry in meta_b.items():
+                    entry['orientation'] = ori_b.get(id_, float('nan'))
+        return meta
+
+    # ------------------------------------------------------------------ optional score maps
+    def _add_scores(self, r, logits, pan, pan_sem, tables):
+        """panoptic.py:171-239 (`compute_scores=True`, SURVEY.md section 8(f) item 3, "next"):
+        dense semantic / instance / panoptic score maps and the per-instance score fields.
+        Host-side torch glue over the kernel outputs (not part of the measured hot path)."""
+        probs = r['semantic_softmax_scores']
+        idx = pan_sem.to(torch.int64).unsqueeze(1)
+        void = idx == 0
+        sem_score = torch.take_along_dim(probs, (idx - 1).clamp_(min=0), dim=1)
+        sem_score[void] = 0.0
+        sem_score = sem_score.squeeze(1)
+        inst_score = torch.zeros_like(sem_score)
+        pan_score = sem_score.clone()
+        meta = r['panoptic_segmentation_deeplab_instance_meta']
+        ids = r['panoptic_segmentation_deeplab_ids']
+        for b in range(pan.shape[0]):
+            for pan_id, ins_id in ids[b].items():
+                mask = pan[b] == pan_id
+                score = meta[b][ins_id]['score']
+                inst_score[b][mask] = score
+                mean_sem = torch.mean(sem_score[b][mask])
+                entry = meta[b][ins_id]
+                entry['semantic_score'] = mean_sem.item()
+                entry['semantic_idx'] = int(pan_sem[b][mask][0].item())
+                pscore = mean_sem * score
+                pan_score[b][mask] = pscore
+                entry['panoptic_score'] = pscore.item()
+                entry['panoptic_id'] = pan_id
+        r['panoptic_segmentation_deeplab_semantic_score'] = sem_score
+        r['panoptic_segmentation_deeplab_instance_score'] = inst_score
+        r['panoptic_segmentation_deeplab_panoptic_score'] = pan_score

@@ -1,0 +1,241 @@
+"""mIoU / PQ kernels vs the reference's known-answer tests, the golden vectors and the
+oracle.  float64 PQ states are compared BIT-exactly."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import jload, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _pq(dev, **kw):
+    from nicr_mt_scene_analysis_b200.metric import PanopticQuality
+    return PanopticQuality(device=dev, **kw)
+
+
+def _states(m):
+    return [getattr(m, n).cpu().numpy() for n in
+            ('iou_per_class', 'tp_per_class', 'fn_per_class', 'fp_per_class')]
+
+
+# ---- the reference's known-answer cases (tests/test_metrics.py:76-446) ----------------------
+INST_A = [[1, 1, 1, 1, 1, 1], [1, 2, 2, 2, 2, 1], [1, 2, 2, 2, 2, 1],
+          [1, 2, 2, 2, 2, 1], [1, 2, 2, 1, 1, 1], [1, 2, 1, 1, 1, 1]]
+GT_B = [[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1], [1, 1, 2, 2, 2, 1],
+        [1, 2, 2, 2, 2, 1], [1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1]]
+GOOD_B = [[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1], [1, 2, 2, 2, 2, 1],
+          [1, 2, 2, 2, 1, 1], [1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1]]
+BAD_B = [[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1], [1, 1, 1, 2, 2, 1],
+         [1, 1, 1, 2, 2, 1], [1, 1, 1, 2, 2, 1], [1, 1, 1, 1, 1, 1]]
+CAT_C = [[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1], [1, 2, 2, 1, 2, 2],
+         [1, 2, 2, 1, 2, 2], [1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1]]
+
+
+def _t(a, dev):
+    return torch.tensor(a, dtype=torch.int64, device=dev)[None]
+
+
+def test_pq_perfect_match(cuda_device):
+    m = _pq(cuda_device, num_categories=1, ignored_label=2, max_instances_per_category=16,
+            offset=16, is_thing=torch.tensor([True]))
+    x = _t(INST_A, cuda_device)
+    m.update(x, x)
+    iou, tp, fn, fp = _states(m)
+    assert (iou, tp, fn, fp) == ([2.0], [2], [0], [0])
+    r = m.compute()
+    assert r['pq_per_class'].tolist() == [1.0] and r['rq_per_class'].tolist() == [1.0]
+    assert r['all_pq'] == 1.0 and r['all_rq'] == 1.0 and r['all_sq'] == 1.0
+    assert r['all_num_categories'] == 1
+
+
+def test_pq_totally_wrong(cuda_device):
+    cat = torch.tensor([[0, 0, 0, 0, 0, 0], [0, 1, 0, 0, 1, 0], [0, 1, 1, 1, 1, 0],
+                        [0, 1, 1, 1, 1, 0], [0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0]],
+                       dtype=torch.int64, device=cuda_device)[None]
+    m = _pq(cuda_device, num_categories=2, ignored_label=2, max_instances_per_category=1,
+            offset=16, is_thing=torch.tensor([True, True]))
+    m.update(1 - cat, cat)
+    iou, tp, fn, fp = _states(m)
+    assert (iou.tolist(), tp.tolist(), fn.tolist(), fp.tolist()) == ([0, 0], [0, 0], [1, 1], [1, 1])
+    r = m.compute()
+    assert r['all_pq'] == 0.0 and r['all_num_categories'] == 2
+
+
+def test_pq_matches_by_iou(cuda_device):
+    m = _pq(cuda_device, num_categories=1, ignored_label=2, max_instances_per_category=16,
+            offset=16, is_thing=torch.tensor([True]))
+    m.update(_t(GOOD_B, cuda_device), _t(GT_B, cuda_device))
+    iou, tp, fn, fp = _states(m)
+    assert iou[0] == 28 / 30 + 6 / 8 and (tp, fn, fp) == ([2], [0], [0])
+    r = m.compute()
+    assert r['pq_per_class'].tolist() == [(28 / 30 + 6 / 8) / 2]
+    assert r['all_sq'] == (28 / 30 + 6 / 8) / 2 and r['all_rq'] == 1.0
+    m.reset()
+    m.update(_t(BAD_B, cuda_device), _t(GT_B, cuda_device))
+    iou, tp, fn, fp = _states(m)
+    assert iou[0] == 27 / 32 and (tp, fn, fp) == ([1], [1], [1])
+    r = m.compute()
+    assert r['all_pq'] == 27 / 32 / 2 and r['all_rq'] == 0.5 and r['all_sq'] == 27 / 32
+
+
+def test_pq_wrong_instances_and_arbitrary_order(cuda_device):
+    cat = torch.tensor(CAT_C, dtype=torch.int64, device=cuda_device)[None]
+    pinst = torch.zeros_like(cat)
+    pinst[:, 2:4, 4:6] = 1
+    kw = dict(num_categories=3, ignored_label=0, max_instances_per_category=10, offset=100,
+              is_thing=[True, True, True])
+    m = _pq(cuda_device, **kw)
+    m.update(cat * 10 + pinst, cat * 10)
+    iou, tp, fn, fp = _states(m)
+    assert (iou.tolist(), tp.tolist(), fn.tolist(), fp.tolist()) == \
+        ([0, 1, 0], [0, 1, 0], [0, 0, 1], [0, 0, 2])
+    r = m.compute()
+    assert r['all_pq'] == 0.5 and r['all_num_categories'] == 2
+    ginst = torch.zeros_like(cat)
+    ginst[:, 2:4, 1:3] = 1
+    m = _pq(cuda_device, **kw)
+    m.update(cat * 10 + pinst, cat * 10 + ginst)
+    iou, tp, fn, fp = _states(m)
+    assert (iou.tolist(), tp.tolist(), fn.tolist(), fp.tolist()) == \
+        ([0, 1, 2], [0, 1, 2], [0, 0, 0], [0, 0, 0])
+    assert m.compute()['all_pq'] == 1.0
+
+
+def test_pq_multiple_batches(cuda_device):
+    m = _pq(cuda_device, num_categories=1, ignored_label=2, max_instances_per_category=16,
+            offset=16, is_thing=[True])
+    gt = torch.cat((_t(GT_B, cuda_device),) * 2)
+    m.update(gt, torch.cat((_t(GOOD_B, cuda_device),) * 2))
+    m.update(gt, torch.cat((_t(BAD_B, cuda_device),) * 2))
+    r = m.compute()
+    assert r['pq_per_class'].tolist() == [((28 / 30 + 6 / 8) + (27 / 32)) / 2 / 2]
+    assert r['rq_per_class'].tolist() == [3 / 4]
+    assert r['sq_per_class'].tolist() == [((28 / 30 + 6 / 8) + (27 / 32)) / 3]
+    assert r['all_rq'] == 0.75 and r['all_num_categories'] == 1
+
+
+# ---- golden vectors / oracle -----------------------------------------------------------------
+def test_pq_golden_frames(cuda_device):
+    from nicr_mt_scene_analysis_b200.metric import compare_and_accumulate
+    z = load_golden('pq')
+    NC, L, OFF = int(z['num_categories']), int(z['L']), int(z['offset'])
+    pred = torch.from_numpy(z['pred']).to(cuda_device)
+    tgt = torch.from_numpy(z['target']).to(cuda_device)
+    matches = jload(z['matches'])
+    for b in range(pred.shape[0]):
+        iou, tp, fn, fp, m = compare_and_accumulate(pred[b], tgt[b], NC, 0, L, OFF, 0)
+        assert iou.dtype == torch.float64
+        assert np.array_equal(iou.numpy(), z['iou'][b])          # bit-exact float64
+        assert np.array_equal(tp.numpy(), z['tp'][b])
+        assert np.array_equal(fn.numpy(), z['fn'][b])
+        assert np.array_equal(fp.numpy(), z['fp'][b])
+        assert sorted([list(x) for x in m]) == matches[b]
+    pq = _pq(cuda_device, num_categories=NC, ignored_label=0, max_instances_per_category=L,
+             offset=OFF, is_thing=z['is_thing'].tolist())
+    pq.update(pred[:4], tgt[:4])
+    pq.update(pred[4:], tgt[4:])
+    assert np.array_equal(np.stack(_states(pq)), z['state'])   # frame-order accumulation
+    res = pq.compute()
+    ref = oracle.pq_results(*z['state'], z['is_thing'], 0)
+    for k, v in ref.items():
+        np.testing.assert_allclose(np.asarray(res[k], dtype=np.float64), v, rtol=1e-12)
+
+
+def test_pq_zero_division_raises(cuda_device):
+    m = _pq(cuda_device, num_categories=2, ignored_label=0, max_instances_per_category=10,
+            offset=100, is_thing=[True, True])
+    m.update(torch.full((1, 4, 4), 3, dtype=torch.int64, device=cuda_device),
+             torch.zeros((1, 4, 4), dtype=torch.int64, device=cuda_device))
+    with pytest.raises(ZeroDivisionError):
+        m.compute()
+
+
+@pytest.mark.parametrize('n', [6, 41, 200])
+def test_miou_golden(n, cuda_device):
+    from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion
+    z = load_golden('miou')
+    for flag in (False, True):
+        m = MeanIntersectionOverUnion(n_classes=n, ignore_first_class=flag, device=cuda_device)
+        for p, t in zip(z[f'pred_{n}'], z[f'target_{n}']):
+            tt = torch.from_numpy(t)
+            m.update(torch.from_numpy(p).to(cuda_device),
+                     (tt.to(torch.uint8) if n <= 255 and not flag else tt).to(cuda_device))
+        assert m.confmat.dtype == torch.int64
+        assert np.array_equal(m.confmat.cpu().numpy(), z[f'confmat_{n}'])
+        miou, ious = m.compute(return_ious=True)
+        assert miou.numpy() == z[f'miou{int(flag)}_{n}']
+        assert np.array_equal(ious.numpy(), z[f'ious{int(flag)}_{n}'], equal_nan=True)
+        m.reset()
+        assert int(m.confmat.sum()) == 0
+
+
+def test_miou_out_of_range_raises(cuda_device):
+    from nicr_mt_scene_analysis_b200 import _lib
+    from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion
+    m = MeanIntersectionOverUnion(n_classes=4, device=cuda_device)
+    m.update(torch.tensor([0, 1, 7], device=cuda_device), torch.tensor([0, 1, 2], device=cuda_device))
+    with pytest.raises(_lib.NpbError):
+        m.compute()
+
+
+@pytest.mark.parametrize('shape', [(3, 120, 160), (2, 97, 131), (2, 530, 730)])
+def test_fused_evaluation_against_oracle(shape, cuda_device):
+    """PanopticEvaluation (one pixel pass) == separate PQ + mIoU updates == oracle."""
+    from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, PanopticEvaluation,
+                                                    PanopticQuality)
+    B, H, W = shape
+    C, L, OFF = 12, 1 << 16, 256 ** 3
+    g = torch.Generator().manual_seed(B * H)
+    def blocky(n, blk):
+        low = torch.randint(0, n, (B, (H + blk - 1) // blk, (W + blk - 1) // blk), generator=g)
+        return low.repeat_interleave(blk, 1).repeat_interleave(blk, 2)[:, :H, :W].contiguous()
+    is_thing = torch.tensor([False] + [bool(c % 2) for c in range(C)])
+    cat_t, inst_t = blocky(C + 1, 24), blocky(4, 10)
+    cat_p = torch.where(torch.rand(B, H, W, generator=g) < 0.1, blocky(C + 1, 24), cat_t)
+    tgt = cat_t * L + torch.where(is_thing[cat_t], inst_t + 1, 0)
+    pred = cat_p * L + torch.where(is_thing[cat_p], torch.roll(inst_t, 3, -1) + 1, 0)
+    sem_t = cat_t.to(torch.uint8)
+    kw = dict(num_categories=C + 1, ignored_label=0, max_instances_per_category=L, offset=OFF,
+              is_thing=is_thing.tolist(), device=cuda_device)
+    pq_f, pq_s = PanopticQuality(**kw), PanopticQuality(**kw)
+    mi_f = MeanIntersectionOverUnion(C + 1, True, device=cuda_device)
+    mi_s = MeanIntersectionOverUnion(C + 1, True, device=cuda_device)
+    d = lambda t: t.to(cuda_device)
+    PanopticEvaluation(pq_f, mi_f).update(d(pred), d(tgt), d(sem_t))
+    pq_s.update(d(pred), d(tgt))
+    mi_s.update(d(pred) // L, d(sem_t))
+    pq_f.check_status()
+    state = np.zeros((4, C + 1))
+    for b in range(B):
+        out = oracle.pq_compare_and_accumulate(pred[b].numpy(), tgt[b].numpy(), C + 1, 0, L, OFF, 0)
+        for s, v in zip(state, out[:4]):
+            s += v
+    assert np.array_equal(np.stack(_states(pq_f)), state)
+    assert np.array_equal(np.stack(_states(pq_s)), state)
+    cm = oracle.confmat((pred // L).numpy(), sem_t.numpy(), C + 1)
+    assert np.array_equal(mi_f.confmat.cpu().numpy(), cm)
+    assert np.array_equal(mi_s.confmat.cpu().numpy(), cm)
+    # checksum property at any size: every pixel lands in exactly one confusion-matrix cell
+    assert int(mi_f.confmat.sum()) == B * H * W
+
+
+def test_pq_with_orientation_mae(cuda_device):
+    from nicr_mt_scene_analysis_b200.metric import PanopticQualityWithOrientationMAE
+    L = 1 << 16
+    tgt = torch.zeros((1, 8, 8), dtype=torch.int64)
+    tgt[:, :4] = 1 * L + 1
+    tgt[:, 4:] = 1 * L + 2
+    m = PanopticQualityWithOrientationMAE(num_categories=2, ignored_label=0,
+                                          max_instances_per_category=L, offset=256 ** 3,
+                                          is_thing=[False, True], device=cuda_device)
+    m.update(tgt.to(cuda_device), [{7: 0.5, 9: 3.0}], [{1 * L + 1: 7, 1 * L + 2: 9}],
+             tgt.to(cuda_device), [{3: 0.25, 4: -3.0}], [{1 * L + 1: 3, 1 * L + 2: 4}])
+    r = m.compute(suffix='_deeplab')
+    assert m.tp_per_class.tolist() == [0, 2]
+    assert int(m.n_elements) == 2
+    import math
+    want = (0.25 + (2 * math.pi - 6.0)) / 2
+    assert float(r['mae_deeplab_rad']) == pytest.approx(want, rel=1e-6)
+    assert 'all_deeplab_pq' in r and 'mae_deeplab_deg' in r

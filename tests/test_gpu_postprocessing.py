@@ -1,0 +1,302 @@
+"""CUDA path vs (a) the golden vectors produced by the unmodified reference and (b) the C
+oracle on seeded synthetic inputs.  Everything integer is compared bit-exactly."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import int_keys, jload, load_golden
+
+pytestmark = pytest.mark.gpu
+
+POST_CASES = ['q10', 'tie', 'odd', 'pixel_offsets', 'scores']
+
+
+def _build(cfg, is_thing, has_ori, **extra):
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    sem = get_postprocessing_class('semantic')()
+    ins = get_postprocessing_class(
+        'instance', heatmap_threshold=cfg['thr'], heatmap_nms_kernel_size=cfg['ks'],
+        top_k_instances=cfg['top_k'], heatmap_apply_foreground_mask=cfg['apply_fg'],
+        normalized_offset=cfg['normalized'], offset_distance_threshold=cfg['dist_thr'])()
+    pan = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=sem, instance_postprocessing=ins,
+        semantic_classes_is_thing=tuple(bool(x) for x in is_thing),
+        semantic_class_has_orientation=tuple(bool(x) for x in has_ori),
+        normalized_offset=cfg['normalized'], compute_scores=cfg.get('compute_scores', False),
+        **extra)()
+    return sem, ins, pan
+
+
+def _run(pan, logits, heat, offset, orientation, dev):
+    from nicr_mt_scene_analysis_b200 import testing
+    B, _, H, W = logits.shape
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    inst = (t(heat), t(offset)) + ((t(orientation),) if orientation is not None else ())
+    return pan.postprocess(((t(logits), inst), (None, None)), testing.make_batch_dict(B, H, W),
+                           is_training=False)
+
+
+def _check_meta(ref_meta, got_meta):
+    assert len(ref_meta) == len(got_meta)
+    for rm, gm in zip(ref_meta, got_meta):
+        rm = {int(k): v for k, v in rm.items()}
+        assert sorted(rm) == sorted(gm)
+        for i in rm:
+            assert tuple(rm[i]['center_yx']) == tuple(gm[i]['center_yx'])
+            assert rm[i]['area'] == gm[i]['area']
+            assert rm[i]['score'] == pytest.approx(gm[i]['score'], rel=1e-6)
+
+
+def _check_orient(ref, got):
+    assert [sorted(d) for d in ref] == [sorted(d) for d in got]
+    for dr, dg in zip(ref, got):
+        for k in dr:
+            assert math.isclose(dg[k], dr[k], rel_tol=1e-5, abs_tol=1e-6), (k, dg[k], dr[k])
+
+
+@pytest.mark.parametrize('name', POST_CASES)
+@pytest.mark.parametrize('async_results', [False, True])
+def test_golden_postprocess(name, async_results, cuda_device):
+    z = load_golden('post_' + name)
+    cfg = jload(z['cfg'])
+    _, _, pan = _build(cfg, z['is_thing'], z['has_orientation'], async_results=async_results)
+    r = _run(pan, z['logits'], z['heat'], z['offset'], z.get('orientation'), cuda_device)
+    g = lambda k: r[k].cpu().numpy()
+    assert np.array_equal(g('semantic_segmentation_idx'), z['semantic_segmentation_idx'])
+    assert r['semantic_segmentation_idx'].dtype == torch.int64
+    assert np.array_equal(g('panoptic_foreground_mask'), z['panoptic_foreground_mask'])
+    assert np.array_equal(g('panoptic_segmentation_deeplab'), z['panoptic_segmentation_deeplab'])
+    assert r['panoptic_segmentation_deeplab'].dtype == torch.int64
+    assert np.array_equal(g('panoptic_segmentation_deeplab_instance_idx'),
+                          z['panoptic_segmentation_deeplab_instance_idx'])
+    assert r['panoptic_segmentation_deeplab_instance_idx'].dtype == torch.uint8
+    assert np.array_equal(g('panoptic_segmentation_deeplab_semantic_idx'),
+                          z['panoptic_segmentation_deeplab_semantic_idx'])
+    assert r['panoptic_segmentation_deeplab_ids'] == int_keys(jload(z['ids']))
+    _check_meta(jload(z['meta']), r['panoptic_segmentation_deeplab_instance_meta'])
+    np.testing.assert_allclose(g('semantic_segmentation_score'), z['semantic_segmentation_score'],
+                               rtol=1e-5)
+    if 'orientations' in z:
+        _check_orient(int_keys(jload(z['orientations'])),
+                      r['orientations_panoptic_segmentation_deeplab_instance'])
+    if 'semantic_score' in z:
+        for k in ('semantic_score', 'instance_score', 'panoptic_score'):
+            np.testing.assert_allclose(g(f'panoptic_segmentation_deeplab_{k}'), z[k], rtol=1e-5,
+                                       atol=1e-7)
+    # identity full-res twins alias the same results
+    assert np.array_equal(r['panoptic_segmentation_deeplab_fullres'].cpu().numpy(),
+                          z['panoptic_segmentation_deeplab'])
+
+
+def test_result_keys_like_reference(cuda_device):
+    """tests/test_decoders+postprocessing.py:208-250 of the reference: key presence"""
+    z = load_golden('post_scores')
+    cfg = jload(z['cfg'])
+    _, _, pan = _build(cfg, z['is_thing'], z['has_orientation'])
+    r = _run(pan, z['logits'], z['heat'], z['offset'], z['orientation'], cuda_device)
+    keys = ['semantic_output', 'semantic_side_outputs', 'semantic_softmax_scores',
+            'semantic_segmentation_score', 'semantic_segmentation_idx', 'semantic_output_fullres',
+            'semantic_softmax_scores_fullres', 'semantic_segmentation_score_fullres',
+            'semantic_segmentation_idx_fullres', 'instance_output', 'instance_side_outputs',
+            'instance_centers', 'instance_offsets', 'instance_orientation',
+            'panoptic_foreground_mask', 'panoptic_segmentation_deeplab',
+            'panoptic_segmentation_deeplab_fullres', 'panoptic_segmentation_deeplab_ids',
+            'panoptic_segmentation_deeplab_semantic_idx',
+            'panoptic_segmentation_deeplab_semantic_idx_fullres',
+            'panoptic_segmentation_deeplab_semantic_score',
+            'panoptic_segmentation_deeplab_semantic_score_fullres',
+            'panoptic_segmentation_deeplab_instance_idx',
+            'panoptic_segmentation_deeplab_instance_idx_fullres',
+            'panoptic_segmentation_deeplab_instance_meta',
+            'panoptic_segmentation_deeplab_instance_score',
+            'panoptic_segmentation_deeplab_instance_score_fullres',
+            'panoptic_segmentation_deeplab_panoptic_score',
+            'panoptic_segmentation_deeplab_panoptic_score_fullres',
+            'orientations_panoptic_segmentation_deeplab_instance']
+    for k in keys:
+        assert k in list(r.keys()), k
+    r.materialize()
+    assert r['semantic_softmax_scores'].shape == z['logits'].shape
+
+
+def test_centers_tie_cases(cuda_device):
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    for c in jload(load_golden('centers')['cases']):
+        post = get_postprocessing_class(
+            'instance', heatmap_threshold=c['thr'], heatmap_nms_kernel_size=c['ks'],
+            top_k_instances=c['k'], heatmap_apply_foreground_mask=c['apply_fg'])()
+        heat = torch.tensor(c['heat'], dtype=torch.float32, device=cuda_device)
+        fg = torch.tensor(c['fg'], dtype=torch.bool, device=cuda_device)
+        mask, centers = post._get_instance_centers(heat, fg)
+        assert np.array_equal(mask.cpu().numpy(), np.array(c['mask'], bool)), (c['ks'], c['k'])
+        assert [x.tolist() for x in centers] == c['centers']
+        assert all(x.dtype == torch.int32 for x in centers)
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(B=3, C=40, H=120, W=160, K=12, seed=11, quantize='q10'),
+    dict(B=2, C=37, H=106, W=146, K=20, seed=12, quantize='q10'),       # 530x730 / 5
+    dict(B=2, C=19, H=128, W=256, K=100, seed=13, quantize='q10', top_k=100),
+    dict(B=2, C=9, H=97, W=131, K=7, seed=14, quantize='tie', top_k=4),  # P % 4 != 0 -> scalar path
+    dict(B=2, C=5, H=64, W=64, K=0, seed=15, quantize='q10'),            # no centres at all
+    dict(B=1, C=1, H=32, W=48, K=2, seed=16, quantize='q10'),            # single class
+    dict(B=2, C=255, H=24, W=32, K=3, seed=17, quantize='q10'),          # maximum class count
+])
+def test_against_oracle(cfg, cuda_device):
+    from nicr_mt_scene_analysis_b200 import testing
+    B, C, H, W, K = (cfg[k] for k in 'BCHWK')
+    data = testing.make_batch(B, C, H, W, max(K, 1), seed=cfg['seed'], quantize=cfg['quantize'])
+    if K == 0:
+        data['heat'].zero_()
+    is_thing = testing.default_is_thing(C) if C > 1 else (True,)
+    has_ori = tuple(bool(t and c % 4 == 1) for c, t in enumerate(is_thing)) if C > 1 else (True,)
+    pcfg = dict(thr=0.1, ks=3, top_k=cfg.get('top_k', 64), apply_fg=False, normalized=True,
+                dist_thr=None)
+    _, _, pan = _build(pcfg, is_thing, has_ori)
+    r = _run(pan, *(data[k].numpy() for k in ('logits', 'heat', 'offset', 'orientation')),
+             cuda_device)
+    ref = oracle.panoptic_postprocess(
+        data['logits'].numpy(), data['heat'].numpy(), data['offset'].numpy(),
+        data['orientation'].numpy(), is_thing, has_ori, top_k=pcfg['top_k'])
+    assert np.array_equal(r['_semantic_segmentation_idx_u8'].cpu().numpy(), ref['semantic_idx'])
+    assert np.array_equal(r['panoptic_segmentation_deeplab_instance_idx'].cpu().numpy(),
+                          ref['instance_idx'])
+    assert np.array_equal(r['panoptic_segmentation_deeplab'].cpu().numpy(), ref['panoptic'])
+    assert r['panoptic_segmentation_deeplab_ids'] == ref['ids']
+    for gm, rm in zip(r['panoptic_segmentation_deeplab_instance_meta'], ref['meta']):
+        assert sorted(gm) == sorted(rm)
+        for i in rm:
+            assert gm[i]['center_yx'] == rm[i]['center_yx'] and gm[i]['area'] == rm[i]['area']
+    _check_orient(ref['orientations'], r['orientations_panoptic_segmentation_deeplab_instance'])
+
+
+def test_too_many_centers_raises(cuda_device):
+    """> 255 centres (only reachable through k-th value ties): the reference wraps uint8
+    ids silently (instance.py:236); this implementation refuses."""
+    from nicr_mt_scene_analysis_b200 import _lib
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    heat = torch.zeros(1, 1, 96, 96, device=cuda_device)
+    heat[:, :, 2:94:3, 2:94:3] = 0.5          # 31 * 31 = 961 equal isolated peaks
+    post = get_postprocessing_class('instance', top_k_instances=10)()
+    with pytest.raises(_lib.NpbError) as e:
+        post._get_instance_centers(heat)
+    assert e.value.code == _lib.ERR_TOO_MANY_CENTERS
+
+
+def test_instance_postprocessing_like_reference_test(cuda_device):
+    """port of the reference's tests/test_instance_postprocessing.py:90-150 (rectangles with
+    exact pixel offsets; found centres == planted centres; segmentation is a relabelling)"""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.model.postprocessing import InstancePostprocessing
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 4, 480, 640
+    inst = torch.zeros(B, 1, H, W, dtype=torch.uint8)
+    heat = torch.zeros(B, 1, H, W)
+    off = torch.zeros(B, 2, H, W)
+    fg = torch.zeros(B, 1, H, W, dtype=torch.bool)
+    yy = torch.arange(H, dtype=torch.float32)[:, None].expand(H, W)
+    xx = torch.arange(W, dtype=torch.float32)[None, :].expand(H, W)
+    planted = []
+    for b in range(B):
+        cs = []
+        for i in range(2):
+            x = int(torch.randint(0, W, (1,), generator=g))
+            y = int(torch.randint(0, H, (1,), generator=g))
+            s = int(torch.randint(20, 40, (1,), generator=g))
+            x0, x1, y0, y1 = max(x - s, 0), min(x + s, W), max(y - s, 0), min(y + s, H)
+            cx, cy = int(x1 - (x1 - x0) / 2), int(y1 - (y1 - y0) / 2)
+            heat[b, 0, cy, cx] = 1
+            cs.append((cy, cx))
+            inst[b, 0, y0:y1, x0:x1] = i + 1
+            off[b, 0, y0:y1, x0:x1] = cy - yy[y0:y1, x0:x1]
+            off[b, 1, y0:y1, x0:x1] = cx - xx[y0:y1, x0:x1]
+            fg[b, 0, y0:y1, x0:x1] = True
+        planted.append(sorted(cs))
+    post = InstancePostprocessing(normalized_offset=False)
+    _, found = post._get_instance_centers(heat.to(cuda_device))
+    _, ref_centers = oracle.instance_centers(heat.numpy())
+    assert [f.tolist() for f in found] == [c.tolist() for c in ref_centers]
+    for f, cs in zip(found, planted):       # every planted centre is found (ref test :106-112)
+        assert set(map(tuple, f.tolist())) == set(cs)
+    batch = testing.make_batch_dict(B, H, W)
+    batch['instance_foreground'] = fg
+    r = post.postprocess(((heat.to(cuda_device), off.to(cuda_device)), None), batch,
+                         is_training=False)
+    seg = r['instance_segmentation_gt_foreground'].cpu()
+    assert 'instance_segmentation_gt_foreground_fullres' in r and 'instance_segmentation_gt_meta' in r
+    ref_seg, ref_meta = oracle.instance_segmentation(heat.numpy(), off.numpy(), fg[:, 0].numpy(),
+                                                     normalized_offset=False)
+    assert np.array_equal(seg.numpy(), ref_seg)
+    for gm, rm in zip(r['instance_segmentation_gt_meta'], ref_meta):
+        assert {k: (v['center_yx'], v['area']) for k, v in gm.items()} == \
+            {k: (v['center_yx'], v['area']) for k, v in rm.items()}
+
+
+def test_merge_standalone_golden(cuda_device):
+    from nicr_mt_scene_analysis_b200.utils import deeplab_merge_batch
+    z = load_golden('merge')
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    pan, ids = deeplab_merge_batch(t(z['sem']), t(z['ins']), t(z['fg']), int(z['L']),
+                                   z['thing_ids'], 0)
+    assert np.array_equal(pan.cpu().numpy(), z['pan'])
+    assert ids == int_keys(jload(z['ids']))
+    pan, ids = deeplab_merge_batch(t(z['sem']), t(z['ins']), t(z['fg']), 1000, z['thing_ids'], 3)
+    assert np.array_equal(pan.cpu().numpy(), z['pan_L1000_void3'])
+    assert ids == int_keys(jload(z['ids_L1000_void3']))
+
+
+def test_orientation_standalone_golden(cuda_device):
+    from nicr_mt_scene_analysis_b200.model.postprocessing import InstancePostprocessing
+    z = load_golden('orientation')
+    post = InstancePostprocessing()
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    _check_orient(int_keys(jload(z['with_mask'])),
+                  post._get_instance_orientation(t(z['ori']), t(z['seg']), t(z['mask'])))
+    _check_orient(int_keys(jload(z['without_mask'])),
+                  post._get_instance_orientation(t(z['ori']), t(z['seg']), None))
+
+
+def test_cpu_tensors_are_rejected(cuda_device):
+    """no CPU fallback: host tensors raise instead of silently running somewhere else"""
+    z = load_golden('post_q10')
+    cfg = jload(z['cfg'])
+    _, _, pan = _build(cfg, z['is_thing'], z['has_orientation'])
+    with pytest.raises(RuntimeError, match='CUDA tensor'):
+        _run(pan, z['logits'], z['heat'], z['offset'], z['orientation'], torch.device('cpu'))
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE-size frame (530x730, C=37, 20 centres): size-independent invariants +
+    agreement with the oracle on one frame."""
+    from nicr_mt_scene_analysis_b200 import testing
+    B, C, H, W, K = 2, 37, 530, 730, 20
+    data = testing.make_batch(B, C, H, W, K, seed=5)
+    is_thing = testing.default_is_thing(C)
+    has_ori = tuple(bool(t and c % 4 == 1) for c, t in enumerate(is_thing))
+    pcfg = dict(thr=0.1, ks=3, top_k=64, apply_fg=False, normalized=True, dist_thr=None)
+    _, _, pan = _build(pcfg, is_thing, has_ori)
+    r = _run(pan, *(data[k].numpy() for k in ('logits', 'heat', 'offset', 'orientation')),
+             cuda_device)
+    pan_map = r['panoptic_segmentation_deeplab']
+    sem = r['semantic_segmentation_idx']
+    inst = r['panoptic_segmentation_deeplab_instance_idx']
+    L = 1 << 16
+    thing = torch.tensor(is_thing, device=cuda_device)
+    # instances only on thing pixels; stuff pixels carry (class+1)*L; ids decode consistently
+    assert bool(((inst > 0) <= thing[sem]).all())
+    stuff = ~thing[sem]
+    assert bool((pan_map[stuff] == (sem[stuff] + 1) * L).all())
+    assert bool((pan_map[thing[sem] & (inst == 0)] == 0).all())
+    for b in range(B):
+        for pan_id, ins_id in r['panoptic_segmentation_deeplab_ids'][b].items():
+            assert bool(((pan_map[b] == pan_id) == (inst[b] == ins_id)).all())
+        areas = {i: m['area'] for i, m in r['panoptic_segmentation_deeplab_instance_meta'][b].items()}
+        counts = torch.bincount(inst[b].flatten().long(), minlength=256).cpu()
+        assert all(int(counts[i]) == a for i, a in areas.items())
+    ref = oracle.panoptic_postprocess(data['logits'].numpy()[:1], data['heat'].numpy()[:1],
+                                      data['offset'].numpy()[:1], data['orientation'].numpy()[:1],
+                                      is_thing, has_ori)
+    assert np.array_equal(pan_map[:1].cpu().numpy(), ref['panoptic'])

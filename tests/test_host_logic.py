@@ -1,0 +1,177 @@
+"""CPU-only tests: the C-ABI library loads and exports what the header declares, host-side
+helpers behave like the reference's, the product package never touches the oracle, and the
+cross-rank metric reduction works with world_size 2 (gloo)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'nicr-multitask-scene-analysis_b200')
+
+
+@pytest.fixture(scope='session', autouse=True)
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+    __graft_entry__.build()
+
+
+def test_library_exports_every_declared_symbol():
+    from nicr_mt_scene_analysis_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'nicr_panoptic_b200.h')).read()
+    declared = set(re.findall(r'\b(npb_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    handle = _lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), f'{name} declared in the header but not exported'
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert handle.npb_abi_version() == 1
+    assert handle.npb_error_string(-2).decode().startswith('more than 255')
+
+
+def test_host_argument_validation_without_gpu():
+    """bad arguments are rejected on the host before any launch (no GPU needed)"""
+    from nicr_mt_scene_analysis_b200 import _lib
+    L = _lib.lib()
+    assert L.npb_semantic_argmax(None, 1, 4, 8, 8, None, None, None) == _lib.ERR_ARG
+    assert L.npb_instance_centers(None, 1, 8, 8, 0.1, 3, 4, None, 0, None, None, None, None, None,
+                                  None) == _lib.ERR_ARG
+    assert L.npb_instance_centers_workspace_bytes(2, 480, 640, 3) >= 2 * 240 * 320 * 8
+    assert L.npb_pq_update_workspace_bytes(4, 41) > 4 * 8192 * 12
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(import|from)\s+oracle\b', text, re.M), f
+                assert 'panoptic_oracle' not in text, f
+
+
+def test_no_cpu_fallback():
+    from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion, PanopticQuality
+    from nicr_mt_scene_analysis_b200.utils import deeplab_merge_batch
+    m = MeanIntersectionOverUnion(4, device='cpu')
+    with pytest.raises(RuntimeError):
+        m.update(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64))
+    pq = PanopticQuality(2, 0, 16, 256, [False, True], device='cpu')
+    with pytest.raises(RuntimeError):
+        pq.update(torch.zeros(1, 2, 2, dtype=torch.int64), torch.zeros(1, 2, 2, dtype=torch.int64))
+    with pytest.raises(RuntimeError):
+        deeplab_merge_batch(torch.zeros(1, 2, 2, dtype=torch.int64),
+                            torch.zeros(1, 2, 2, dtype=torch.uint8),
+                            torch.zeros(1, 2, 2, dtype=torch.bool), 16, [1], 0)
+
+
+def test_factory_and_constructor_contract():
+    from nicr_mt_scene_analysis_b200.model.postprocessing import (
+        InstancePostprocessing, PanopticPostprocessing, get_postprocessing_class)
+    cls = get_postprocessing_class('instance', top_k_instances=100, heatmap_threshold=0.2)
+    post = cls()
+    assert isinstance(post, InstancePostprocessing)
+    assert post._top_k_instances == 100 and post._heatmap_threshold == 0.2
+    assert get_postprocessing_class('instance', top_k_instances=100, heatmap_threshold=0.2) is cls
+    with pytest.raises(ValueError):
+        get_postprocessing_class('does-not-exist')
+    with pytest.raises(AssertionError):
+        InstancePostprocessing(top_k_instances=255)
+    with pytest.raises(AssertionError):
+        InstancePostprocessing(heatmap_nms_kernel_size=4)
+    pan = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+        instance_postprocessing=post, semantic_classes_is_thing=(False, True, True),
+        semantic_class_has_orientation=(False, False, True))()
+    assert isinstance(pan, PanopticPostprocessing)
+    assert pan.max_instances_per_category == 65536
+    assert pan._thing_ids_panoptic.tolist() == [2, 3] and pan._orientation_ids.tolist() == [3]
+    # training mode only forwards the raw decoder outputs (panoptic.py:57-75)
+    out = pan.postprocess((('S', 'I'), ('s', 'i')), {}, is_training=True)
+    assert out == {'semantic_output': 'S', 'semantic_side_outputs': 's',
+                   'instance_output': 'I', 'instance_side_outputs': 'i'}
+
+
+def test_fullres_helpers():
+    from nicr_mt_scene_analysis_b200.utils.fullres import (fullres_shape,
+                                                           valid_region_and_fullres_shape)
+    batch = {'rgb_fullres': torch.zeros(2, 3, 10, 12),
+             '_applied_preprocessing': [[{'type': 'Other'}, {'type': 'Resize',
+                                                             'valid_region_slice_y': slice(0, 5),
+                                                             'valid_region_slice_x': slice(1, 6)}]]}
+    assert fullres_shape(batch, 'semantic') == (10, 12)
+    assert valid_region_and_fullres_shape(batch, 'instance') == ((slice(0, 5), slice(1, 6)), (10, 12))
+    with pytest.raises(ValueError):
+        fullres_shape({}, 'semantic')
+    with pytest.raises(ValueError):
+        valid_region_and_fullres_shape({'rgb_fullres': torch.zeros(1, 3, 4, 4)}, 'semantic')
+
+
+def test_result_dict_defers_and_aliases():
+    from nicr_mt_scene_analysis_b200._results import ResultDict
+    calls = []
+    r = ResultDict(a=1)
+    r.defer('b', lambda: calls.append('b') or 2)
+    r.alias('b_fullres', 'b')
+    assert 'b' in r and set(r.keys()) == {'a', 'b', 'b_fullres'} and not calls
+    assert r.is_deferred('b')
+    assert r['b_fullres'] == 2 and r['b'] == 2 and calls == ['b']
+    assert dict(r.items()) == {'a': 1, 'b': 2, 'b_fullres': 2}
+    assert r.get('zzz', 5) == 5
+
+
+def test_pq_compute_matches_oracle_formulae():
+    """compute() on hand-set states (CPU): pq.py:304-361"""
+    import numpy as np
+    import oracle
+    from nicr_mt_scene_analysis_b200.metric import PanopticQuality
+    is_thing = [False, True, False, True, True]
+    m = PanopticQuality(5, 0, 1 << 16, 256 ** 3, is_thing, device='cpu')
+    m.iou_per_class = torch.tensor([0.3, 4.2, 0.0, 1.7, 0.0], dtype=torch.float64)
+    m.tp_per_class = torch.tensor([1.0, 5.0, 0.0, 2.0, 0.0], dtype=torch.float64)
+    m.fn_per_class = torch.tensor([0.0, 1.0, 0.0, 3.0, 0.0], dtype=torch.float64)
+    m.fp_per_class = torch.tensor([2.0, 0.0, 0.0, 1.0, 4.0], dtype=torch.float64)
+    got = m.compute(suffix='_x')
+    ref = oracle.pq_results(m.iou_per_class.numpy(), m.tp_per_class.numpy(),
+                            m.fn_per_class.numpy(), m.fp_per_class.numpy(), is_thing, 0, '_x')
+    assert set(got) == set(ref)
+    for k in ref:
+        np.testing.assert_allclose(np.asarray(got[k], dtype=np.float64), ref[k], rtol=1e-12)
+    assert int(got['all_x_num_categories']) == 3 and int(got['all_with_gt_x_num_categories']) == 2
+
+
+def test_metric_states_allreduce_world_size_2(tmp_path):
+    """the N>1 path: per-rank states are summed at compute() (dist_reduce_fx='sum' of the
+    reference, miou.py:24 / pq.py:231-246) -- two gloo ranks on the CPU."""
+    script = tmp_path / 'rank.py'
+    script.write_text(f'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r})
+from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion, PanopticQuality
+dist.init_process_group('gloo')
+rank = dist.get_rank()
+pq = PanopticQuality(3, 0, 16, 256, [False, True, True], device='cpu')
+pq.tp_per_class += torch.tensor([0., 1., 2.], dtype=torch.float64) * (rank + 1)
+pq.iou_per_class += torch.tensor([0., .75, 1.5], dtype=torch.float64) * (rank + 1)
+pq.fn_per_class += torch.tensor([0., 1., 0.], dtype=torch.float64)
+mi = MeanIntersectionOverUnion(3, ignore_first_class=True, device='cpu')
+mi.confmat += torch.tensor([[1, 0, 0], [0, 2 + rank, 1], [0, 1, 3]])
+r = pq.compute()
+miou = mi.compute()
+assert pq.tp_per_class.tolist() == [0., 1. * (rank + 1), 2. * (rank + 1)]   # local state untouched
+if rank == 0:
+    assert abs(float(r['all_sq']) - 0.75) < 1e-12, r
+    assert abs(float(r['rq_per_class'][1]) - 3 / 4) < 1e-12, r
+    want = ((5 / 9) + (6 / 10)) / 2
+    assert abs(float(miou) - want) < 1e-6, (float(miou), want)
+    print('RANK0 OK')
+dist.destroy_process_group()
+''')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+                          '--nproc-per-node=2', '--master-addr', '127.0.0.1', '--master-port',
+                          '29541', str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'RANK0 OK' in out.stdout
