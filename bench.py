@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- panoptic frames/s (post-processing + merge + mIoU/PQ) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): SUNRGB-D-shaped frames 530x730, 37 classes, batch 64 per
+GPU with orientation head, 20 instances per frame, synthetic decoder outputs.
+One "step" = one batch through PanopticPostprocessing (centre NMS/top-k, fused arg-max +
+offset grouping + votes + orientation, instance table, panoptic ids) followed by the fused
+PQ + mIoU update against shifted targets.  Every rank owns its own frames (weak scaling, no
+data-path collective); the metric states are all-reduced once, at compute(), inside the
+timed region.
+
+Prints ONE JSON line (see the task contract): `value` = frames/s with inputs resident in HBM,
+`e2e` = the same through the host-buffer pipeline (pinned host inputs, H2D + D2H inside the
+timed region), `roofline` for the dominant kernel (group_pixels_kernel), `cpu_baseline` = the
+C oracle port timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name='sunrgbd_530x730_c37_b64_orientation', B=64, C=37, H=530, W=730, K=20)
+L = 1 << 16
+OFFSET = 256 ** 3
+METRIC = 'panoptic frames/s (postproc+merge+mIoU/PQ)'
+UNIT = 'frames/s'
+
+
+def bytes_post_per_frame(C, H, W, orientation=True):
+    """compulsory reads of decoder outputs + writes of dense API outputs."""
+    return H * W * (4 * C + 4 + 8 + (8 if orientation else 0) + 8 + 1)
+
+
+def bytes_eval_per_frame(H, W):
+    return 17 * H * W
+
+
+def bytes_group_kernel_per_frame(C, H, W, orientation=True):
+    """The share of 8(d) the dominant kernel is responsible for: logits, offsets,
+    orientation in; uint8 instance map out."""
+    return H * W * (4 * C + 8 + (8 if orientation else 0) + 1)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.QUERY}',
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = max((int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()), default=None)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6])
+                          if v.lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+def oracle_baseline(sample_frames, steps, warmup, threads=None):
+    """The CPU path ("port": C restatement of the reference, OpenMP over frames) on a
+    bounded sample of the workload: post-processing + PQ + confusion matrix per frame."""
+    import numpy as np
+    import torch
+    import oracle
+    from nicr_mt_scene_analysis_b200 import testing
+    w = WORKLOAD
+    if threads:
+        oracle.set_num_threads(threads)
+    cores = oracle.num_threads()
+    data = testing.make_batch(sample_frames, w['C'], w['H'], w['W'], w['K'], seed=1,
+                              with_orientation=True, quantize=None)
+    arrs = {k: v.numpy() for k, v in data.items()}
+    is_thing = testing.default_is_thing(w['C'])
+    has_ori = tuple(bool(t and c % 4 == 1) for c, t in enumerate(is_thing))
+
+    def step():
+        r = oracle.panoptic_postprocess(arrs['logits'], arrs['heat'], arrs['offset'],
+                                        arrs['orientation'], is_thing, has_ori)
+        pan = r['panoptic']
+        tgt = np.roll(pan, 5, axis=-1)
+        sem_t = (tgt // L).astype(np.uint8)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(cores) as ex:       # ctypes releases the GIL
+            list(ex.map(lambda b: oracle.pq_compare_and_accumulate(
+                pan[b], tgt[b], w['C'] + 1, 0, L, OFFSET, 0), range(sample_frames)))
+        oracle.confmat(pan // L, sem_t, w['C'] + 1)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return sample_frames * steps / dt, cores, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sample = 16
+    fps, cores, s_per_step = oracle_baseline(sample, max(args.steps, 1), min(args.warmup, 1))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': s_per_step * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': {'workload': WORKLOAD['name'], 'sample_frames_per_step': sample},
+        'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{sample} frames of the workload per step, C oracle '
+                                   '(oracle/panoptic_oracle.c), OpenMP over frames'},
+        'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nicr_mt_scene_analysis_b200 import _lib, testing
+    from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, PanopticEvaluation,
+                                                    PanopticQualityWithOrientationMAE)
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    from nicr_mt_scene_analysis_b200.pipeline import PanopticHostPipeline
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference '
+                         'for the CPU baseline')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    w = WORKLOAD
+    B, C, H, W, K = w['B'], w['C'], w['H'], w['W'], w['K']
+    is_thing = testing.default_is_thing(C)
+    has_ori = tuple(bool(t and c % 4 == 1) for c, t in enumerate(is_thing))
+
+    # ---- synthetic decoder outputs, generated on the device (distinct frames per rank) ----
+    pool = 16            # distinct frames; the batch cycles them (inputs stay > L2: 4.4 GB)
+    frames = [testing.make_frame(C, H, W, K, seed=1000 * (rank + 1) + i, with_orientation=True,
+                                 device=dev, quantize=None) for i in range(pool)]
+    data = {k: torch.stack([frames[i % pool][k] for i in range(B)]).contiguous() for k in frames[0]}
+    del frames
+    batch = testing.make_batch_dict(B, H, W)
+
+    def new_post(**kw):
+        return get_postprocessing_class(
+            'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+            instance_postprocessing=get_postprocessing_class('instance')(),
+            semantic_classes_is_thing=is_thing, semantic_class_has_orientation=has_ori, **kw)()
+
+    post = new_post(async_results=True)
+    pq = PanopticQualityWithOrientationMAE(C + 1, 0, L, OFFSET, (False,) + is_thing, device=dev)
+    miou = MeanIntersectionOverUnion(C + 1, ignore_first_class=True, device=dev)
+    evaluation = PanopticEvaluation(pq, miou)
+
+    inst_out = (data['heat'], data['offset'], data['orientation'])
+    raw = ((data['logits'], inst_out), (None, None))
+    # evaluation targets: prediction rolled by 5 px, fixed for the run
+    r0 = post.postprocess(raw, batch, is_training=False)
+    tgt_pan, tgt_sem = testing.make_eval_targets(r0['panoptic_segmentation_deeplab'], L)
+    del r0
+    KERNELS_PER_STEP = 8     # nms, select, group, finalize, write, pair_count, match, accumulate
+
+    def step():
+        r = post.postprocess(raw, batch, is_training=False)
+        evaluation.update(r['panoptic_segmentation_deeplab'], tgt_pan, tgt_sem)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    evaluation.reset()
+    barrier()
+
+    # ---- timed region: device-resident inputs ------------------------------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            last = step()
+        results = evaluation.compute(suffix='_deeplab')        # one all-reduce of the states
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    frames_total = B * args.steps * world
+    value = frames_total / (ms * 1e-3)
+    last['_panoptic_instance_tables'].wait()        # per-frame status words of the last step
+    pq.check_status()
+
+    # ---- dominant kernel in isolation: npb_group_pixels (CUDA events on its stream) --------------
+    from ctypes import c_float, c_int
+    tabs = last['_panoptic_instance_tables']
+    sem = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    inst = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    hist = torch.empty((B, _lib.MAX_INST, C), dtype=torch.int32, device=dev)
+    osum = torch.empty((B, _lib.MAX_INST, 2), dtype=torch.float64, device=dev)
+    lut = _lib.host_lut(is_thing, C)
+
+    def group_only():
+        _lib.check(_lib.lib().npb_group_pixels(
+            _lib.ptr(data['logits']), None, None, _lib.ptr(data['offset']),
+            _lib.ptr(data['orientation']), c_int(B), c_int(C), c_int(H), c_int(W), lut,
+            tabs.dptr('centers_yx'), tabs.dptr('n_centers'), c_int(1), c_int(0), c_float(0.0),
+            _lib.ptr(sem), _lib.ptr(inst), _lib.ptr(hist), _lib.ptr(osum), _lib.stream_ptr(dev)))
+
+    for _ in range(3):
+        group_only()
+    reps = max(args.steps, 5)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    k0.record()
+    for _ in range(reps):
+        group_only()
+    k1.record()
+    torch.cuda.synchronize(dev)
+    kernel_ms = k0.elapsed_time(k1) / reps      # includes the two small memsets of the call
+    peak, peak_src = measured_peak_gbs()
+    kbytes = bytes_group_kernel_per_frame(C, H, W) * B
+    achieved = kbytes / (kernel_ms * 1e-3) / 1e9
+
+    # ---- end to end: pinned host buffers in, panoptic ids in host memory out -------------------
+    e2e = None
+    if not args.no_e2e:
+        host_in = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v)
+                   for k, v in data.items()}
+        host_tgt = {'panoptic': torch.empty(tgt_pan.shape, dtype=torch.int64, pin_memory=True).copy_(tgt_pan),
+                    'semantic': torch.empty(tgt_sem.shape, dtype=torch.uint8, pin_memory=True).copy_(tgt_sem)}
+        out = {'panoptic_segmentation_deeplab': torch.empty((B, H, W), dtype=torch.int64, pin_memory=True),
+               'panoptic_segmentation_deeplab_instance_idx': torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)}
+        evaluation.reset()
+        pipe = PanopticHostPipeline(new_post(async_results=True), evaluation, chunk_frames=8, device=dev)
+        e2e_steps = max(1, min(args.steps, 5))
+
+        def e2e_step():
+            o = pipe.run(host_in, batch, host_tgt, out=dict(out))
+            return PanopticHostPipeline.finish(o)      # blocks; builds ids / meta / orientations
+
+        e2e_step()
+        evaluation.reset()
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        t0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        evaluation.compute(suffix='_deeplab')
+        t1.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        ems = torch.tensor([max(t0.elapsed_time(t1), wall * 1e3)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {'value': B * e2e_steps * world / (float(ems.item()) * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': pipe.h2d_bytes, 'd2h_bytes_per_step': pipe.d2h_bytes,
+               'steps': e2e_steps, 'chunk_frames': 8}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, cores, _ = oracle_baseline(16, 2, 1)
+        cpu = {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': '16 frames of the workload x 2 steps, C oracle '
+                         '(oracle/panoptic_oracle.c), OpenMP over frames'}
+
+    if rank == 0:
+        bpf = bytes_post_per_frame(C, H, W) + bytes_eval_per_frame(H, W)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': w['name'], 'frames_per_gpu_per_step': B, 'classes': C,
+                       'height': H, 'width': W, 'instances_per_frame': K,
+                       'parallelism': f'frames sharded over {world} GPU(s), metric states '
+                                      'all-reduced at compute()',
+                       'l2_policy': 'inputs (4.4 GB per step) larger than L2, no flush needed'},
+            'clocks': clocks.summary(),
+            'e2e': e2e,
+            'gpu_launches': KERNELS_PER_STEP * args.steps,
+            'roofline': {'bound': 'hbm', 'kernel': 'group_pixels_kernel<4,logits,orientation>',
+                         'achieved': achieved, 'peak': peak, 'peak_source': peak_src,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'kernel_ms': kernel_ms, 'algorithmic_bytes_per_launch': kbytes},
+            'roofline_path': {'bytes_per_frame': bpf,
+                              'achieved': value / world * bpf / 1e9, 'unit': 'GB/s',
+                              'frac': value / world * bpf / 1e9 / peak},
+            'cpu_baseline': cpu,
+            'quality': {'all_pq': float(results['all_deeplab_pq']),
+                        'miou': float(results['semantic_deeplab_miou'])},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

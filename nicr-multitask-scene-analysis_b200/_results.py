@@ -72,8 +72,8 @@ class ResultDict(dict):
 class InstanceTables:
     """Per-instance tables of one batch (rows of `_lib.MAX_INST`, row 0 unused).
 
-    One packed device buffer -> one asynchronous copy into pinned host memory; `wait()`
-    blocks on the copy, checks the per-frame status words and exposes numpy views.
+    One packed device buffer -> ONE device->host copy (a few hundred KB), done on first
+    access by `wait()`, which also checks the per-frame status words and exposes numpy views.
     """
 
     FIELDS = (('status', np.int32, 1), ('n_centers', np.int32, 1),
@@ -81,20 +81,24 @@ class InstanceTables:
               ('inst_class', np.int32, _lib.MAX_INST), ('inst_area', np.int32, _lib.MAX_INST),
               ('inst_angle', np.float32, _lib.MAX_INST), ('inst_pan_id', np.int64, _lib.MAX_INST))
 
-    def __init__(self, batch_size: int, device: torch.device):
+    @classmethod
+    def layout(cls, batch_size: int):
+        """byte offsets of the fields inside the packed buffer (largest alignment first)"""
+        offsets, off = {}, 0
+        for name, dt, per_frame in sorted(cls.FIELDS, key=lambda f: -np.dtype(f[1]).itemsize):
+            nbytes = np.dtype(dt).itemsize * per_frame * batch_size
+            offsets[name] = (off, nbytes, dt, per_frame)
+            off += (nbytes + 15) // 16 * 16
+        return offsets, off
+
+    def __init__(self, batch_size: int, device: torch.device, storage: torch.Tensor = None):
+        """`storage`: optional uint8 device tensor of `layout(B)[1]` bytes to live in (the
+        status words inside it must be zero on entry of the kernels that report into it)."""
         self.B = batch_size
         self.device = device
-        self._offsets = {}
-        off = 0
-        # int64 field first-aligned: lay fields out in descending alignment
-        for name, dt, per_frame in sorted(self.FIELDS, key=lambda f: -np.dtype(f[1]).itemsize):
-            nbytes = np.dtype(dt).itemsize * per_frame * batch_size
-            self._offsets[name] = (off, nbytes, dt, per_frame)
-            off += (nbytes + 15) // 16 * 16
-        self.nbytes = off
-        self.dev = torch.zeros(off, dtype=torch.uint8, device=device)
-        self._host = None
-        self._event = None
+        self._offsets, self.nbytes = self.layout(batch_size)
+        self.dev = storage if storage is not None else \
+            torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
         self._np = None
         self._where = 'panoptic post-processing'
 
@@ -109,18 +113,9 @@ class InstanceTables:
         v = self.dev[off:off + nbytes].view(tdt)
         return v.view(self.B, per_frame) if per_frame > 1 else v
 
-    def start_download(self) -> None:
-        self._host = torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=True)
-        self._host.copy_(self.dev, non_blocking=True)
-        self._event = torch.cuda.Event()
-        self._event.record(torch.cuda.current_stream(self.device))
-
     def wait(self) -> 'InstanceTables':
         if self._np is None:
-            if self._event is None:
-                self.start_download()
-            self._event.synchronize()
-            raw = self._host.numpy()
+            raw = self.dev.cpu().numpy()        # blocks until the producing kernels are done
             self._np = {}
             for name, (off, nbytes, dt, per_frame) in self._offsets.items():
                 a = raw[off:off + nbytes].view(dt)

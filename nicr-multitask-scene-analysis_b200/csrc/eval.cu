@@ -13,9 +13,10 @@
 // (pair_count_kernel) streams pred / target once (17 B/px with the fused semantic target),
 // counts pairs in a per-CTA shared-memory hash table after warp-level aggregation
 // (neighbouring pixels nearly always share the pair) and flushes it into a small per-frame
-// global hash table.  match_frames_kernel (one CTA per frame) sorts the <= 2048 pairs by
+// global hash table.  match_frames_kernel (one CTA per frame) sorts the <= 4096 pairs by
 // `target*offset + pred` -- the reference's visiting order, which fixes the float64
-// summation order -- and does the matching; accumulate_frames_kernel adds the frames to
+// summation order -- derives the per-segment quantities with two sorted-run passes (O(m log m),
+// no pair x pair loops) and does the matching; accumulate_frames_kernel adds the frames to
 // the running state in frame order.  Both float64 orders equal the reference's, so the
 // states are bit-identical, not merely close.
 #include "common.cuh"
@@ -23,9 +24,9 @@
 namespace npb {
 
 constexpr int kPairThreads = 256;
-constexpr int kSmemSlots = 512;        // per-CTA pair hash table
-constexpr int kFrameSlots = 8192;      // per-frame global pair hash table
-constexpr int kMaxPairs = 2048;        // pairs per frame handled by the matcher
+constexpr int kSmemSlots = 1024;       // per-CTA pair hash table
+constexpr int kFrameSlots = 16384;     // per-frame global pair hash table
+constexpr int kMaxPairs = 4096;        // pairs per frame handled by the matcher
 constexpr int kMatchThreads = 512;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kSmemConfmatMaxN = 96;   // n*n*4 B <= 36 KB privatised in shared memory
@@ -96,9 +97,8 @@ __global__ void __launch_bounds__(kPairThreads) pair_count_kernel(const PairPara
         const size_t fb = (size_t)b * P + p0;
         unsigned long long key[VEC];
         int ckey[VEC];
-        bool valid[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { valid[j] = false; key[j] = 0; ckey[j] = -1; }
+        for (int j = 0; j < VEC; ++j) { key[j] = 0; ckey[j] = -1; }
         if (p0 < P) {  // P % VEC == 0 guaranteed by the launcher
             long long pv[VEC], tv[VEC];
             if (VEC == 4) {
@@ -121,11 +121,8 @@ __global__ void __launch_bounds__(kPairThreads) pair_count_kernel(const PairPara
             int last_c = 0;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                valid[j] = true;
-                if (pv[j] < 0 || pv[j] >= prm.offset || tv[j] < 0) {
+                if (pv[j] < 0 || pv[j] >= prm.offset || tv[j] < 0)
                     set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
-                    valid[j] = false;
-                }
                 key[j] = (unsigned long long)tv[j] * (unsigned long long)prm.offset +
                          (unsigned long long)pv[j];
                 if (CONFMAT) {
@@ -137,7 +134,7 @@ __global__ void __launch_bounds__(kPairThreads) pair_count_kernel(const PairPara
                     }
                     const int st = (sw >> (8 * j)) & 255;
                     if (last_c < 0 || st >= n) {
-                        if (valid[j]) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
+                        set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                         ckey[j] = -1;
                     } else {
                         ckey[j] = st * n + last_c;
@@ -146,53 +143,39 @@ __global__ void __launch_bounds__(kPairThreads) pair_count_kernel(const PairPara
             }
         }
 
-        // ---- pair counts: warp-aggregate equal keys, then one shared-memory insert each ----
-        unsigned pending = 0u;
+        // ---- warp aggregation: lanes whose 4 pixels carry the same (pair, confusion cell) are
+        // found with MATCH.ANY, their pixel counts summed with REDUX, and the lowest lane of each
+        // group does ONE insert; pixels that differ from their thread's first pixel (segment
+        // boundaries, 1 thread in ~8) are inserted individually.
+        const bool act = p0 < P;
+        const unsigned long long k0 = act ? key[0] : kEmptyKey;
+        const int c0 = act ? ckey[0] : -2;
+        unsigned peers = __match_any_sync(kFullMask, k0);
+        if (CONFMAT) peers &= __match_any_sync(kFullMask, c0);
+        int cnt0 = 0;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) pending |= (valid[j] ? 1u : 0u) << j;
-        while (true) {
-            const unsigned has = __ballot_sync(kFullMask, pending != 0u);
-            if (!has) break;
-            const int leader = __ffs(has) - 1;
-            unsigned long long mine = 0;
-#pragma unroll
-            for (int j = VEC - 1; j >= 0; --j)
-                if ((pending >> j) & 1u) mine = key[j];
-            const unsigned long long cur = __shfl_sync(kFullMask, mine, leader);
-            int cnt = 0;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j)
-                if (((pending >> j) & 1u) && key[j] == cur) { ++cnt; pending &= ~(1u << j); }
-            cnt = __reduce_add_sync(kFullMask, cnt);
-            if (lane == 0) {
-                if (!table_add(s_keys, s_cnts, kSmemSlots, 16, cur, (unsigned)cnt))
-                    if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, cur, (unsigned)cnt))
+        for (int j = 0; j < VEC; ++j) cnt0 += (act && key[j] == k0 && ckey[j] == c0) ? 1 : 0;
+        const int total = __reduce_add_sync(peers, cnt0);
+        if (act) {
+            if (lane == __ffs(peers) - 1) {
+                if (!table_add(s_keys, s_cnts, kSmemSlots, 16, k0, (unsigned)total))
+                    if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, k0, (unsigned)total))
                         set_status(prm.status + b, NPB_ERR_CAPACITY);
+                if (CONFMAT && c0 >= 0) {
+                    if (cm_smem) atomicAdd(s_cm + c0, (unsigned)total);
+                    else atomicAdd(prm.confmat + c0, (unsigned long long)total);
+                }
             }
-        }
-
-        // ---- confusion matrix: same aggregation on (target class, pred class) -------------
-        if (CONFMAT) {
-            unsigned cpend = 0u;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) cpend |= (ckey[j] >= 0 ? 1u : 0u) << j;
-            while (true) {
-                const unsigned has = __ballot_sync(kFullMask, cpend != 0u);
-                if (!has) break;
-                const int leader = __ffs(has) - 1;
-                int mine = -1;
-#pragma unroll
-                for (int j = VEC - 1; j >= 0; --j)
-                    if ((cpend >> j) & 1u) mine = ckey[j];
-                const int cur = __shfl_sync(kFullMask, mine, leader);
-                int cnt = 0;
-#pragma unroll
-                for (int j = 0; j < VEC; ++j)
-                    if (((cpend >> j) & 1u) && ckey[j] == cur) { ++cnt; cpend &= ~(1u << j); }
-                cnt = __reduce_add_sync(kFullMask, cnt);
-                if (lane == 0) {
-                    if (cm_smem) atomicAdd(s_cm + cur, (unsigned)cnt);
-                    else atomicAdd(prm.confmat + cur, (unsigned long long)cnt);
+            for (int j = 1; j < VEC; ++j) {
+                if (key[j] != k0 || ckey[j] != c0) {
+                    if (!table_add(s_keys, s_cnts, kSmemSlots, 16, key[j], 1u))
+                        if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, key[j], 1u))
+                            set_status(prm.status + b, NPB_ERR_CAPACITY);
+                    if (CONFMAT && ckey[j] >= 0) {
+                        if (cm_smem) atomicAdd(s_cm + ckey[j], 1u);
+                        else atomicAdd(prm.confmat + ckey[j], 1ull);
+                    }
                 }
             }
         }
@@ -224,16 +207,40 @@ struct MatchParams {
     int32_t *status;       // [B]
 };
 
+// bitonic sort of s_a[0..npad) ascending by (s_a, s_b) carrying nothing else: callers pack
+// what they need into the two arrays.  npad is a power of two.
+template <typename KA, typename KB>
+__device__ __forceinline__ void bitonic_sort_pairs(KA *a, KB *b2, int npad, int tid)
+{
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += kMatchThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = ((i & k) == 0);
+                    const KA a0 = a[i], a1 = a[ixj];
+                    const KB b0 = b2[i], b1 = b2[ixj];
+                    const bool gt = (a0 > a1) || (a0 == a1 && b0 > b1);
+                    if (gt == up) { a[i] = a1; a[ixj] = a0; b2[i] = b1; b2[ixj] = b0; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const MatchParams prm)
 {
     extern __shared__ unsigned char smem_raw[];
-    long long *s_key = (long long *)smem_raw;                   // [kMaxPairs]
-    long long *s_g = s_key + kMaxPairs;                         // gt segment id
-    long long *s_p = s_g + kMaxPairs;                           // pred segment id
-    double *s_iou = (double *)(s_p + kMaxPairs);                // IoU of matched pairs
-    unsigned *s_cnt = (unsigned *)(s_iou + kMaxPairs);          // intersection area
+    long long *s_key = (long long *)smem_raw;                   // [kMaxPairs] target*offset+pred
+    long long *s_p = s_key + kMaxPairs;                         // pred segment id (sort scratch)
+    unsigned *s_cnt = (unsigned *)(s_p + kMaxPairs);            // intersection area
     int *s_gcat = (int *)(s_cnt + kMaxPairs);                   // category of the gt segment
-    unsigned char *s_flag = (unsigned char *)(s_gcat + kMaxPairs);  // bit0 = matched (TP)
+    unsigned *s_tsa = (unsigned *)(s_gcat + kMaxPairs);         // area of the gt segment
+    unsigned *s_psa = s_tsa + kMaxPairs;                        // area of the pred segment
+    unsigned *s_void = s_psa + kMaxPairs;                       // |pred & gt void segment|
+    int *s_ord = (int *)(s_void + kMaxPairs);                   // pair indices sorted by pred id
+    unsigned char *s_flag = (unsigned char *)(s_ord + kMaxPairs);   // 1 = matched (TP)
     __shared__ int s_m, s_nm;
     __shared__ int s_tp[256], s_fn[256], s_fp[256];
 
@@ -257,61 +264,72 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         if (tid == 0) set_status(prm.status + b, NPB_ERR_CAPACITY);
         m = kMaxPairs;
     }
-    // bitonic sort by key ascending (= torch.unique order of target*offset + pred, pq.py:109)
     int npad = 1;
     while (npad < m) npad <<= 1;
     for (int i = m + tid; i < npad; i += kMatchThreads) { s_key[i] = 0x7fffffffffffffffll; s_cnt[i] = 0; }
     __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < npad; i += kMatchThreads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool up = ((i & k) == 0);
-                    const long long a = s_key[i], c = s_key[ixj];
-                    if ((a > c) == up) {
-                        s_key[i] = c; s_key[ixj] = a;
-                        const unsigned t = s_cnt[i]; s_cnt[i] = s_cnt[ixj]; s_cnt[ixj] = t;
-                    }
-                }
-            }
-            __syncthreads();
+    // (1) pairs in ascending key order = torch.unique order of target*offset + pred (pq.py:109)
+    bitonic_sort_pairs(s_key, s_cnt, npad, tid);
+
+    // (2) decode; gt segments are runs of equal key / offset: run heads sum the run (area of
+    //     the gt segment, pq.py:83) and broadcast it to the run
+    for (int t = tid; t < npad; t += kMatchThreads) {
+        s_ord[t] = t;
+        if (t < m) {
+            const long long key = s_key[t];
+            const long long g = key / prm.offset;       // ids are validated non-negative
+            s_p[t] = key - g * prm.offset;
+            const long long gc = g / prm.L;
+            s_gcat[t] = (gc >= 0 && gc < 0x7fffffff) ? (int)gc : 0x7fffffff;
+            // bit 1: first pair of its gt segment (run head); bit 0 (set later): matched
+            s_flag[t] = (t == 0 || s_key[t - 1] / prm.offset != g) ? 2 : 0;
+        } else {
+            s_p[t] = 0x7fffffffffffffffll;
         }
     }
+    __syncthreads();
     for (int t = tid; t < m; t += kMatchThreads) {
-        const long long key = s_key[t];
-        const long long g = key / prm.offset;       // ids are validated non-negative
-        s_g[t] = g;
-        s_p[t] = key - g * prm.offset;
-        const long long gc = g / prm.L;
-        s_gcat[t] = (gc >= 0 && gc < 0x7fffffff) ? (int)gc : 0x7fffffff;
-        s_flag[t] = 0;
-        s_iou[t] = 0.0;
+        if (s_flag[t] & 2) {
+            unsigned area = s_cnt[t];
+            int e = t + 1;
+            for (; e < m && !(s_flag[e] & 2); ++e) area += s_cnt[e];
+            for (int u = t; u < e; ++u) s_tsa[u] = area;
+        }
+    }
+    // (3) pred segments: sort the pair indices by pred id, then the same run trick gives the
+    //     pred area (pq.py:84) and the overlap with the gt void segment (pq.py:34-43)
+    __syncthreads();
+    bitonic_sort_pairs(s_p, s_ord, npad, tid);
+    for (int k = tid; k < m; k += kMatchThreads) {
+        const long long p = s_p[k];
+        if (k == 0 || s_p[k - 1] != p) {
+            const long long void_key = prm.void_segment_id * prm.offset + p;
+            unsigned area = 0, vo = 0;
+            int e = k;
+            for (; e < m && s_p[e] == p; ++e) {
+                const int u = s_ord[e];
+                area += s_cnt[u];
+                if (s_key[u] == void_key) vo = s_cnt[u];
+            }
+            for (int q = k; q < e; ++q) { s_psa[s_ord[q]] = area; s_void[s_ord[q]] = vo; }
+        }
     }
     __syncthreads();
 
-    // pass 1: areas, IoU, match decision                                    pq.py:119-152
+    // (4) IoU + match decision per intersecting pair                       pq.py:119-152
     for (int t = tid; t < m; t += kMatchThreads) {
-        const long long g = s_g[t], p = s_p[t], key = s_key[t];
+        const long long key = s_key[t];
         if (key == prm.void_segment_id) continue;                          // pq.py:120
+        const long long g = key / prm.offset, p = key - g * prm.offset;
         const long long gcat = s_gcat[t], pcat = p / prm.L;
         if (gcat != pcat) continue;                                        // pq.py:128
-        const long long void_key = prm.void_segment_id * prm.offset + p;
-        long long tsa = 0, psa = 0, r = 0;
-        for (int u = 0; u < m; ++u) {
-            const long long cu = s_cnt[u];
-            if (s_g[u] == g) tsa += cu;
-            if (s_p[u] == p) psa += cu;
-            if (s_key[u] == void_key) r = cu;
-        }
         const long long ia = s_cnt[t];
-        const long long uni = tsa + psa - ia - r;                          // pq.py:143
+        const long long uni = (long long)s_tsa[t] + (long long)s_psa[t] - ia - (long long)s_void[t];
         if (uni == 0) { set_status(prm.status + b, NPB_ERR_ZERO_DIVISION); continue; }
         const double iou = (double)ia / (double)uni;                       // pq.py:145
         if (iou > 0.5) {
             if (gcat >= NC || gcat >= 256) { set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE); continue; }
-            s_flag[t] = 1;
-            s_iou[t] = iou;
+            s_flag[t] |= 1;
             atomicAdd(&s_tp[(int)gcat], 1);
             if (prm.matches) {
                 const int slot = atomicAdd(&s_nm, 1);
@@ -327,31 +345,31 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     }
     __syncthreads();
 
-    // pass 2: false negatives / false positives                            pq.py:155-177
+    // (5) false negatives: gt segments (runs in key order) without a match    pq.py:155-163
     for (int t = tid; t < m; t += kMatchThreads) {
-        const long long g = s_g[t], p = s_p[t];
-        const bool first_g = (t == 0) || (s_g[t - 1] != g);
-        bool first_p = true, g_matched = false, p_matched = false;
-        long long psa = 0, pio = 0;
-        for (int u = 0; u < m; ++u) {
-            const bool same_p = (s_p[u] == p);
-            if (same_p) {
-                if (u < t) first_p = false;
-                psa += s_cnt[u];
-                if ((long long)s_gcat[u] == prm.ignored_label) pio += s_cnt[u];   // pq.py:47-57
-                if (s_flag[u]) p_matched = true;
-            }
-            if (s_flag[u] && s_g[u] == g) g_matched = true;
-        }
-        if (first_g && !g_matched) {
+        if (s_flag[t] & 2) {
+            bool matched = (s_flag[t] & 1) != 0;
+            for (int e = t + 1; e < m && !(s_flag[e] & 2); ++e) matched |= (s_flag[e] & 1) != 0;
             const long long cat = s_gcat[t];
-            if (cat != prm.ignored_label) {                                 // pq.py:161
+            if (!matched && cat != prm.ignored_label) {
                 if (cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                 else atomicAdd(&s_fn[(int)cat], 1);
             }
         }
-        if (first_p && !p_matched) {
-            if (!((double)pio / (double)psa > 0.5)) {                       // pq.py:174
+    }
+    // (6) false positives: pred segments (runs in pred order) without a match, unless more
+    //     than half of their area lies in ignored gt segments                 pq.py:165-177
+    for (int k = tid; k < m; k += kMatchThreads) {
+        const long long p = s_p[k];
+        if (k == 0 || s_p[k - 1] != p) {
+            bool matched = false;
+            long long pio = 0;
+            for (int e = k; e < m && s_p[e] == p; ++e) {
+                const int u = s_ord[e];
+                matched |= (s_flag[u] & 1) != 0;
+                if ((long long)s_gcat[u] == prm.ignored_label) pio += s_cnt[u];
+            }
+            if (!matched && !((double)pio / (double)s_psa[s_ord[k]] > 0.5)) {
                 const long long cat = p / prm.L;
                 if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                 else atomicAdd(&s_fp[(int)cat], 1);
@@ -360,12 +378,33 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     }
     __syncthreads();
 
-    // per category: IoU sum in ascending pair order (the reference's float64 add order)
+    // (7) matched pairs, compacted in ascending pair order by one warp (ballot prefix), then
+    //     per category the IoU sum in that order -- the reference's float64 add order
+    __shared__ int s_nmatched;
+    if (tid < 32) {
+        int base = 0;
+        for (int t0 = 0; t0 < m; t0 += 32) {
+            const int t = t0 + tid;
+            const bool f = t < m && (s_flag[t] & 1);
+            const unsigned bal = __ballot_sync(kFullMask, f);
+            if (f) s_ord[base + __popc(bal & ((1u << tid) - 1u))] = t;
+            base += __popc(bal);
+        }
+        if (tid == 0) s_nmatched = base;
+    }
+    __syncthreads();
+    const int n_matched = s_nmatched;
     for (int c = tid; c < NC; c += kMatchThreads) {
         double acc = 0.0;
         if (c < 256 && s_tp[c] > 0)
-            for (int t = 0; t < m; ++t)
-                if (s_flag[t] && s_gcat[t] == c) acc += s_iou[t];
+            for (int i = 0; i < n_matched; ++i) {
+                const int t = s_ord[i];
+                if (s_gcat[t] == c) {
+                    const long long uni = (long long)s_tsa[t] + (long long)s_psa[t] -
+                                          (long long)s_cnt[t] - (long long)s_void[t];
+                    acc += (double)s_cnt[t] / (double)uni;
+                }
+            }
         double *fs = prm.frame_stats + (size_t)b * 4 * NC;
         fs[c] = acc;
         fs[NC + c] = c < 256 ? (double)s_tp[c] : 0.0;
@@ -375,21 +414,26 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     if (tid == 0 && prm.n_matches) prm.n_matches[b] = s_nm < prm.match_cap ? s_nm : prm.match_cap;
 }
 
-// state += frame result, frames in order (PanopticQuality.update, pq.py:298-303)
-__global__ void accumulate_frames_kernel(const double *__restrict__ frame_stats, int B, int NC,
-                                         double *iou, double *tp, double *fn, double *fp)
+// state += frame result, frames in order (PanopticQuality.update, pq.py:298-303).
+// One warp per (category, statistic): the lanes fetch 32 frames at once (the loads are
+// independent), lane 0 then adds them strictly in frame order -- the float64 order of the
+// reference -- so the sequential part touches registers only.
+__global__ void __launch_bounds__(128)
+accumulate_frames_kernel(const double *__restrict__ frame_stats, int B, int NC,
+                         double *iou, double *tp, double *fn, double *fp)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= NC) return;
-    double a0 = iou[c], a1 = tp[c], a2 = fn[c], a3 = fp[c];
-    for (int b = 0; b < B; ++b) {
-        const double *fs = frame_stats + (size_t)b * 4 * NC;
-        a0 += fs[c];
-        a1 += fs[NC + c];
-        a2 += fs[2 * NC + c];
-        a3 += fs[3 * NC + c];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= 4 * NC) return;
+    const int stat = warp / NC, c = warp - stat * NC;
+    double *dst = stat == 0 ? iou : stat == 1 ? tp : stat == 2 ? fn : fp;
+    double acc = dst[c];
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int b = b0 + lane;
+        const double v = b < B ? frame_stats[((size_t)b * 4 + stat) * NC + c] : 0.0;
+        const int n = min(32, B - b0);
+        for (int j = 0; j < n; ++j) acc += __shfl_sync(kFullMask, v, j);
     }
-    iou[c] = a0; tp[c] = a1; fn[c] = a2; fp[c] = a3;
+    if (lane == 0) dst[c] = acc;
 }
 
 // ---- stand-alone confusion matrix over arbitrary integer dtypes ---------------------------
@@ -447,7 +491,7 @@ confmat_kernel(const void *__restrict__ preds, int pd, const void *__restrict__ 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t match_smem_bytes()
 {
-    return (size_t)kMaxPairs * (8 + 8 + 8 + 8 + 4 + 4 + 1) + 16;
+    return (size_t)kMaxPairs * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + 16;
 }
 
 }  // namespace npb
@@ -550,7 +594,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
         attr_set = true;
     }
     match_frames_kernel<<<B, kMatchThreads, match_smem_bytes(), s>>>(mp);
-    accumulate_frames_kernel<<<(num_categories + 127) / 128, 128, 0, s>>>(fstats, B, num_categories,
+    accumulate_frames_kernel<<<(4 * num_categories * 32 + 127) / 128, 128, 0, s>>>(fstats, B, num_categories,
                                                                          iou, tp, fn, fp);
     return record_launch("npb_pq_update");
 }

@@ -27,12 +27,22 @@ def _safe_divide(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
 class _PQKernel:
     """Workspace + launch helper shared by PanopticQuality and compare_and_accumulate."""
 
+    _scratch = {}      # (device, B, num_categories) -> reusable workspace (stream ordered)
+
+    @classmethod
+    def _workspace(cls, dev, B, num_categories):
+        key = (dev, B, num_categories)
+        if key not in cls._scratch:
+            nbytes = _lib.lib().npb_pq_update_workspace_bytes(B, num_categories)
+            cls._scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return cls._scratch[key]
+
     @staticmethod
     def run(pred: torch.Tensor, target: torch.Tensor, num_categories: int, ignored_label: int,
             max_instances_per_category: int, offset: int, void_segment_id: int,
             iou, tp, fn, fp, sem_target: Optional[torch.Tensor] = None,
             confmat: Optional[torch.Tensor] = None, want_matches: bool = False,
-            want_frame_stats: bool = False):
+            want_frame_stats: bool = False, status: Optional[torch.Tensor] = None):
         dev = iou.device
         if not dev.type == 'cuda':
             raise RuntimeError('PanopticQuality.update needs its states on a CUDA device')
@@ -42,9 +52,9 @@ class _PQKernel:
         B = pred.shape[0]
         P = pred.shape[1] * pred.shape[2]
         L = _lib.lib()
-        ws = torch.empty(L.npb_pq_update_workspace_bytes(B, num_categories), dtype=torch.uint8,
-                         device=dev)
-        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        ws = _PQKernel._workspace(dev, B, num_categories)
+        if status is None or status.numel() < B:
+            status = torch.zeros(B, dtype=torch.int32, device=dev)
         matches = n_matches = frame_stats = None
         if want_matches:
             matches = torch.empty((B, MATCH_CAP, 2), dtype=torch.int64, device=dev)
@@ -114,17 +124,23 @@ class PanopticQuality(MetricState):
         for name in ('iou_per_class', 'tp_per_class', 'fn_per_class', 'fp_per_class'):
             self.add_state(name, torch.zeros(num_categories, dtype=torch.float64),
                            dist_reduce_fx='sum')
-        self._pending_status: List[torch.Tensor] = []
+        # one status buffer per batch size, shared by all updates (errors merge by atomicMin)
+        self._status: Dict[int, torch.Tensor] = {}
 
     # ---- update --------------------------------------------------------------------------
     def _launch(self, preds, targets, **kw):
         assert preds.ndim == 3
         assert targets.shape == preds.shape
-        status, matches, n_matches, frame_stats = _PQKernel.run(
+        B = preds.shape[0]
+        status = self._status.get(B)
+        if status is None or status.device != self.iou_per_class.device:
+            status = torch.zeros(B, dtype=torch.int32, device=self.iou_per_class.device)
+            self._status[B] = status
+        _, matches, n_matches, frame_stats = _PQKernel.run(
             preds, targets, self.num_categories, self.ignored_label,
             self.max_instances_per_category, self.offset, self.void_segment_id,
-            self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class, **kw)
-        self._pending_status.append(status)
+            self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
+            status=status, **kw)
         return matches, n_matches, frame_stats
 
     def update(self, preds: torch.Tensor, targets: torch.Tensor) -> None:
@@ -133,13 +149,15 @@ class PanopticQuality(MetricState):
         self._launch(preds, targets)
 
     def check_status(self) -> None:
-        pending, self._pending_status = self._pending_status, []
-        for status in pending:
-            _lib.raise_for_status(status.cpu().tolist(), type(self).__name__ + '.update')
+        for status in self._status.values():
+            codes = status.cpu().tolist()
+            status.zero_()
+            _lib.raise_for_status(codes, type(self).__name__ + '.update')
 
     def reset(self) -> None:
         super().reset()
-        self._pending_status = []
+        for status in self._status.values():
+            status.zero_()
 
     # ---- compute (pq.py:254-361) -----------------------------------------------------------
     @staticmethod

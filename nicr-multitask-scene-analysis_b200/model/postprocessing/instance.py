@@ -136,7 +136,6 @@ class InstancePostprocessing(DensePostprocessingBase):
         fg = self._as_fg_u8(foreground_mask, dev)
         tables = self._run_centers(center_heatmap, fg)
         inst = self._group(tables, center_offset, fg, normalized)
-        tables.start_download()
         return inst, tables.meta()
 
     def _get_instance_orientation(

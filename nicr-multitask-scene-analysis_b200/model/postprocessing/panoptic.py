@@ -54,6 +54,7 @@ class PanopticPostprocessing(DensePostprocessingBase):
         self._compute_scores = compute_scores
         self._max_instances_per_category = 1 << 16
         self._async_results = bool(kwargs.get('async_results', False))
+        self._ws = None
 
     @property
     def max_instances_per_category(self):
@@ -82,13 +83,24 @@ class PanopticPostprocessing(DensePostprocessingBase):
             raise ValueError('instance outputs do not match the semantic logits in shape')
         L = _lib.lib()
         ks = post._heatmap_nms_kernel_size
-        ws = torch.empty(L.npb_panoptic_forward_workspace_bytes(B, C, H, W, ks),
-                         dtype=torch.uint8, device=dev)
-        sem = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-        inst = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-        pan = torch.empty((B, H, W), dtype=torch.int64, device=dev)
-        pan_sem = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-        tables = InstanceTables(B, dev)
+        # scratch (candidate lists, vote histograms, orientation sums) is reused across calls:
+        # the calls are ordered on the stream, nothing in it outlives a call
+        ws_bytes = L.npb_panoptic_forward_workspace_bytes(B, C, H, W, ks)
+        if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = self._ws
+        # all outputs of a call live in ONE fresh allocation: [pan i64 | tables | sem | inst | pan_sem]
+        P = H * W
+        _, tab_bytes = InstanceTables.layout(B)
+        pan_bytes = B * P * 8
+        u8_bytes = (B * P + 15) // 16 * 16
+        buf = torch.empty(pan_bytes + tab_bytes + 3 * u8_bytes, dtype=torch.uint8, device=dev)
+        pan = buf[:pan_bytes].view(torch.int64).view(B, H, W)
+        tables = InstanceTables(B, dev, storage=buf[pan_bytes:pan_bytes + tab_bytes])
+        o = pan_bytes + tab_bytes
+        sem = buf[o:o + B * P].view(B, H, W)
+        inst = buf[o + u8_bytes:o + u8_bytes + B * P].view(B, H, W)
+        pan_sem = buf[o + 2 * u8_bytes:o + 2 * u8_bytes + B * P].view(B, H, W)
         use_thr = post._offset_distance_threshold is not None
         _lib.check(L.npb_panoptic_forward(
             _lib.ptr(logits), _lib.ptr(heat), _lib.ptr(offset), _lib.ptr(orientation),
@@ -102,7 +114,6 @@ class PanopticPostprocessing(DensePostprocessingBase):
             tables.dptr('center_score'), tables.dptr('inst_class'), tables.dptr('inst_pan_id'),
             tables.dptr('inst_area'), tables.dptr('inst_angle'), tables.dptr('status'),
             _lib.stream_ptr(dev)), 'npb_panoptic_forward')
-        tables.start_download()
         return sem, inst, pan, pan_sem, tables
 
     def _thing_mask(self, sem_u8: torch.Tensor) -> torch.Tensor:

@@ -41,7 +41,7 @@ def test_host_argument_validation_without_gpu():
     assert L.npb_instance_centers(None, 1, 8, 8, 0.1, 3, 4, None, 0, None, None, None, None, None,
                                   None) == _lib.ERR_ARG
     assert L.npb_instance_centers_workspace_bytes(2, 480, 640, 3) >= 2 * 240 * 320 * 8
-    assert L.npb_pq_update_workspace_bytes(4, 41) > 4 * 8192 * 12
+    assert L.npb_pq_update_workspace_bytes(4, 41) > 4 * 16384 * 12
 
 
 def test_product_never_imports_the_oracle():
