@@ -13,15 +13,16 @@
 // Only survivors with value >= 0 can ever be selected, so only those are materialised
 // ("candidates"); everything else is equivalent to the -1 fill.
 //
-// Kernel 1 (nms_candidates_kernel): shared-memory halo tiles, warp-aggregated append.
+// Kernel 1 (nms_candidates_kernel): shared-memory halo tiles (8 x 128 pixels + halo per CTA,
+//   a warp per tile row), whole-tile early out, warp-aggregated append of the survivors.
 // Kernel 2 (select_centers_kernel): one CTA per frame, exact radix select of the k-th
 //   largest value over the candidate list, compaction, rank sort by pixel index.
 #include "common.cuh"
 
 namespace npb {
 
-constexpr int kTileW = 64;
-constexpr int kTileH = 16;
+constexpr int kTileW = 128;   // one warp covers one tile row, 4 consecutive pixels per lane
+constexpr int kTileH = 8;
 constexpr int kNmsThreads = 256;
 constexpr int kSelThreads = 1024;
 
@@ -29,41 +30,49 @@ __global__ void __launch_bounds__(kNmsThreads)
 nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, int r,
                       uint2 *__restrict__ cand, int cap, int32_t *__restrict__ cand_cnt)
 {
-    extern __shared__ float tile[];  // (kTileH + 2r) x (kTileW + 2r)
+    extern __shared__ float tile[];  // (kTileH + 2r) x (kTileW + 2r), thresholded heat + halo
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
     const int pitch = kTileW + 2 * r, rows = kTileH + 2 * r;
     const size_t P = (size_t)H * W;
     const float *hb = heat + (size_t)b * P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (int i = threadIdx.x; i < rows * pitch; i += kNmsThreads) {
-        const int ty = i / pitch, tx = i - ty * pitch;
-        const int y = y0 - r + ty, x = x0 - r + tx;
-        float v = -1.0f;
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            v = __ldg(hb + (size_t)y * W + x);
-            v = (v > thr) ? v : -1.0f;
+    // warp per tile row: coalesced row segments, no index division
+    bool any = false;
+    for (int ty = warp; ty < rows; ty += kNmsThreads / 32) {
+        const int y = y0 - r + ty;
+        const bool row_ok = (y >= 0 && y < H);
+        for (int tx = lane; tx < pitch; tx += 32) {
+            const int x = x0 - r + tx;
+            float v = -1.0f;
+            if (row_ok && x >= 0 && x < W) {
+                v = __ldg(hb + (size_t)y * W + x);
+                v = (v > thr) ? v : -1.0f;
+            }
+            tile[ty * pitch + tx] = v;
+            any |= (v >= 0.0f);
         }
-        tile[i] = v;
     }
-    __syncthreads();
+    // most tiles of a real heat-map hold nothing above the threshold: nothing to do there
+    if (!__syncthreads_or(any)) return;
 
-    const int tx = threadIdx.x & (kTileW - 1);
-    const int ty0 = threadIdx.x / kTileW;  // 0..3
-    const int lane = threadIdx.x & 31;
+    const int ty = warp;                 // kTileH == number of warps
+    const int y = y0 + ty;
+    const float *center_row = tile + (ty + r) * pitch + r;
 #pragma unroll
-    for (int j = 0; j < kTileH / (kNmsThreads / kTileW); ++j) {
-        const int ty = ty0 + j * (kNmsThreads / kTileW);
-        const int y = y0 + ty, x = x0 + tx;
+    for (int j = 0; j < 4; ++j) {
+        const int tx = lane * 4 + j;
+        const int x = x0 + tx;
         bool surv = false;
         float v = -1.0f;
         if (y < H && x < W) {
             if (y >= r && y < H - r && x >= r && x < W - r) {
-                v = tile[(ty + r) * pitch + tx + r];
+                v = center_row[tx];
                 if (v >= 0.0f) {
                     surv = true;
                     for (int dy = -r; dy <= r; ++dy) {
-                        const float *row = tile + (ty + r + dy) * pitch + tx + r;
+                        const float *row = center_row + dy * pitch + tx;
                         for (int dx = -r; dx <= r; ++dx) {
                             const float w = row[dx];
                             const bool before = (dy < 0) || (dy == 0 && dx < 0);
@@ -73,12 +82,12 @@ nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, i
                     }
                 }
             } else if (r > 0 && y == 0 && x == 0) {
-                v = tile[r * pitch + r];
+                v = center_row[tx];
                 surv = (v == 0.0f);
             }
         }
         const unsigned m = __ballot_sync(kFullMask, surv);
-        if (m) {
+        if (m) {   // warp-aggregated append: one atomic per warp and pixel slot
             const int leader = __ffs(m) - 1;
             int base = 0;
             if (lane == leader) base = atomicAdd(cand_cnt + b, __popc(m));

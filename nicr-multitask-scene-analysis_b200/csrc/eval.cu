@@ -56,6 +56,24 @@ __device__ __forceinline__ bool table_add(unsigned long long *keys, unsigned *cn
     return false;
 }
 
+// CTA table first; the per-frame global table takes what does not fit (kept out of line: it
+// is the rare path and the pixel loop should stay small in the instruction cache)
+__device__ __noinline__ void pair_insert_global(unsigned long long *fkeys, unsigned *fcnts,
+                                                unsigned long long key, unsigned cnt,
+                                                int32_t *status)
+{
+    if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, key, cnt))
+        set_status(status, NPB_ERR_CAPACITY);
+}
+
+__device__ __forceinline__ void pair_insert(unsigned long long *s_keys, unsigned *s_cnts,
+                                            unsigned long long *fkeys, unsigned *fcnts,
+                                            unsigned long long key, unsigned cnt, int32_t *status)
+{
+    if (!table_add(s_keys, s_cnts, kSmemSlots, 16, key, cnt))
+        pair_insert_global(fkeys, fcnts, key, cnt, status);
+}
+
 struct PairParams {
     const long long *pred;
     const long long *target;
@@ -143,39 +161,29 @@ __global__ void __launch_bounds__(kPairThreads) pair_count_kernel(const PairPara
             }
         }
 
-        // ---- warp aggregation: lanes whose 4 pixels carry the same (pair, confusion cell) are
-        // found with MATCH.ANY, their pixel counts summed with REDUX, and the lowest lane of each
-        // group does ONE insert; pixels that differ from their thread's first pixel (segment
-        // boundaries, 1 thread in ~8) are inserted individually.
-        const bool act = p0 < P;
-        const unsigned long long k0 = act ? key[0] : kEmptyKey;
-        const int c0 = act ? ckey[0] : -2;
-        unsigned peers = __match_any_sync(kFullMask, k0);
-        if (CONFMAT) peers &= __match_any_sync(kFullMask, c0);
-        int cnt0 = 0;
+        // ---- warp aggregation in rounds: every lane offers the first of its not yet counted
+        // pixels; lanes offering the same (pair, confusion cell) are found with MATCH.ANY, their
+        // pixel counts summed with REDUX and the lowest lane of the group does ONE insert.
+        // A lane needs a second round only when a segment boundary runs through its 4 pixels.
+        unsigned todo = (p0 < P) ? ((1u << VEC) - 1u) : 0u;
+        while (__any_sync(kFullMask, todo != 0u)) {
+            unsigned long long k0 = kEmptyKey;
+            int c0 = -2;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) cnt0 += (act && key[j] == k0 && ckey[j] == c0) ? 1 : 0;
-        const int total = __reduce_add_sync(peers, cnt0);
-        if (act) {
-            if (lane == __ffs(peers) - 1) {
-                if (!table_add(s_keys, s_cnts, kSmemSlots, 16, k0, (unsigned)total))
-                    if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, k0, (unsigned)total))
-                        set_status(prm.status + b, NPB_ERR_CAPACITY);
+            for (int j = VEC - 1; j >= 0; --j)
+                if ((todo >> j) & 1u) { k0 = key[j]; c0 = ckey[j]; }
+            int cnt0 = 0;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (((todo >> j) & 1u) && key[j] == k0 && ckey[j] == c0) { ++cnt0; todo &= ~(1u << j); }
+            unsigned peers = __match_any_sync(kFullMask, k0);
+            if (CONFMAT) peers &= __match_any_sync(kFullMask, c0);
+            const int total = __reduce_add_sync(peers, cnt0);
+            if (cnt0 > 0 && lane == __ffs(peers) - 1) {
+                pair_insert(s_keys, s_cnts, fkeys, fcnts, k0, (unsigned)total, prm.status + b);
                 if (CONFMAT && c0 >= 0) {
                     if (cm_smem) atomicAdd(s_cm + c0, (unsigned)total);
                     else atomicAdd(prm.confmat + c0, (unsigned long long)total);
-                }
-            }
-#pragma unroll
-            for (int j = 1; j < VEC; ++j) {
-                if (key[j] != k0 || ckey[j] != c0) {
-                    if (!table_add(s_keys, s_cnts, kSmemSlots, 16, key[j], 1u))
-                        if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, key[j], 1u))
-                            set_status(prm.status + b, NPB_ERR_CAPACITY);
-                    if (CONFMAT && ckey[j] >= 0) {
-                        if (cm_smem) atomicAdd(s_cm + ckey[j], 1u);
-                        else atomicAdd(prm.confmat + ckey[j], 1ull);
-                    }
                 }
             }
         }
@@ -185,9 +193,7 @@ __global__ void __launch_bounds__(kPairThreads) pair_count_kernel(const PairPara
     __syncthreads();
     for (int i = tid; i < kSmemSlots; i += kPairThreads) {
         const unsigned long long k = s_keys[i];
-        if (k != kEmptyKey && s_cnts[i])
-            if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, k, s_cnts[i]))
-                set_status(prm.status + b, NPB_ERR_CAPACITY);
+        if (k != kEmptyKey && s_cnts[i]) pair_insert_global(fkeys, fcnts, k, s_cnts[i], prm.status + b);
     }
     if (cm_smem)
         for (int i = tid; i < n * n; i += kPairThreads)

@@ -79,10 +79,23 @@ struct PixVec<1> {
     __device__ static void storeb(uint8_t *p, const int (&v)[1]) { *p = (uint8_t)v[0]; }
 };
 
-template <int VEC, int MODE, bool ORI>
-__global__ void __launch_bounds__(kGroupThreads) group_pixels_kernel(const GroupParams prm)
+// exact "does centre i beat the current best" test on squared distances (see header)
+__device__ __forceinline__ void consider_center(float s, int i, float &sbest, int &ibest)
 {
-    __shared__ float2 s_centers[kMaxInst];
+    const float kSafe = 0.99999905f;  // 1 - 2^-20
+    if (s < sbest) {
+        if (s < __fmul_rn(sbest, kSafe) || __fsqrt_rn(s) < __fsqrt_rn(sbest)) {
+            sbest = s;
+            ibest = i;
+        }
+    }
+}
+
+template <int VEC, int MODE, bool ORI>
+__global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const GroupParams prm)
+{
+    // centres of the frame as (cy, cy, cx, cx): one LDS.128 feeds two packed f32x2 operands
+    __shared__ float4 s_centers[kMaxInst];
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
@@ -91,7 +104,8 @@ __global__ void __launch_bounds__(kGroupThreads) group_pixels_kernel(const Group
     const int n = prm.n_centers[b];
     for (int i = tid; i < n; i += kGroupThreads) {
         const int32_t *c = prm.centers_yx + ((size_t)b * kMaxInst + i) * 2;
-        s_centers[i] = make_float2((float)c[0], (float)c[1]);
+        const float cy = (float)c[0], cx = (float)c[1];
+        s_centers[i] = make_float4(cy, cy, cx, cx);
     }
     __syncthreads();
 
@@ -109,13 +123,33 @@ __global__ void __launch_bounds__(kGroupThreads) group_pixels_kernel(const Group
             const float *lp = prm.logits + (size_t)b * C * P + p0;
             float best[VEC];
             PixVec<VEC>::loadf(lp, best, true);
-#pragma unroll 8
-            for (int c = 1; c < C; ++c) {
-                float v[VEC];
-                PixVec<VEC>::loadf(lp + (size_t)c * P, v, true);
+            // batches of 8 independent 128-bit loads in flight per thread before the first
+            // compare: the loop is latency bound, bytes in flight are what buys bandwidth
+            constexpr int U = 8;
+            int c = 1;
+            for (; c + U <= C; c += U) {
+                float v[U][VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j)
-                    if (v[j] > best[j]) { best[j] = v[j]; cls[j] = c; }
+                for (int u = 0; u < U; ++u) PixVec<VEC>::loadf(lp + (size_t)(c + u) * P, v[u], true);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        if (v[u][j] > best[j]) { best[j] = v[u][j]; cls[j] = c + u; }
+            }
+            if (c < C) {   // tail: one more batch, loads of planes >= C predicated off
+                float v[U][VEC];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v[u][j] = __int_as_float(0xff800000);  // -inf
+                    if (c + u < C) PixVec<VEC>::loadf(lp + (size_t)(c + u) * P, v[u], true);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        if (v[u][j] > best[j]) { best[j] = v[u][j]; cls[j] = c + u; }
             }
             PixVec<VEC>::storeb(prm.sem_out + fb, cls);
         } else if (MODE == kFromSemMap) {
@@ -137,38 +171,63 @@ __global__ void __launch_bounds__(kGroupThreads) group_pixels_kernel(const Group
     bool any_fg = false;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { inst[j] = 0; any_fg |= fg[j]; }
+    any_fg = any_fg && n > 0;
 
-    if (any_fg && n > 0) {
+    float oc[VEC], os[VEC];
+    if (ORI) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { oc[j] = 0.0f; os[j] = 0.0f; }
+    }
+    if (any_fg) {
         float oy[VEC], ox[VEC];
         PixVec<VEC>::loadf(prm.offset + (size_t)b * 2 * P + p0, oy, true);
         PixVec<VEC>::loadf(prm.offset + (size_t)b * 2 * P + P + p0, ox, true);
-        float ly[VEC], lx[VEC];
+        if (ORI) {   // issued here so that the distance loop hides their latency
+            PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + p0, oc, true);
+            PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + P + p0, os, true);
+        }
+        float nly[VEC], nlx[VEC];   // NEGATED locations: c - l == c + (-l) exactly
         int y = p0 / W, x = p0 - y * W;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float dy = oy[j], dx = ox[j];
             if (prm.normalized) { dy = __fmul_rn(dy, prm.fH); dx = __fmul_rn(dx, prm.fW); }
-            ly[j] = __fadd_rn((float)y, dy);
-            lx[j] = __fadd_rn((float)x, dx);
+            nly[j] = -__fadd_rn((float)y, dy);
+            nlx[j] = -__fadd_rn((float)x, dx);
             if (++x == W) { x = 0; ++y; }
         }
         float sbest[VEC];
         int ibest[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { sbest[j] = __int_as_float(0x7f800000); ibest[j] = 0; }
-        const float kSafe = 0.99999905f;  // 1 - 2^-20
-        for (int i = 0; i < n; ++i) {
-            const float2 c = s_centers[i];
+        if (VEC == 4) {
+            // Blackwell packed FP32 (FADD2 / FMUL2 / FFMA2): two pixels per instruction, each
+            // lane individually IEEE-rounded exactly like the scalar sequence
+            const float2 nlyA = make_float2(nly[0], nly[1 % VEC]), nlyB = make_float2(nly[2 % VEC], nly[3 % VEC]);
+            const float2 nlxA = make_float2(nlx[0], nlx[1 % VEC]), nlxB = make_float2(nlx[2 % VEC], nlx[3 % VEC]);
+            for (int i = 0; i < n; ++i) {
+                const float4 c = s_centers[i];
+                const float2 cy2 = make_float2(c.x, c.y), cx2 = make_float2(c.z, c.w);
+                const float2 a0 = __fadd2_rn(cy2, nlyA), a1 = __fadd2_rn(cx2, nlxA);
+                const float2 b0 = __fadd2_rn(cy2, nlyB), b1 = __fadd2_rn(cx2, nlxB);
+                const float2 sA = __ffma2_rn(a1, a1, __fmul2_rn(a0, a0));
+                const float2 sB = __ffma2_rn(b1, b1, __fmul2_rn(b0, b0));
+                if ((sA.x < sbest[0]) | (sA.y < sbest[1 % VEC]) | (sB.x < sbest[2 % VEC]) |
+                    (sB.y < sbest[3 % VEC])) {
+                    consider_center(sA.x, i, sbest[0], ibest[0]);
+                    consider_center(sA.y, i, sbest[1 % VEC], ibest[1 % VEC]);
+                    consider_center(sB.x, i, sbest[2 % VEC], ibest[2 % VEC]);
+                    consider_center(sB.y, i, sbest[3 % VEC], ibest[3 % VEC]);
+                }
+            }
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const float4 c = s_centers[i];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const float d0 = __fsub_rn(c.x, ly[j]);
-                const float d1 = __fsub_rn(c.y, lx[j]);
-                const float s = __fmaf_rn(d1, d1, __fmul_rn(d0, d0));
-                if (s < sbest[j]) {
-                    if (s < __fmul_rn(sbest[j], kSafe) || __fsqrt_rn(s) < __fsqrt_rn(sbest[j])) {
-                        sbest[j] = s;
-                        ibest[j] = i;
-                    }
+                for (int j = 0; j < VEC; ++j) {
+                    const float d0 = __fadd_rn(c.x, nly[j]);
+                    const float d1 = __fadd_rn(c.z, nlx[j]);
+                    consider_center(__fmaf_rn(d1, d1, __fmul_rn(d0, d0)), i, sbest[j], ibest[j]);
                 }
             }
         }
@@ -182,59 +241,66 @@ __global__ void __launch_bounds__(kGroupThreads) group_pixels_kernel(const Group
     }
     if (active) PixVec<VEC>::storeb(prm.inst_out + fb, inst);
 
-    // ---- 3. votes + orientation sums (warp aggregated) ----------------------------------
+    // ---- 3. class votes (warp aggregated: MATCH.ANY + REDUX, one RED per group) -----------
+    const int CH = (MODE == kFromFgMask) ? 1 : C;
+    uint32_t *hist = prm.vote_hist + (size_t)b * kMaxInst * CH;
     int key[VEC];
     bool any_inst = false;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-        key[j] = inst[j] > 0 ? (inst[j] << 8) | (MODE == kFromFgMask ? 0 : cls[j]) : -1;
+        key[j] = inst[j] > 0 ? inst[j] * CH + (MODE == kFromFgMask ? 0 : cls[j]) : -1;
         any_inst |= (inst[j] > 0);
     }
     if (!__any_sync(kFullMask, any_inst)) return;
-
-    float oc[VEC], os[VEC];
-    if (ORI) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { oc[j] = 0.0f; os[j] = 0.0f; }
-        if (any_inst) {
-            PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + p0, oc, true);
-            PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + P + p0, os, true);
-        }
-    }
-    const int CH = (MODE == kFromFgMask) ? 1 : C;
-    uint32_t *hist = prm.vote_hist + (size_t)b * kMaxInst * CH;
-    double *osum = ORI ? prm.ori_sum + (size_t)b * kMaxInst * 2 : nullptr;
-
-    unsigned pending = 0u;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) pending |= (key[j] >= 0 ? 1u : 0u) << j;
-    while (true) {
-        const unsigned has = __ballot_sync(kFullMask, pending != 0u);
-        if (!has) break;
-        const int leader = __ffs(has) - 1;
-        int mine = -1;
+    {
+        // the thread's first instance pixel leads; pixels with another key go individually
+        int k0 = -1;
 #pragma unroll
         for (int j = VEC - 1; j >= 0; --j)
-            if ((pending >> j) & 1u) mine = key[j];
-        const int cur = __shfl_sync(kFullMask, mine, leader);
-        int cnt = 0;
-        float sc = 0.0f, ss = 0.0f;
+            if (key[j] >= 0) k0 = key[j];
+        int cnt0 = 0;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            if (((pending >> j) & 1u) && key[j] == cur) {
-                ++cnt;
-                if (ORI) { sc += oc[j]; ss += os[j]; }
-                pending &= ~(1u << j);
-            }
+        for (int j = 0; j < VEC; ++j) cnt0 += (key[j] == k0 && k0 >= 0) ? 1 : 0;
+        const unsigned peers = __match_any_sync(kFullMask, k0);
+        const int total = __reduce_add_sync(peers, cnt0);
+        if (k0 >= 0) {
+            if (lane == __ffs(peers) - 1) atomicAdd(hist + k0, (uint32_t)total);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (key[j] >= 0 && key[j] != k0) atomicAdd(hist + key[j], 1u);
         }
-        cnt = __reduce_add_sync(kFullMask, cnt);
-        if (ORI) { sc = warp_sum(sc); ss = warp_sum(ss); }
-        if (lane == 0) {
-            const int ii = cur >> 8, cc = cur & 255;
-            atomicAdd(hist + (size_t)ii * CH + cc, (uint32_t)cnt);
-            if (ORI) {
-                atomicAdd(osum + 2 * ii, (double)sc);
-                atomicAdd(osum + 2 * ii + 1, (double)ss);
+    }
+
+    // ---- 4. orientation sums per instance: loop over the (few) distinct instances of the warp,
+    //         f32 shuffle tree inside the warp, one f64 RED pair per instance ----------------
+    if (ORI) {
+        double *osum = prm.ori_sum + (size_t)b * kMaxInst * 2;
+        unsigned pending = 0u;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) pending |= (inst[j] > 0 ? 1u : 0u) << j;
+        while (true) {
+            const unsigned has = __ballot_sync(kFullMask, pending != 0u);
+            if (!has) break;
+            const int leader = __ffs(has) - 1;
+            int mine = 0;
+#pragma unroll
+            for (int j = VEC - 1; j >= 0; --j)
+                if ((pending >> j) & 1u) mine = inst[j];
+            const int cur = __shfl_sync(kFullMask, mine, leader);
+            float sc = 0.0f, ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                if (((pending >> j) & 1u) && inst[j] == cur) {
+                    sc += oc[j];
+                    ss += os[j];
+                    pending &= ~(1u << j);
+                }
+            }
+            sc = warp_sum(sc);
+            ss = warp_sum(ss);
+            if (lane == 0) {
+                atomicAdd(osum + 2 * cur, (double)sc);
+                atomicAdd(osum + 2 * cur + 1, (double)ss);
             }
         }
     }
