@@ -24,19 +24,23 @@
 namespace npb {
 
 constexpr int kPairThreads = 256;
-constexpr int kSmemSlots = 1024;       // per-CTA pair hash table
+constexpr int kSmemSlots = 2048;       // per-CTA pair hash table (instance pairs; class pairs go dense)
 constexpr int kFrameSlots = 16384;     // per-frame global pair hash table
 constexpr int kMaxPairs = 4096;        // pairs per frame handled by the matcher
 constexpr int kMatchThreads = 512;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kSmemConfmatMaxN = 96;   // n*n*4 B <= 36 KB privatised in shared memory
 
+// 64-bit pair key -> 32-bit hash.  Pair keys are highly structured (class << 16 | instance in
+// both halves, most bits zero), so both words go through multiplicative hashing followed by
+// an avalanche step; table indices are taken after the final mix.
 __device__ __forceinline__ unsigned hash64(unsigned long long k)
 {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33;
-    return (unsigned)k;
+    unsigned h = (unsigned)k * 0x9E3779B1u + (unsigned)(k >> 32) * 0x85EBCA6Bu;
+    h ^= h >> 16;
+    h *= 0x7FEB352Du;
+    h ^= h >> 15;
+    return h;
 }
 
 // insert (key, cnt) into an open-addressing table; returns false when no slot was found
@@ -56,22 +60,14 @@ __device__ __forceinline__ bool table_add(unsigned long long *keys, unsigned *cn
     return false;
 }
 
-// CTA table first; the per-frame global table takes what does not fit (kept out of line: it
-// is the rare path and the pixel loop should stay small in the instruction cache)
+// the per-frame global table (flush target, and overflow of the CTA table); out of line: it is
+// the rare path and the pixel loop should stay small in the instruction cache
 __device__ __noinline__ void pair_insert_global(unsigned long long *fkeys, unsigned *fcnts,
                                                 unsigned long long key, unsigned cnt,
                                                 int32_t *status)
 {
     if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, key, cnt))
         set_status(status, NPB_ERR_CAPACITY);
-}
-
-__device__ __forceinline__ void pair_insert(unsigned long long *s_keys, unsigned *s_cnts,
-                                            unsigned long long *fkeys, unsigned *fcnts,
-                                            unsigned long long key, unsigned cnt, int32_t *status)
-{
-    if (!table_add(s_keys, s_cnts, kSmemSlots, 16, key, cnt))
-        pair_insert_global(fkeys, fcnts, key, cnt, status);
 }
 
 struct PairParams {
@@ -81,43 +77,114 @@ struct PairParams {
     long long P;
     long long offset, L;
     int L_shift;                // >= 0 when L is a power of two
+    int O_shift;                // >= 0 when offset is a power of two
     int n;                      // confusion-matrix size (0 = no confmat)
+    int nd;                     // side of the dense class-pair table (0 = disabled)
     unsigned long long *frame_keys;  // [B][kFrameSlots]
     unsigned *frame_cnts;
     unsigned long long *confmat;     // [n][n] int64, accumulated
     int32_t *status;                 // [B]
 };
 
-template <int VEC, bool CONFMAT>
-__global__ void __launch_bounds__(kPairThreads) pair_count_kernel(const PairParams prm)
+// Shared-memory state of one CTA of the pixel pass.
+//   keys/cnts : open-addressing table (pair key -> pixels) for pairs that involve an instance
+//   dense     : [nd][nd] counters for (class, class) pairs of two instance-free segments
+//               (stuff / void / misclassified single pixels): no hashing, no probing
+//   cm        : privatised confusion matrix
+//   q_*       : one work queue per warp (see pair_count_kernel)
+struct PairTables {
+    unsigned long long *keys;
+    unsigned *cnts;
+    unsigned *dense;
+    unsigned *cm;
+};
+
+constexpr int kQueueCap = 192;   // < 32 left over + at most 128 pixels + 32 group entries
+
+// one queue entry = `cnt` pixels of pair `key` whose semantic target is `st`
+template <bool CONFMAT>
+__device__ __forceinline__ void pair_consume(const PairTables &t, const PairParams &prm, int b,
+                                             unsigned long long key, unsigned cnt, int st,
+                                             bool cm_smem)
 {
-    __shared__ unsigned long long s_keys[kSmemSlots];
-    __shared__ unsigned s_cnts[kSmemSlots];
-    extern __shared__ unsigned s_cm[];  // n*n when privatised
+    long long tv, pv;
+    if (prm.O_shift >= 0) {
+        tv = (long long)(key >> prm.O_shift);
+        pv = (long long)(key & ((unsigned long long)prm.offset - 1ull));
+    } else {
+        tv = (long long)(key / (unsigned long long)prm.offset);
+        pv = (long long)(key - (unsigned long long)tv * (unsigned long long)prm.offset);
+    }
+    long long pc = -1;
+    if (prm.L_shift >= 0) pc = pv >> prm.L_shift;
+    else if (CONFMAT) pc = pv / prm.L;
+    bool dense = false;
+    if (prm.nd > 0 && ((pv | tv) & (prm.L - 1)) == 0) {          // two instance-free segments
+        const long long tc = tv >> prm.L_shift;
+        if (pc < prm.nd && tc < prm.nd) {
+            atomicAdd(t.dense + (int)tc * prm.nd + (int)pc, cnt);
+            dense = true;
+        }
+    }
+    if (!dense && !table_add(t.keys, t.cnts, kSmemSlots, 8, key, cnt))
+        pair_insert_global(prm.frame_keys + (size_t)b * kFrameSlots,
+                           prm.frame_cnts + (size_t)b * kFrameSlots, key, cnt, prm.status + b);
+    if (CONFMAT) {
+        if (pc < 0 || pc >= prm.n || st >= prm.n) {
+            set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
+        } else {
+            const int cell = st * prm.n + (int)pc;
+            if (cm_smem) atomicAdd(t.cm + cell, cnt);
+            else atomicAdd(prm.confmat + cell, (unsigned long long)cnt);
+        }
+    }
+}
+
+// Pixel pass.  A thread reads 4 consecutive pixels (128-bit loads).  Inside a segment all 4
+// agree ("pure" lane): pure lanes with the same pair are grouped with MATCH.ANY and the lowest
+// lane of a group emits ONE entry for 4 * |group| pixels.  Lanes cut by a segment boundary or
+// holding isolated pixels emit their 4 pixels as single entries.  Entries go to a per-warp
+// shared-memory queue and are consumed 32 at a time, one entry per lane, so the table updates
+// (the expensive, divergent part) always run with a full warp.
+template <int VEC, bool CONFMAT>
+__global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairParams prm)
+{
+    extern __shared__ unsigned long long s_dyn[];
+    PairTables t;
+    t.keys = s_dyn;                                           // [kSmemSlots]
+    unsigned long long *q_key_all = t.keys + kSmemSlots;      // [warps][kQueueCap]
+    t.cnts = (unsigned *)(q_key_all + (kPairThreads / 32) * kQueueCap);   // [kSmemSlots]
+    t.dense = t.cnts + kSmemSlots;                            // [nd*nd]
+    t.cm = t.dense + prm.nd * prm.nd;                         // [n*n] when privatised
 
     const int b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int n = prm.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = prm.n, nd = prm.nd;
     const bool cm_smem = CONFMAT && n <= kSmemConfmatMaxN;
-    for (int i = tid; i < kSmemSlots; i += kPairThreads) { s_keys[i] = kEmptyKey; s_cnts[i] = 0; }
+    unsigned short *q_meta_all = (unsigned short *)(t.cm + (cm_smem ? n * n : 0));
+    unsigned long long *q_key = q_key_all + warp * kQueueCap;
+    unsigned short *q_meta = q_meta_all + warp * kQueueCap;
+    for (int i = tid; i < kSmemSlots; i += kPairThreads) { t.keys[i] = kEmptyKey; t.cnts[i] = 0; }
+    for (int i = tid; i < nd * nd; i += kPairThreads) t.dense[i] = 0;
     if (cm_smem)
-        for (int i = tid; i < n * n; i += kPairThreads) s_cm[i] = 0;
+        for (int i = tid; i < n * n; i += kPairThreads) t.cm[i] = 0;
     __syncthreads();
 
-    unsigned long long *fkeys = prm.frame_keys + (size_t)b * kFrameSlots;
-    unsigned *fcnts = prm.frame_cnts + (size_t)b * kFrameSlots;
     const long long P = prm.P;
     const long long chunk = (long long)kPairThreads * VEC;
     const long long n_chunks = (P + chunk - 1) / chunk;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int q_len = 0;      // warp-uniform
 
     for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const long long p0 = ch * chunk + (long long)tid * VEC;
         const size_t fb = (size_t)b * P + p0;
+        const bool act = p0 < P;    // P % VEC == 0 guaranteed by the launcher
         unsigned long long key[VEC];
-        int ckey[VEC];
+        unsigned sw = 0;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { key[j] = 0; ckey[j] = -1; }
-        if (p0 < P) {  // P % VEC == 0 guaranteed by the launcher
+        for (int j = 0; j < VEC; ++j) key[j] = 0;
+        if (act) {
             long long pv[VEC], tv[VEC];
             if (VEC == 4) {
                 const longlong2 a0 = __ldcs((const longlong2 *)(prm.pred + fb));
@@ -130,74 +197,85 @@ __global__ void __launch_bounds__(kPairThreads) pair_count_kernel(const PairPara
                 pv[0] = __ldcs(prm.pred + fb);
                 tv[0] = __ldcs(prm.target + fb);
             }
-            unsigned sw = 0;
             if (CONFMAT) {
                 if (VEC == 4) sw = *(const unsigned *)(prm.sem_target + fb);
                 else sw = prm.sem_target[fb];
             }
-            long long last_p = -1;
-            int last_c = 0;
+            // ids must satisfy 0 <= pred < offset, 0 <= target (checked on the OR of the lane)
+            long long any_neg = 0;
+            bool too_big = false;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                if (pv[j] < 0 || pv[j] >= prm.offset || tv[j] < 0)
-                    set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
-                key[j] = (unsigned long long)tv[j] * (unsigned long long)prm.offset +
-                         (unsigned long long)pv[j];
-                if (CONFMAT) {
-                    if (pv[j] != last_p) {  // pred // L, once per run of equal ids
-                        last_p = pv[j];
-                        const long long c =
-                            prm.L_shift >= 0 ? (pv[j] >> prm.L_shift) : (pv[j] / prm.L);
-                        last_c = (c >= 0 && c < n) ? (int)c : -1;
-                    }
-                    const int st = (sw >> (8 * j)) & 255;
-                    if (last_c < 0 || st >= n) {
-                        set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
-                        ckey[j] = -1;
-                    } else {
-                        ckey[j] = st * n + last_c;
-                    }
-                }
+                any_neg |= pv[j] | tv[j];
+                too_big |= pv[j] >= prm.offset;
+                key[j] = prm.O_shift >= 0
+                             ? (((unsigned long long)tv[j] << prm.O_shift) | (unsigned long long)pv[j])
+                             : (unsigned long long)tv[j] * (unsigned long long)prm.offset +
+                                   (unsigned long long)pv[j];
             }
+            if (any_neg < 0 || too_big) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
         }
 
-        // ---- warp aggregation in rounds: every lane offers the first of its not yet counted
-        // pixels; lanes offering the same (pair, confusion cell) are found with MATCH.ANY, their
-        // pixel counts summed with REDUX and the lowest lane of the group does ONE insert.
-        // A lane needs a second round only when a segment boundary runs through its 4 pixels.
-        unsigned todo = (p0 < P) ? ((1u << VEC) - 1u) : 0u;
-        while (__any_sync(kFullMask, todo != 0u)) {
-            unsigned long long k0 = kEmptyKey;
-            int c0 = -2;
+        bool pure = act;
 #pragma unroll
-            for (int j = VEC - 1; j >= 0; --j)
-                if ((todo >> j) & 1u) { k0 = key[j]; c0 = ckey[j]; }
-            int cnt0 = 0;
+        for (int j = 1; j < VEC; ++j) pure = pure && key[j] == key[0];
+        if (CONFMAT && VEC == 4) pure = pure && sw == (sw & 255u) * 0x01010101u;
+        const unsigned long long mk = pure ? key[0] : (kEmptyKey - 1ull - (unsigned)lane);
+        unsigned peers = __match_any_sync(kFullMask, mk);
+        if (CONFMAT) peers &= __match_any_sync(kFullMask, pure ? (int)(sw & 255u) : -2 - lane);
+        const bool leader = pure && lane == __ffs(peers) - 1;
+        const unsigned mixed_mask = __ballot_sync(kFullMask, act && !pure);
+        const unsigned leader_mask = __ballot_sync(kFullMask, leader);
+
+        // push: mixed lanes VEC single-pixel entries each, group leaders one entry each
+        if (act && !pure) {
+            const int pos = q_len + VEC * __popc(mixed_mask & lt_mask);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j)
-                if (((todo >> j) & 1u) && key[j] == k0 && ckey[j] == c0) { ++cnt0; todo &= ~(1u << j); }
-            unsigned peers = __match_any_sync(kFullMask, k0);
-            if (CONFMAT) peers &= __match_any_sync(kFullMask, c0);
-            const int total = __reduce_add_sync(peers, cnt0);
-            if (cnt0 > 0 && lane == __ffs(peers) - 1) {
-                pair_insert(s_keys, s_cnts, fkeys, fcnts, k0, (unsigned)total, prm.status + b);
-                if (CONFMAT && c0 >= 0) {
-                    if (cm_smem) atomicAdd(s_cm + c0, (unsigned)total);
-                    else atomicAdd(prm.confmat + c0, (unsigned long long)total);
-                }
+            for (int j = 0; j < VEC; ++j) {
+                q_key[pos + j] = key[j];
+                q_meta[pos + j] = (unsigned short)((1u << 8) | ((sw >> (8 * j)) & 255u));
             }
+        } else if (leader) {
+            const int pos = q_len + VEC * __popc(mixed_mask) + __popc(leader_mask & lt_mask);
+            q_key[pos] = key[0];
+            q_meta[pos] = (unsigned short)(((unsigned)(VEC * __popc(peers)) << 8) | (sw & 255u));
+        }
+        q_len += VEC * __popc(mixed_mask) + __popc(leader_mask);
+        __syncwarp();
+        while (q_len >= 32) {           // consume full warps of entries from the tail
+            q_len -= 32;
+            const unsigned long long k = q_key[q_len + lane];
+            const unsigned m = q_meta[q_len + lane];
+            pair_consume<CONFMAT>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
+            __syncwarp();
         }
     }
+    if (lane < q_len) {
+        const unsigned long long k = q_key[lane];
+        const unsigned m = q_meta[lane];
+        pair_consume<CONFMAT>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
+    }
 
-    // ---- flush the CTA tables ----------------------------------------------------------
+    // ---- flush the CTA tables into the per-frame table / the global confusion matrix --------
     __syncthreads();
+    unsigned long long *fkeys = prm.frame_keys + (size_t)b * kFrameSlots;
+    unsigned *fcnts = prm.frame_cnts + (size_t)b * kFrameSlots;
     for (int i = tid; i < kSmemSlots; i += kPairThreads) {
-        const unsigned long long k = s_keys[i];
-        if (k != kEmptyKey && s_cnts[i]) pair_insert_global(fkeys, fcnts, k, s_cnts[i], prm.status + b);
+        const unsigned long long k = t.keys[i];
+        if (k != kEmptyKey && t.cnts[i]) pair_insert_global(fkeys, fcnts, k, t.cnts[i], prm.status + b);
+    }
+    for (int i = tid; i < nd * nd; i += kPairThreads) {
+        const unsigned c = t.dense[i];
+        if (c) {
+            const unsigned long long tc = (unsigned)(i / nd), pc = (unsigned)(i % nd);
+            const unsigned long long key = (tc << prm.L_shift) * (unsigned long long)prm.offset +
+                                           (pc << prm.L_shift);
+            pair_insert_global(fkeys, fcnts, key, c, prm.status + b);
+        }
     }
     if (cm_smem)
         for (int i = tid; i < n * n; i += kPairThreads)
-            if (s_cm[i]) atomicAdd(prm.confmat + i, (unsigned long long)s_cm[i]);
+            if (t.cm[i]) atomicAdd(prm.confmat + i, (unsigned long long)t.cm[i]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -563,9 +641,14 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     pp.pred = (const long long *)pred; pp.target = (const long long *)target;
     pp.sem_target = sem_target; pp.P = P; pp.offset = offset; pp.L = max_instances_per_category;
     pp.L_shift = -1;
-    for (int sh = 0; sh < 62; ++sh)
+    pp.O_shift = -1;
+    for (int sh = 0; sh < 62; ++sh) {
         if ((1ll << sh) == max_instances_per_category) pp.L_shift = sh;
+        if ((1ll << sh) == offset) pp.O_shift = sh;
+    }
     pp.n = confmat ? confmat_n : 0;
+    // dense class-pair table: needs `id >> shift` decoding and a table that fits next to the rest
+    pp.nd = (pp.L_shift >= 0 && num_categories <= kSmemConfmatMaxN) ? num_categories : 0;
     pp.frame_keys = fkeys; pp.frame_cnts = fcnts;
     pp.confmat = (unsigned long long *)confmat; pp.status = status;
 
@@ -573,18 +656,30 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
                       ((uintptr_t)sem_target & 3u) == 0;
     const int vec = vec4 ? 4 : 1;
     const long long n_chunks = (P + (long long)kPairThreads * vec - 1) / ((long long)kPairThreads * vec);
-    long long bx = (148ll * 8 + B - 1) / B;   // ~8 CTAs per SM over the whole batch
+    long long bx = (148ll * 4 + B - 1) / B;   // ~4 CTAs (48 KB tables each) per SM, one wave
     if (bx > n_chunks) bx = n_chunks;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, B);
-    const size_t cm_smem = (confmat && confmat_n <= kSmemConfmatMaxN)
-                               ? (size_t)confmat_n * confmat_n * sizeof(unsigned) : 0;
+    // [hash keys | queue keys | hash counts | dense | confmat (if privatised) | queue meta]
+    const size_t pc_smem = (size_t)kSmemSlots * 12 + (size_t)(kPairThreads / 32) * kQueueCap * 10 +
+                           (size_t)pp.nd * pp.nd * sizeof(unsigned) +
+                           ((confmat && confmat_n <= kSmemConfmatMaxN)
+                                ? (size_t)confmat_n * confmat_n * sizeof(unsigned) : 0) + 16;
+    static bool pc_attr_set = false;
+    if (!pc_attr_set) {
+        const int mx = 200 * 1024;
+        cudaFuncSetAttribute(pair_count_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(pair_count_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(pair_count_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(pair_count_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        pc_attr_set = true;
+    }
     if (confmat) {
-        if (vec4) pair_count_kernel<4, true><<<grid, kPairThreads, cm_smem, s>>>(pp);
-        else pair_count_kernel<1, true><<<grid, kPairThreads, cm_smem, s>>>(pp);
+        if (vec4) pair_count_kernel<4, true><<<grid, kPairThreads, pc_smem, s>>>(pp);
+        else pair_count_kernel<1, true><<<grid, kPairThreads, pc_smem, s>>>(pp);
     } else {
-        if (vec4) pair_count_kernel<4, false><<<grid, kPairThreads, 0, s>>>(pp);
-        else pair_count_kernel<1, false><<<grid, kPairThreads, 0, s>>>(pp);
+        if (vec4) pair_count_kernel<4, false><<<grid, kPairThreads, pc_smem, s>>>(pp);
+        else pair_count_kernel<1, false><<<grid, kPairThreads, pc_smem, s>>>(pp);
     }
 
     MatchParams mp;
