@@ -29,8 +29,10 @@ class MetricState:
         setattr(self, name, default.detach().clone().to(self._device))
 
     def reset(self) -> None:
+        """Back to the defaults IN PLACE: the state tensors keep their addresses, so kernels
+        captured in a CUDA graph keep accumulating into the live states."""
         for name, default in self._defaults.items():
-            setattr(self, name, default.clone().to(self._device))
+            getattr(self, name).copy_(default)
 
     def to(self, device) -> 'MetricState':
         self._device = torch.device(device)
