@@ -110,8 +110,8 @@ def oracle_baseline(sample_frames, steps, warmup, threads=None):
     import oracle
     from nicr_mt_scene_analysis_b200 import testing
     w = WORKLOAD
-    if threads:
-        oracle.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on
+    oracle.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = oracle.num_threads()
     data = testing.make_batch(sample_frames, w['C'], w['H'], w['W'], w['K'], seed=1,
                               with_orientation=True, quantize=None)

@@ -108,6 +108,8 @@ nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, i
 // heat-map ~95 % of the threads).  Only pixels above the threshold look at their window,
 // through the read-only path (neighbouring rows are L1 / L2 hits), stopping at the first
 // neighbour that beats them.  4 B/px of compulsory traffic and ~15 instructions per thread.
+constexpr int kNmsGroups = 4;   // independent 128-bit loads per thread
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 nms_candidates_direct_kernel(const float *__restrict__ heat, int H, int W, float thr, int r,
@@ -115,52 +117,105 @@ nms_candidates_direct_kernel(const float *__restrict__ heat, int H, int W, float
 {
     const int b = blockIdx.y;
     const int P = H * W;
-    const int p0 = (blockIdx.x * 256 + threadIdx.x) * VEC;
-    if (p0 >= P) return;
+    const int base = blockIdx.x * (256 * VEC * kNmsGroups) + threadIdx.x * VEC;
     const float *hb = heat + (size_t)b * P;
-    float v[VEC];
-    if (VEC == 4) {
-        const float4 t = __ldg((const float4 *)(hb + p0));
-        v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
-    } else {
-        v[0] = __ldg(hb + p0);
-    }
+    float v[kNmsGroups][VEC];
     bool any = false;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        v[j] = (v[j] > thr) ? v[j] : -1.0f;
-        any |= (v[j] >= 0.0f);
-    }
-    if (!any) return;
-    int y = p0 / W, x = p0 - y * W;
+    for (int u = 0; u < kNmsGroups; ++u) {
+        const int p0 = base + u * 256 * VEC;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const float vj = v[j];
-        bool surv = false;
-        if (vj >= 0.0f) {
-            if (y >= r && y < H - r && x >= r && x < W - r) {
-                surv = true;
-                for (int dy = -r; dy <= r && surv; ++dy) {
-                    const float *row = hb + (size_t)(y + dy) * W + x;
-                    for (int dx = -r; dx <= r; ++dx) {
-                        if (dy == 0 && dx == 0) continue;
-                        float w = __ldg(row + dx);
-                        w = (w > thr) ? w : -1.0f;
-                        const bool before = (dy < 0) || (dy == 0 && dx < 0);
-                        if (before ? !(vj > w) : (w > vj)) { surv = false; break; }
-                    }
-                }
-            } else if (r > 0 && y == 0 && x == 0) {
-                surv = (vj == 0.0f);
+        for (int j = 0; j < VEC; ++j) v[u][j] = -1.0f;
+        if (p0 < P) {
+            if (VEC == 4) {
+                const float4 t = __ldg((const float4 *)(hb + p0));
+                v[u][0] = t.x; v[u][1 % VEC] = t.y; v[u][2 % VEC] = t.z; v[u][3 % VEC] = t.w;
+            } else {
+                v[u][0] = __ldg(hb + p0);
             }
         }
-        if (surv) {     // survivors are a handful per frame: plain atomics
-            const int slot = atomicAdd(cand_cnt + b, 1);
-            if (slot < cap)
-                cand[(size_t)b * cap + slot] =
-                    make_uint2(__float_as_uint(vj + 0.0f), (unsigned)(y * W + x));
+    }
+#pragma unroll
+    for (int u = 0; u < kNmsGroups; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            v[u][j] = (v[u][j] > thr) ? v[u][j] : -1.0f;
+            any |= (v[u][j] >= 0.0f);
         }
-        if (++x == W) { x = 0; ++y; }
+    if (!any) return;
+#pragma unroll
+    for (int u = 0; u < kNmsGroups; ++u) {
+        const int p0 = base + u * 256 * VEC;
+        if (p0 >= P) continue;
+        bool hot = false;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) hot |= (v[u][j] >= 0.0f);
+        if (!hot) continue;
+        int y = p0 / W, x = p0 - y * W;
+        if (VEC == 4 && r == 1 && y >= 1 && y < H - 1 && x >= 1 && x + 4 <= W - 1) {
+            // all 4 pixels are interior and in one row: fetch the 3 x 6 neighbourhood with
+            // independent loads (one latency round), then decide in registers
+            float top[6], bot[6], mid[6];
+            const float *rt = hb + (size_t)(y - 1) * W + x - 1;
+            const float *rb = hb + (size_t)(y + 1) * W + x - 1;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { top[q] = __ldg(rt + q); bot[q] = __ldg(rb + q); }
+            mid[0] = __ldg(hb + p0 - 1);
+            mid[5] = __ldg(hb + p0 + 4);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                top[q] = (top[q] > thr) ? top[q] : -1.0f;
+                bot[q] = (bot[q] > thr) ? bot[q] : -1.0f;
+            }
+            mid[0] = (mid[0] > thr) ? mid[0] : -1.0f;
+            mid[5] = (mid[5] > thr) ? mid[5] : -1.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mid[j + 1] = v[u][j % VEC];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float vj = mid[j + 1];
+                // strictly greater than the 4 window entries before it, >= the 4 after it
+                const bool surv = vj >= 0.0f && vj > top[j] && vj > top[j + 1] && vj > top[j + 2] &&
+                                  vj > mid[j] && !(mid[j + 2] > vj) && !(bot[j] > vj) &&
+                                  !(bot[j + 1] > vj) && !(bot[j + 2] > vj);
+                if (surv) {
+                    const int slot = atomicAdd(cand_cnt + b, 1);
+                    if (slot < cap)
+                        cand[(size_t)b * cap + slot] =
+                            make_uint2(__float_as_uint(vj + 0.0f), (unsigned)(p0 + j));
+                }
+            }
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const float vj = v[u][j];
+            bool surv = false;
+            if (vj >= 0.0f) {
+                if (y >= r && y < H - r && x >= r && x < W - r) {
+                    surv = true;
+                    for (int dy = -r; dy <= r && surv; ++dy) {
+                        const float *row = hb + (size_t)(y + dy) * W + x;
+                        for (int dx = -r; dx <= r; ++dx) {
+                            if (dy == 0 && dx == 0) continue;
+                            float w = __ldg(row + dx);
+                            w = (w > thr) ? w : -1.0f;
+                            const bool before = (dy < 0) || (dy == 0 && dx < 0);
+                            if (before ? !(vj > w) : (w > vj)) { surv = false; break; }
+                        }
+                    }
+                } else if (r > 0 && y == 0 && x == 0) {
+                    surv = (vj == 0.0f);
+                }
+            }
+            if (surv) {     // survivors are a handful per frame: plain atomics
+                const int slot = atomicAdd(cand_cnt + b, 1);
+                if (slot < cap)
+                    cand[(size_t)b * cap + slot] =
+                        make_uint2(__float_as_uint(vj + 0.0f), (unsigned)(y * W + x));
+            }
+            if (++x == W) { x = 0; ++y; }
+        }
     }
 }
 
@@ -294,11 +349,11 @@ extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, floa
         // small window: per-pixel early out beats staging tiles (see kernel comment)
         const int P = H * W;
         if (P % 4 == 0 && W >= 4 && ((uintptr_t)heat & 15u) == 0) {
-            dim3 grid((P / 4 + 255) / 256, B);
+            dim3 grid((P / 4 + 256 * kNmsGroups - 1) / (256 * kNmsGroups), B);
             nms_candidates_direct_kernel<4><<<grid, 256, 0, s>>>(heat, H, W, threshold, r, cand,
                                                                  cap, cand_cnt);
         } else {
-            dim3 grid((P + 255) / 256, B);
+            dim3 grid((P + 256 * kNmsGroups - 1) / (256 * kNmsGroups), B);
             nms_candidates_direct_kernel<1><<<grid, 256, 0, s>>>(heat, H, W, threshold, r, cand,
                                                                  cap, cand_cnt);
         }

@@ -13,11 +13,11 @@
 // (pair_count_kernel) streams pred / target once (17 B/px with the fused semantic target),
 // counts pairs in a per-CTA shared-memory hash table after warp-level aggregation
 // (neighbouring pixels nearly always share the pair) and flushes it into a small per-frame
-// global hash table.  match_frames_kernel (one CTA per frame) sorts the <= 4096 pairs by
-// `target*offset + pred` -- the reference's visiting order, which fixes the float64
-// summation order -- derives the per-segment quantities with two sorted-run passes (O(m log m),
-// no pair x pair loops) and does the matching; accumulate_frames_kernel adds the frames to
-// the running state in frame order.  Both float64 orders equal the reference's, so the
+// global hash table.  match_frames_kernel (one CTA per frame) builds the per-segment tables
+// (areas, void / ignored overlap) in shared-memory hash tables straight from the pairs
+// (O(m)), does the matching, and sorts only the MATCHED pairs by `target*offset + pred` --
+// the reference's visiting order, which fixes the float64 summation order;
+// accumulate_frames_kernel adds the frames to the running state in frame order.  Both float64 orders equal the reference's, so the
 // states are bit-identical, not merely close.
 #include "common.cuh"
 
@@ -291,42 +291,59 @@ struct MatchParams {
     int32_t *status;       // [B]
 };
 
-// bitonic sort of s_a[0..npad) ascending by (s_a, s_b) carrying nothing else: callers pack
-// what they need into the two arrays.  npad is a power of two.
-template <typename KA, typename KB>
-__device__ __forceinline__ void bitonic_sort_pairs(KA *a, KB *b2, int npad, int tid)
+// ---- matcher: one CTA per frame ------------------------------------------------------------
+// Segment tables (distinct gt ids / pred ids of the frame) are shared-memory hash tables filled
+// from the frame's pair table with atomics; only the matched pairs (one per matched gt segment
+// at most) are sorted, because only their float64 IoU sum depends on the visiting order.
+constexpr int kSegSlots = 2048;       // distinct gt (and pred) segments per frame: <= 1536
+constexpr int kMaxMatched = 1024;
+
+struct SegTable {
+    unsigned long long *id;   // [kSegSlots], kEmptyKey = free
+    unsigned *area;           // [kSegSlots] pixels of the segment
+    unsigned *aux;            // gt: unused; pred: pixels inside the gt void segment
+    unsigned *pio;            // pred: pixels inside ignored gt segments
+    unsigned *matched;        // 1 once the segment took part in a match
+};
+
+// returns the slot of `id` (inserting it), or -1 when the table is full
+__device__ __forceinline__ int seg_slot(SegTable &tb, unsigned long long id)
 {
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < npad; i += kMatchThreads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool up = ((i & k) == 0);
-                    const KA a0 = a[i], a1 = a[ixj];
-                    const KB b0 = b2[i], b1 = b2[ixj];
-                    const bool gt = (a0 > a1) || (a0 == a1 && b0 > b1);
-                    if (gt == up) { a[i] = a1; a[ixj] = a0; b2[i] = b1; b2[ixj] = b0; }
-                }
-            }
-            __syncthreads();
-        }
+    unsigned h = hash64(id) & (unsigned)(kSegSlots - 1);
+    for (int probe = 0; probe < kSegSlots; ++probe) {
+        unsigned long long k = tb.id[h];
+        if (k == kEmptyKey) k = atomicCAS(tb.id + h, kEmptyKey, id);
+        if (k == kEmptyKey || k == id) return (int)h;
+        h = (h + 1) & (unsigned)(kSegSlots - 1);
     }
+    return -1;
 }
 
 __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const MatchParams prm)
 {
     extern __shared__ unsigned char smem_raw[];
-    long long *s_key = (long long *)smem_raw;                   // [kMaxPairs] target*offset+pred
-    long long *s_p = s_key + kMaxPairs;                         // pred segment id (sort scratch)
-    unsigned *s_cnt = (unsigned *)(s_p + kMaxPairs);            // intersection area
-    int *s_gcat = (int *)(s_cnt + kMaxPairs);                   // category of the gt segment
-    unsigned *s_tsa = (unsigned *)(s_gcat + kMaxPairs);         // area of the gt segment
-    unsigned *s_psa = s_tsa + kMaxPairs;                        // area of the pred segment
-    unsigned *s_void = s_psa + kMaxPairs;                       // |pred & gt void segment|
-    int *s_ord = (int *)(s_void + kMaxPairs);                   // pair indices sorted by pred id
-    unsigned char *s_flag = (unsigned char *)(s_ord + kMaxPairs);   // 1 = matched (TP)
+    // pairs of the frame
+    long long *s_key = (long long *)smem_raw;                       // [kMaxPairs]
+    // matched pairs: key, intersection, union
+    long long *s_mkey = s_key + kMaxPairs;                          // [kMaxMatched]
+    unsigned long long *g_id = (unsigned long long *)(s_mkey + kMaxMatched);   // [kSegSlots]
+    unsigned long long *p_id = g_id + kSegSlots;                    // [kSegSlots]
+    unsigned *s_cnt = (unsigned *)(p_id + kSegSlots);               // [kMaxPairs]
+    unsigned *s_mia = s_cnt + kMaxPairs;                            // [kMaxMatched]
+    unsigned *s_muni = s_mia + kMaxMatched;                         // [kMaxMatched]
+    unsigned *g_area = s_muni + kMaxMatched;                        // [kSegSlots] ...
+    unsigned *g_matched = g_area + kSegSlots;
+    unsigned *p_area = g_matched + kSegSlots;
+    unsigned *p_void = p_area + kSegSlots;
+    unsigned *p_pio = p_void + kSegSlots;
+    unsigned *p_matched = p_pio + kSegSlots;
+    unsigned short *s_gslot = (unsigned short *)(p_matched + kSegSlots);   // [kMaxPairs]
+    unsigned short *s_pslot = s_gslot + kMaxPairs;                         // [kMaxPairs]
     __shared__ int s_m, s_nm;
     __shared__ int s_tp[256], s_fn[256], s_fp[256];
+
+    SegTable gt{g_id, g_area, nullptr, nullptr, g_matched};
+    SegTable pt{p_id, p_area, p_void, p_pio, p_matched};
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int NC = prm.num_categories;
@@ -334,12 +351,30 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     const unsigned *fcnts = prm.frame_cnts + (size_t)b * kFrameSlots;
     if (tid == 0) { s_m = 0; s_nm = 0; }
     for (int c = tid; c < 256; c += kMatchThreads) { s_tp[c] = 0; s_fn[c] = 0; s_fp[c] = 0; }
+    for (int i = tid; i < kSegSlots; i += kMatchThreads) {
+        g_id[i] = kEmptyKey; p_id[i] = kEmptyKey;
+        g_area[i] = 0; g_matched[i] = 0; p_area[i] = 0; p_void[i] = 0; p_pio[i] = 0; p_matched[i] = 0;
+    }
     __syncthreads();
-    for (int i = tid; i < kFrameSlots; i += kMatchThreads) {
-        const unsigned long long k = fkeys[i];
-        if (k != kEmptyKey) {
-            const int slot = atomicAdd(&s_m, 1);
-            if (slot < kMaxPairs) { s_key[slot] = (long long)k; s_cnt[slot] = fcnts[i]; }
+
+    // (0) gather the frame's pairs (independent loads first: the loop is latency bound)
+    constexpr int kGather = 8;
+    for (int i0 = tid; i0 < kFrameSlots; i0 += kMatchThreads * kGather) {
+        unsigned long long k[kGather];
+#pragma unroll
+        for (int u = 0; u < kGather; ++u) {
+            const int i = i0 + u * kMatchThreads;
+            k[u] = i < kFrameSlots ? fkeys[i] : kEmptyKey;
+        }
+#pragma unroll
+        for (int u = 0; u < kGather; ++u) {
+            if (k[u] != kEmptyKey) {
+                const int slot = atomicAdd(&s_m, 1);
+                if (slot < kMaxPairs) {
+                    s_key[slot] = (long long)k[u];
+                    s_cnt[slot] = fcnts[i0 + u * kMatchThreads];
+                }
+            }
         }
     }
     __syncthreads();
@@ -348,75 +383,53 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         if (tid == 0) set_status(prm.status + b, NPB_ERR_CAPACITY);
         m = kMaxPairs;
     }
-    int npad = 1;
-    while (npad < m) npad <<= 1;
-    for (int i = m + tid; i < npad; i += kMatchThreads) { s_key[i] = 0x7fffffffffffffffll; s_cnt[i] = 0; }
-    __syncthreads();
-    // (1) pairs in ascending key order = torch.unique order of target*offset + pred (pq.py:109)
-    bitonic_sort_pairs(s_key, s_cnt, npad, tid);
 
-    // (2) decode; gt segments are runs of equal key / offset: run heads sum the run (area of
-    //     the gt segment, pq.py:83) and broadcast it to the run
-    for (int t = tid; t < npad; t += kMatchThreads) {
-        s_ord[t] = t;
-        if (t < m) {
-            const long long key = s_key[t];
-            const long long g = key / prm.offset;       // ids are validated non-negative
-            s_p[t] = key - g * prm.offset;
-            const long long gc = g / prm.L;
-            s_gcat[t] = (gc >= 0 && gc < 0x7fffffff) ? (int)gc : 0x7fffffff;
-            // bit 1: first pair of its gt segment (run head); bit 0 (set later): matched
-            s_flag[t] = (t == 0 || s_key[t - 1] / prm.offset != g) ? 2 : 0;
-        } else {
-            s_p[t] = 0x7fffffffffffffffll;
-        }
-    }
-    __syncthreads();
+    // (1) segment tables: areas (pq.py:83-84), void overlap (pq.py:34-43), ignored overlap
+    //     (pq.py:47-57); every pair remembers the slots of its two segments
     for (int t = tid; t < m; t += kMatchThreads) {
-        if (s_flag[t] & 2) {
-            unsigned area = s_cnt[t];
-            int e = t + 1;
-            for (; e < m && !(s_flag[e] & 2); ++e) area += s_cnt[e];
-            for (int u = t; u < e; ++u) s_tsa[u] = area;
-        }
-    }
-    // (3) pred segments: sort the pair indices by pred id, then the same run trick gives the
-    //     pred area (pq.py:84) and the overlap with the gt void segment (pq.py:34-43)
-    __syncthreads();
-    bitonic_sort_pairs(s_p, s_ord, npad, tid);
-    for (int k = tid; k < m; k += kMatchThreads) {
-        const long long p = s_p[k];
-        if (k == 0 || s_p[k - 1] != p) {
-            const long long void_key = prm.void_segment_id * prm.offset + p;
-            unsigned area = 0, vo = 0;
-            int e = k;
-            for (; e < m && s_p[e] == p; ++e) {
-                const int u = s_ord[e];
-                area += s_cnt[u];
-                if (s_key[u] == void_key) vo = s_cnt[u];
-            }
-            for (int q = k; q < e; ++q) { s_psa[s_ord[q]] = area; s_void[s_ord[q]] = vo; }
-        }
+        const long long key = s_key[t];
+        const unsigned cnt = s_cnt[t];
+        const long long g = key / prm.offset;       // ids are validated non-negative
+        const long long p = key - g * prm.offset;
+        const int gs = seg_slot(gt, (unsigned long long)g);
+        const int ps = seg_slot(pt, (unsigned long long)p);
+        if (gs < 0 || ps < 0) { set_status(prm.status + b, NPB_ERR_CAPACITY); continue; }
+        s_gslot[t] = (unsigned short)gs;
+        s_pslot[t] = (unsigned short)ps;
+        atomicAdd(g_area + gs, cnt);
+        atomicAdd(p_area + ps, cnt);
+        if (g == prm.void_segment_id) p_void[ps] = cnt;     // key == void*offset + p, unique
+        if (g / prm.L == prm.ignored_label) atomicAdd(p_pio + ps, cnt);
     }
     __syncthreads();
 
-    // (4) IoU + match decision per intersecting pair                       pq.py:119-152
+    // (2) IoU + match decision per intersecting pair                       pq.py:119-152
     for (int t = tid; t < m; t += kMatchThreads) {
         const long long key = s_key[t];
         if (key == prm.void_segment_id) continue;                          // pq.py:120
         const long long g = key / prm.offset, p = key - g * prm.offset;
-        const long long gcat = s_gcat[t], pcat = p / prm.L;
+        const long long gcat = g / prm.L, pcat = p / prm.L;
         if (gcat != pcat) continue;                                        // pq.py:128
+        const int gs = s_gslot[t], ps = s_pslot[t];
         const long long ia = s_cnt[t];
-        const long long uni = (long long)s_tsa[t] + (long long)s_psa[t] - ia - (long long)s_void[t];
+        const long long uni = (long long)g_area[gs] + (long long)p_area[ps] - ia -
+                              (long long)p_void[ps];                       // pq.py:143
         if (uni == 0) { set_status(prm.status + b, NPB_ERR_ZERO_DIVISION); continue; }
         const double iou = (double)ia / (double)uni;                       // pq.py:145
         if (iou > 0.5) {
-            if (gcat >= NC || gcat >= 256) { set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE); continue; }
-            s_flag[t] |= 1;
+            if (gcat < 0 || gcat >= NC || gcat >= 256) { set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE); continue; }
+            g_matched[gs] = 1;
+            p_matched[ps] = 1;
             atomicAdd(&s_tp[(int)gcat], 1);
+            const int slot = atomicAdd(&s_nm, 1);
+            if (slot < kMaxMatched) {
+                s_mkey[slot] = key;
+                s_mia[slot] = (unsigned)ia;
+                s_muni[slot] = (unsigned)uni;
+            } else {
+                set_status(prm.status + b, NPB_ERR_CAPACITY);
+            }
             if (prm.matches) {
-                const int slot = atomicAdd(&s_nm, 1);
                 if (slot < prm.match_cap) {
                     long long *o = prm.matches + ((size_t)b * prm.match_cap + slot) * 2;
                     o[0] = g;
@@ -429,66 +442,56 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     }
     __syncthreads();
 
-    // (5) false negatives: gt segments (runs in key order) without a match    pq.py:155-163
-    for (int t = tid; t < m; t += kMatchThreads) {
-        if (s_flag[t] & 2) {
-            bool matched = (s_flag[t] & 1) != 0;
-            for (int e = t + 1; e < m && !(s_flag[e] & 2); ++e) matched |= (s_flag[e] & 1) != 0;
-            const long long cat = s_gcat[t];
-            if (!matched && cat != prm.ignored_label) {
-                if (cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
+    // (3) false negatives: unmatched gt segments outside the ignored label    pq.py:155-163
+    //     false positives: unmatched pred segments, unless more than half of their area lies
+    //     in ignored gt segments                                            pq.py:165-177
+    for (int i = tid; i < kSegSlots; i += kMatchThreads) {
+        if (g_id[i] != kEmptyKey && !g_matched[i]) {
+            const long long cat = (long long)g_id[i] / prm.L;
+            if (cat != prm.ignored_label) {
+                if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                 else atomicAdd(&s_fn[(int)cat], 1);
             }
         }
-    }
-    // (6) false positives: pred segments (runs in pred order) without a match, unless more
-    //     than half of their area lies in ignored gt segments                 pq.py:165-177
-    for (int k = tid; k < m; k += kMatchThreads) {
-        const long long p = s_p[k];
-        if (k == 0 || s_p[k - 1] != p) {
-            bool matched = false;
-            long long pio = 0;
-            for (int e = k; e < m && s_p[e] == p; ++e) {
-                const int u = s_ord[e];
-                matched |= (s_flag[u] & 1) != 0;
-                if ((long long)s_gcat[u] == prm.ignored_label) pio += s_cnt[u];
-            }
-            if (!matched && !((double)pio / (double)s_psa[s_ord[k]] > 0.5)) {
-                const long long cat = p / prm.L;
+        if (p_id[i] != kEmptyKey && !p_matched[i]) {
+            if (!((double)p_pio[i] / (double)p_area[i] > 0.5)) {
+                const long long cat = (long long)p_id[i] / prm.L;
                 if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                 else atomicAdd(&s_fp[(int)cat], 1);
             }
         }
     }
-    __syncthreads();
 
-    // (7) matched pairs, compacted in ascending pair order by one warp (ballot prefix), then
-    //     per category the IoU sum in that order -- the reference's float64 add order
-    __shared__ int s_nmatched;
-    if (tid < 32) {
-        int base = 0;
-        for (int t0 = 0; t0 < m; t0 += 32) {
-            const int t = t0 + tid;
-            const bool f = t < m && (s_flag[t] & 1);
-            const unsigned bal = __ballot_sync(kFullMask, f);
-            if (f) s_ord[base + __popc(bal & ((1u << tid) - 1u))] = t;
-            base += __popc(bal);
-        }
-        if (tid == 0) s_nmatched = base;
-    }
+    // (4) matched pairs in ascending key order (= the reference's visiting order, pq.py:109/119):
+    //     small bitonic sort, then per category the float64 IoU sum in that order
+    int nm = s_nm < kMaxMatched ? s_nm : kMaxMatched;
+    int npad = 1;
+    while (npad < nm) npad <<= 1;
+    for (int i = nm + tid; i < npad; i += kMatchThreads) s_mkey[i] = 0x7fffffffffffffffll;
     __syncthreads();
-    const int n_matched = s_nmatched;
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += kMatchThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = ((i & k) == 0);
+                    const long long a0 = s_mkey[i], a1 = s_mkey[ixj];
+                    if ((a0 > a1) == up) {
+                        s_mkey[i] = a1; s_mkey[ixj] = a0;
+                        unsigned x = s_mia[i]; s_mia[i] = s_mia[ixj]; s_mia[ixj] = x;
+                        x = s_muni[i]; s_muni[i] = s_muni[ixj]; s_muni[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
     for (int c = tid; c < NC; c += kMatchThreads) {
         double acc = 0.0;
         if (c < 256 && s_tp[c] > 0)
-            for (int i = 0; i < n_matched; ++i) {
-                const int t = s_ord[i];
-                if (s_gcat[t] == c) {
-                    const long long uni = (long long)s_tsa[t] + (long long)s_psa[t] -
-                                          (long long)s_cnt[t] - (long long)s_void[t];
-                    acc += (double)s_cnt[t] / (double)uni;
-                }
-            }
+            for (int i = 0; i < nm; ++i)
+                if ((s_mkey[i] / prm.offset) / prm.L == c)
+                    acc += (double)s_mia[i] / (double)s_muni[i];
         double *fs = prm.frame_stats + (size_t)b * 4 * NC;
         fs[c] = acc;
         fs[NC + c] = c < 256 ? (double)s_tp[c] : 0.0;
@@ -575,7 +578,8 @@ confmat_kernel(const void *__restrict__ preds, int pd, const void *__restrict__ 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t match_smem_bytes()
 {
-    return (size_t)kMaxPairs * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 1) + 16;
+    return (size_t)kMaxPairs * (8 + 4 + 2 + 2) + (size_t)kMaxMatched * (8 + 4 + 4) +
+           (size_t)kSegSlots * (8 + 8 + 6 * 4) + 16;
 }
 
 }  // namespace npb

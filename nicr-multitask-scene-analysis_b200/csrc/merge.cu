@@ -57,7 +57,10 @@ finalize_instances_kernel(const uint32_t *__restrict__ vote_hist,
     if (inst_angle) inst_angle[o] = ang;
 }
 
-// 4 pixels per thread: 32-bit loads of the two uint8 maps, two 128-bit stores of int64 ids
+// 4 pixels per group (32-bit loads of the two uint8 maps, two 128-bit streaming stores of
+// int64 ids), kWriteGroups independent groups per thread so that enough bytes are in flight
+constexpr int kWriteGroups = 2;
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 write_panoptic_kernel(const uint8_t *__restrict__ sem, const uint8_t *__restrict__ inst,
@@ -75,42 +78,54 @@ write_panoptic_kernel(const uint8_t *__restrict__ sem, const uint8_t *__restrict
         s_cls[threadIdx.x] = c < 0 ? 0 : c;  // dropped instance -> void
     }
     __syncthreads();
-    const int p0 = (blockIdx.x * 256 + threadIdx.x) * VEC;
-    if (p0 >= P) return;
-    const size_t fb = (size_t)b * P + p0;
-    uint32_t sw, iw;
-    if (VEC == 4) {
-        sw = *(const uint32_t *)(sem + fb);
-        iw = *(const uint32_t *)(inst + fb);
-    } else {
-        sw = sem[fb];
-        iw = inst[fb];
-    }
-    long long out[VEC];
-    uint32_t psw = 0;
+    const int base = blockIdx.x * (256 * VEC * kWriteGroups) + threadIdx.x * VEC;
+    uint32_t sw[kWriteGroups], iw[kWriteGroups];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const int c = (sw >> (8 * j)) & 255, ii = (iw >> (8 * j)) & 255;
-        long long v;
-        int pc;  // panoptic class = v / L without the 64-bit division
-        if (ii > 0) {
-            v = s_pan[ii];
-            pc = pan_sem_out ? s_cls[ii] : 0;
-        } else {
-            pc = thing.has(c) ? 0 : c + 1;
-            v = (long long)pc * L;
+    for (int u = 0; u < kWriteGroups; ++u) {
+        const int p0 = base + u * 256 * VEC;
+        sw[u] = 0; iw[u] = 0;
+        if (p0 < P) {
+            const size_t fb = (size_t)b * P + p0;
+            if (VEC == 4) {
+                sw[u] = *(const uint32_t *)(sem + fb);
+                iw[u] = *(const uint32_t *)(inst + fb);
+            } else {
+                sw[u] = sem[fb];
+                iw[u] = inst[fb];
+            }
         }
-        out[j] = v;
-        psw |= (uint32_t)pc << (8 * j);
     }
-    if (VEC == 4) {
-        longlong2 *o = (longlong2 *)(pan_out + fb);
-        o[0] = make_longlong2(out[0], out[1]);
-        o[1] = make_longlong2(out[2], out[3]);
-        if (pan_sem_out) *(uint32_t *)(pan_sem_out + fb) = psw;
-    } else {
-        pan_out[fb] = out[0];
-        if (pan_sem_out) pan_sem_out[fb] = (uint8_t)psw;
+#pragma unroll
+    for (int u = 0; u < kWriteGroups; ++u) {
+        const int p0 = base + u * 256 * VEC;
+        if (p0 >= P) continue;
+        const size_t fb = (size_t)b * P + p0;
+        long long out[VEC];
+        uint32_t psw = 0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int c = (sw[u] >> (8 * j)) & 255, ii = (iw[u] >> (8 * j)) & 255;
+            long long v;
+            int pc;  // panoptic class = v / L without the 64-bit division
+            if (ii > 0) {
+                v = s_pan[ii];
+                pc = pan_sem_out ? s_cls[ii] : 0;
+            } else {
+                pc = thing.has(c) ? 0 : c + 1;
+                v = (long long)pc * L;
+            }
+            out[j] = v;
+            psw |= (uint32_t)pc << (8 * j);
+        }
+        if (VEC == 4) {
+            longlong2 *o = (longlong2 *)(pan_out + fb);
+            __stcs(o, make_longlong2(out[0], out[1 % VEC]));
+            __stcs(o + 1, make_longlong2(out[2 % VEC], out[3 % VEC]));
+            if (pan_sem_out) *(uint32_t *)(pan_sem_out + fb) = psw;
+        } else {
+            pan_out[fb] = out[0];
+            if (pan_sem_out) pan_sem_out[fb] = (uint8_t)psw;
+        }
     }
 }
 
@@ -215,12 +230,12 @@ extern "C" int npb_write_panoptic(const uint8_t *sem, const uint8_t *inst,
                       (((uintptr_t)sem | (uintptr_t)inst | (uintptr_t)pan_sem_out) & 3u) == 0 &&
                       ((uintptr_t)pan_out & 15u) == 0;
     if (vec4) {
-        dim3 grid((P / 4 + 255) / 256, B);
+        dim3 grid((P / 4 + 256 * kWriteGroups - 1) / (256 * kWriteGroups), B);
         write_panoptic_kernel<4><<<grid, 256, 0, s>>>(sem, inst, inst_pan_id, inst_class, P,
                                                       (long long)max_instances_per_category,
                                                       thing, pan_out, pan_sem_out);
     } else {
-        dim3 grid((P + 255) / 256, B);
+        dim3 grid((P + 256 * kWriteGroups - 1) / (256 * kWriteGroups), B);
         write_panoptic_kernel<1><<<grid, 256, 0, s>>>(sem, inst, inst_pan_id, inst_class, P,
                                                       (long long)max_instances_per_category,
                                                       thing, pan_out, pan_sem_out);
