@@ -176,31 +176,44 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     const unsigned lt_mask = (1u << lane) - 1u;
     int q_len = 0;      // warp-uniform
 
+    // software pipeline: the loads of the next chunk are issued before the current chunk is
+    // processed, so their DRAM latency hides behind the (instruction bound) table updates
+    long long n_pv[VEC], n_tv[VEC];
+    unsigned n_sw = 0;
+    auto fetch = [&](long long ch) {
+        const long long q0 = ch * chunk + (long long)tid * VEC;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { n_pv[j] = 0; n_tv[j] = 0; }
+        n_sw = 0;
+        if (ch < n_chunks && q0 < P) {
+            const size_t fq = (size_t)b * P + q0;
+            if (VEC == 4) {
+                const longlong2 a0 = __ldcs((const longlong2 *)(prm.pred + fq));
+                const longlong2 a1 = __ldcs((const longlong2 *)(prm.pred + fq) + 1);
+                const longlong2 t0 = __ldcs((const longlong2 *)(prm.target + fq));
+                const longlong2 t1 = __ldcs((const longlong2 *)(prm.target + fq) + 1);
+                n_pv[0] = a0.x; n_pv[1 % VEC] = a0.y; n_pv[2 % VEC] = a1.x; n_pv[3 % VEC] = a1.y;
+                n_tv[0] = t0.x; n_tv[1 % VEC] = t0.y; n_tv[2 % VEC] = t1.x; n_tv[3 % VEC] = t1.y;
+                if (CONFMAT) n_sw = *(const unsigned *)(prm.sem_target + fq);
+            } else {
+                n_pv[0] = __ldcs(prm.pred + fq);
+                n_tv[0] = __ldcs(prm.target + fq);
+                if (CONFMAT) n_sw = prm.sem_target[fq];
+            }
+        }
+    };
+    fetch(blockIdx.x);
+
     for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const long long p0 = ch * chunk + (long long)tid * VEC;
-        const size_t fb = (size_t)b * P + p0;
         const bool act = p0 < P;    // P % VEC == 0 guaranteed by the launcher
         unsigned long long key[VEC];
-        unsigned sw = 0;
+        unsigned sw = n_sw;
+        long long pv[VEC], tv[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) key[j] = 0;
+        for (int j = 0; j < VEC; ++j) { key[j] = 0; pv[j] = n_pv[j]; tv[j] = n_tv[j]; }
+        fetch(ch + gridDim.x);
         if (act) {
-            long long pv[VEC], tv[VEC];
-            if (VEC == 4) {
-                const longlong2 a0 = __ldcs((const longlong2 *)(prm.pred + fb));
-                const longlong2 a1 = __ldcs((const longlong2 *)(prm.pred + fb) + 1);
-                const longlong2 t0 = __ldcs((const longlong2 *)(prm.target + fb));
-                const longlong2 t1 = __ldcs((const longlong2 *)(prm.target + fb) + 1);
-                pv[0] = a0.x; pv[1 % VEC] = a0.y; pv[2 % VEC] = a1.x; pv[3 % VEC] = a1.y;
-                tv[0] = t0.x; tv[1 % VEC] = t0.y; tv[2 % VEC] = t1.x; tv[3 % VEC] = t1.y;
-            } else {
-                pv[0] = __ldcs(prm.pred + fb);
-                tv[0] = __ldcs(prm.target + fb);
-            }
-            if (CONFMAT) {
-                if (VEC == 4) sw = *(const unsigned *)(prm.sem_target + fb);
-                else sw = prm.sem_target[fb];
-            }
             // ids must satisfy 0 <= pred < offset, 0 <= target (checked on the OR of the lane)
             long long any_neg = 0;
             bool too_big = false;
@@ -660,24 +673,46 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
                       ((uintptr_t)sem_target & 3u) == 0;
     const int vec = vec4 ? 4 : 1;
     const long long n_chunks = (P + (long long)kPairThreads * vec - 1) / ((long long)kPairThreads * vec);
-    long long bx = (148ll * 4 + B - 1) / B;   // ~4 CTAs (48 KB tables each) per SM, one wave
-    if (bx > n_chunks) bx = n_chunks;
-    if (bx < 1) bx = 1;
-    dim3 grid((unsigned)bx, B);
     // [hash keys | queue keys | hash counts | dense | confmat (if privatised) | queue meta]
     const size_t pc_smem = (size_t)kSmemSlots * 12 + (size_t)(kPairThreads / 32) * kQueueCap * 10 +
                            (size_t)pp.nd * pp.nd * sizeof(unsigned) +
                            ((confmat && confmat_n <= kSmemConfmatMaxN)
                                 ? (size_t)confmat_n * confmat_n * sizeof(unsigned) : 0) + 16;
     static bool pc_attr_set = false;
+    static int n_sm = 148;
     if (!pc_attr_set) {
         const int mx = 200 * 1024;
         cudaFuncSetAttribute(pair_count_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(pair_count_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(pair_count_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(pair_count_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         pc_attr_set = true;
     }
+    // persistent CTAs: the whole batch in ONE wave (a second, partial wave would leave most SMs
+    // idle for the length of a CTA), every CTA of a frame gets the same number of chunks
+    static size_t occ_smem[4] = {0, 0, 0, 0};
+    static int occ_blocks[4] = {0, 0, 0, 0};
+    const int variant = (confmat ? 2 : 0) + (vec4 ? 1 : 0);
+    int per_sm = occ_blocks[variant];
+    if (per_sm == 0 || occ_smem[variant] != pc_smem) {
+    if (confmat) {
+        if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_count_kernel<4, true>, kPairThreads, pc_smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_count_kernel<1, true>, kPairThreads, pc_smem);
+    } else {
+        if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_count_kernel<4, false>, kPairThreads, pc_smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_count_kernel<1, false>, kPairThreads, pc_smem);
+    }
+    if (per_sm < 1) per_sm = 1;
+    occ_smem[variant] = pc_smem;
+    occ_blocks[variant] = per_sm;
+    }
+    long long bx = ((long long)n_sm * per_sm) / B;
+    if (bx < 1) bx = 1;
+    if (bx > n_chunks) bx = n_chunks;
+    dim3 grid((unsigned)bx, B);
     if (confmat) {
         if (vec4) pair_count_kernel<4, true><<<grid, kPairThreads, pc_smem, s>>>(pp);
         else pair_count_kernel<1, true><<<grid, kPairThreads, pc_smem, s>>>(pp);
