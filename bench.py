@@ -351,7 +351,10 @@ def run_ours(args):
             'gpu_launches': KERNELS_PER_STEP * args.steps,
             'roofline': {'bound': 'hbm', 'kernel': 'group_pixels_kernel<4,logits,orientation>',
                          'achieved': achieved, 'peak': peak, 'peak_source': peak_src,
-                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'unit': 'GB/s', 'frac': achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                         # capture of this command (profiles/r01_group_pixels_ncu_raw.csv)
+                         'traffic': 4.0195e9,
                          'kernel_ms': kernel_ms, 'algorithmic_bytes_per_launch': kbytes},
             'roofline_path': {'bytes_per_frame': bpf,
                               'achieved': value / world * bpf / 1e9, 'unit': 'GB/s',
