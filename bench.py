@@ -28,7 +28,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name='sunrgbd_530x730_c37_b64_orientation', B=64, C=37, H=530, W=730, K=20)
+# BASELINE.json configs; the default (and the only one the driver runs) is configs[1].
+WORKLOADS = {
+    'nyuv2': dict(name='nyuv2_480x640_c40_b8', B=8, C=40, H=480, W=640, K=12, top_k=64, ori=False),
+    'sunrgbd': dict(name='sunrgbd_530x730_c37_b64_orientation', B=64, C=37, H=530, W=730, K=20,
+                    top_k=64, ori=True),
+    'scannet': dict(name='scannet_968x1296_c40_b128', B=128, C=40, H=968, W=1296, K=30, top_k=64,
+                    ori=False),
+    'cityscapes': dict(name='cityscapes_1024x2048_c19_b256_k100', B=256, C=19, H=1024, W=2048,
+                       K=100, top_k=100, ori=False),
+}
+WORKLOAD = dict(WORKLOADS['sunrgbd'])
 L = 1 << 16
 OFFSET = 256 ** 3
 METRIC = 'panoptic frames/s (postproc+merge+mIoU/PQ)'
@@ -114,14 +124,15 @@ def oracle_baseline(sample_frames, steps, warmup, threads=None):
     oracle.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = oracle.num_threads()
     data = testing.make_batch(sample_frames, w['C'], w['H'], w['W'], w['K'], seed=1,
-                              with_orientation=True, quantize=None)
+                              with_orientation=w['ori'], quantize=None)
     arrs = {k: v.numpy() for k, v in data.items()}
     is_thing = testing.default_is_thing(w['C'])
     has_ori = tuple(bool(t and c % 4 == 1) for c, t in enumerate(is_thing))
 
     def step():
         r = oracle.panoptic_postprocess(arrs['logits'], arrs['heat'], arrs['offset'],
-                                        arrs['orientation'], is_thing, has_ori)
+                                        arrs.get('orientation'), is_thing, has_ori,
+                                        top_k=w['top_k'])
         pan = r['panoptic']
         tgt = np.roll(pan, 5, axis=-1)
         sem_t = (tgt // L).astype(np.uint8)
@@ -187,7 +198,8 @@ def run_ours(args):
 
     # ---- synthetic decoder outputs, generated on the device (distinct frames per rank) ----
     pool = 16            # distinct frames; the batch cycles them (inputs stay > L2: 4.4 GB)
-    frames = [testing.make_frame(C, H, W, K, seed=1000 * (rank + 1) + i, with_orientation=True,
+    ORI = w['ori']
+    frames = [testing.make_frame(C, H, W, K, seed=1000 * (rank + 1) + i, with_orientation=ORI,
                                  device=dev, quantize=None) for i in range(pool)]
     data = {k: torch.stack([frames[i % pool][k] for i in range(B)]).contiguous() for k in frames[0]}
     del frames
@@ -196,7 +208,8 @@ def run_ours(args):
     def new_post(**kw):
         return get_postprocessing_class(
             'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
-            instance_postprocessing=get_postprocessing_class('instance')(),
+            instance_postprocessing=get_postprocessing_class(
+                'instance', top_k_instances=w['top_k'])(),
             semantic_classes_is_thing=is_thing, semantic_class_has_orientation=has_ori, **kw)()
 
     post = new_post(async_results=True)
@@ -204,7 +217,7 @@ def run_ours(args):
     miou = MeanIntersectionOverUnion(C + 1, ignore_first_class=True, device=dev)
     evaluation = PanopticEvaluation(pq, miou)
 
-    inst_out = (data['heat'], data['offset'], data['orientation'])
+    inst_out = (data['heat'], data['offset']) + ((data['orientation'],) if ORI else ())
     raw = ((data['logits'], inst_out), (None, None))
     # evaluation targets: prediction rolled by 5 px, fixed for the run
     r0 = post.postprocess(raw, batch, is_training=False)
@@ -266,13 +279,13 @@ def run_ours(args):
     sem = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
     inst = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
     hist = torch.empty((B, _lib.MAX_INST, C), dtype=torch.int32, device=dev)
-    osum = torch.empty((B, _lib.MAX_INST, 2), dtype=torch.float64, device=dev)
+    osum = torch.empty((B, _lib.MAX_INST, 2), dtype=torch.float64, device=dev) if ORI else None
     lut = _lib.host_lut(is_thing, C)
 
     def group_only():
         _lib.check(_lib.lib().npb_group_pixels(
             _lib.ptr(data['logits']), None, None, _lib.ptr(data['offset']),
-            _lib.ptr(data['orientation']), c_int(B), c_int(C), c_int(H), c_int(W), lut,
+            _lib.ptr(data.get('orientation')), c_int(B), c_int(C), c_int(H), c_int(W), lut,
             tabs.dptr('centers_yx'), tabs.dptr('n_centers'), c_int(1), c_int(0), c_float(0.0),
             _lib.ptr(sem), _lib.ptr(inst), _lib.ptr(hist), _lib.ptr(osum), _lib.stream_ptr(dev)))
 
@@ -288,7 +301,7 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     kernel_ms = k0.elapsed_time(k1) / reps      # includes the two small memsets of the call
     peak, peak_src = measured_peak_gbs()
-    kbytes = bytes_group_kernel_per_frame(C, H, W) * B
+    kbytes = bytes_group_kernel_per_frame(C, H, W, ORI) * B
     achieved = kbytes / (kernel_ms * 1e-3) / 1e9
 
     # ---- end to end: pinned host buffers in, panoptic ids in host memory out -------------------
@@ -306,7 +319,7 @@ def run_ours(args):
 
         def e2e_step():
             o = pipe.run(host_in, batch, host_tgt, out=dict(out))
-            return PanopticHostPipeline.finish(o)      # blocks; builds ids / meta / orientations
+            return PanopticHostPipeline.finish(o, with_orientation=ORI)   # blocks; builds the dicts
 
         e2e_step()
         evaluation.reset()
@@ -335,7 +348,7 @@ def run_ours(args):
                          '(oracle/panoptic_oracle.c), OpenMP over frames'}
 
     if rank == 0:
-        bpf = bytes_post_per_frame(C, H, W) + bytes_eval_per_frame(H, W)
+        bpf = bytes_post_per_frame(C, H, W, ORI) + bytes_eval_per_frame(H, W)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': n_warm, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -344,17 +357,18 @@ def run_ours(args):
                        'height': H, 'width': W, 'instances_per_frame': K,
                        'parallelism': f'frames sharded over {world} GPU(s), metric states '
                                       'all-reduced at compute()',
-                       'l2_policy': 'inputs (4.4 GB per step) larger than L2, no flush needed',
+                       'l2_policy': f'inputs ({B * bytes_post_per_frame(C, H, W, ORI) / 1e9:.1f} GB per step) '
+                                    'larger than L2, no flush needed',
                        'launch': 'eager' if args.no_graph else 'cuda graph replay'},
             'clocks': clocks.summary(),
             'e2e': e2e,
             'gpu_launches': KERNELS_PER_STEP * args.steps,
-            'roofline': {'bound': 'hbm', 'kernel': 'group_pixels_kernel<4,logits,orientation>',
+            'roofline': {'bound': 'hbm', 'kernel': 'group_pixels_kernel<4,logits,%s>' % ('orientation' if ORI else 'no orientation'),
                          'achieved': achieved, 'peak': peak, 'peak_source': peak_src,
                          'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
                          # capture of this command (profiles/r01_group_pixels_ncu_raw.csv)
-                         'traffic': 4.0195e9,
+                         'traffic': 4.0195e9 if args.config == 'sunrgbd' and not args.frames else None,
                          'kernel_ms': kernel_ms, 'algorithmic_bytes_per_launch': kbytes},
             'roofline_path': {'bytes_per_frame': bpf,
                               'achieved': value / world * bpf / 1e9, 'unit': 'GB/s',
@@ -370,6 +384,9 @@ def run_ours(args):
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--config', default='sunrgbd', choices=sorted(WORKLOADS),
+                    help='BASELINE.json shape (default: configs[1], the metric\'s configuration)')
+    ap.add_argument('--frames', type=int, default=0, help='override frames per GPU per step')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
@@ -378,6 +395,10 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='issue every step from Python')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    WORKLOAD.clear()
+    WORKLOAD.update(WORKLOADS[args.config])
+    if args.frames:
+        WORKLOAD['B'] = args.frames
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { oc[j] = 0.0f; os[j] = 0.0f; }
     }
+    float nly[VEC], nlx[VEC];   // NEGATED locations: c - l == c + (-l) exactly
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { nly[j] = 0.0f; nlx[j] = 0.0f; }
     if (any_fg) {
         float oy[VEC], ox[VEC];
         PixVec<VEC>::loadf(prm.offset + (size_t)b * 2 * P + p0, oy, true);
@@ -186,7 +189,6 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
             PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + p0, oc, true);
             PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + P + p0, os, true);
         }
-        float nly[VEC], nlx[VEC];   // NEGATED locations: c - l == c + (-l) exactly
         int y = p0 / W, x = p0 - y * W;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -196,28 +198,80 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
             nlx[j] = -__fadd_rn((float)x, dx);
             if (++x == W) { x = 0; ++y; }
         }
+    }
+    // The centre loop is warp-cooperative (it prunes centres per warp), so every lane of a
+    // warp that holds a thing pixel runs it; lanes without one just carry neutral values.
+    if (__any_sync(kFullMask, any_fg)) {
         float sbest[VEC];
         int ibest[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { sbest[j] = __int_as_float(0x7f800000); ibest[j] = 0; }
+
+        // ---- centre pruning.  Bounding box of the warp's thing-pixel locations; for a centre c
+        // lb(c) / ub(c) bound the squared distance from ANY point of the box.  Every pixel's
+        // nearest centre is at most U = min_c ub(c) away, so a centre with lb(c) > U can neither
+        // win nor tie for any pixel of the warp and is skipped.  The 1e-5 slack dwarfs the
+        // f32 rounding of the bounds and of the exact distances (< 1e-6 relative), so the
+        // surviving set always contains every centre the exact arg-min could pick; survivors
+        // are visited in ascending index, which keeps the first-index tie rule.
+        const float kInf = __int_as_float(0x7f800000);
+        float ymin = kInf, ymax = -kInf, xmin = kInf, xmax = -kInf;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (fg[j]) {
+                ymin = fminf(ymin, -nly[j]); ymax = fmaxf(ymax, -nly[j]);
+                xmin = fminf(xmin, -nlx[j]); xmax = fmaxf(xmax, -nlx[j]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ymin = fminf(ymin, __shfl_xor_sync(kFullMask, ymin, o));
+            ymax = fmaxf(ymax, __shfl_xor_sync(kFullMask, ymax, o));
+            xmin = fminf(xmin, __shfl_xor_sync(kFullMask, xmin, o));
+            xmax = fmaxf(xmax, __shfl_xor_sync(kFullMask, xmax, o));
+        }
+        float U = kInf;
+        for (int i = lane; i < n; i += 32) {
+            const float4 c = s_centers[i];
+            const float dy = fmaxf(fabsf(c.x - ymin), fabsf(c.x - ymax));
+            const float dx = fmaxf(fabsf(c.z - xmin), fabsf(c.z - xmax));
+            U = fminf(U, dy * dy + dx * dx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) U = fminf(U, __shfl_xor_sync(kFullMask, U, o));
+        // NaN / Inf boxes (garbage offsets) make U = Inf or NaN: then nothing is pruned
+        const float prune_above = (U == U) ? U * 1.00001f : kInf;
+
         if (VEC == 4) {
             // Blackwell packed FP32 (FADD2 / FMUL2 / FFMA2): two pixels per instruction, each
             // lane individually IEEE-rounded exactly like the scalar sequence
             const float2 nlyA = make_float2(nly[0], nly[1 % VEC]), nlyB = make_float2(nly[2 % VEC], nly[3 % VEC]);
             const float2 nlxA = make_float2(nlx[0], nlx[1 % VEC]), nlxB = make_float2(nlx[2 % VEC], nlx[3 % VEC]);
-            for (int i = 0; i < n; ++i) {
-                const float4 c = s_centers[i];
-                const float2 cy2 = make_float2(c.x, c.y), cx2 = make_float2(c.z, c.w);
-                const float2 a0 = __fadd2_rn(cy2, nlyA), a1 = __fadd2_rn(cx2, nlxA);
-                const float2 b0 = __fadd2_rn(cy2, nlyB), b1 = __fadd2_rn(cx2, nlxB);
-                const float2 sA = __ffma2_rn(a1, a1, __fmul2_rn(a0, a0));
-                const float2 sB = __ffma2_rn(b1, b1, __fmul2_rn(b0, b0));
-                if ((sA.x < sbest[0]) | (sA.y < sbest[1 % VEC]) | (sB.x < sbest[2 % VEC]) |
-                    (sB.y < sbest[3 % VEC])) {
-                    consider_center(sA.x, i, sbest[0], ibest[0]);
-                    consider_center(sA.y, i, sbest[1 % VEC], ibest[1 % VEC]);
-                    consider_center(sB.x, i, sbest[2 % VEC], ibest[2 % VEC]);
-                    consider_center(sB.y, i, sbest[3 % VEC], ibest[3 % VEC]);
+            for (int base = 0; base < n; base += 32) {
+                bool keep = false;
+                if (base + lane < n) {
+                    const float4 c = s_centers[base + lane];
+                    const float dy = fmaxf(fmaxf(ymin - c.x, c.x - ymax), 0.0f);
+                    const float dx = fmaxf(fmaxf(xmin - c.z, c.z - xmax), 0.0f);
+                    keep = !(dy * dy + dx * dx > prune_above);
+                }
+                unsigned todo = __ballot_sync(kFullMask, keep);
+                while (todo) {
+                    const int i = base + __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const float4 c = s_centers[i];
+                    const float2 cy2 = make_float2(c.x, c.y), cx2 = make_float2(c.z, c.w);
+                    const float2 a0 = __fadd2_rn(cy2, nlyA), a1 = __fadd2_rn(cx2, nlxA);
+                    const float2 b0 = __fadd2_rn(cy2, nlyB), b1 = __fadd2_rn(cx2, nlxB);
+                    const float2 sA = __ffma2_rn(a1, a1, __fmul2_rn(a0, a0));
+                    const float2 sB = __ffma2_rn(b1, b1, __fmul2_rn(b0, b0));
+                    if ((sA.x < sbest[0]) | (sA.y < sbest[1 % VEC]) | (sB.x < sbest[2 % VEC]) |
+                        (sB.y < sbest[3 % VEC])) {
+                        consider_center(sA.x, i, sbest[0], ibest[0]);
+                        consider_center(sA.y, i, sbest[1 % VEC], ibest[1 % VEC]);
+                        consider_center(sB.x, i, sbest[2 % VEC], ibest[2 % VEC]);
+                        consider_center(sB.y, i, sbest[3 % VEC], ibest[3 % VEC]);
+                    }
                 }
             }
         } else {

@@ -173,6 +173,42 @@ def test_against_oracle(cfg, cuda_device):
     _check_orient(ref['orientations'], r['orientations_panoptic_segmentation_deeplab_instance'])
 
 
+@pytest.mark.parametrize('mode', ['dense_ties', 'wild_offsets', 'nonfinite_offsets'])
+def test_grouping_with_many_centres_is_exact(mode, cuda_device):
+    """stress for the per-warp centre pruning of group_pixels_kernel: up to 254 centres, exact
+    distance ties (integer pixel targets), offsets pointing all over the frame, NaN / Inf"""
+    from nicr_mt_scene_analysis_b200.model.postprocessing import InstancePostprocessing
+    g = torch.Generator().manual_seed({'dense_ties': 1, 'wild_offsets': 2, 'nonfinite_offsets': 3}[mode])
+    B, H, W = 2, 120, 200
+    heat = torch.zeros(B, 1, H, W)
+    ys = torch.arange(4, H - 4, 7)
+    xs = torch.arange(4, W - 4, 13)
+    heat[:, 0, ys[:, None], xs[None, :]] = 0.5 + 0.5 * torch.rand(B, len(ys), len(xs), generator=g)
+    n_planted = len(ys) * len(xs)
+    assert 200 < n_planted <= 254
+    fg = torch.rand(B, H, W, generator=g) > 0.2
+    if mode == 'dense_ties':          # every pixel points exactly at an integer location
+        off = torch.stack((torch.randint(-9, 10, (B, H, W), generator=g).float(),
+                           torch.randint(-9, 10, (B, H, W), generator=g).float()), 1)
+    else:
+        off = torch.stack(((torch.rand(B, H, W, generator=g) - 0.5) * 2 * H,
+                           (torch.rand(B, H, W, generator=g) - 0.5) * 2 * W), 1)
+    if mode == 'nonfinite_offsets':
+        bad = torch.rand(B, 2, H, W, generator=g)
+        off[bad < 0.02] = float('nan')
+        off[(bad > 0.02) & (bad < 0.04)] = float('inf')
+        off[(bad > 0.04) & (bad < 0.06)] = float('-inf')
+    post = InstancePostprocessing(normalized_offset=False, top_k_instances=254)
+    seg, meta = post._get_instance_segmentation(heat.to(cuda_device), off.to(cuda_device),
+                                                fg.to(cuda_device))
+    ref_seg, ref_meta = oracle.instance_segmentation(heat.numpy(), off.numpy(), fg.numpy(),
+                                                     top_k=254, normalized_offset=False)
+    assert [len(m) for m in ref_meta] == [n_planted] * B
+    assert np.array_equal(seg.cpu().numpy(), ref_seg)
+    assert [{k: v['area'] for k, v in m.items()} for m in meta] == \
+        [{k: v['area'] for k, v in m.items()} for m in ref_meta]
+
+
 def test_too_many_centers_raises(cuda_device):
     """> 255 centres (only reachable through k-th value ties): the reference wraps uint8
     ids silently (instance.py:236); this implementation refuses."""
