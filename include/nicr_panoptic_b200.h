@@ -67,6 +67,25 @@ int npb_semantic_argmax(const float *logits, int B, int C, int H, int W,
                         uint8_t *sem_out, float *score_out, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Crop to the valid region [y0, y0+Hc) x [x0, x0+Wc) and resize to (Hout, Wout).
+ * Replaces: DensePostprocessingBase._crop_to_valid_region_and_resize_prediction,
+ *           model/postprocessing/dense_base.py:15-58 (F.interpolate).
+ * npb_resize_nearest: `planes` planes of elem_size 1 / 4 / 8 bytes (index maps, masks, score
+ *   maps; panoptic.py:246-291, instance.py:385-397) -- exact.
+ * npb_resize_bilinear: f32 planes, align_corners=False (semantic.py:63-66, lazily, only when
+ *   the resized logits themselves are read).
+ * npb_semantic_argmax_resized: bilinear resize of the C logit planes on the fly + arg-max
+ *   (+ soft-max score), semantic.py:63-72 without materialising the resized logits.
+ * ------------------------------------------------------------------------- */
+int npb_resize_nearest(const void *src, int elem_size, int planes, int Hin, int Win, int y0,
+                       int x0, int Hc, int Wc, int Hout, int Wout, void *dst, void *stream);
+int npb_resize_bilinear(const float *src, int planes, int Hin, int Win, int y0, int x0, int Hc,
+                        int Wc, int Hout, int Wout, float *dst, void *stream);
+int npb_semantic_argmax_resized(const float *logits, int B, int C, int Hin, int Win, int y0,
+                                int x0, int Hc, int Wc, int Hout, int Wout, uint8_t *sem_out,
+                                float *score_out, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Class-set mask: mask_out[i] = h_class_lut[sem[i]] (uint8 0/1), N = number of pixels.
  * Replaces: torch.isin(semantic_idx, thing_class_ids), model/postprocessing/panoptic.py:123-127
  *           (and :296-300 for the orientation classes).

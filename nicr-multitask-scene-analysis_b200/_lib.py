@@ -33,6 +33,12 @@ _SIGNATURES = {
     'npb_semantic_argmax': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     'npb_thing_mask': (c_int, [_P, c_int64, c_int, _P, _P, _P]),
     'npb_widen_u8': (c_int, [_P, c_int64, c_int64, _P, _P]),
+    'npb_resize_nearest': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, _P, _P]),
+    'npb_resize_bilinear': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, _P, _P]),
+    'npb_semantic_argmax_resized': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                            c_int, c_int, c_int, _P, _P, _P]),
     'npb_instance_centers_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'npb_instance_centers': (c_int, [_P, c_int, c_int, c_int, c_float, c_int, c_int, _P, c_int,
                                      _P, _P, _P, _P, _P, _P]),

@@ -28,6 +28,22 @@ def semantic_argmax(logits: torch.Tensor, with_score: bool = False):
     return sem, score
 
 
+def semantic_argmax_resized(logits: torch.Tensor, crop_geometry, shape):
+    """Bilinear resize (align_corners=False) of the cropped logits to `shape` fused with the
+    arg-max: -> (classes uint8 (B,h,w), score f32 (B,h,w)); `npb_semantic_argmax_resized`."""
+    logits = _lib.require_cuda(logits, 'semantic logits', torch.float32, 4)
+    B, C, H, W = logits.shape
+    y0, x0, hc, wc = crop_geometry
+    h, w = shape
+    sem = torch.empty((B, h, w), dtype=torch.uint8, device=logits.device)
+    score = torch.empty((B, h, w), dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.lib().npb_semantic_argmax_resized(
+        _lib.ptr(logits), c_int(B), c_int(C), c_int(H), c_int(W), c_int(y0), c_int(x0), c_int(hc),
+        c_int(wc), c_int(h), c_int(w), _lib.ptr(sem), _lib.ptr(score),
+        _lib.stream_ptr(logits.device)), 'npb_semantic_argmax_resized')
+    return sem, score
+
+
 def widen_u8(x: torch.Tensor, add: int = 0) -> torch.Tensor:
     """uint8 map -> int64 map (+ add) on the device (`npb_widen_u8`)."""
     x = _lib.require_cuda(x, 'uint8 map', torch.uint8)
@@ -75,19 +91,25 @@ class SemanticPostprocessing(DensePostprocessingBase):
                       'semantic_segmentation_idx'):
                 r.alias(fullres_key(k), k)
         else:
-            # bilinear resize of the logits, then the same
-            # arg-max kernel on the resized logits (semantic.py:63-72)
-            full = self._crop_to_valid_region_and_resize_prediction(
-                logits, crop, shape, mode='bilinear').contiguous()
+            # network resolution != dataset resolution (semantic.py:63-72): the class map and
+            # its score come from ONE fused kernel (bilinear resize on the fly + arg-max); the
+            # resized logits / soft-max tensors are only materialised if somebody reads them
             fcache = {}
+            geom = self._crop_geometry(tuple(logits.shape[-2:]), crop)
 
             def full_pair():
-                if not fcache:
-                    fcache['sem'], fcache['score'] = semantic_argmax(full, with_score=True)
+                if 'sem' not in fcache:
+                    fcache['sem'], fcache['score'] = semantic_argmax_resized(logits, geom, shape)
                 return fcache
 
-            r['semantic_output_fullres'] = full
-            r.defer('semantic_softmax_scores_fullres', lambda: torch.softmax(full, dim=1))
+            def full_logits():
+                if 'logits' not in fcache:
+                    fcache['logits'] = self._crop_to_valid_region_and_resize_prediction(
+                        logits, crop, shape, mode='bilinear')
+                return fcache['logits']
+
+            r.defer('semantic_output_fullres', full_logits)
+            r.defer('semantic_softmax_scores_fullres', lambda: torch.softmax(full_logits(), dim=1))
             r.defer('semantic_segmentation_score_fullres', lambda: full_pair()['score'])
             r.defer('semantic_segmentation_idx_fullres', lambda: widen_u8(full_pair()['sem']))
         return r

@@ -104,6 +104,41 @@ def run_postprocess(name, B, C, H, W, K, seed, quantize, with_orientation=True, 
           'instances', [len(d) for d in r['panoptic_segmentation_deeplab_ids']])
 
 
+def run_fullres():
+    """network resolution != dataset resolution: crop to the valid region, then resize
+    (dense_base.py:15-58; nearest for index maps, bilinear on the logits before a second
+    softmax/arg-max, semantic.py:63-72 and panoptic.py:242-291)."""
+    B, C, H, W, K = 2, 6, 96, 128, 4
+    FH, FW = 150, 190
+    data = testing.make_batch(B, C, H, W, K, seed=6, with_orientation=True, quantize='q10')
+    is_thing = testing.default_is_thing(C)
+    has_ori = tuple(bool(t and (c % 4 == 1)) for c, t in enumerate(is_thing))
+    sem = get_postprocessing_class('semantic')()
+    ins = get_postprocessing_class('instance')()
+    pan = get_postprocessing_class('panoptic', semantic_postprocessing=sem,
+                                   instance_postprocessing=ins,
+                                   semantic_classes_is_thing=is_thing,
+                                   semantic_class_has_orientation=has_ori)()
+    sl_y, sl_x = slice(0, 90), slice(4, 124)
+    batch = {'semantic_fullres': torch.zeros(B, FH, FW), 'instance_fullres': torch.zeros(B, FH, FW),
+             '_applied_preprocessing': [[{'type': 'Resize', 'valid_region_slice_y': sl_y,
+                                          'valid_region_slice_x': sl_x}]] * B}
+    r = pan.postprocess(((data['logits'], (data['heat'], data['offset'], data['orientation'])),
+                         (None, None)), batch, is_training=False)
+    out = {'logits': data['logits'].numpy(), 'heat': data['heat'].numpy(),
+           'offset': data['offset'].numpy(), 'orientation': data['orientation'].numpy(),
+           'is_thing': np.array(is_thing), 'has_orientation': np.array(has_ori),
+           'fullres_shape': np.array([FH, FW]), 'valid_y': np.array([0, 90]),
+           'valid_x': np.array([4, 124])}
+    for k in ('semantic_segmentation_idx_fullres', 'panoptic_segmentation_deeplab_fullres',
+              'panoptic_segmentation_deeplab_instance_idx_fullres',
+              'panoptic_segmentation_deeplab_semantic_idx_fullres',
+              'semantic_segmentation_score_fullres', 'semantic_output_fullres'):
+        out[k] = r[k].numpy()
+    np.savez_compressed(os.path.join(HERE, 'fullres.npz'), **out)
+    print('fullres', {k: v.shape for k, v in out.items() if k.endswith('fullres')})
+
+
 def run_centers():
     """tie-heavy heat-maps straight into _get_instance_centers (instance.py:78-168)."""
     g = torch.Generator().manual_seed(7)
@@ -247,6 +282,7 @@ if __name__ == '__main__':
                     normalized=False, with_orientation=False)
     run_postprocess('scores', B=2, C=6, H=64, W=96, K=4, seed=5, quantize='q10',
                     compute_scores=True)
+    run_fullres()
     run_centers()
     run_merge()
     run_pq()

@@ -336,3 +336,39 @@ def test_full_size_properties(cuda_device):
                                       data['offset'].numpy()[:1], data['orientation'].numpy()[:1],
                                       is_thing, has_ori)
     assert np.array_equal(pan_map[:1].cpu().numpy(), ref['panoptic'])
+
+
+def test_fullres_golden(cuda_device):
+    """network resolution != dataset resolution (dense_base.py:15-58): nearest-resized index
+    maps bit-exact; bilinear-resized logits to f32 rounding; the full-res class map may only
+    differ from the reference where the two best resized logits are (nearly) tied."""
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    z = load_golden('fullres')
+    B, C, H, W = z['logits'].shape
+    FH, FW = (int(v) for v in z['fullres_shape'])
+    pan = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+        instance_postprocessing=get_postprocessing_class('instance')(),
+        semantic_classes_is_thing=tuple(bool(x) for x in z['is_thing']),
+        semantic_class_has_orientation=tuple(bool(x) for x in z['has_orientation']))()
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    batch = {'semantic_fullres': torch.zeros(B, FH, FW), 'instance_fullres': torch.zeros(B, FH, FW),
+             '_applied_preprocessing': [[{'type': 'Resize',
+                                          'valid_region_slice_y': slice(*z['valid_y'].tolist()),
+                                          'valid_region_slice_x': slice(*z['valid_x'].tolist())}]] * B}
+    r = pan.postprocess(((t(z['logits']), (t(z['heat']), t(z['offset']), t(z['orientation']))),
+                         (None, None)), batch, is_training=False)
+    for k in ('panoptic_segmentation_deeplab_fullres',
+              'panoptic_segmentation_deeplab_instance_idx_fullres',
+              'panoptic_segmentation_deeplab_semantic_idx_fullres'):
+        assert r[k].shape[-2:] == (FH, FW)
+        assert np.array_equal(r[k].cpu().numpy(), z[k]), k
+    full = r['semantic_output_fullres'].cpu().numpy()
+    np.testing.assert_allclose(full, z['semantic_output_fullres'], rtol=1e-5, atol=2e-6)
+    idx = r['semantic_segmentation_idx_fullres'].cpu().numpy()
+    differs = idx != z['semantic_segmentation_idx_fullres']
+    top2 = np.sort(z['semantic_output_fullres'], axis=1)[:, -2:]
+    assert np.all((top2[:, 1] - top2[:, 0])[differs] < 1e-5)
+    assert differs.mean() < 1e-3
+    np.testing.assert_allclose(r['semantic_segmentation_score_fullres'].cpu().numpy()[~differs],
+                               z['semantic_segmentation_score_fullres'][~differs], rtol=2e-5)
