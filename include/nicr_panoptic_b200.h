@@ -191,6 +191,22 @@ int npb_panoptic_forward(const float *logits, const float *heat, const float *of
                          int32_t *inst_area, float *inst_angle, int32_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Dense score maps of `compute_scores=True`.
+ * Replaces: model/postprocessing/panoptic.py:171-239.
+ * Inputs: logits (B,C,H,W); pan_sem / inst (B,H,W) u8 and the per-instance tables from
+ * npb_panoptic_forward.  Outputs (B,H,W) f32: semantic score (soft-max probability of the
+ * pixel's panoptic class, 0 for void), instance score (centre heat of the pixel's instance),
+ * panoptic score (semantic score for stuff, mean semantic score x instance score for things);
+ * per instance [B][256] f32: mean semantic score, panoptic score (-1 = instance dropped).
+ * inst_sum [B][256] f64 is scratch (zeroed by the call).
+ * ------------------------------------------------------------------------- */
+int npb_panoptic_scores(const float *logits, const uint8_t *pan_sem, const uint8_t *inst,
+                        const int32_t *inst_class, const int32_t *inst_area,
+                        const float *center_score, int B, int C, int H, int W, double *inst_sum,
+                        float *sem_score, float *inst_score, float *pan_score,
+                        float *inst_mean_sem, float *inst_pan_score, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Stand-alone deeplab merge for arbitrary semantic / instance / foreground maps.
  * Replaces: deeplab_merge_batch, utils/panoptic_merge.py:18-40, 172-225.
  * sem (B,P) int64 in [0, n_classes) (0 = void), ins (B,P) u8, fg (B,P) u8.

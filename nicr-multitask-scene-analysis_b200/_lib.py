@@ -52,6 +52,8 @@ _SIGNATURES = {
     'npb_panoptic_forward': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_float,
                                      c_int, c_int, c_int, c_int, c_int, c_float, c_int64, _P, _P,
                                      _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'npb_panoptic_scores': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,
+                                    _P, _P, _P, _P]),
     'npb_deeplab_merge_workspace_bytes': (c_size_t, [c_int, c_int]),
     'npb_deeplab_merge': (c_int, [_P, _P, _P, c_int, c_int64, c_int, c_int64, _P, c_int64, _P, _P,
                                   _P, _P, _P, _P, _P]),

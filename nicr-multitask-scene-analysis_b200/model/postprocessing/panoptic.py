@@ -197,32 +197,40 @@ class PanopticPostprocessing(DensePostprocessingBase):
 
     # ------------------------------------------------------------------ optional score maps
     def _add_scores(self, r, logits, pan, pan_sem, tables):
-        """panoptic.py:171-239 (`compute_scores=True`, SURVEY.md section 8(f) item 3, "next"):
-        dense semantic / instance / panoptic score maps and the per-instance score fields.
-        Host-side torch glue over the kernel outputs (not part of the measured hot path)."""
-        probs = r['semantic_softmax_scores']
-        idx = pan_sem.to(torch.int64).unsqueeze(1)
-        void = idx == 0
-        sem_score = torch.take_along_dim(probs, (idx - 1).clamp_(min=0), dim=1)
-        sem_score[void] = 0.0
-        sem_score = sem_score.squeeze(1)
-        inst_score = torch.zeros_like(sem_score)
-        pan_score = sem_score.clone()
-        meta = r['panoptic_segmentation_deeplab_instance_meta']
-        ids = r['panoptic_segmentation_deeplab_ids']
-        for b in range(pan.shape[0]):
-            for pan_id, ins_id in ids[b].items():
-                mask = pan[b] == pan_id
-                score = meta[b][ins_id]['score']
-                inst_score[b][mask] = score
-                mean_sem = torch.mean(sem_score[b][mask])
-                entry = meta[b][ins_id]
-                entry['semantic_score'] = mean_sem.item()
-                entry['semantic_idx'] = int(pan_sem[b][mask][0].item())
-                pscore = mean_sem * score
-                pan_score[b][mask] = pscore
-                entry['panoptic_score'] = pscore.item()
-                entry['panoptic_id'] = pan_id
-        r['panoptic_segmentation_deeplab_semantic_score'] = sem_score
-        r['panoptic_segmentation_deeplab_instance_score'] = inst_score
-        r['panoptic_segmentation_deeplab_panoptic_score'] = pan_score
+        """panoptic.py:171-239 (`compute_scores=True`): dense semantic / instance / panoptic
+        score maps from `npb_panoptic_scores` (csrc/scores.cu) and the per-instance score
+        fields of the meta dicts."""
+        logits = _lib.require_cuda(logits, 'semantic logits', torch.float32, 4)
+        B, C, H, W = logits.shape
+        dev = logits.device
+        inst = r['panoptic_segmentation_deeplab_instance_idx']
+        maps = torch.empty((3, B, H, W), dtype=torch.float32, device=dev)
+        per_inst = torch.empty((2, B, _lib.MAX_INST), dtype=torch.float32, device=dev)
+        inst_sum = torch.empty((B, _lib.MAX_INST), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().npb_panoptic_scores(
+            _lib.ptr(logits), _lib.ptr(pan_sem), _lib.ptr(inst), tables.dptr('inst_class'),
+            tables.dptr('inst_area'), tables.dptr('center_score'), c_int(B), c_int(C), c_int(H),
+            c_int(W), _lib.ptr(inst_sum), _lib.ptr(maps[0]), _lib.ptr(maps[1]), _lib.ptr(maps[2]),
+            _lib.ptr(per_inst[0]), _lib.ptr(per_inst[1]), _lib.stream_ptr(dev)),
+            'npb_panoptic_scores')
+        r['panoptic_segmentation_deeplab_semantic_score'] = maps[0]
+        r['panoptic_segmentation_deeplab_instance_score'] = maps[1]
+        r['panoptic_segmentation_deeplab_panoptic_score'] = maps[2]
+
+        def fill(meta):
+            mean_sem, pan_score = (x.tolist() for x in per_inst.cpu())
+            cls = tables['inst_class']
+            for b, ids_b in enumerate(tables.panoptic_ids()):
+                for pan_id, ins_id in ids_b.items():
+                    entry = meta[b][ins_id]
+                    entry['semantic_score'] = mean_sem[b][ins_id]
+                    entry['semantic_idx'] = int(cls[b, ins_id])
+                    entry['panoptic_score'] = pan_score[b][ins_id]
+                    entry['panoptic_id'] = pan_id
+            return meta
+
+        key = 'panoptic_segmentation_deeplab_instance_meta'
+        if r.is_deferred(key):
+            r.defer(key, lambda: fill(self._meta(r, tables)))
+        else:
+            fill(r[key])

@@ -48,6 +48,18 @@ def _check_meta(ref_meta, got_meta):
             assert tuple(rm[i]['center_yx']) == tuple(gm[i]['center_yx'])
             assert rm[i]['area'] == gm[i]['area']
             assert rm[i]['score'] == pytest.approx(gm[i]['score'], rel=1e-6)
+            for k in ('semantic_score', 'panoptic_score'):      # compute_scores=True
+                if k in rm[i]:
+                    assert gm[i][k] == pytest.approx(rm[i][k], rel=1e-5), (i, k)
+            for k in ('semantic_idx', 'panoptic_id'):
+                if k in rm[i]:
+                    assert gm[i][k] == rm[i][k], (i, k)
+            if 'orientation' in rm[i]:
+                if math.isnan(rm[i]['orientation']):
+                    assert math.isnan(gm[i]['orientation'])
+                else:
+                    assert math.isclose(gm[i]['orientation'], rm[i]['orientation'],
+                                        rel_tol=1e-5, abs_tol=1e-6)
 
 
 def _check_orient(ref, got):
