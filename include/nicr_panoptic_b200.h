@@ -66,6 +66,10 @@ const char *npb_last_cuda_error(void);
 int npb_semantic_argmax(const float *logits, int B, int C, int H, int W,
                         uint8_t *sem_out, float *score_out, void *stream);
 
+/* probs = softmax(logits, dim=1), (B,C,H,W) f32: the `semantic_softmax_scores` entry of
+ * semantic.py:52, 55 (materialised on demand only). */
+int npb_softmax(const float *logits, int B, int C, int H, int W, float *probs, void *stream);
+
 /* ---------------------------------------------------------------------------
  * Crop to the valid region [y0, y0+Hc) x [x0, x0+Wc) and resize to (Hout, Wout).
  * Replaces: DensePostprocessingBase._crop_to_valid_region_and_resize_prediction,

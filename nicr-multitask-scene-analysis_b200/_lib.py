@@ -31,6 +31,7 @@ _SIGNATURES = {
     'npb_error_string': (c_char_p, [c_int]),
     'npb_last_cuda_error': (c_char_p, []),
     'npb_semantic_argmax': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    'npb_softmax': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     'npb_thing_mask': (c_int, [_P, c_int64, c_int, _P, _P, _P]),
     'npb_widen_u8': (c_int, [_P, c_int64, c_int64, _P, _P]),
     'npb_resize_nearest': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -60,9 +60,71 @@ semantic_argmax_kernel(const float *__restrict__ logits, int C, int P,
     }
 }
 
+// soft-max over the class planes (the reference's `semantic_softmax_scores`, semantic.py:52):
+// pass 1 running max + rescaled sum, pass 2 re-reads the (L2 resident) logits and writes the
+// probabilities.  Only launched when somebody reads that (B,C,H,W) entry of the result dict.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+softmax_kernel(const float *__restrict__ logits, int C, int P, float *__restrict__ probs)
+{
+    const int b = blockIdx.y;
+    const int p0 = (blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (p0 >= P) return;
+    const float *lp = logits + (size_t)b * C * P + p0;
+    float *op = probs + (size_t)b * C * P + p0;
+    float mx[VEC], sum[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { mx[j] = __int_as_float(0xff800000); sum[j] = 0.0f; }
+    for (int c = 0; c < C; ++c) {
+        float v[VEC];
+        if (VEC == 4) {
+            const float4 t = *(const float4 *)(lp + (size_t)c * P);
+            v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+        } else {
+            v[0] = lp[(size_t)c * P];
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (v[j] > mx[j]) { sum[j] = sum[j] * expf(mx[j] - v[j]) + 1.0f; mx[j] = v[j]; }
+            else sum[j] += expf(v[j] - mx[j]);
+        }
+    }
+    for (int c = 0; c < C; ++c) {
+        float v[VEC];
+        if (VEC == 4) {
+            const float4 t = *(const float4 *)(lp + (size_t)c * P);
+            v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+            *(float4 *)(op + (size_t)c * P) =
+                make_float4(expf(v[0] - mx[0]) / sum[0], expf(v[1 % VEC] - mx[1 % VEC]) / sum[1 % VEC],
+                            expf(v[2 % VEC] - mx[2 % VEC]) / sum[2 % VEC],
+                            expf(v[3 % VEC] - mx[3 % VEC]) / sum[3 % VEC]);
+        } else {
+            op[(size_t)c * P] = expf(lp[(size_t)c * P] - mx[0]) / sum[0];
+        }
+    }
+}
+
 }  // namespace npb
 
 using namespace npb;
+
+extern "C" int npb_softmax(const float *logits, int B, int C, int H, int W, float *probs,
+                           void *stream)
+{
+    if (!logits || !probs) return NPB_ERR_ARG;
+    if (B < 1 || B > 65535 || C < 1 || H < 1 || W < 1) return NPB_ERR_ARG;
+    if ((long long)H * W >= (1ll << 30)) return NPB_ERR_ARG;
+    const int P = H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P % 4 == 0 && (((uintptr_t)logits | (uintptr_t)probs) & 15u) == 0) {
+        dim3 grid((P / 4 + 255) / 256, B);
+        softmax_kernel<4><<<grid, 256, 0, s>>>(logits, C, P, probs);
+    } else {
+        dim3 grid((P + 255) / 256, B);
+        softmax_kernel<1><<<grid, 256, 0, s>>>(logits, C, P, probs);
+    }
+    return record_launch("npb_softmax");
+}
 
 extern "C" int npb_semantic_argmax(const float *logits, int B, int C, int H, int W,
                                    uint8_t *sem_out, float *score_out, void *stream)

@@ -28,6 +28,17 @@ def semantic_argmax(logits: torch.Tensor, with_score: bool = False):
     return sem, score
 
 
+def softmax_scores(logits: torch.Tensor) -> torch.Tensor:
+    """softmax over the class axis of (B,C,H,W) f32 logits (`npb_softmax`)."""
+    logits = _lib.require_cuda(logits, 'semantic logits', torch.float32, 4)
+    B, C, H, W = logits.shape
+    probs = torch.empty_like(logits)
+    _lib.check(_lib.lib().npb_softmax(_lib.ptr(logits), c_int(B), c_int(C), c_int(H), c_int(W),
+                                      _lib.ptr(probs), _lib.stream_ptr(logits.device)),
+               'npb_softmax')
+    return probs
+
+
 def semantic_argmax_resized(logits: torch.Tensor, crop_geometry, shape):
     """Bilinear resize (align_corners=False) of the cropped logits to `shape` fused with the
     arg-max: -> (classes uint8 (B,h,w), score f32 (B,h,w)); `npb_semantic_argmax_resized`."""
@@ -80,7 +91,7 @@ class SemanticPostprocessing(DensePostprocessingBase):
             return cache['score']
 
         r['_semantic_segmentation_idx_u8'] = classes() if sem_u8 is None else sem_u8
-        r.defer('semantic_softmax_scores', lambda: torch.softmax(logits, dim=1))
+        r.defer('semantic_softmax_scores', lambda: softmax_scores(logits))
         r.defer('semantic_segmentation_score', score)
         r.defer('semantic_segmentation_idx', lambda: widen_u8(classes()))
 
@@ -109,7 +120,7 @@ class SemanticPostprocessing(DensePostprocessingBase):
                 return fcache['logits']
 
             r.defer('semantic_output_fullres', full_logits)
-            r.defer('semantic_softmax_scores_fullres', lambda: torch.softmax(full_logits(), dim=1))
+            r.defer('semantic_softmax_scores_fullres', lambda: softmax_scores(full_logits()))
             r.defer('semantic_segmentation_score_fullres', lambda: full_pair()['score'])
             r.defer('semantic_segmentation_idx_fullres', lambda: widen_u8(full_pair()['sem']))
         return r

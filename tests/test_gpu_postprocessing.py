@@ -132,6 +132,9 @@ def test_result_keys_like_reference(cuda_device):
         assert k in list(r.keys()), k
     r.materialize()
     assert r['semantic_softmax_scores'].shape == z['logits'].shape
+    np.testing.assert_allclose(r['semantic_softmax_scores'].cpu().numpy(),
+                               torch.softmax(torch.from_numpy(z['logits']), dim=1).numpy(),
+                               rtol=1e-5, atol=1e-8)
 
 
 def test_centers_tie_cases(cuda_device):
