@@ -251,6 +251,7 @@ def run_ours(args):
         n_warm += 1
         if n_warm % 16 == 0:
             torch.cuda.synchronize(dev)
+    evaluation.compute(suffix='_deeplab')   # warm-up of the metric all-reduce (NCCL connections)
     evaluation.reset()
     barrier()
 
