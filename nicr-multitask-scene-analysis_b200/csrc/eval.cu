@@ -19,6 +19,8 @@
 // the reference's visiting order, which fixes the float64 summation order;
 // accumulate_frames_kernel adds the frames to the running state in frame order.  Both float64 orders equal the reference's, so the
 // states are bit-identical, not merely close.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace npb {
@@ -709,6 +711,14 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     occ_smem[variant] = pc_smem;
     occ_blocks[variant] = per_sm;
     }
+    // NPB_PAIR_CTAS_PER_SM=<n> caps the residency of the pixel pass, leaving registers / shared
+    // memory for kernels of another stream (evaluation overlapped with the next batch)
+    static int env_cap = -1;
+    if (env_cap < 0) {
+        const char *e = getenv("NPB_PAIR_CTAS_PER_SM");
+        env_cap = e ? atoi(e) : 0;
+    }
+    if (env_cap > 0 && per_sm > env_cap) per_sm = env_cap;
     long long bx = ((long long)n_sm * per_sm) / B;
     if (bx < 1) bx = 1;
     if (bx > n_chunks) bx = n_chunks;
