@@ -299,6 +299,7 @@ struct MatchParams {
     const unsigned *frame_cnts;
     int num_categories;
     long long ignored_label, L, offset, void_segment_id;
+    int L_shift, O_shift;  // >= 0 when L / offset are powers of two (shifts instead of 64-bit divisions)
     double *frame_stats;   // [B][4][num_categories]
     long long *matches;    // [B][match_cap][2] nullable
     int match_cap;
@@ -320,6 +321,11 @@ struct SegTable {
     unsigned *pio;            // pred: pixels inside ignored gt segments
     unsigned *matched;        // 1 once the segment took part in a match
 };
+
+__device__ __forceinline__ long long div_pow2(long long v, long long d, int shift)
+{
+    return shift >= 0 ? (v >> shift) : (v / d);     // v is validated non-negative
+}
 
 // returns the slot of `id` (inserting it), or -1 when the table is full
 __device__ __forceinline__ int seg_slot(SegTable &tb, unsigned long long id)
@@ -354,6 +360,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     unsigned *p_matched = p_pio + kSegSlots;
     unsigned short *s_gslot = (unsigned short *)(p_matched + kSegSlots);   // [kMaxPairs]
     unsigned short *s_pslot = s_gslot + kMaxPairs;                         // [kMaxPairs]
+    unsigned short *s_mcat = s_pslot + kMaxPairs;                          // [kMaxMatched]
     __shared__ int s_m, s_nm;
     __shared__ int s_tp[256], s_fn[256], s_fp[256];
 
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     for (int t = tid; t < m; t += kMatchThreads) {
         const long long key = s_key[t];
         const unsigned cnt = s_cnt[t];
-        const long long g = key / prm.offset;       // ids are validated non-negative
+        const long long g = div_pow2(key, prm.offset, prm.O_shift);
         const long long p = key - g * prm.offset;
         const int gs = seg_slot(gt, (unsigned long long)g);
         const int ps = seg_slot(pt, (unsigned long long)p);
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         atomicAdd(g_area + gs, cnt);
         atomicAdd(p_area + ps, cnt);
         if (g == prm.void_segment_id) p_void[ps] = cnt;     // key == void*offset + p, unique
-        if (g / prm.L == prm.ignored_label) atomicAdd(p_pio + ps, cnt);
+        if (div_pow2(g, prm.L, prm.L_shift) == prm.ignored_label) atomicAdd(p_pio + ps, cnt);
     }
     __syncthreads();
 
@@ -422,8 +429,8 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     for (int t = tid; t < m; t += kMatchThreads) {
         const long long key = s_key[t];
         if (key == prm.void_segment_id) continue;                          // pq.py:120
-        const long long g = key / prm.offset, p = key - g * prm.offset;
-        const long long gcat = g / prm.L, pcat = p / prm.L;
+        const long long g = div_pow2(key, prm.offset, prm.O_shift), p = key - g * prm.offset;
+        const long long gcat = div_pow2(g, prm.L, prm.L_shift), pcat = div_pow2(p, prm.L, prm.L_shift);
         if (gcat != pcat) continue;                                        // pq.py:128
         const int gs = s_gslot[t], ps = s_pslot[t];
         const long long ia = s_cnt[t];
@@ -441,6 +448,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
                 s_mkey[slot] = key;
                 s_mia[slot] = (unsigned)ia;
                 s_muni[slot] = (unsigned)uni;
+                s_mcat[slot] = (unsigned short)gcat;
             } else {
                 set_status(prm.status + b, NPB_ERR_CAPACITY);
             }
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     //     in ignored gt segments                                            pq.py:165-177
     for (int i = tid; i < kSegSlots; i += kMatchThreads) {
         if (g_id[i] != kEmptyKey && !g_matched[i]) {
-            const long long cat = (long long)g_id[i] / prm.L;
+            const long long cat = div_pow2((long long)g_id[i], prm.L, prm.L_shift);
             if (cat != prm.ignored_label) {
                 if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                 else atomicAdd(&s_fn[(int)cat], 1);
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         }
         if (p_id[i] != kEmptyKey && !p_matched[i]) {
             if (!((double)p_pio[i] / (double)p_area[i] > 0.5)) {
-                const long long cat = (long long)p_id[i] / prm.L;
+                const long long cat = div_pow2((long long)p_id[i], prm.L, prm.L_shift);
                 if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                 else atomicAdd(&s_fp[(int)cat], 1);
             }
@@ -495,6 +503,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
                         s_mkey[i] = a1; s_mkey[ixj] = a0;
                         unsigned x = s_mia[i]; s_mia[i] = s_mia[ixj]; s_mia[ixj] = x;
                         x = s_muni[i]; s_muni[i] = s_muni[ixj]; s_muni[ixj] = x;
+                        const unsigned short cc = s_mcat[i]; s_mcat[i] = s_mcat[ixj]; s_mcat[ixj] = cc;
                     }
                 }
             }
@@ -505,8 +514,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         double acc = 0.0;
         if (c < 256 && s_tp[c] > 0)
             for (int i = 0; i < nm; ++i)
-                if ((s_mkey[i] / prm.offset) / prm.L == c)
-                    acc += (double)s_mia[i] / (double)s_muni[i];
+                if (s_mcat[i] == c) acc += (double)s_mia[i] / (double)s_muni[i];
         double *fs = prm.frame_stats + (size_t)b * 4 * NC;
         fs[c] = acc;
         fs[NC + c] = c < 256 ? (double)s_tp[c] : 0.0;
@@ -593,7 +601,7 @@ confmat_kernel(const void *__restrict__ preds, int pd, const void *__restrict__ 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t match_smem_bytes()
 {
-    return (size_t)kMaxPairs * (8 + 4 + 2 + 2) + (size_t)kMaxMatched * (8 + 4 + 4) +
+    return (size_t)kMaxPairs * (8 + 4 + 2 + 2) + (size_t)kMaxMatched * (8 + 4 + 4 + 2) +
            (size_t)kSegSlots * (8 + 8 + 6 * 4) + 16;
 }
 
@@ -735,6 +743,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     mp.frame_keys = fkeys; mp.frame_cnts = fcnts; mp.num_categories = num_categories;
     mp.ignored_label = ignored_label; mp.L = max_instances_per_category; mp.offset = offset;
     mp.void_segment_id = void_segment_id; mp.frame_stats = fstats;
+    mp.L_shift = pp.L_shift; mp.O_shift = pp.O_shift;
     mp.matches = (long long *)matches; mp.match_cap = match_cap; mp.n_matches = n_matches;
     mp.status = status;
     static bool attr_set = false;
