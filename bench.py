@@ -89,7 +89,7 @@ class ClockSampler:
                                       '--format=csv,noheader,nounits'], capture_output=True,
                                      text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([x.strip() for x in out.split(',')])
+                    self.samples.append((time.perf_counter(), [x.strip() for x in out.split(',')]))
             except Exception:
                 pass
             self._stop.wait(0.05)
@@ -102,14 +102,22 @@ class ClockSampler:
         self._stop.set()
         self._thread.join(timeout=6)
 
-    def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = max((int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()), default=None)
+    def summary(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples taken inside [t0, t1] (the timed
+        region).  When the timed region is too short to hold 3 samples, the samples of the
+        steady-state warm-up that ran the identical load right before it are used as well."""
+        inside = [f for t, f in self.samples if t0 is None or t0 <= t <= t1]
+        window = 'timed region'
+        if len(inside) < 3:
+            inside = [f for _, f in self.samples]
+            window = 'steady-state warm-up (same load) + timed region'
+        sm = sorted(int(s[0]) for s in inside if s and s[0].isdigit())
+        mx = max((int(s[1]) for s in inside if len(s) > 1 and s[1].isdigit()), default=None)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6])
+        reasons = sorted({n for s in inside for n, v in zip(names, s[2:6])
                           if v.lower().startswith('active')})
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': reasons,
-                'samples': len(self.samples)}
+                'samples': len(inside), 'window': window}
 
 
 def oracle_baseline(sample_frames, steps, warmup, threads=None):
@@ -244,6 +252,8 @@ def run_ours(args):
 
     # W warm-up steps (at least 3), extended until the GPU has been busy for ~1 s so that the
     # timed region sees steady-state clocks even when it is only a few milliseconds long
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
     t_warm = time.perf_counter()
     n_warm = 0
     while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm < 1.0:
@@ -257,14 +267,16 @@ def run_ours(args):
 
     # ---- timed region: device-resident inputs ------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            last = step()
-        results = evaluation.compute(suffix='_deeplab')        # one all-reduce of the states
-        e1.record()
-        barrier()
+    barrier()
+    region0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        last = step()
+    results = evaluation.compute(suffix='_deeplab')        # one all-reduce of the states
+    e1.record()
+    barrier()
+    region1 = time.perf_counter()
+    clocks.__exit__(None, None, None)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -361,7 +373,7 @@ def run_ours(args):
                        'l2_policy': f'inputs ({B * bytes_post_per_frame(C, H, W, ORI) / 1e9:.1f} GB per step) '
                                     'larger than L2, no flush needed',
                        'launch': 'eager' if args.no_graph else 'cuda graph replay'},
-            'clocks': clocks.summary(),
+            'clocks': clocks.summary(region0, region1),
             'e2e': e2e,
             'gpu_launches': KERNELS_PER_STEP * args.steps,
             'roofline': {'bound': 'hbm', 'kernel': 'group_pixels_kernel<4,logits,%s>' % ('orientation' if ORI else 'no orientation'),
@@ -389,7 +401,7 @@ def main():
                     help='BASELINE.json shape (default: configs[1], the metric\'s configuration)')
     ap.add_argument('--frames', type=int, default=0, help='override frames per GPU per step')
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
