@@ -688,23 +688,32 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
                            (size_t)pp.nd * pp.nd * sizeof(unsigned) +
                            ((confmat && confmat_n <= kSmemConfmatMaxN)
                                 ? (size_t)confmat_n * confmat_n * sizeof(unsigned) : 0) + 16;
-    static bool pc_attr_set = false;
-    static int n_sm = 148;
+    // one process may drive several devices: function attributes and the SM count are per device
+    static bool pc_attr_set_dev[64] = {false};
+    static int n_sm_dev[64];
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    const int dslot = cur_dev & 63;
+    bool &pc_attr_set = pc_attr_set_dev[dslot];
+    int &n_sm = n_sm_dev[dslot];
     if (!pc_attr_set) {
         const int mx = 200 * 1024;
         cudaFuncSetAttribute(pair_count_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(pair_count_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(pair_count_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(pair_count_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cur_dev);
+        cudaFuncSetAttribute(match_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)match_smem_bytes());
         pc_attr_set = true;
     }
     // persistent CTAs: the whole batch in ONE wave (a second, partial wave would leave most SMs
     // idle for the length of a CTA), every CTA of a frame gets the same number of chunks
-    static size_t occ_smem[4] = {0, 0, 0, 0};
-    static int occ_blocks[4] = {0, 0, 0, 0};
+    static size_t occ_smem_dev[64][4] = {{0}};
+    static int occ_blocks_dev[64][4] = {{0}};
+    size_t *occ_smem = occ_smem_dev[dslot];
+    int *occ_blocks = occ_blocks_dev[dslot];
     const int variant = (confmat ? 2 : 0) + (vec4 ? 1 : 0);
     int per_sm = occ_blocks[variant];
     if (per_sm == 0 || occ_smem[variant] != pc_smem) {
@@ -746,12 +755,6 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     mp.L_shift = pp.L_shift; mp.O_shift = pp.O_shift;
     mp.matches = (long long *)matches; mp.match_cap = match_cap; mp.n_matches = n_matches;
     mp.status = status;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(match_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)match_smem_bytes());
-        attr_set = true;
-    }
     match_frames_kernel<<<B, kMatchThreads, match_smem_bytes(), s>>>(mp);
     accumulate_frames_kernel<<<(4 * num_categories * 32 + 127) / 128, 128, 0, s>>>(fstats, B, num_categories,
                                                                          iou, tp, fn, fp);

@@ -27,11 +27,13 @@ def _safe_divide(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
 class _PQKernel:
     """Workspace + launch helper shared by PanopticQuality and compare_and_accumulate."""
 
-    _scratch = {}      # (device, B, num_categories) -> reusable workspace (stream ordered)
+    _scratch = {}      # (device, stream, B, num_categories) -> reusable workspace
 
     @classmethod
     def _workspace(cls, dev, B, num_categories):
-        key = (dev, B, num_categories)
+        # scratch only lives for the duration of one call, so calls issued on the same stream
+        # can share it; calls on different streams get their own
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream, B, num_categories)
         if key not in cls._scratch:
             nbytes = _lib.lib().npb_pq_update_workspace_bytes(B, num_categories)
             cls._scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)

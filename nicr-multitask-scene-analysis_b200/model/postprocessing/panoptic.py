@@ -4,8 +4,9 @@
 `_postprocess_inference` issues ONE C-ABI call, `npb_panoptic_forward`, which enqueues
     centre NMS/top-k  ->  fused arg-max + offset grouping + votes + orientation sums
     ->  per-frame instance table  ->  panoptic id map
-on the current CUDA stream, followed by one asynchronous device->host copy of the packed
-per-instance tables from which the python dicts of the reference API are built.
+on the current CUDA stream; the packed per-instance tables reach the host in one copy when the
+python dicts of the reference API are built (immediately, or on first access with
+`async_results=True`).
 
 Differences to the reference that a caller can observe (all documented in DESIGN.md):
   * dense outputs stay on the CUDA device (the reference moves the panoptic outputs to the
@@ -54,7 +55,7 @@ class PanopticPostprocessing(DensePostprocessingBase):
         self._compute_scores = compute_scores
         self._max_instances_per_category = 1 << 16
         self._async_results = bool(kwargs.get('async_results', False))
-        self._ws = None
+        self._ws = {}
 
     @property
     def max_instances_per_category(self):
@@ -85,10 +86,12 @@ class PanopticPostprocessing(DensePostprocessingBase):
         ks = post._heatmap_nms_kernel_size
         # scratch (candidate lists, vote histograms, orientation sums) is reused across calls:
         # the calls are ordered on the stream, nothing in it outlives a call
+        # (one scratch buffer per stream: calls on different streams may run concurrently)
         ws_bytes = L.npb_panoptic_forward_workspace_bytes(B, C, H, W, ks)
-        if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
-            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        ws = self._ws
+        ws_key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._ws.get(ws_key)
+        if ws is None or ws.numel() < ws_bytes:
+            ws = self._ws[ws_key] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         # all outputs of a call live in ONE fresh allocation: [pan i64 | tables | sem | inst | pan_sem]
         P = H * W
         _, tab_bytes = InstanceTables.layout(B)
