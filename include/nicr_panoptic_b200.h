@@ -225,6 +225,21 @@ int npb_deeplab_merge(const int64_t *sem, const uint8_t *ins, const uint8_t *fg,
                       int32_t *inst_area, int32_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Ground-truth panoptic targets ("naive" merge: every (instance, class) part gets its own id).
+ * Replaces: naive_merge_semantic_and_instance_np, utils/panoptic_merge.py:43-107, i.e. the body
+ *           of PanopticTargetGenerator (data/preprocessing/panoptic.py:16-85).
+ * sem (B,P) u8 (0 = void), ins (B,P) i32 ids in [0, 65535]; h_thing_lut [n_classes].
+ * Outputs: pan_out (B,P) i64; per frame the sorted parts: part_keys_out [B][4096] u32
+ * (instance << 16 | class), part_pan_out [B][4096] i64 (their panoptic ids), n_parts [B].
+ * status [1].
+ * ------------------------------------------------------------------------- */
+size_t npb_naive_merge_workspace_bytes(int B);
+int npb_naive_merge(const uint8_t *sem, const int32_t *ins, int B, int64_t P,
+                    int64_t max_instances_per_category, const uint8_t *h_thing_lut, int n_classes,
+                    int64_t void_label, void *workspace, int64_t *pan_out, uint32_t *part_keys_out,
+                    int64_t *part_pan_out, int32_t *n_parts, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Stand-alone per-instance orientation for arbitrary instance maps.
  * Replaces: InstancePostprocessing._get_instance_orientation, instance.py:270-319.
  * orientation (B,2,P) f32, seg (B,P) of dtype seg_dtype (NPB_U8 / NPB_I32 / NPB_I64),

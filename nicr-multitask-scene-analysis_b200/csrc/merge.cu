@@ -280,3 +280,185 @@ extern "C" int npb_deeplab_merge(const int64_t *sem, const uint8_t *ins, const u
                                             (long long)void_label, d_lut, pan_out);
     return record_launch("npb_deeplab_merge");
 }
+
+// ---- naive merge: ground-truth panoptic targets ----------------------------------------------
+// Replaces naive_merge_semantic_and_instance_np (reference: utils/panoptic_merge.py:43-107), the
+// body of PanopticTargetGenerator (data/preprocessing/panoptic.py:16-85):
+//   :64-90   for instance ids ascending, for the semantic classes present inside the instance
+//            ascending (void skipped): number = ++counter[class]; pan id = class * L + number;
+//            every (instance, class) part gets its own id; id_dict[pan id] = instance id
+//   :93-105  every non-void, non-thing class c: pan[(sem == c) & (ins == 0)] = c * L
+// Instance ids are arbitrary (uint16 in the datasets), so the (instance, class) parts of a frame
+// are collected in a per-frame hash table (pixel pass 1), sorted and numbered by one CTA per
+// frame, and looked up again by pixel pass 2.
+namespace npb {
+
+constexpr int kPartSlots = 8192;     // (instance, class) parts per frame: <= 4096
+constexpr int kMaxParts = 4096;
+
+__device__ __forceinline__ unsigned hash32(unsigned h)
+{
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+
+// sem (B,P) u8 classes, ins (B,P) i32 ids in [0, 65535]; part key = ins << 16 | class
+__global__ void __launch_bounds__(256)
+naive_parts_kernel(const uint8_t *__restrict__ sem, const int32_t *__restrict__ ins, long long P,
+                   unsigned *__restrict__ part_keys, int32_t *__restrict__ status)
+{
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    unsigned *keys = part_keys + (size_t)b * kPartSlots;
+    const long long stride = (long long)gridDim.x * 256;
+    const long long n_round = ((P + 31) / 32) * 32;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n_round; p += stride) {
+        unsigned key = 0xffffffffu;
+        if (p < P) {
+            const size_t q = (size_t)b * P + p;
+            const int id = ins[q];
+            const unsigned c = sem[q];
+            if (id < 0 || id > 65535) set_status(status, NPB_ERR_CATEGORY_RANGE);
+            else if (id != 0 && c != 0) key = ((unsigned)id << 16) | c;
+        }
+        // one insert per distinct key of the warp
+        const unsigned peers = __match_any_sync(kFullMask, key);
+        if (key != 0xffffffffu && lane == __ffs(peers) - 1) {
+            unsigned h = hash32(key) & (kPartSlots - 1);
+            bool done = false;
+            for (int probe = 0; probe < kPartSlots && !done; ++probe) {
+                unsigned k = keys[h];
+                if (k == 0xffffffffu) k = atomicCAS(keys + h, 0xffffffffu, key);
+                done = (k == 0xffffffffu || k == key);
+                h = (h + 1) & (kPartSlots - 1);
+            }
+            if (!done) set_status(status, NPB_ERR_CAPACITY);
+        }
+    }
+}
+
+// one CTA per frame: sort the parts (instance major, class minor), number them per class in
+// that order; part_keys is rewritten as a sorted list, part_pan holds the ids, n_parts the count
+__global__ void __launch_bounds__(512)
+naive_number_kernel(unsigned *__restrict__ part_keys, long long *__restrict__ part_pan,
+                    int32_t *__restrict__ n_parts, long long L, int32_t *__restrict__ status)
+{
+    __shared__ unsigned s_key[kMaxParts];
+    __shared__ int s_m;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    unsigned *keys = part_keys + (size_t)b * kPartSlots;
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    for (int i = tid; i < kPartSlots; i += 512) {
+        const unsigned k = keys[i];
+        if (k != 0xffffffffu) {
+            const int slot = atomicAdd(&s_m, 1);
+            if (slot < kMaxParts) s_key[slot] = k;
+        }
+    }
+    __syncthreads();
+    int m = s_m;
+    if (m > kMaxParts) {
+        if (tid == 0) set_status(status, NPB_ERR_CAPACITY);
+        m = kMaxParts;
+    }
+    int npad = 1;
+    while (npad < m) npad <<= 1;
+    for (int i = m + tid; i < npad; i += 512) s_key[i] = 0xffffffffu;
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += 512) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = ((i & k) == 0);
+                    const unsigned a = s_key[i], c = s_key[ixj];
+                    if ((a > c) == up) { s_key[i] = c; s_key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = tid; t < kPartSlots; t += 512) keys[t] = t < m ? s_key[t] : 0xffffffffu;
+    for (int t = tid; t < m; t += 512) {
+        const unsigned cls = s_key[t] & 0xffffu;
+        int number = 1;
+        for (int u = 0; u < t; ++u) number += ((s_key[u] & 0xffffu) == cls);
+        part_pan[(size_t)b * kMaxParts + t] = (long long)cls * L + number;
+    }
+    if (tid == 0) n_parts[b] = m;
+}
+
+__global__ void __launch_bounds__(256)
+naive_write_kernel(const uint8_t *__restrict__ sem, const int32_t *__restrict__ ins, long long P,
+                   const unsigned *__restrict__ part_keys, const long long *__restrict__ part_pan,
+                   const int32_t *__restrict__ n_parts, long long L, long long void_label,
+                   ClassSet thing, int64_t *__restrict__ pan_out)
+{
+    const int b = blockIdx.y;
+    const unsigned *keys = part_keys + (size_t)b * kPartSlots;      // sorted, n_parts[b] entries
+    const long long *pans = part_pan + (size_t)b * kMaxParts;
+    const int m = n_parts[b];
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += stride) {
+        const size_t q = (size_t)b * P + p;
+        const int id = ins[q];
+        const unsigned c = sem[q];
+        long long v = void_label;
+        if (id != 0) {
+            if (c != 0) {
+                const unsigned key = ((unsigned)id << 16) | c;
+                int lo = 0, hi = m - 1;
+                while (lo < hi) {               // the part exists by construction
+                    const int mid = (lo + hi) >> 1;
+                    if (keys[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                v = pans[lo];
+            }
+        } else if (c != 0 && !thing.has((int)c)) {
+            v = (long long)c * L;
+        }
+        pan_out[q] = v;
+    }
+}
+
+}  // namespace npb
+
+extern "C" size_t npb_naive_merge_workspace_bytes(int B)
+{
+    return ((size_t)B * npb::kPartSlots * sizeof(unsigned) + 255) & ~(size_t)255;
+}
+
+extern "C" int npb_naive_merge(const uint8_t *sem, const int32_t *ins, int B, int64_t P,
+                               int64_t max_instances_per_category, const uint8_t *h_thing_lut,
+                               int n_classes, int64_t void_label, void *workspace, int64_t *pan_out,
+                               uint32_t *part_keys_out, int64_t *part_pan_out, int32_t *n_parts,
+                               int32_t *status, void *stream)
+{
+    using namespace npb;
+    if (!sem || !ins || !workspace || !pan_out || !part_keys_out || !part_pan_out || !n_parts ||
+        !status || !h_thing_lut)
+        return NPB_ERR_ARG;
+    if (B < 1 || B > 65535 || P < 1 || n_classes < 1 || n_classes > 256 ||
+        max_instances_per_category < 1)
+        return NPB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned *keys = (unsigned *)workspace;
+    cudaMemsetAsync(keys, 0xff, (size_t)B * kPartSlots * sizeof(unsigned), s);
+    long long bx = (P + 256 * 8 - 1) / (256 * 8);
+    if (bx > 148 * 8 / B + 1) bx = 148 * 8 / B + 1;
+    dim3 grid((unsigned)bx, B);
+    naive_parts_kernel<<<grid, 256, 0, s>>>(sem, ins, (long long)P, keys, status);
+    naive_number_kernel<<<B, 512, 0, s>>>(keys, (long long *)part_pan_out, n_parts,
+                                          (long long)max_instances_per_category, status);
+    naive_write_kernel<<<grid, 256, 0, s>>>(sem, ins, (long long)P, keys,
+                                            (const long long *)part_pan_out, n_parts,
+                                            (long long)max_instances_per_category,
+                                            (long long)void_label,
+                                            make_class_set(h_thing_lut, n_classes), pan_out);
+    // sorted keys (instance << 16 | class) of the first kMaxParts slots are the id-dict source
+    cudaMemcpy2DAsync(part_keys_out, (size_t)kMaxParts * sizeof(unsigned), keys,
+                      (size_t)kPartSlots * sizeof(unsigned), (size_t)kMaxParts * sizeof(unsigned),
+                      (size_t)B, cudaMemcpyDeviceToDevice, s);
+    return record_launch("npb_naive_merge");
+}

@@ -55,3 +55,48 @@ def deeplab_merge_batch(
     ids = [{int(pan_h[b, i]): i for i in range(1, _lib.MAX_INST) if cls_h[b, i] >= 0}
            for b in range(B)]
     return pan, ids
+
+
+PART_CAP = 4096     # (instance, class) parts per frame (kMaxParts in csrc/merge.cu)
+
+
+def naive_merge_semantic_and_instance_batch(
+    semantic_batch: torch.Tensor,
+    instance_batch: torch.Tensor,
+    max_instances_per_category: int,
+    thing_ids: Sequence[int],
+    void_label: int
+) -> Tuple[torch.Tensor, List[Dict[int, int]]]:
+    """Ground-truth panoptic targets for a batch: the batched GPU form of
+    `naive_merge_semantic_and_instance_np` (utils/panoptic_merge.py:43-107), which
+    `PanopticTargetGenerator` (data/preprocessing/panoptic.py:16-85) applies per sample.
+    `semantic_batch` (B,H,W) integer classes in [0, 255] (0 = void), `instance_batch` (B,H,W)
+    integer ids in [0, 65535].  Returns (panoptic ids int64 (B,H,W), list of
+    {panoptic id: instance id}) -- `panoptic` and `panoptic_ids_to_instance_dict` of a batch."""
+    if not semantic_batch.is_cuda:
+        raise RuntimeError('naive_merge_semantic_and_instance_batch: expected CUDA tensors')
+    dev = semantic_batch.device
+    sem = _lib.require_cuda(semantic_batch.to(torch.uint8), 'semantic_batch', ndim=3)
+    ins = _lib.require_cuda(instance_batch.to(dev).to(torch.int32), 'instance_batch', ndim=3)
+    B = sem.shape[0]
+    P = sem[0].numel()
+    thing_ids = [int(t) for t in thing_ids]
+    n_classes = 256
+    lut = _lib.host_lut([c in thing_ids for c in range(n_classes)], n_classes)
+    L = _lib.lib()
+    ws = torch.empty(L.npb_naive_merge_workspace_bytes(B), dtype=torch.uint8, device=dev)
+    pan = torch.empty(sem.shape, dtype=torch.int64, device=dev)
+    part_keys = torch.empty((B, PART_CAP), dtype=torch.int32, device=dev)
+    part_pan = torch.empty((B, PART_CAP), dtype=torch.int64, device=dev)
+    n_parts = torch.empty(B, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.npb_naive_merge(
+        _lib.ptr(sem), _lib.ptr(ins), c_int(B), c_int64(P), c_int64(max_instances_per_category),
+        lut, c_int(n_classes), c_int64(void_label), _lib.ptr(ws), _lib.ptr(pan),
+        _lib.ptr(part_keys), _lib.ptr(part_pan), _lib.ptr(n_parts), _lib.ptr(status),
+        _lib.stream_ptr(dev)), 'npb_naive_merge')
+    _lib.raise_for_status(status.cpu().tolist(), 'naive_merge_semantic_and_instance_batch')
+    n_h, keys_h, pan_h = n_parts.cpu().tolist(), part_keys.cpu(), part_pan.cpu()
+    ids = [{int(pan_h[b, t]): (int(keys_h[b, t]) >> 16) & 0xffff for t in range(n_h[b])}
+           for b in range(B)]
+    return pan, ids

@@ -142,6 +142,26 @@ def deeplab_merge_batch(semantic, instance, instance_fg, max_instances_per_categ
     return pan, dicts
 
 
+def naive_merge_batch(semantic, instance, max_instances_per_category, thing_ids, void_label,
+                      cap=4096) -> Tuple[np.ndarray, List[Dict[int, int]]]:
+    """utils/panoptic_merge.py:43-107 for a batch."""
+    sem = _c(semantic, np.uint8)
+    ins = _c(instance, np.int32)
+    B = sem.shape[0]
+    P = int(np.prod(sem.shape[1:]))
+    thing = np.zeros((256,), np.uint8)
+    thing[np.asarray(list(thing_ids), dtype=np.int64)] = 1
+    pan = np.empty(sem.shape, np.int64)
+    pairs = np.zeros((B, cap, 2), np.int64)
+    n_pairs = np.zeros((B,), np.int32)
+    _check(lib().orc_naive_merge_batch(_p(sem), _p(ins), c_int(B), c_long(P),
+                                       c_int64(max_instances_per_category), _p(thing),
+                                       c_int64(void_label), _p(pan), _p(pairs), c_int(cap),
+                                       _p(n_pairs)))
+    return pan, [{int(pairs[b, i, 0]): int(pairs[b, i, 1]) for i in range(n_pairs[b])}
+                 for b in range(B)]
+
+
 def instance_orientation(orientation, instance_segmentation, foreground_mask=None
                          ) -> List[Dict[int, float]]:
     """instance.py:270-319."""

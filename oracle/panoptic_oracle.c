@@ -367,6 +367,58 @@ int orc_deeplab_merge_batch(const int32_t *sem, const uint8_t *ins, const uint8_
 }
 
 /* ------------------------------------------------------------------------ */
+/* naive merge (ground-truth targets)  utils/panoptic_merge.py:43-107           */
+/*  instance ids ascending, inside each the present classes ascending (void     */
+/*  skipped): number = ++counter[class]; pan = class*L + number on the part;    */
+/*  then every non-void non-thing class c: pan[(sem==c)&(ins==0)] = c*L         */
+/* sem [B][P] u8, ins [B][P] i32 in [0,65535]; id_pairs [B][cap][2] (pan, ins)  */
+/* ------------------------------------------------------------------------ */
+int orc_naive_merge_batch(const uint8_t *sem, const int32_t *ins, int B, long P, int64_t L,
+                          const uint8_t *thing_lut /* [256] */, int64_t void_label, int64_t *pan,
+                          int64_t *id_pairs, int cap, int32_t *n_pairs)
+{
+    int status = ORC_OK;
+    for (int b = 0; b < B; ++b) {
+        const uint8_t *sb = sem + (size_t)b * P;
+        const int32_t *ib = ins + (size_t)b * P;
+        int64_t *pb = pan + (size_t)b * P;
+        /* presence of (instance, class) parts */
+        uint8_t *present = (uint8_t *)calloc((size_t)65536 * 256, 1);
+        for (long p = 0; p < P; ++p) {
+            if (ib[p] < 0 || ib[p] > 65535) { free(present); return ORC_ERR_CATEGORY_RANGE; }
+            present[(size_t)ib[p] * 256 + sb[p]] = 1;
+        }
+        int64_t *part_pan = (int64_t *)calloc((size_t)65536 * 256, sizeof(int64_t));
+        int64_t counter[256] = {0};
+        int np = 0;
+        for (int id = 1; id < 65536; ++id) {
+            for (int c = 1; c < 256; ++c) {
+                if (!present[(size_t)id * 256 + c]) continue;
+                counter[c] += 1;
+                const int64_t v = (int64_t)c * L + counter[c];
+                part_pan[(size_t)id * 256 + c] = v;
+                if (np < cap) { id_pairs[((size_t)b * cap + np) * 2] = v; id_pairs[((size_t)b * cap + np) * 2 + 1] = id; }
+                ++np;
+            }
+        }
+        n_pairs[b] = np;
+        if (np > cap) status = ORC_ERR_CAPACITY;
+        for (long p = 0; p < P; ++p) {
+            int64_t v = void_label;
+            if (ib[p] != 0) {
+                if (sb[p] != 0) v = part_pan[(size_t)ib[p] * 256 + sb[p]];
+            } else if (sb[p] != 0 && !thing_lut[sb[p]]) {
+                v = (int64_t)sb[p] * L;
+            }
+            pb[p] = v;
+        }
+        free(present);
+        free(part_pan);
+    }
+    return status;
+}
+
+/* ------------------------------------------------------------------------ */
 /* a6  per-instance orientation  model/postprocessing/instance.py:270-319     */
 /*  :301-313 for every instance id != 0 present inside the mask:              */
 /*     v = sum(orientation[:, mask & seg==id])  (f32 sum in ATen; order-      */

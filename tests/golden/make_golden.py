@@ -193,6 +193,28 @@ def run_merge():
     print('merge', [len(d) for d in ids])
 
 
+def run_naive_merge():
+    """ground-truth targets: naive_merge_semantic_and_instance_np (panoptic_merge.py:43-107),
+    the body of PanopticTargetGenerator; uint16 instance ids up to 65535, instances that span
+    several classes, void inside instances."""
+    from nicr_mt_scene_analysis.utils.panoptic_merge import naive_merge_semantic_and_instance_np
+    g = torch.Generator().manual_seed(23)
+    B, H, W = 3, 60, 84
+    sem = blocky(g, B, H, W, 9, 9).numpy().astype(np.uint8)
+    ins = blocky(g, B, H, W, 12, 14).numpy().astype(np.uint16)
+    ins[ins == 7] = 40000
+    ins[ins == 11] = 65535
+    thing_ids = np.array([2, 3, 5, 8])
+    pans, dicts = [], []
+    for b in range(B):
+        pan, d = naive_merge_semantic_and_instance_np(sem[b], ins[b], 1 << 16, thing_ids, 0)
+        pans.append(pan.astype(np.int64))
+        dicts.append(d)
+    np.savez_compressed(os.path.join(HERE, 'naive_merge.npz'), sem=sem, ins=ins.astype(np.int32),
+                        thing_ids=thing_ids, pan=np.stack(pans), ids=dicts_to_json(dicts))
+    print('naive merge', [len(d) for d in dicts])
+
+
 def run_pq():
     """compare_and_accumulate on random blocky panoptic maps (pq.py:60-179)."""
     g = torch.Generator().manual_seed(13)
@@ -285,6 +307,7 @@ if __name__ == '__main__':
     run_fullres()
     run_centers()
     run_merge()
+    run_naive_merge()
     run_pq()
     run_miou()
     run_orientation()

@@ -387,3 +387,24 @@ def test_fullres_golden(cuda_device):
     assert differs.mean() < 1e-3
     np.testing.assert_allclose(r['semantic_segmentation_score_fullres'].cpu().numpy()[~differs],
                                z['semantic_segmentation_score_fullres'][~differs], rtol=2e-5)
+
+
+def test_naive_merge_ground_truth_targets(cuda_device):
+    """PanopticTargetGenerator's merge (panoptic_merge.py:43-107) on the GPU: golden + oracle"""
+    from nicr_mt_scene_analysis_b200.utils import naive_merge_semantic_and_instance_batch
+    z = load_golden('naive_merge')
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    pan, ids = naive_merge_semantic_and_instance_batch(t(z['sem']), t(z['ins']), 1 << 16,
+                                                       z['thing_ids'], 0)
+    assert np.array_equal(pan.cpu().numpy(), z['pan'])
+    assert ids == int_keys(jload(z['ids']))
+    g = torch.Generator().manual_seed(5)
+    sem = torch.randint(0, 30, (2, 48, 64), generator=g).repeat_interleave(4, 1) \
+        .repeat_interleave(2, 2).to(torch.uint8)
+    ins = torch.randint(0, 100, (2, 24, 32), generator=g).repeat_interleave(8, 1).repeat_interleave(4, 2)
+    ins = (ins * 211) % 65536
+    pan, ids = naive_merge_semantic_and_instance_batch(sem.to(cuda_device), ins.to(cuda_device),
+                                                       1000, [1, 4, 9, 29], 7)
+    ref_pan, ref_ids = oracle.naive_merge_batch(sem.numpy(), ins.numpy(), 1000, [1, 4, 9, 29], 7)
+    assert np.array_equal(pan.cpu().numpy(), ref_pan)
+    assert ids == ref_ids

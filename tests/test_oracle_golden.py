@@ -190,3 +190,11 @@ def test_orientation_standalone():
         for dr, dg in zip(ref, got):
             for k in dr:
                 assert math.isclose(dg[k], dr[k], rel_tol=1e-5, abs_tol=1e-6)
+
+
+def test_naive_merge_ground_truth_targets():
+    z = load_golden('naive_merge')
+    pan, ids = oracle.naive_merge_batch(z['sem'], z['ins'], 1 << 16, z['thing_ids'].tolist(), 0)
+    assert np.array_equal(pan, z['pan'])
+    assert ids == int_keys(jload(z['ids']))
+    assert [list(d) for d in ids] == [[int(k) for k in d] for d in jload(z['ids'])]   # creation order
