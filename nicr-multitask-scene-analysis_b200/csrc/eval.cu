@@ -103,26 +103,30 @@ struct PairTables {
 
 constexpr int kQueueCap = 192;   // < 32 left over + at most 128 pixels + 32 group entries
 
-// one queue entry = `cnt` pixels of pair `key` whose semantic target is `st`
-template <bool CONFMAT>
+// one queue entry = `cnt` pixels of pair `key` whose semantic target is `st`.
+// STD = the standard id geometry of the reference's task helper (offset = 256^3, 65536
+// instances per category, task_helper/panoptic.py:42,61): shifts and masks become immediates.
+template <bool CONFMAT, bool STD>
 __device__ __forceinline__ void pair_consume(const PairTables &t, const PairParams &prm, int b,
                                              unsigned long long key, unsigned cnt, int st,
                                              bool cm_smem)
 {
+    const int OS = STD ? 24 : prm.O_shift, LS = STD ? 16 : prm.L_shift;
+    const long long offset = STD ? (1ll << 24) : prm.offset, L = STD ? (1ll << 16) : prm.L;
     long long tv, pv;
-    if (prm.O_shift >= 0) {
-        tv = (long long)(key >> prm.O_shift);
-        pv = (long long)(key & ((unsigned long long)prm.offset - 1ull));
+    if (STD || OS >= 0) {
+        tv = (long long)(key >> OS);
+        pv = (long long)(key & ((unsigned long long)offset - 1ull));
     } else {
-        tv = (long long)(key / (unsigned long long)prm.offset);
-        pv = (long long)(key - (unsigned long long)tv * (unsigned long long)prm.offset);
+        tv = (long long)(key / (unsigned long long)offset);
+        pv = (long long)(key - (unsigned long long)tv * (unsigned long long)offset);
     }
     long long pc = -1;
-    if (prm.L_shift >= 0) pc = pv >> prm.L_shift;
-    else if (CONFMAT) pc = pv / prm.L;
+    if (STD || LS >= 0) pc = pv >> LS;
+    else if (CONFMAT) pc = pv / L;
     bool dense = false;
-    if (prm.nd > 0 && ((pv | tv) & (prm.L - 1)) == 0) {          // two instance-free segments
-        const long long tc = tv >> prm.L_shift;
+    if (prm.nd > 0 && ((pv | tv) & (L - 1)) == 0) {          // two instance-free segments
+        const long long tc = tv >> LS;
         if (pc < prm.nd && tc < prm.nd) {
             atomicAdd(t.dense + (int)tc * prm.nd + (int)pc, cnt);
             dense = true;
@@ -148,7 +152,7 @@ __device__ __forceinline__ void pair_consume(const PairTables &t, const PairPara
 // holding isolated pixels emit their 4 pixels as single entries.  Entries go to a per-warp
 // shared-memory queue and are consumed 32 at a time, one entry per lane, so the table updates
 // (the expensive, divergent part) always run with a full warp.
-template <int VEC, bool CONFMAT>
+template <int VEC, bool CONFMAT, bool STD>
 __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairParams prm)
 {
     extern __shared__ unsigned long long s_dyn[];
@@ -222,11 +226,16 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 any_neg |= pv[j] | tv[j];
-                too_big |= pv[j] >= prm.offset;
-                key[j] = prm.O_shift >= 0
-                             ? (((unsigned long long)tv[j] << prm.O_shift) | (unsigned long long)pv[j])
-                             : (unsigned long long)tv[j] * (unsigned long long)prm.offset +
-                                   (unsigned long long)pv[j];
+                if (STD) {
+                    too_big |= (pv[j] >> 24) != 0;
+                    key[j] = ((unsigned long long)tv[j] << 24) | (unsigned long long)pv[j];
+                } else {
+                    too_big |= pv[j] >= prm.offset;
+                    key[j] = prm.O_shift >= 0
+                                 ? (((unsigned long long)tv[j] << prm.O_shift) | (unsigned long long)pv[j])
+                                 : (unsigned long long)tv[j] * (unsigned long long)prm.offset +
+                                       (unsigned long long)pv[j];
+                }
             }
             if (any_neg < 0 || too_big) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
         }
@@ -261,14 +270,14 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             q_len -= 32;
             const unsigned long long k = q_key[q_len + lane];
             const unsigned m = q_meta[q_len + lane];
-            pair_consume<CONFMAT>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
+            pair_consume<CONFMAT, STD>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
             __syncwarp();
         }
     }
     if (lane < q_len) {
         const unsigned long long k = q_key[lane];
         const unsigned m = q_meta[lane];
-        pair_consume<CONFMAT>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
+        pair_consume<CONFMAT, STD>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
     }
 
     // ---- flush the CTA tables into the per-frame table / the global confusion matrix --------
@@ -689,44 +698,42 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
                            ((confmat && confmat_n <= kSmemConfmatMaxN)
                                 ? (size_t)confmat_n * confmat_n * sizeof(unsigned) : 0) + 16;
     // one process may drive several devices: function attributes and the SM count are per device
+    // specialisation for the reference's id geometry (offset = 256^3, L = 65536)
+    const bool std_geom = pp.O_shift == 24 && pp.L_shift == 16;
+    typedef void (*PairKernel)(const PairParams);
+    static const PairKernel kernels[8] = {
+        pair_count_kernel<1, false, false>, pair_count_kernel<4, false, false>,
+        pair_count_kernel<1, true, false>,  pair_count_kernel<4, true, false>,
+        pair_count_kernel<1, false, true>,  pair_count_kernel<4, false, true>,
+        pair_count_kernel<1, true, true>,   pair_count_kernel<4, true, true>};
+    const int variant = (std_geom ? 4 : 0) + (confmat ? 2 : 0) + (vec4 ? 1 : 0);
+    const PairKernel kernel = kernels[variant];
+    // one process may drive several devices: function attributes and the SM count are per device
     static bool pc_attr_set_dev[64] = {false};
     static int n_sm_dev[64];
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     const int dslot = cur_dev & 63;
-    bool &pc_attr_set = pc_attr_set_dev[dslot];
-    int &n_sm = n_sm_dev[dslot];
-    if (!pc_attr_set) {
-        const int mx = 200 * 1024;
-        cudaFuncSetAttribute(pair_count_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(pair_count_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(pair_count_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(pair_count_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        n_sm = 148;
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cur_dev);
+    if (!pc_attr_set_dev[dslot]) {
+        for (int v = 0; v < 8; ++v)
+            cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(match_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)match_smem_bytes());
-        pc_attr_set = true;
+        n_sm_dev[dslot] = 148;
+        cudaDeviceGetAttribute(&n_sm_dev[dslot], cudaDevAttrMultiProcessorCount, cur_dev);
+        pc_attr_set_dev[dslot] = true;
     }
+    const int n_sm = n_sm_dev[dslot];
     // persistent CTAs: the whole batch in ONE wave (a second, partial wave would leave most SMs
     // idle for the length of a CTA), every CTA of a frame gets the same number of chunks
-    static size_t occ_smem_dev[64][4] = {{0}};
-    static int occ_blocks_dev[64][4] = {{0}};
-    size_t *occ_smem = occ_smem_dev[dslot];
-    int *occ_blocks = occ_blocks_dev[dslot];
-    const int variant = (confmat ? 2 : 0) + (vec4 ? 1 : 0);
-    int per_sm = occ_blocks[variant];
-    if (per_sm == 0 || occ_smem[variant] != pc_smem) {
-    if (confmat) {
-        if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_count_kernel<4, true>, kPairThreads, pc_smem);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_count_kernel<1, true>, kPairThreads, pc_smem);
-    } else {
-        if (vec4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_count_kernel<4, false>, kPairThreads, pc_smem);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_count_kernel<1, false>, kPairThreads, pc_smem);
-    }
-    if (per_sm < 1) per_sm = 1;
-    occ_smem[variant] = pc_smem;
-    occ_blocks[variant] = per_sm;
+    static size_t occ_smem_dev[64][8] = {{0}};
+    static int occ_blocks_dev[64][8] = {{0}};
+    int per_sm = occ_blocks_dev[dslot][variant];
+    if (per_sm == 0 || occ_smem_dev[dslot][variant] != pc_smem) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPairThreads, pc_smem);
+        if (per_sm < 1) per_sm = 1;
+        occ_smem_dev[dslot][variant] = pc_smem;
+        occ_blocks_dev[dslot][variant] = per_sm;
     }
     // NPB_PAIR_CTAS_PER_SM=<n> caps the residency of the pixel pass, leaving registers / shared
     // memory for kernels of another stream (evaluation overlapped with the next batch)
@@ -740,13 +747,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     if (bx < 1) bx = 1;
     if (bx > n_chunks) bx = n_chunks;
     dim3 grid((unsigned)bx, B);
-    if (confmat) {
-        if (vec4) pair_count_kernel<4, true><<<grid, kPairThreads, pc_smem, s>>>(pp);
-        else pair_count_kernel<1, true><<<grid, kPairThreads, pc_smem, s>>>(pp);
-    } else {
-        if (vec4) pair_count_kernel<4, false><<<grid, kPairThreads, pc_smem, s>>>(pp);
-        else pair_count_kernel<1, false><<<grid, kPairThreads, pc_smem, s>>>(pp);
-    }
+    kernel<<<grid, kPairThreads, pc_smem, s>>>(pp);
 
     MatchParams mp;
     mp.frame_keys = fkeys; mp.frame_cnts = fcnts; mp.num_categories = num_categories;
