@@ -240,6 +240,27 @@ int npb_naive_merge(const uint8_t *sem, const int32_t *ins, int B, int64_t P,
                     int64_t *part_pan_out, int32_t *n_parts, int32_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Instance targets from ground-truth maps (centre heat-map, offsets, masks).
+ * Replaces: InstanceTargetGenerator._preprocess, data/preprocessing/instance.py:151-286
+ *           (the step before the hot path; per sample there, per batch here).
+ * sem (B,H,W) u8 semantic labels WITH void (0), ins (B,H,W) i32 ids in [0, 65535];
+ * h_thing_lut [n_classes] (index = label, void included); gauss [(6*sigma+3)^2] f32 = the
+ * reference's precomputed stamp (instance.py:140-147), supplied by the caller.
+ * Outputs: center (B,H,W) f32; offset (B,2,H,W) f32 if normalized_offset else int16 (ch0 = y,
+ * ch1 = x); fg, center_mask (B,H,W) u8; per frame the ids of the encoded instances and of those
+ * skipped because their majority class is stuff ([B][list_cap], unordered) and their counts.
+ * status [1]: NPB_ERR_ARG if a skipped instance still covers pixels (the reference asserts,
+ * instance.py:260), NPB_ERR_CAPACITY on table overflow.
+ * ------------------------------------------------------------------------- */
+size_t npb_instance_targets_workspace_bytes(int B);
+int npb_instance_targets(const uint8_t *sem, const int32_t *ins, int B, int H, int W,
+                         const uint8_t *h_thing_lut, int n_classes, int sigma, const float *gauss,
+                         int normalized_offset, void *workspace, float *center_out,
+                         void *offset_out, uint8_t *fg_out, uint8_t *center_mask_out,
+                         int32_t *encoded_ids, int32_t *skipped_ids, int32_t *n_encoded,
+                         int32_t *n_skipped, int list_cap, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Stand-alone per-instance orientation for arbitrary instance maps.
  * Replaces: InstancePostprocessing._get_instance_orientation, instance.py:270-319.
  * orientation (B,2,P) f32, seg (B,P) of dtype seg_dtype (NPB_U8 / NPB_I32 / NPB_I64),

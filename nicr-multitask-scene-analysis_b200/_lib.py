@@ -61,6 +61,9 @@ _SIGNATURES = {
     'npb_naive_merge_workspace_bytes': (c_size_t, [c_int]),
     'npb_naive_merge': (c_int, [_P, _P, c_int, c_int64, c_int64, _P, c_int, c_int64, _P, _P, _P, _P,
                                 _P, _P, _P]),
+    'npb_instance_targets_workspace_bytes': (c_size_t, [c_int]),
+    'npb_instance_targets': (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, _P, _P,
+                                     _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     'npb_instance_orientation': (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P,
                                          _P, _P]),
     'npb_confmat_update': (c_int, [_P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P]),

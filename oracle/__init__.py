@@ -162,6 +162,37 @@ def naive_merge_batch(semantic, instance, max_instances_per_category, thing_ids,
                  for b in range(B)]
 
 
+def gauss_stamp(sigma: int) -> np.ndarray:
+    """instance.py:140-147, float64 -> float32."""
+    size = 6 * sigma + 3
+    x = np.arange(0, size, 1, float)
+    y = x[:, np.newaxis]
+    c = 3 * sigma + 1
+    return np.exp(-((x - c) ** 2 + (y - c) ** 2) / (2 * sigma ** 2)).astype(np.float32)
+
+
+def instance_targets(semantic, instance, sigma, is_thing_with_void, normalized_offset=True):
+    """data/preprocessing/instance.py:151-286 for a batch -> dict of arrays, offset (B,2,H,W)."""
+    sem = _c(semantic, np.uint8)
+    ins = _c(instance, np.int32)
+    B, H, W = sem.shape
+    thing = np.zeros((256,), np.uint8)
+    thing[:len(is_thing_with_void)] = np.asarray(is_thing_with_void, np.uint8)
+    gauss = np.ascontiguousarray(gauss_stamp(sigma))
+    center = np.empty((B, H, W), np.float32)
+    offset = np.empty((B, 2, H, W), np.float32)
+    fg = np.empty((B, H, W), np.uint8)
+    cmask = np.empty((B, H, W), np.uint8)
+    code = lib().orc_instance_targets(_p(sem), _p(ins), c_int(B), c_int(H), c_int(W), _p(thing),
+                                      c_int(sigma), _p(gauss), c_int(int(normalized_offset)),
+                                      _p(center), _p(offset), _p(fg), _p(cmask))
+    if code == -1:
+        raise AssertionError('stuff pixels carry instance ids')
+    _check(code)
+    return {'instance_center': center, 'instance_offset': offset,
+            'instance_foreground': fg.astype(bool), 'instance_center_mask': cmask.astype(bool)}
+
+
 def instance_orientation(orientation, instance_segmentation, foreground_mask=None
                          ) -> List[Dict[int, float]]:
     """instance.py:270-319."""

@@ -419,6 +419,79 @@ int orc_naive_merge_batch(const uint8_t *sem, const int32_t *ins, int B, long P,
 }
 
 /* ------------------------------------------------------------------------ */
+/* instance targets   data/preprocessing/instance.py:151-286                    */
+/*  per instance id != 0 (ascending): class = bincount(sem[mask]).argmax();     */
+/*  skipped unless a thing; fg |= mask; centre = (int(mean y), int(mean x));    */
+/*  heat = max(heat, gauss stamp); offset[mask] = (cy - y, cx - x);             */
+/*  normalised: float32(offset) / (H, W); centre mask = fg | stuff (no void)    */
+/* gauss: [(6s+3)^2] f32 stamp supplied by the caller (numpy float64 -> f32)    */
+/* offset: [B][2][P] f32 (normalised) or the same integers as f32 (pixels)      */
+/* returns -1 if a non-foreground pixel carries an instance id (the assert)     */
+/* ------------------------------------------------------------------------ */
+int orc_instance_targets(const uint8_t *sem, const int32_t *ins, int B, int H, int W,
+                         const uint8_t *thing_lut /* [256] with void */, int sigma,
+                         const float *gauss, int normalized, float *center, float *offset,
+                         uint8_t *fg, uint8_t *cmask)
+{
+    const long P = (long)H * W;
+    const int size = 6 * sigma + 3;
+    int status = ORC_OK;
+    for (int b = 0; b < B; ++b) {
+        const uint8_t *sb = sem + (size_t)b * P;
+        const int32_t *ib = ins + (size_t)b * P;
+        float *cb = center + (size_t)b * P, *oy = offset + (size_t)b * 2 * P, *ox = oy + P;
+        uint8_t *fb = fg + (size_t)b * P, *mb = cmask + (size_t)b * P;
+        for (long p = 0; p < P; ++p) { cb[p] = 0.0f; oy[p] = 0.0f; ox[p] = 0.0f; fb[p] = 0; }
+        int64_t *hist = (int64_t *)calloc((size_t)65536 * 256, sizeof(int64_t));
+        int64_t *sy = (int64_t *)calloc(65536, sizeof(int64_t));
+        int64_t *sx = (int64_t *)calloc(65536, sizeof(int64_t));
+        int64_t *n = (int64_t *)calloc(65536, sizeof(int64_t));
+        for (long p = 0; p < P; ++p) {
+            const int id = ib[p];
+            if (id < 0 || id > 65535) { status = ORC_ERR_CATEGORY_RANGE; continue; }
+            hist[(size_t)id * 256 + sb[p]] += 1;
+            sy[id] += p / W; sx[id] += p % W; n[id] += 1;
+        }
+        int32_t *cyx = (int32_t *)malloc(sizeof(int32_t) * 65536 * 2);
+        for (int id = 1; id < 65536; ++id) {
+            cyx[2 * id] = -1;
+            if (!n[id]) continue;
+            int cls = 0; int64_t best = -1;
+            for (int c = 0; c < 256; ++c)
+                if (hist[(size_t)id * 256 + c] > best) { best = hist[(size_t)id * 256 + c]; cls = c; }
+            if (!thing_lut[cls]) continue;
+            const int cy = (int)(sy[id] / n[id]), cx = (int)(sx[id] / n[id]);
+            cyx[2 * id] = cy; cyx[2 * id + 1] = cx;
+            const int ul_x = cx - 3 * sigma - 1, ul_y = cy - 3 * sigma - 1;
+            for (int gy = 0; gy < size; ++gy)
+                for (int gx = 0; gx < size; ++gx) {
+                    const int y = ul_y + gy, x = ul_x + gx;
+                    if (y < 0 || y >= H || x < 0 || x >= W) continue;
+                    const float v = gauss[gy * size + gx];
+                    if (v > cb[(long)y * W + x]) cb[(long)y * W + x] = v;
+                }
+        }
+        for (long p = 0; p < P; ++p) {
+            const int id = ib[p];
+            if (id > 0 && id <= 65535) {
+                if (cyx[2 * id] >= 0) {
+                    const float dy = (float)(cyx[2 * id] - (int)(p / W));
+                    const float dx = (float)(cyx[2 * id + 1] - (int)(p % W));
+                    oy[p] = normalized ? dy / (float)H : dy;
+                    ox[p] = normalized ? dx / (float)W : dx;
+                    fb[p] = 1;
+                } else {
+                    status = ORC_ERR_ARG;
+                }
+            }
+            mb[p] = fb[p] || (sb[p] != 0 && !thing_lut[sb[p]]);
+        }
+        free(hist); free(sy); free(sx); free(n); free(cyx);
+    }
+    return status;
+}
+
+/* ------------------------------------------------------------------------ */
 /* a6  per-instance orientation  model/postprocessing/instance.py:270-319     */
 /*  :301-313 for every instance id != 0 present inside the mask:              */
 /*     v = sum(orientation[:, mask & seg==id])  (f32 sum in ATen; order-      */

@@ -215,6 +215,54 @@ def run_naive_merge():
     print('naive merge', [len(d) for d in dicts])
 
 
+def run_instance_targets():
+    """InstanceTargetGenerator (data/preprocessing/instance.py:97-286) on random blocky GT:
+    uint16 instance ids, instances whose majority class is stuff (skipped), exact bincount ties,
+    centres near the borders (clipped stamps)."""
+    from nicr_mt_scene_analysis.data.preprocessing.instance import InstanceTargetGenerator
+    g = torch.Generator().manual_seed(29)
+    B, H, W = 3, 72, 100
+    is_thing = (False, True, False, True, True, False)          # with void
+    out = {'is_thing': np.array(is_thing)}
+    sems, inss = [], []
+    res = {k: [] for k in ('instance_center', 'instance_offset', 'instance_foreground',
+                           'instance_center_mask')}
+    res_px = []
+    enc, skip = [], []
+    for b in range(B):
+        ins = blocky(g, 1, H, W, 9, 13)[0].numpy().astype(np.uint16)
+        ins[ins == 5] = 51234
+        sem = np.zeros((H, W), np.uint8)
+        for i in np.unique(ins):                     # mostly one class per instance, some noise
+            cls = int(torch.randint(1, 6, (1,), generator=g))
+            sem[ins == i] = cls
+        noise = torch.rand(H, W, generator=g).numpy() < 0.2
+        sem[noise] = torch.randint(0, 6, (int(noise.sum()),), generator=g).numpy().astype(np.uint8)
+        ins[ins == 0] = 0
+        # make the assert of the reference hold: stuff-majority instances are cleared
+        for i in np.unique(ins):
+            if i and not is_thing[int(np.bincount(sem[ins == i]).argmax())]:
+                ins[ins == i] = 0
+        sems.append(sem); inss.append(ins)
+        for norm, store in ((True, res), (False, None)):
+            gen = InstanceTargetGenerator(sigma=5, semantic_classes_is_thing=is_thing,
+                                          normalized_offset=norm)
+            s = gen({'semantic': sem.copy(), 'instance': ins.copy()})
+            if norm:
+                for k in res:
+                    res[k].append(s[k])
+            else:
+                res_px.append(s['instance_offset'])
+        enc.append(sorted(int(i) for i in np.unique(ins) if i))
+    for k in res:
+        out[k] = np.stack(res[k])
+    out['instance_offset_px'] = np.stack(res_px)
+    out['sem'] = np.stack(sems); out['ins'] = np.stack(inss).astype(np.int32)
+    out['encoded'] = jdump(enc)
+    np.savez_compressed(os.path.join(HERE, 'instance_targets.npz'), **out)
+    print('instance targets', [len(e) for e in enc], out['instance_center'].max())
+
+
 def run_pq():
     """compare_and_accumulate on random blocky panoptic maps (pq.py:60-179)."""
     g = torch.Generator().manual_seed(13)
@@ -308,6 +356,7 @@ if __name__ == '__main__':
     run_centers()
     run_merge()
     run_naive_merge()
+    run_instance_targets()
     run_pq()
     run_miou()
     run_orientation()

@@ -408,3 +408,44 @@ def test_naive_merge_ground_truth_targets(cuda_device):
     ref_pan, ref_ids = oracle.naive_merge_batch(sem.numpy(), ins.numpy(), 1000, [1, 4, 9, 29], 7)
     assert np.array_equal(pan.cpu().numpy(), ref_pan)
     assert ids == ref_ids
+
+
+def test_instance_target_generator(cuda_device):
+    """InstanceTargetGenerator (data/preprocessing/instance.py:97-286), batched on the GPU"""
+    from nicr_mt_scene_analysis_b200.utils import InstanceTargetGenerator
+    z = load_golden('instance_targets')
+    t = lambda a: torch.from_numpy(a).to(cuda_device)
+    gen = InstanceTargetGenerator(sigma=5, semantic_classes_is_thing=z['is_thing'].tolist())
+    r = gen(t(z['sem']), t(z['ins']))
+    assert np.array_equal(r['instance_center'].cpu().numpy(), z['instance_center'])   # bit-exact
+    assert np.array_equal(r['instance_offset'].cpu().numpy(),
+                          z['instance_offset'].transpose(0, 3, 1, 2))
+    assert np.array_equal(r['instance_foreground'].cpu().numpy(), z['instance_foreground'])
+    assert np.array_equal(r['instance_center_mask'].cpu().numpy(), z['instance_center_mask'])
+    assert r['encoded_instances'] == jload(z['encoded'])
+    assert r['skipped_instances_due_to_stuff'] == [[], [], []]
+    gen_px = InstanceTargetGenerator(sigma=5, semantic_classes_is_thing=z['is_thing'].tolist(),
+                                     normalized_offset=False)
+    r = gen_px(t(z['sem']), t(z['ins']))
+    assert r['instance_offset'].dtype == torch.int16
+    assert np.array_equal(r['instance_offset'].cpu().numpy(),
+                          z['instance_offset_px'].transpose(0, 3, 1, 2))
+    # a bigger random case against the oracle (many instances, ids up to 65535)
+    g = torch.Generator().manual_seed(8)
+    B, H, W = 2, 200, 300
+    ins = torch.randint(0, 400, (B, H // 10, W // 10), generator=g).repeat_interleave(10, 1) \
+        .repeat_interleave(10, 2)
+    ins = (ins * 163) % 65536
+    sem = torch.randint(1, 12, (B, H // 10, W // 10), generator=g).repeat_interleave(10, 1) \
+        .repeat_interleave(10, 2).to(torch.uint8)
+    is_thing = [False] + [bool(c % 2) for c in range(1, 12)]
+    ins[~torch.tensor(is_thing)[sem.long()]] = 0
+    gen = InstanceTargetGenerator(sigma=8, semantic_classes_is_thing=is_thing)
+    r = gen(sem.to(cuda_device), ins.to(cuda_device))
+    ref = oracle.instance_targets(sem.numpy(), ins.numpy(), 8, is_thing, True)
+    for k in ref:
+        assert np.array_equal(r[k].cpu().numpy(), ref[k]), k
+    bad = ins.clone()
+    bad[0][~torch.tensor(is_thing)[sem[0].long()]] = 7
+    with pytest.raises(AssertionError):
+        gen(sem.to(cuda_device), bad.to(cuda_device))

@@ -198,3 +198,20 @@ def test_naive_merge_ground_truth_targets():
     assert np.array_equal(pan, z['pan'])
     assert ids == int_keys(jload(z['ids']))
     assert [list(d) for d in ids] == [[int(k) for k in d] for d in jload(z['ids'])]   # creation order
+
+
+def test_instance_targets():
+    z = load_golden('instance_targets')
+    r = oracle.instance_targets(z['sem'], z['ins'], 5, z['is_thing'].tolist(), True)
+    assert np.array_equal(r['instance_center'], z['instance_center'])            # bit-exact f32
+    assert np.array_equal(r['instance_offset'], z['instance_offset'].transpose(0, 3, 1, 2))
+    assert np.array_equal(r['instance_foreground'], z['instance_foreground'])
+    assert np.array_equal(r['instance_center_mask'], z['instance_center_mask'])
+    r = oracle.instance_targets(z['sem'], z['ins'], 5, z['is_thing'].tolist(), False)
+    assert np.array_equal(r['instance_offset'], z['instance_offset_px'].transpose(0, 3, 1, 2))
+    bad = z['ins'].copy()
+    bad[0, 0, 0] = 999 if z['sem'][0, 0, 0] in (0, 2, 5) else bad[0, 0, 0]
+    stuff_px = np.argwhere(~z['is_thing'][z['sem'][0]])[0]
+    bad[0, stuff_px[0], stuff_px[1]] = 999          # a lone stuff pixel with an instance id
+    with pytest.raises(AssertionError):
+        oracle.instance_targets(z['sem'], bad, 5, z['is_thing'].tolist(), True)
