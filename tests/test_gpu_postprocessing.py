@@ -449,3 +449,35 @@ def test_instance_target_generator(cuda_device):
     bad[0][~torch.tensor(is_thing)[sem[0].long()]] = 7
     with pytest.raises(AssertionError):
         gen(sem.to(cuda_device), bad.to(cuda_device))
+
+
+def test_semantic_postprocessing_standalone(cuda_device):
+    """SemanticPostprocessing on its own (semantic.py:37-82): keys, dtypes, values"""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    z = load_golden('post_q10')
+    B, C, H, W = z['logits'].shape
+    post = get_postprocessing_class('semantic')()
+    logits = torch.from_numpy(z['logits']).to(cuda_device)
+    r = post.postprocess((logits, None), testing.make_batch_dict(B, H, W), is_training=False)
+    for k in ('semantic_output', 'semantic_side_outputs', 'semantic_softmax_scores',
+              'semantic_segmentation_score', 'semantic_segmentation_idx', 'semantic_output_fullres',
+              'semantic_softmax_scores_fullres', 'semantic_segmentation_score_fullres',
+              'semantic_segmentation_idx_fullres'):
+        assert k in r
+    assert r['semantic_segmentation_idx'].dtype == torch.int64
+    assert np.array_equal(r['semantic_segmentation_idx'].cpu().numpy(),
+                          z['semantic_segmentation_idx'])
+    assert np.array_equal(r['semantic_segmentation_idx_fullres'].cpu().numpy(),
+                          z['semantic_segmentation_idx'])
+    np.testing.assert_allclose(r['semantic_segmentation_score'].cpu().numpy(),
+                               z['semantic_segmentation_score'], rtol=1e-5)
+    assert r['semantic_output_fullres'] is logits
+    # training mode only forwards
+    t = post.postprocess((logits, 'side'), {}, is_training=True)
+    assert t == {'semantic_output': logits, 'semantic_side_outputs': 'side'}
+    # out-of-scope tasks are refused loudly, unknown names like the reference
+    with pytest.raises(NotImplementedError):
+        get_postprocessing_class('normal')
+    with pytest.raises(ValueError):
+        get_postprocessing_class('nope')
