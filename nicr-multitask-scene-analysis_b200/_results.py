@@ -126,6 +126,10 @@ class InstanceTables:
     def __getitem__(self, name: str) -> np.ndarray:
         return self.wait()._np[name]
 
+    def invalidate(self) -> None:
+        """Forget the host copy: the device buffer was rewritten (CUDA-graph replay)."""
+        self._np = None
+
     # ---- python structures of the reference API ------------------------------------------
     def centers_list(self) -> List[torch.Tensor]:
         """instance.py:163-166: list of (n, 2) int32 tensors (y, x), raster order."""

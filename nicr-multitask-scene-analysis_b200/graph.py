@@ -33,5 +33,12 @@ class CapturedStep:
             self.result = fn()
 
     def replay(self) -> Any:
+        """Launch the captured step again.  Host copies of per-instance tables taken from an
+        earlier replay are dropped, so dict / list entries read afterwards are current (entries
+        that were already materialised from a ResultDict are plain python objects and stay as
+        they were: read them from a fresh `InstanceTables` accessor instead)."""
         self.graph.replay()
+        tables = self.result.get('_panoptic_instance_tables') if isinstance(self.result, dict) else None
+        if tables is not None:
+            tables.invalidate()
         return self.result
