@@ -146,12 +146,12 @@ __device__ __forceinline__ void pair_consume(const PairTables &t, const PairPara
     }
 }
 
-// Pixel pass.  A thread reads 4 consecutive pixels (128-bit loads).  Inside a segment all 4
-// agree ("pure" lane): pure lanes with the same pair are grouped with MATCH.ANY and the lowest
-// lane of a group emits ONE entry for 4 * |group| pixels.  Lanes cut by a segment boundary or
-// holding isolated pixels emit their 4 pixels as single entries.  Entries go to a per-warp
-// shared-memory queue and are consumed 32 at a time, one entry per lane, so the table updates
-// (the expensive, divergent part) always run with a full warp.
+// Pixel pass.  A thread reads 4 consecutive pixels (128-bit loads).  The pixels of a lane that
+// agree with its lead pixel (all 4 inside a segment, 3 next to an isolated pixel, 2 at a
+// boundary) join the group of lanes with the same pair (MATCH.ANY); the lowest lane of a group
+// emits ONE entry for all pixels of the group, the remaining pixels are emitted singly.  Entries
+// go to a per-warp shared-memory queue and are consumed 32 at a time, one entry per lane, so
+// the table updates (the expensive, divergent part) always run with a full warp.
 template <int VEC, bool CONFMAT, bool STD>
 __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairParams prm)
 {
@@ -240,31 +240,67 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             if (any_neg < 0 || too_big) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
         }
 
-        bool pure = act;
+        // ---- grouping.  kk = pair key with the semantic target folded into the top byte, so one
+        // 64-bit compare / MATCH decides "same pair AND same confusion cell" (ids that reach
+        // into the top byte take the degenerate every-pixel-alone path below).
+        unsigned long long kk[VEC];
+        bool big = false;
 #pragma unroll
-        for (int j = 1; j < VEC; ++j) pure = pure && key[j] == key[0];
-        if (CONFMAT && VEC == 4) pure = pure && sw == (sw & 255u) * 0x01010101u;
-        const unsigned long long mk = pure ? key[0] : (kEmptyKey - 1ull - (unsigned)lane);
-        unsigned peers = __match_any_sync(kFullMask, mk);
-        if (CONFMAT) peers &= __match_any_sync(kFullMask, pure ? (int)(sw & 255u) : -2 - lane);
-        const bool leader = pure && lane == __ffs(peers) - 1;
-        const unsigned mixed_mask = __ballot_sync(kFullMask, act && !pure);
+        for (int j = 0; j < VEC; ++j) {
+            big |= (key[j] >> 56) != 0;
+            kk[j] = key[j] ^ ((unsigned long long)((sw >> (8 * j)) & 255u) << 56);
+        }
+        // lead pixel of the lane: the first one that agrees with another pixel of the lane (the
+        // background segment when an isolated pixel or a boundary cuts the lane); its `cnt0`
+        // agreeing pixels join the warp-wide group of that key, the others ("minors") are
+        // queued as single pixels
+        int lj = 0;
+        unsigned member = 1u;                     // bit j: pixel j agrees with the lead
+        if (VEC == 4 && !big) {
+            const bool e01 = kk[0] == kk[1 % VEC], e02 = kk[0] == kk[2 % VEC], e03 = kk[0] == kk[3 % VEC];
+            const bool e12 = kk[1 % VEC] == kk[2 % VEC], e13 = kk[1 % VEC] == kk[3 % VEC];
+            const bool e23 = kk[2 % VEC] == kk[3 % VEC];
+            if (e01 | e02 | e03) { lj = 0; member = 1u | (e01 ? 2u : 0u) | (e02 ? 4u : 0u) | (e03 ? 8u : 0u); }
+            else if (e12 | e13) { lj = 1; member = 2u | (e12 ? 4u : 0u) | (e13 ? 8u : 0u); }
+            else if (e23) { lj = 2; member = 4u | 8u; }
+        }
+        const int cnt0 = act ? __popc(member) : 0;
+        const unsigned long long lk = lj == 0 ? kk[0] : lj == 1 ? kk[1 % VEC] : kk[2 % VEC];
+        const unsigned long long mk = (act && !big) ? lk : (kEmptyKey - 1ull - (unsigned)lane);
+        const unsigned peers = __match_any_sync(kFullMask, mk);
+        // pixels of the group = sum of cnt0 over its lanes = 4 * lanes - deficits (no REDUX:
+        // a reduction with per-group masks would serialise over the groups)
+        const unsigned d1 = __ballot_sync(kFullMask, cnt0 == VEC - 1);
+        const unsigned d2 = __ballot_sync(kFullMask, cnt0 == VEC - 2);
+        const unsigned d3 = __ballot_sync(kFullMask, cnt0 == VEC - 3);
+        const int total = VEC * __popc(peers) - __popc(peers & d1) - 2 * __popc(peers & d2) -
+                          3 * __popc(peers & d3);
+        const bool leader = act && lane == __ffs(peers) - 1;
         const unsigned leader_mask = __ballot_sync(kFullMask, leader);
+        const int n_minor = act ? VEC - cnt0 : 0;
+        const unsigned b1 = __ballot_sync(kFullMask, n_minor >= 1);
+        const unsigned b2 = __ballot_sync(kFullMask, n_minor >= 2);
+        const unsigned b3 = __ballot_sync(kFullMask, n_minor >= 3);
+        const int total_minor = __popc(b1) + __popc(b2) + __popc(b3);
 
-        // push: mixed lanes VEC single-pixel entries each, group leaders one entry each
-        if (act && !pure) {
-            const int pos = q_len + VEC * __popc(mixed_mask & lt_mask);
+        // push: minors as single pixels, then one entry per group leader
+        if (n_minor > 0) {
+            int pos = q_len + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                q_key[pos + j] = key[j];
-                q_meta[pos + j] = (unsigned short)((1u << 8) | ((sw >> (8 * j)) & 255u));
+                if (!((member >> j) & 1u)) {
+                    q_key[pos] = key[j];
+                    q_meta[pos] = (unsigned short)((1u << 8) | ((sw >> (8 * j)) & 255u));
+                    ++pos;
+                }
             }
-        } else if (leader) {
-            const int pos = q_len + VEC * __popc(mixed_mask) + __popc(leader_mask & lt_mask);
-            q_key[pos] = key[0];
-            q_meta[pos] = (unsigned short)(((unsigned)(VEC * __popc(peers)) << 8) | (sw & 255u));
         }
-        q_len += VEC * __popc(mixed_mask) + __popc(leader_mask);
+        if (leader) {
+            const int pos = q_len + total_minor + __popc(leader_mask & lt_mask);
+            q_key[pos] = lj == 0 ? key[0] : lj == 1 ? key[1 % VEC] : key[2 % VEC];
+            q_meta[pos] = (unsigned short)(((unsigned)total << 8) | ((sw >> (8 * lj)) & 255u));
+        }
+        q_len += total_minor + __popc(leader_mask);
         __syncwarp();
         while (q_len >= 32) {           // consume full warps of entries from the tail
             q_len -= 32;
