@@ -137,16 +137,27 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
                     for (int j = 0; j < VEC; ++j)
                         if (v[u][j] > best[j]) { best[j] = v[u][j]; cls[j] = c + u; }
             }
-            if (c < C) {   // tail: one more batch, loads of planes >= C predicated off
-                float v[U][VEC];
+            if (c + 4 <= C) {   // tail: one batch of 4 ...
+                float v[4][VEC];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
+                for (int u = 0; u < 4; ++u) PixVec<VEC>::loadf(lp + (size_t)(c + u) * P, v[u], true);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        if (v[u][j] > best[j]) { best[j] = v[u][j]; cls[j] = c + u; }
+                c += 4;
+            }
+            if (c < C) {        // ... and up to 3 planes, loads of planes >= C predicated off
+                float v[3][VEC];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) v[u][j] = __int_as_float(0xff800000);  // -inf
                     if (c + u < C) PixVec<VEC>::loadf(lp + (size_t)(c + u) * P, v[u], true);
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u)
+                for (int u = 0; u < 3; ++u)
 #pragma unroll
                     for (int j = 0; j < VEC; ++j)
                         if (v[u][j] > best[j]) { best[j] = v[u][j]; cls[j] = c + u; }
