@@ -59,7 +59,7 @@ finalize_instances_kernel(const uint32_t *__restrict__ vote_hist,
 
 // 4 pixels per group (32-bit loads of the two uint8 maps, two 128-bit streaming stores of
 // int64 ids), kWriteGroups independent groups per thread so that enough bytes are in flight
-constexpr int kWriteGroups = 2;
+constexpr int kWriteGroups = 4;
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
