@@ -175,3 +175,34 @@ dist.destroy_process_group()
                           '29541', str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'RANK0 OK' in out.stdout
+
+
+def test_mean_absolute_angular_error_host_logic():
+    """MeanAbsoluteAngularError / abs_angle_error_rad (mae.py:16-64): pure host arithmetic"""
+    import math
+    from nicr_mt_scene_analysis_b200.metric import MeanAbsoluteAngularError
+    from nicr_mt_scene_analysis_b200.metric.mae import abs_angle_error_rad
+    e = abs_angle_error_rad(torch.tensor(0.1), torch.tensor(2 * math.pi - 0.1))
+    assert float(e) == pytest.approx(0.2, abs=1e-6)
+    e = abs_angle_error_rad(torch.tensor(-3.0), torch.tensor(3.0))
+    assert float(e) == pytest.approx(2 * math.pi - 6.0, abs=1e-6)
+    m = MeanAbsoluteAngularError(device='cpu')
+    m.update([{1: 0.5, 2: 1.0}, {7: -1.0}], [{1: 0.25, 2: 1.5, 3: 9.0}, {7: 1.0}])
+    rad, deg = m.compute()
+    assert int(m.n_elements) == 3
+    assert float(rad) == pytest.approx((0.25 + 0.5 + 2.0) / 3, rel=1e-6)
+    assert float(deg) == pytest.approx(math.degrees((0.25 + 0.5 + 2.0) / 3), rel=1e-6)
+    m.reset()
+    assert int(m.n_elements) == 0 and float(m.sum_angular_error) == 0.0
+
+
+def test_instance_tables_layout_is_aligned():
+    from nicr_mt_scene_analysis_b200._results import InstanceTables
+    for B in (1, 3, 64):
+        offsets, total = InstanceTables.layout(B)
+        assert total % 16 == 0
+        spans = sorted((off, off + nbytes) for off, nbytes, _, _ in offsets.values())
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))          # no overlap
+        import numpy as np
+        for off, _, dt, _ in offsets.values():
+            assert off % np.dtype(dt).itemsize == 0
