@@ -481,3 +481,43 @@ def test_semantic_postprocessing_standalone(cuda_device):
         get_postprocessing_class('normal')
     with pytest.raises(ValueError):
         get_postprocessing_class('nope')
+
+
+@pytest.mark.parametrize('shape', [
+    dict(name='nyuv2', B=8, C=40, H=480, W=640, K=12, top_k=64, ori=False),
+    dict(name='scannet', B=1, C=40, H=968, W=1296, K=30, top_k=64, ori=False),
+    dict(name='cityscapes', B=1, C=19, H=1024, W=2048, K=100, top_k=100, ori=False),
+])
+def test_baseline_shapes_full_size(shape, cuda_device):
+    """the other BASELINE.json shapes at full frame size: bit-exact against the oracle,
+    plus the evaluation checksum (every pixel lands in exactly one confusion cell / pair)"""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, PanopticEvaluation,
+                                                    PanopticQuality)
+    B, C, H, W, K = (shape[k] for k in 'BCHWK')
+    data = testing.make_batch(B, C, H, W, K, seed=77, with_orientation=False, quantize='q10')
+    is_thing = testing.default_is_thing(C)
+    pcfg = dict(thr=0.1, ks=3, top_k=shape['top_k'], apply_fg=False, normalized=True, dist_thr=None)
+    _, _, pan = _build(pcfg, is_thing, (False,) * C)
+    r = _run(pan, data['logits'].numpy(), data['heat'].numpy(), data['offset'].numpy(), None,
+             cuda_device)
+    ref = oracle.panoptic_postprocess(data['logits'].numpy(), data['heat'].numpy(),
+                                      data['offset'].numpy(), None, is_thing, None,
+                                      top_k=shape['top_k'])
+    assert np.array_equal(r['panoptic_segmentation_deeplab'].cpu().numpy(), ref['panoptic'])
+    assert np.array_equal(r['panoptic_segmentation_deeplab_instance_idx'].cpu().numpy(),
+                          ref['instance_idx'])
+    assert r['panoptic_segmentation_deeplab_ids'] == ref['ids']
+    pred = r['panoptic_segmentation_deeplab']
+    tgt, tgt_sem = testing.make_eval_targets(pred)
+    pq = PanopticQuality(C + 1, 0, 1 << 16, 256 ** 3, (False,) + is_thing, device=cuda_device)
+    miou = MeanIntersectionOverUnion(C + 1, ignore_first_class=True, device=cuda_device)
+    PanopticEvaluation(pq, miou).update(pred, tgt, tgt_sem)
+    pq.check_status()
+    assert int(miou.confmat.sum()) == B * H * W
+    out = oracle.pq_compare_and_accumulate(ref['panoptic'][0], tgt[0].cpu().numpy(), C + 1, 0,
+                                           1 << 16, 256 ** 3, 0)
+    if B == 1:
+        got = np.stack([getattr(pq, n).cpu().numpy() for n in
+                        ('iou_per_class', 'tp_per_class', 'fn_per_class', 'fp_per_class')])
+        assert np.array_equal(got, np.stack(out[:4]))
