@@ -146,6 +146,56 @@ __device__ __forceinline__ void pair_consume(const PairTables &t, const PairPara
     }
 }
 
+// The same for the standard geometry when both ids passed the range check of the pixel loop
+// (0 <= pred, target < 2^24).  One queue entry is ONE 64-bit word:
+//     lo = pred | (target & 0xff) << 24,   hi = target >> 8 | st << 16 | pixels << 24
+// so `hi & 0xffff : lo` is the pair key `target << 24 | pred` and every field is a 32-bit
+// shift / mask away (no 64-bit arithmetic in the hot loop).
+template <bool CONFMAT>
+__device__ __forceinline__ void pair_consume_std(const PairTables &t, const PairParams &prm, int b,
+                                                 unsigned lo, unsigned hi, bool cm_smem)
+{
+    const unsigned cnt = hi >> 24;
+    const unsigned st = (hi >> 16) & 255u;
+    const unsigned pc = (lo >> 16) & 255u;            // predicted category  (pred >> 16)
+    const unsigned tc = (hi >> 8) & 255u;             // target category     (target >> 16)
+    // instance-free on both sides: pred & 0xffff == 0 and target & 0xffff == 0
+    const bool inst_free = ((lo & 0xff00ffffu) | (hi & 255u)) == 0u;
+    bool dense = false;
+    if (inst_free && pc < (unsigned)prm.nd && tc < (unsigned)prm.nd) {
+        atomicAdd(t.dense + tc * (unsigned)prm.nd + pc, cnt);
+        dense = true;
+    }
+    if (!dense) {
+        const unsigned long long key = ((unsigned long long)(hi & 0xffffu) << 32) | lo;
+        if (!table_add(t.keys, t.cnts, kSmemSlots, 8, key, cnt))
+            pair_insert_global(prm.frame_keys + (size_t)b * kFrameSlots,
+                               prm.frame_cnts + (size_t)b * kFrameSlots, key, cnt, prm.status + b);
+    }
+    if (CONFMAT) {
+        if (pc >= (unsigned)prm.n || st >= (unsigned)prm.n) {
+            set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
+        } else {
+            const unsigned cell = st * (unsigned)prm.n + pc;
+            if (cm_smem) atomicAdd(t.cm + cell, cnt);
+            else atomicAdd(prm.confmat + cell, (unsigned long long)cnt);
+        }
+    }
+}
+
+// queue accesses of that loop by 32-bit shared-memory address (no generic -> shared conversion
+// per access)
+__device__ __forceinline__ void sts_entry(unsigned addr, unsigned lo, unsigned hi)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ uint2 lds_entry(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
 // Pixel pass.  A thread reads 4 consecutive pixels (128-bit loads).  The pixels of a lane that
 // agree with its lead pixel (all 4 inside a segment, 3 next to an isolated pixel, 2 at a
 // boundary) join the group of lanes with the same pair (MATCH.ANY); the lowest lane of a group
@@ -182,138 +232,271 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     const unsigned lt_mask = (1u << lane) - 1u;
     int q_len = 0;      // warp-uniform
 
-    // software pipeline: the loads of the next chunk are issued before the current chunk is
-    // processed, so their DRAM latency hides behind the (instruction bound) table updates
-    long long n_pv[VEC], n_tv[VEC];
-    unsigned n_sw = 0;
-    auto fetch = [&](long long ch) {
-        const long long q0 = ch * chunk + (long long)tid * VEC;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { n_pv[j] = 0; n_tv[j] = 0; }
-        n_sw = 0;
-        if (ch < n_chunks && q0 < P) {
-            const size_t fq = (size_t)b * P + q0;
-            if (VEC == 4) {
-                const longlong2 a0 = __ldcs((const longlong2 *)(prm.pred + fq));
-                const longlong2 a1 = __ldcs((const longlong2 *)(prm.pred + fq) + 1);
-                const longlong2 t0 = __ldcs((const longlong2 *)(prm.target + fq));
-                const longlong2 t1 = __ldcs((const longlong2 *)(prm.target + fq) + 1);
-                n_pv[0] = a0.x; n_pv[1 % VEC] = a0.y; n_pv[2 % VEC] = a1.x; n_pv[3 % VEC] = a1.y;
-                n_tv[0] = t0.x; n_tv[1 % VEC] = t0.y; n_tv[2 % VEC] = t1.x; n_tv[3 % VEC] = t1.y;
-                if (CONFMAT) n_sw = *(const unsigned *)(prm.sem_target + fq);
-            } else {
-                n_pv[0] = __ldcs(prm.pred + fq);
-                n_tv[0] = __ldcs(prm.target + fq);
-                if (CONFMAT) n_sw = prm.sem_target[fq];
+    if constexpr (STD && VEC == 4) {
+        // ---- standard geometry, 4 pixels per thread: everything in 32-bit words ----------------
+        // entry of a pixel (see pair_consume_std): lo = pred | target << 24, hi = target >> 8 |
+        // st << 16, one PRMT each; valid when 0 <= pred, target < 2^24, which one OR over the
+        // lane's words checks.  Comparing / MATCHing the 64-bit entry decides "same pair and
+        // same confusion cell" at once.
+        const long long stride = (long long)gridDim.x * chunk;
+        long long q_next = (long long)blockIdx.x * chunk + (long long)tid * 4;   // next pixel to fetch
+        const long long *pred_b = prm.pred + (size_t)b * P;
+        const long long *target_b = prm.target + (size_t)b * P;
+        const uint8_t *sem_b = CONFMAT ? prm.sem_target + (size_t)b * P : nullptr;
+        const unsigned q_base = (unsigned)__cvta_generic_to_shared(q_key);   // this warp's queue
+        uint4 n_p0, n_p1, n_t0, n_t1;
+        unsigned n_sw;
+        // software pipeline: the loads of the next chunk are issued before the current chunk is
+        // processed, so their DRAM latency hides behind the (instruction bound) table updates
+        auto fetch = [&]() {
+            n_p0 = n_p1 = n_t0 = n_t1 = make_uint4(0u, 0u, 0u, 0u);
+            n_sw = 0u;
+            if (q_next < P) {
+                const uint4 *pp = (const uint4 *)(pred_b + q_next);
+                const uint4 *tp = (const uint4 *)(target_b + q_next);
+                n_p0 = __ldcs(pp); n_p1 = __ldcs(pp + 1);
+                n_t0 = __ldcs(tp); n_t1 = __ldcs(tp + 1);
+                if (CONFMAT) n_sw = __ldcs((const unsigned *)(sem_b + q_next));
             }
-        }
-    };
-    fetch(blockIdx.x);
-
-    for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-        const long long p0 = ch * chunk + (long long)tid * VEC;
-        const bool act = p0 < P;    // P % VEC == 0 guaranteed by the launcher
-        unsigned long long key[VEC];
-        unsigned sw = n_sw;
-        long long pv[VEC], tv[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { key[j] = 0; pv[j] = n_pv[j]; tv[j] = n_tv[j]; }
-        fetch(ch + gridDim.x);
-        if (act) {
-            // ids must satisfy 0 <= pred < offset, 0 <= target (checked on the OR of the lane)
-            long long any_neg = 0;
-            bool too_big = false;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                any_neg |= pv[j] | tv[j];
-                if (STD) {
-                    too_big |= (pv[j] >> 24) != 0;
-                    key[j] = ((unsigned long long)tv[j] << 24) | (unsigned long long)pv[j];
+            q_next += stride;
+        };
+        fetch();
+        for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+            bool act = q_next - stride < P;
+            const unsigned sw = n_sw;
+            const unsigned hi_or = n_p0.y | n_p0.w | n_p1.y | n_p1.w | n_t0.y | n_t0.w | n_t1.y | n_t1.w;
+            const unsigned p_or = n_p0.x | n_p0.z | n_p1.x | n_p1.z;
+            const unsigned t_or = n_t0.x | n_t0.z | n_t1.x | n_t1.z;
+            if ((hi_or | ((p_or | t_or) >> 24)) != 0u) {
+                // rare: the lane's ids fail the 24-bit range check -- an error (pred outside
+                // [0, offset) or a negative target), or a target id >= 2^24 (a category >= 256:
+                // only meaningful as the ignored label) whose pixels are counted one by one
+                // with the full 64-bit key
+                const unsigned p_bad = n_p0.y | n_p0.w | n_p1.y | n_p1.w | (p_or >> 24);
+                const unsigned t_neg = (n_t0.y | n_t0.w | n_t1.y | n_t1.w) >> 31;
+                if ((p_bad | t_neg) != 0u) {
+                    set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                 } else {
-                    too_big |= pv[j] >= prm.offset;
-                    key[j] = prm.O_shift >= 0
-                                 ? (((unsigned long long)tv[j] << prm.O_shift) | (unsigned long long)pv[j])
-                                 : (unsigned long long)tv[j] * (unsigned long long)prm.offset +
-                                       (unsigned long long)pv[j];
+#pragma unroll 1
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 pw = j < 2 ? n_p0 : n_p1, tw = j < 2 ? n_t0 : n_t1;
+                        const unsigned plo = (j & 1) ? pw.z : pw.x;
+                        const unsigned long long tv =
+                            ((unsigned long long)((j & 1) ? tw.w : tw.y) << 32) | ((j & 1) ? tw.z : tw.x);
+                        pair_consume<CONFMAT, true>(t, prm, b, (tv << 24) | plo, 1u,
+                                                    (int)((sw >> (8 * j)) & 255u), cm_smem);
+                    }
+                }
+                act = false;
+            }
+            unsigned klo[4], khi[4];
+            {
+                const unsigned plo[4] = {n_p0.x, n_p0.z, n_p1.x, n_p1.z};
+                const unsigned tlo[4] = {n_t0.x, n_t0.z, n_t1.x, n_t1.z};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    klo[j] = __byte_perm(plo[j], tlo[j], 0x4210);                    // p0 p1 p2 t0
+                    khi[j] = __byte_perm(tlo[j], sw, 0x3021 | ((4 + j) << 8));       // t1 t2 st 0
                 }
             }
-            if (any_neg < 0 || too_big) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
-        }
+            fetch();
 
-        // ---- grouping.  kk = pair key with the semantic target folded into the top byte, so one
-        // 64-bit compare / MATCH decides "same pair AND same confusion cell" (ids that reach
-        // into the top byte take the degenerate every-pixel-alone path below).
-        unsigned long long kk[VEC];
-        bool big = false;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            big |= (key[j] >> 56) != 0;
-            kk[j] = key[j] ^ ((unsigned long long)((sw >> (8 * j)) & 255u) << 56);
-        }
-        // lead pixel of the lane: the first one that agrees with another pixel of the lane (the
-        // background segment when an isolated pixel or a boundary cuts the lane); its `cnt0`
-        // agreeing pixels join the warp-wide group of that key, the others ("minors") are
-        // queued as single pixels
-        int lj = 0;
-        unsigned member = 1u;                     // bit j: pixel j agrees with the lead
-        if (VEC == 4 && !big) {
-            const bool e01 = kk[0] == kk[1 % VEC], e02 = kk[0] == kk[2 % VEC], e03 = kk[0] == kk[3 % VEC];
-            const bool e12 = kk[1 % VEC] == kk[2 % VEC], e13 = kk[1 % VEC] == kk[3 % VEC];
-            const bool e23 = kk[2 % VEC] == kk[3 % VEC];
-            if (e01 | e02 | e03) { lj = 0; member = 1u | (e01 ? 2u : 0u) | (e02 ? 4u : 0u) | (e03 ? 8u : 0u); }
-            else if (e12 | e13) { lj = 1; member = 2u | (e12 ? 4u : 0u) | (e13 ? 8u : 0u); }
-            else if (e23) { lj = 2; member = 4u | 8u; }
-        }
-        const int cnt0 = act ? __popc(member) : 0;
-        const unsigned long long lk = lj == 0 ? kk[0] : lj == 1 ? kk[1 % VEC] : kk[2 % VEC];
-        const unsigned long long mk = (act && !big) ? lk : (kEmptyKey - 1ull - (unsigned)lane);
-        const unsigned peers = __match_any_sync(kFullMask, mk);
-        // pixels of the group = sum of cnt0 over its lanes = 4 * lanes - deficits (no REDUX:
-        // a reduction with per-group masks would serialise over the groups)
-        const unsigned d1 = __ballot_sync(kFullMask, cnt0 == VEC - 1);
-        const unsigned d2 = __ballot_sync(kFullMask, cnt0 == VEC - 2);
-        const unsigned d3 = __ballot_sync(kFullMask, cnt0 == VEC - 3);
-        const int total = VEC * __popc(peers) - __popc(peers & d1) - 2 * __popc(peers & d2) -
-                          3 * __popc(peers & d3);
-        const bool leader = act && lane == __ffs(peers) - 1;
-        const unsigned leader_mask = __ballot_sync(kFullMask, leader);
-        const int n_minor = act ? VEC - cnt0 : 0;
-        const unsigned b1 = __ballot_sync(kFullMask, n_minor >= 1);
-        const unsigned b2 = __ballot_sync(kFullMask, n_minor >= 2);
-        const unsigned b3 = __ballot_sync(kFullMask, n_minor >= 3);
-        const int total_minor = __popc(b1) + __popc(b2) + __popc(b3);
+            // lead pixel of the lane: the first one that agrees with another pixel of the lane
+            // (the background segment when an isolated pixel or a boundary cuts the lane); its
+            // agreeing pixels join the warp-wide group of that entry, the others ("minors")
+            // are queued as single pixels.  Branch free: nearly every warp has lanes of each kind.
+            const bool e01 = klo[0] == klo[1] && khi[0] == khi[1];
+            const bool e02 = klo[0] == klo[2] && khi[0] == khi[2];
+            const bool e03 = klo[0] == klo[3] && khi[0] == khi[3];
+            const bool e12 = klo[1] == klo[2] && khi[1] == khi[2];
+            const bool e13 = klo[1] == klo[3] && khi[1] == khi[3];
+            const bool e23 = klo[2] == klo[3] && khi[2] == khi[3];
+            const unsigned m0 = (e01 ? 2u : 0u) | (e02 ? 4u : 0u) | (e03 ? 8u : 0u);
+            const unsigned m1 = (e12 ? 4u : 0u) | (e13 ? 8u : 0u);
+            const bool lead0 = m0 != 0u, lead1 = !lead0 && m1 != 0u, lead2 = !lead0 && !lead1 && e23;
+            // bit j: pixel j agrees with the lead
+            const unsigned member = lead0 ? (m0 | 1u) : lead1 ? (m1 | 2u) : lead2 ? 12u : 1u;
+            const unsigned lk_lo = lead1 ? klo[1] : lead2 ? klo[2] : klo[0];
+            const unsigned lk_hi = lead1 ? khi[1] : lead2 ? khi[2] : khi[0];
+            const unsigned actm = __ballot_sync(kFullMask, act);
+            const unsigned peers =
+                __match_any_sync(kFullMask, ((unsigned long long)lk_hi << 32) | lk_lo) & actm;
+            const int n_minor = 4 - __popc(member);
+            // pixels of the group = 4 * lanes - minors of its lanes (no REDUX: a reduction with
+            // per-group masks would serialise over the groups)
+            const unsigned b1 = __ballot_sync(kFullMask, n_minor == 1) & actm;
+            const unsigned b2 = __ballot_sync(kFullMask, n_minor == 2) & actm;
+            const unsigned b3 = __ballot_sync(kFullMask, n_minor == 3) & actm;
+            const unsigned total = 4 * __popc(peers) - __popc(peers & b1) - 2 * __popc(peers & b2) -
+                                   3 * __popc(peers & b3);
+            const bool leader = act && (peers & lt_mask) == 0u;
+            const unsigned leader_mask = __ballot_sync(kFullMask, leader);
+            const int total_minor = __popc(b1) + 2 * __popc(b2) + 3 * __popc(b3);
 
-        // push: minors as single pixels, then one entry per group leader
-        if (n_minor > 0) {
-            int pos = q_len + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+            // push: minors as single pixels, then one entry per group leader
+            const unsigned q_tail = q_base + 8u * (unsigned)q_len;
+            if (act && n_minor > 0) {
+                unsigned a = q_tail + 8u * (unsigned)(__popc(b1 & lt_mask) + 2 * __popc(b2 & lt_mask) +
+                                                      3 * __popc(b3 & lt_mask));
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                if (!((member >> j) & 1u)) {
-                    q_key[pos] = key[j];
-                    q_meta[pos] = (unsigned short)((1u << 8) | ((sw >> (8 * j)) & 255u));
-                    ++pos;
+                for (int j = 0; j < 4; ++j) {
+                    if (!((member >> j) & 1u)) {
+                        sts_entry(a, klo[j], khi[j] | (1u << 24));
+                        a += 8u;
+                    }
                 }
             }
-        }
-        if (leader) {
-            const int pos = q_len + total_minor + __popc(leader_mask & lt_mask);
-            q_key[pos] = lj == 0 ? key[0] : lj == 1 ? key[1 % VEC] : key[2 % VEC];
-            q_meta[pos] = (unsigned short)(((unsigned)total << 8) | ((sw >> (8 * lj)) & 255u));
-        }
-        q_len += total_minor + __popc(leader_mask);
-        __syncwarp();
-        while (q_len >= 32) {           // consume full warps of entries from the tail
-            q_len -= 32;
-            const unsigned long long k = q_key[q_len + lane];
-            const unsigned m = q_meta[q_len + lane];
-            pair_consume<CONFMAT, STD>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
+            if (leader)
+                sts_entry(q_tail + 8u * (unsigned)(total_minor + __popc(leader_mask & lt_mask)), lk_lo,
+                          lk_hi | (total << 24));
+            q_len += total_minor + __popc(leader_mask);
             __syncwarp();
+            while (q_len >= 32) {           // consume full warps of entries from the tail
+                q_len -= 32;
+                const uint2 e = lds_entry(q_base + 8u * (unsigned)(q_len + lane));
+                pair_consume_std<CONFMAT>(t, prm, b, e.x, e.y, cm_smem);
+                __syncwarp();
+            }
         }
-    }
-    if (lane < q_len) {
-        const unsigned long long k = q_key[lane];
-        const unsigned m = q_meta[lane];
-        pair_consume<CONFMAT, STD>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
+        if (lane < q_len) {
+            const uint2 e = lds_entry(q_base + 8u * (unsigned)lane);
+            pair_consume_std<CONFMAT>(t, prm, b, e.x, e.y, cm_smem);
+        }
+    } else {
+        // software pipeline: the loads of the next chunk are issued before the current chunk is
+        // processed, so their DRAM latency hides behind the (instruction bound) table updates
+        long long n_pv[VEC], n_tv[VEC];
+        unsigned n_sw = 0;
+        auto fetch = [&](long long ch) {
+            const long long q0 = ch * chunk + (long long)tid * VEC;
+    #pragma unroll
+            for (int j = 0; j < VEC; ++j) { n_pv[j] = 0; n_tv[j] = 0; }
+            n_sw = 0;
+            if (ch < n_chunks && q0 < P) {
+                const size_t fq = (size_t)b * P + q0;
+                if (VEC == 4) {
+                    const longlong2 a0 = __ldcs((const longlong2 *)(prm.pred + fq));
+                    const longlong2 a1 = __ldcs((const longlong2 *)(prm.pred + fq) + 1);
+                    const longlong2 t0 = __ldcs((const longlong2 *)(prm.target + fq));
+                    const longlong2 t1 = __ldcs((const longlong2 *)(prm.target + fq) + 1);
+                    n_pv[0] = a0.x; n_pv[1 % VEC] = a0.y; n_pv[2 % VEC] = a1.x; n_pv[3 % VEC] = a1.y;
+                    n_tv[0] = t0.x; n_tv[1 % VEC] = t0.y; n_tv[2 % VEC] = t1.x; n_tv[3 % VEC] = t1.y;
+                    if (CONFMAT) n_sw = *(const unsigned *)(prm.sem_target + fq);
+                } else {
+                    n_pv[0] = __ldcs(prm.pred + fq);
+                    n_tv[0] = __ldcs(prm.target + fq);
+                    if (CONFMAT) n_sw = prm.sem_target[fq];
+                }
+            }
+        };
+        fetch(blockIdx.x);
+
+        for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+            const long long p0 = ch * chunk + (long long)tid * VEC;
+            const bool act = p0 < P;    // P % VEC == 0 guaranteed by the launcher
+            unsigned long long key[VEC];
+            unsigned sw = n_sw;
+            long long pv[VEC], tv[VEC];
+    #pragma unroll
+            for (int j = 0; j < VEC; ++j) { key[j] = 0; pv[j] = n_pv[j]; tv[j] = n_tv[j]; }
+            fetch(ch + gridDim.x);
+            if (act) {
+                // ids must satisfy 0 <= pred < offset, 0 <= target (checked on the OR of the lane)
+                long long any_neg = 0;
+                bool too_big = false;
+    #pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    any_neg |= pv[j] | tv[j];
+                    if (STD) {
+                        too_big |= (pv[j] >> 24) != 0;
+                        key[j] = ((unsigned long long)tv[j] << 24) | (unsigned long long)pv[j];
+                    } else {
+                        too_big |= pv[j] >= prm.offset;
+                        key[j] = prm.O_shift >= 0
+                                     ? (((unsigned long long)tv[j] << prm.O_shift) | (unsigned long long)pv[j])
+                                     : (unsigned long long)tv[j] * (unsigned long long)prm.offset +
+                                           (unsigned long long)pv[j];
+                    }
+                }
+                if (any_neg < 0 || too_big) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
+            }
+
+            // ---- grouping.  kk = pair key with the semantic target folded into the top byte, so one
+            // 64-bit compare / MATCH decides "same pair AND same confusion cell" (ids that reach
+            // into the top byte take the degenerate every-pixel-alone path below).
+            unsigned long long kk[VEC];
+            bool big = false;
+    #pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                big |= (key[j] >> 56) != 0;
+                kk[j] = key[j] ^ ((unsigned long long)((sw >> (8 * j)) & 255u) << 56);
+            }
+            // lead pixel of the lane: the first one that agrees with another pixel of the lane (the
+            // background segment when an isolated pixel or a boundary cuts the lane); its `cnt0`
+            // agreeing pixels join the warp-wide group of that key, the others ("minors") are
+            // queued as single pixels
+            int lj = 0;
+            unsigned member = 1u;                     // bit j: pixel j agrees with the lead
+            if (VEC == 4 && !big) {
+                const bool e01 = kk[0] == kk[1 % VEC], e02 = kk[0] == kk[2 % VEC], e03 = kk[0] == kk[3 % VEC];
+                const bool e12 = kk[1 % VEC] == kk[2 % VEC], e13 = kk[1 % VEC] == kk[3 % VEC];
+                const bool e23 = kk[2 % VEC] == kk[3 % VEC];
+                if (e01 | e02 | e03) { lj = 0; member = 1u | (e01 ? 2u : 0u) | (e02 ? 4u : 0u) | (e03 ? 8u : 0u); }
+                else if (e12 | e13) { lj = 1; member = 2u | (e12 ? 4u : 0u) | (e13 ? 8u : 0u); }
+                else if (e23) { lj = 2; member = 4u | 8u; }
+            }
+            const int cnt0 = act ? __popc(member) : 0;
+            const unsigned long long lk = lj == 0 ? kk[0] : lj == 1 ? kk[1 % VEC] : kk[2 % VEC];
+            const unsigned long long mk = (act && !big) ? lk : (kEmptyKey - 1ull - (unsigned)lane);
+            const unsigned peers = __match_any_sync(kFullMask, mk);
+            // pixels of the group = sum of cnt0 over its lanes = 4 * lanes - deficits (no REDUX:
+            // a reduction with per-group masks would serialise over the groups)
+            const unsigned d1 = __ballot_sync(kFullMask, cnt0 == VEC - 1);
+            const unsigned d2 = __ballot_sync(kFullMask, cnt0 == VEC - 2);
+            const unsigned d3 = __ballot_sync(kFullMask, cnt0 == VEC - 3);
+            const int total = VEC * __popc(peers) - __popc(peers & d1) - 2 * __popc(peers & d2) -
+                              3 * __popc(peers & d3);
+            const bool leader = act && lane == __ffs(peers) - 1;
+            const unsigned leader_mask = __ballot_sync(kFullMask, leader);
+            const int n_minor = act ? VEC - cnt0 : 0;
+            const unsigned b1 = __ballot_sync(kFullMask, n_minor >= 1);
+            const unsigned b2 = __ballot_sync(kFullMask, n_minor >= 2);
+            const unsigned b3 = __ballot_sync(kFullMask, n_minor >= 3);
+            const int total_minor = __popc(b1) + __popc(b2) + __popc(b3);
+
+            // push: minors as single pixels, then one entry per group leader
+            if (n_minor > 0) {
+                int pos = q_len + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+    #pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if (!((member >> j) & 1u)) {
+                        q_key[pos] = key[j];
+                        q_meta[pos] = (unsigned short)((1u << 8) | ((sw >> (8 * j)) & 255u));
+                        ++pos;
+                    }
+                }
+            }
+            if (leader) {
+                const int pos = q_len + total_minor + __popc(leader_mask & lt_mask);
+                q_key[pos] = lj == 0 ? key[0] : lj == 1 ? key[1 % VEC] : key[2 % VEC];
+                q_meta[pos] = (unsigned short)(((unsigned)total << 8) | ((sw >> (8 * lj)) & 255u));
+            }
+            q_len += total_minor + __popc(leader_mask);
+            __syncwarp();
+            while (q_len >= 32) {           // consume full warps of entries from the tail
+                q_len -= 32;
+                const unsigned long long k = q_key[q_len + lane];
+                const unsigned m = q_meta[q_len + lane];
+                pair_consume<CONFMAT, STD>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
+                __syncwarp();
+            }
+        }
+        if (lane < q_len) {
+            const unsigned long long k = q_key[lane];
+            const unsigned m = q_meta[lane];
+            pair_consume<CONFMAT, STD>(t, prm, b, k, m >> 8, (int)(m & 255u), cm_smem);
+        }
+
     }
 
     // ---- flush the CTA tables into the per-frame table / the global confusion matrix --------

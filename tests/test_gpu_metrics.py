@@ -152,6 +152,46 @@ def test_pq_zero_division_raises(cuda_device):
         m.compute()
 
 
+def test_pq_wide_target_ids_standard_geometry(cuda_device):
+    """Standard id geometry (offset 256^3, 65536 instances / category) with ground-truth ids
+    beyond 32 bits: those lanes leave the 32-bit fast path of the pixel pass; the result still
+    equals the oracle's int64 arithmetic.  The wide ids belong to the ignored category."""
+    from nicr_mt_scene_analysis_b200.metric import compare_and_accumulate
+    L, OFF, NC, IGN = 1 << 16, 256 ** 3, 5, 1 << 16
+    g = torch.Generator().manual_seed(7)
+    H, W = 64, 96
+    cat = torch.randint(1, NC, (H // 8, W // 8), generator=g).repeat_interleave(8, 0).repeat_interleave(8, 1)
+    inst = torch.randint(0, 3, (H // 4, W // 4), generator=g).repeat_interleave(4, 0).repeat_interleave(4, 1)
+    tgt = cat * L + inst
+    pred = torch.roll(tgt, 2, 1).clone()
+    tgt[10:30, 17:43] = IGN * L + 3          # 2^32 + 3: category == ignored_label
+    tgt[40:44, 1:3] = IGN * L                # a second wide segment, not aligned to 4 pixels
+    ref = oracle.pq_compare_and_accumulate(pred.numpy(), tgt.numpy(), NC, IGN, L, OFF, 0)
+    iou, tp, fn, fp, m = compare_and_accumulate(pred.to(cuda_device), tgt.to(cuda_device), NC, IGN,
+                                                L, OFF, 0)
+    for got, want in zip((iou, tp, fn, fp), ref[:4]):
+        assert np.array_equal(got.numpy(), want)
+    assert sorted([list(x) for x in m]) == sorted([list(x) for x in ref[4]])
+
+
+@pytest.mark.parametrize('bad', ['pred_negative', 'pred_ge_offset', 'target_negative'])
+def test_pq_id_range_errors_standard_geometry(bad, cuda_device):
+    from nicr_mt_scene_analysis_b200._lib import NpbError
+    m = _pq(cuda_device, num_categories=4, ignored_label=0, max_instances_per_category=1 << 16,
+            offset=256 ** 3, is_thing=[False, True, True, False])
+    pred = torch.full((1, 8, 16), (1 << 16) + 1, dtype=torch.int64)
+    tgt = pred.clone()
+    if bad == 'pred_negative':
+        pred[0, 3, 5] = -1
+    elif bad == 'pred_ge_offset':
+        pred[0, 3, 5] = 256 ** 3
+    else:
+        tgt[0, 7, 15] = -5
+    m.update(pred.to(cuda_device), tgt.to(cuda_device))
+    with pytest.raises(NpbError):
+        m.compute()
+
+
 @pytest.mark.parametrize('n', [6, 41, 200])
 def test_miou_golden(n, cuda_device):
     from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion
