@@ -35,6 +35,29 @@ class PanopticEvaluation:
             confmat=self.miou.confmat, want_matches=want_matches)
         return (matches, n_matches) if want_matches else None
 
+    def update_with_orientation(self, panoptic_preds: torch.Tensor, orientation_preds,
+                                panoptic_preds_id_dicts, panoptic_target: torch.Tensor,
+                                orientation_target, panoptic_target_id_dicts,
+                                semantic_target: torch.Tensor) -> None:
+        """The validation step of the reference's panoptic task helper
+        (task_helper/panoptic.py:104-126) in one call: the arguments of
+        `PanopticQualityWithOrientationMAE.update` (mae.py:84-127) plus the semantic target
+        of the mIoU update.  `self.pq` must carry the MAAE state."""
+        assert panoptic_preds.ndim == 3
+        assert len(panoptic_target) == len(panoptic_preds)
+        with_mae = orientation_preds is not None and orientation_target is not None
+        out = self.update(panoptic_preds, panoptic_target, semantic_target, want_matches=with_mae)
+        if not with_mae:
+            return
+        matches, n_matches = out
+        self.pq.check_status()
+        counts = n_matches.cpu().tolist()
+        pairs = matches.cpu()
+        for b, n in enumerate(counts):
+            self.pq.update_mae(orientation_preds[b], panoptic_preds_id_dicts[b],
+                               orientation_target[b], panoptic_target_id_dicts[b],
+                               [tuple(p) for p in pairs[b, :n].tolist()])
+
     def reset(self) -> None:
         self.pq.reset()
         self.miou.reset()

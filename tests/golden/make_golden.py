@@ -342,8 +342,108 @@ def run_orientation():
     print('orientation', [len(d) for d in r_mask])
 
 
+def run_task_helpers():
+    """Validation path of the reference's task helpers (task_helper/panoptic.py:87-212,
+    task_helper/instance.py:289-446): two validation steps + epoch end on random blocky
+    batches.  batch_idx != 0 skips the visualisation examples; the instance helper's loss
+    computation (not on the evaluated path) is bypassed by overriding `_compute_losses`."""
+    from types import SimpleNamespace
+    from nicr_mt_scene_analysis.task_helper.instance import InstanceTaskHelper
+    from nicr_mt_scene_analysis.task_helper.panoptic import PanopticTaskHelper
+
+    g = torch.Generator().manual_seed(29)
+    B, H, W, NC, L = 3, 64, 96, 7, 1 << 16
+    is_thing = [False, True, False, True, True, False, True]     # with void
+    it = torch.tensor(is_thing)
+    labels = SimpleNamespace(colors=[(i, 2 * i, 3 * i) for i in range(NC)],
+                             classes_is_thing=is_thing,
+                             colors_array=np.zeros((NC, 3), np.uint8))
+
+    class InstanceHelperNoLoss(InstanceTaskHelper):
+        def _compute_losses(self, batch, batch_idx, predictions_post):
+            self._with_orientation = 'orientations_present' in batch
+            return {}
+
+    pan_helper = PanopticTaskHelper(NC, is_thing, labels)
+    ins_helper = InstanceHelperNoLoss(NC, is_thing)
+    pan_helper.initialize(torch.device('cpu'))
+    ins_helper.initialize(torch.device('cpu'))
+
+    steps = []
+    for step in range(2):
+        cat_t = blocky(g, B, H, W, NC, 16)
+        inst_t = blocky(g, B, H, W, 4, 8) + 1
+        inst_gt = torch.where(it[cat_t], inst_t + 4 * (cat_t // 2), torch.zeros_like(inst_t))
+        pan_t = cat_t * L + inst_gt
+        # prediction of the panoptic branch: noisy classes, shifted instances
+        cat_p = torch.where(torch.rand(B, H, W, generator=g) < 0.12, blocky(g, B, H, W, NC, 16), cat_t)
+        inst_p = torch.where(it[cat_p], torch.roll(inst_t, 2, -1), torch.zeros_like(inst_t))
+        pan_p = cat_p * L + inst_p
+        # prediction of the instance branch inside the GT foreground (raw centre ids, uint8)
+        inst_fg = torch.where(inst_gt > 0, torch.roll(inst_gt, 1, -2) % 7 + 1,
+                              torch.zeros_like(inst_gt)).to(torch.uint8)
+        tgt_ids, pred_ids, ori_t, ori_p, ori_fg, ori_full_gt = [], [], [], [], [], []
+        for b in range(B):
+            tgt_ids.append({int(v): int(v) % L for v in torch.unique(pan_t[b]) if int(v) % L})
+            pred_ids.append({int(v): int(v) % L + 10 for v in torch.unique(pan_p[b]) if int(v) % L})
+            # orientations for every second GT instance; predictions for most raw ids
+            ori_t.append({i: float(0.37 * i + 0.1 * b + step) for i in set(tgt_ids[b].values())
+                          if i % 2 == 0})
+            ori_p.append({i: float(0.37 * (i - 10) + 0.25 - 0.05 * b) for i in set(pred_ids[b].values())
+                          if i % 3})
+            ori_fg.append({i: float(0.2 * i - 1.0 + step) for i in range(1, 8)})
+            ori_full_gt.append({i: a + 0.125 for i, a in ori_t[b].items()})
+        batch = {'panoptic_fullres': pan_t, 'semantic_fullres': cat_t.to(torch.uint8),
+                 'instance_fullres': inst_gt.to(torch.int32),
+                 'panoptic_ids_to_instance_dict': tgt_ids, 'orientations_present': ori_t}
+        pan_post = {'panoptic_segmentation_deeplab_fullres': pan_p,
+                    'panoptic_segmentation_deeplab_ids': pred_ids,
+                    'orientations_panoptic_segmentation_deeplab_instance': ori_p}
+        ins_post = {'instance_segmentation_gt_foreground_fullres': inst_fg,
+                    'orientations_instance_segmentation_gt_orientation_foreground': ori_fg,
+                    'orientations_gt_instance_gt_orientation_foreground': ori_full_gt}
+        pan_helper.validation_step(batch, 1 + step, pan_post)
+        ins_helper.validation_step(batch, 1 + step, ins_post)
+        steps.append(dict(pan_t=pan_t.numpy(), sem_t=cat_t.to(torch.uint8).numpy(),
+                          inst_gt=inst_gt.to(torch.int32).numpy(), pan_p=pan_p.numpy(),
+                          inst_fg=inst_fg.numpy(), tgt_ids=tgt_ids, pred_ids=pred_ids, ori_t=ori_t,
+                          ori_p=ori_p, ori_fg=ori_fg, ori_full_gt=ori_full_gt))
+
+    def pack(result):
+        artifacts, examples, logs = result
+        assert examples == {}
+        out = {}
+        for kind, d in (('artifacts', artifacts), ('logs', logs)):
+            for k, v in d.items():
+                if k.endswith('_time'):
+                    continue
+                out[f'{kind}/{k}'] = torch.as_tensor(v).double().numpy()
+        return out
+    pan_out = pack(pan_helper.validation_epoch_end())
+    ins_out = pack(ins_helper.validation_epoch_end())
+    arrays = {'is_thing': np.array(is_thing), 'num_categories': NC, 'n_steps': len(steps)}
+    for i, st in enumerate(steps):
+        for k in ('pan_t', 'sem_t', 'inst_gt', 'pan_p', 'inst_fg'):
+            arrays[f'step{i}/{k}'] = st[k]
+        for k in ('tgt_ids', 'pred_ids', 'ori_t', 'ori_p', 'ori_fg', 'ori_full_gt'):
+            arrays[f'step{i}/{k}'] = dicts_to_json(st[k])
+    for k, v in pan_out.items():
+        arrays[f'panoptic/{k}'] = v
+    for k, v in ins_out.items():
+        arrays[f'instance/{k}'] = v
+    np.savez_compressed(os.path.join(HERE, 'task_helpers.npz'), **arrays)
+    print('task helpers: panoptic all_pq', pan_out['logs/panoptic_all_deeplab_pq'],
+          'mae', pan_out['logs/panoptic_mae_deeplab_rad'],
+          '| instance all_pq', ins_out['logs/instance_all_deeplab_pq'],
+          'mae_gt', ins_out['logs/orientation_mae_gt_rad'])
+
+
 if __name__ == '__main__':
     torch.set_num_threads(1)
+    if len(sys.argv) > 1:       # regenerate selected fixtures only: make_golden.py task_helpers pq
+        for name in sys.argv[1:]:
+            globals()[f'run_{name}']()
+        sys.exit(0)
     run_postprocess('q10', B=3, C=8, H=96, W=128, K=5, seed=1, quantize='q10')
     run_postprocess('tie', B=3, C=6, H=96, W=128, K=6, seed=2, quantize='tie', top_k=3)
     run_postprocess('odd', B=2, C=5, H=75, W=91, K=4, seed=3, quantize='q10', ks=5,
@@ -360,3 +460,4 @@ if __name__ == '__main__':
     run_pq()
     run_miou()
     run_orientation()
+    run_task_helpers()

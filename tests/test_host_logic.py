@@ -206,3 +206,13 @@ def test_instance_tables_layout_is_aligned():
         import numpy as np
         for off, _, dt, _ in offsets.values():
             assert off % np.dtype(dt).itemsize == 0
+
+
+def test_task_helper_requires_cuda_device():
+    import torch
+    from nicr_mt_scene_analysis_b200.task_helper import PanopticTaskHelper
+    helper = PanopticTaskHelper(3, [False, True, False])
+    with pytest.raises(RuntimeError):
+        helper.initialize(torch.device('cpu'))
+    with pytest.raises(RuntimeError):
+        helper.device

@@ -215,3 +215,35 @@ def test_instance_targets():
     bad[0, stuff_px[0], stuff_px[1]] = 999          # a lone stuff pixel with an instance id
     with pytest.raises(AssertionError):
         oracle.instance_targets(z['sem'], bad, 5, z['is_thing'].tolist(), True)
+
+
+def test_task_helper_epoch_results():
+    """The oracle reproduces what the reference's PanopticTaskHelper / InstanceTaskHelper log
+    at the end of a validation epoch (tests/golden/task_helpers.npz): PQ states accumulated
+    over two steps, the confusion matrix of `pred // L`, and for the instance helper the merge
+    of GT semantic + predicted instances that precedes the PQ."""
+    z = load_golden('task_helpers')
+    NC, L, OFF = int(z['num_categories']), 1 << 16, 256 ** 3
+    is_thing = z['is_thing']
+    thing_ids = [int(i) for i in np.nonzero(is_thing)[0]]
+    st_pan, st_ins = np.zeros((4, NC)), np.zeros((4, NC))
+    cm = np.zeros((NC, NC), np.int64)
+    for i in range(int(z['n_steps'])):
+        pan_t, pan_p = z[f'step{i}/pan_t'], z[f'step{i}/pan_p']
+        merged, _ = oracle.deeplab_merge_batch(z[f'step{i}/sem_t'], z[f'step{i}/inst_fg'],
+                                               z[f'step{i}/inst_gt'] != 0, L, thing_ids, 0)
+        for b in range(pan_t.shape[0]):
+            for st, pred in ((st_pan, pan_p[b]), (st_ins, merged[b])):
+                out = oracle.pq_compare_and_accumulate(pred, pan_t[b], NC, 0, L, OFF, 0)
+                for s, v in zip(st, out[:4]):
+                    s += v
+        cm += oracle.confmat(pan_p // L, z[f'step{i}/sem_t'], NC)
+    assert np.array_equal(cm, z['panoptic/artifacts/panoptic_deeplab_semantic_cm'])
+    miou, ious = oracle.miou_from_confmat(cm, True)
+    np.testing.assert_allclose(miou, z['panoptic/logs/panoptic_deeplab_semantic_miou'], rtol=1e-6)
+    for prefix, st in (('panoptic', st_pan), ('instance', st_ins)):
+        res = oracle.pq_results(*st, is_thing, 0, suffix='_deeplab')
+        for k, v in res.items():
+            kind = 'artifacts' if np.ndim(v) else 'logs'
+            np.testing.assert_allclose(np.float64(v), z[f'{prefix}/{kind}/{prefix}_{k}'],
+                                       rtol=1e-14, err_msg=k)
