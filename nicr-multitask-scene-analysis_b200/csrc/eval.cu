@@ -27,7 +27,7 @@ namespace npb {
 
 constexpr int kPairThreads = 256;
 constexpr int kSmemSlots = 2048;       // per-CTA pair hash table (instance pairs; class pairs go dense)
-constexpr int kFrameSlots = 16384;     // per-frame global pair hash table
+constexpr int kFrameSlots = 8192;      // per-frame global pair hash table (<= kMaxPairs entries)
 constexpr int kMaxPairs = 4096;        // pairs per frame handled by the matcher
 constexpr int kMatchThreads = 512;
 constexpr unsigned long long kEmptyKey = ~0ull;
@@ -62,14 +62,41 @@ __device__ __forceinline__ bool table_add(unsigned long long *keys, unsigned *cn
     return false;
 }
 
-// the per-frame global table (flush target, and overflow of the CTA table); out of line: it is
-// the rare path and the pixel loop should stay small in the instruction cache
-__device__ __noinline__ void pair_insert_global(unsigned long long *fkeys, unsigned *fcnts,
-                                                unsigned long long key, unsigned cnt,
-                                                int32_t *status)
+// The per-frame global table (flush target, and overflow of the CTA table).  ONE memset of 0xff
+// prepares all of it: an empty key is ~0, a pixel count starts at 0xffffffff (= -1, so the
+// stored value is count - 1), and so does the number of entries.  Every newly claimed slot is
+// appended to the frame's slot list, which lets the matcher read the (few hundred) pairs of a
+// frame directly instead of scanning the table.
+struct FrameTable {
+    unsigned long long *keys;   // [kFrameSlots]
+    unsigned *cnts;             // [kFrameSlots] pixels - 1
+    unsigned short *list;       // [kMaxPairs] claimed slots, in claim order
+    unsigned *n;                // entries - 1
+    int32_t *status;
+};
+
+// out of line: it is the rare path and the pixel loop should stay small in the instruction cache
+__device__ __noinline__ void pair_insert_global(const FrameTable ft, unsigned long long key,
+                                                unsigned cnt)
 {
-    if (!table_add(fkeys, fcnts, kFrameSlots, kFrameSlots, key, cnt))
-        set_status(status, NPB_ERR_CAPACITY);
+    unsigned h = hash64(key) & (unsigned)(kFrameSlots - 1);
+    for (int probe = 0; probe < kFrameSlots; ++probe) {
+        unsigned long long k = ft.keys[h];
+        if (k == kEmptyKey) {
+            k = atomicCAS(ft.keys + h, kEmptyKey, key);
+            if (k == kEmptyKey) {                           // this thread claimed the slot
+                const unsigned idx = atomicAdd(ft.n, 1u) + 1u;
+                if (idx < (unsigned)kMaxPairs) ft.list[idx] = (unsigned short)h;
+                else set_status(ft.status, NPB_ERR_CAPACITY);
+            }
+        }
+        if (k == kEmptyKey || k == key) {
+            atomicAdd(ft.cnts + h, cnt);
+            return;
+        }
+        h = (h + 1) & (unsigned)(kFrameSlots - 1);
+    }
+    set_status(ft.status, NPB_ERR_CAPACITY);
 }
 
 struct PairParams {
@@ -82,8 +109,10 @@ struct PairParams {
     int O_shift;                // >= 0 when offset is a power of two
     int n;                      // confusion-matrix size (0 = no confmat)
     int nd;                     // side of the dense class-pair table (0 = disabled)
-    unsigned long long *frame_keys;  // [B][kFrameSlots]
-    unsigned *frame_cnts;
+    unsigned long long *frame_keys;  // [B][kFrameSlots]   (see FrameTable)
+    unsigned *frame_cnts;            // [B][kFrameSlots]
+    unsigned *frame_n;               // [B]
+    unsigned short *frame_list;      // [B][kMaxPairs]
     unsigned long long *confmat;     // [n][n] int64, accumulated
     int32_t *status;                 // [B]
 };
@@ -94,6 +123,12 @@ struct PairParams {
 //               (stuff / void / misclassified single pixels): no hashing, no probing
 //   cm        : privatised confusion matrix
 //   q_*       : one work queue per warp (see pair_count_kernel)
+__device__ __forceinline__ FrameTable frame_table(const PairParams &prm, int b)
+{
+    return FrameTable{prm.frame_keys + (size_t)b * kFrameSlots, prm.frame_cnts + (size_t)b * kFrameSlots,
+                      prm.frame_list + (size_t)b * kMaxPairs, prm.frame_n + b, prm.status + b};
+}
+
 struct PairTables {
     unsigned long long *keys;
     unsigned *cnts;
@@ -133,8 +168,7 @@ __device__ __forceinline__ void pair_consume(const PairTables &t, const PairPara
         }
     }
     if (!dense && !table_add(t.keys, t.cnts, kSmemSlots, 8, key, cnt))
-        pair_insert_global(prm.frame_keys + (size_t)b * kFrameSlots,
-                           prm.frame_cnts + (size_t)b * kFrameSlots, key, cnt, prm.status + b);
+        pair_insert_global(frame_table(prm, b), key, cnt);
     if (CONFMAT) {
         if (pc < 0 || pc >= prm.n || st >= prm.n) {
             set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
@@ -169,8 +203,7 @@ __device__ __forceinline__ void pair_consume_std(const PairTables &t, const Pair
     if (!dense) {
         const unsigned long long key = ((unsigned long long)(hi & 0xffffu) << 32) | lo;
         if (!table_add(t.keys, t.cnts, kSmemSlots, 8, key, cnt))
-            pair_insert_global(prm.frame_keys + (size_t)b * kFrameSlots,
-                               prm.frame_cnts + (size_t)b * kFrameSlots, key, cnt, prm.status + b);
+            pair_insert_global(frame_table(prm, b), key, cnt);
     }
     if (CONFMAT) {
         if (pc >= (unsigned)prm.n || st >= (unsigned)prm.n) {
@@ -501,11 +534,10 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
 
     // ---- flush the CTA tables into the per-frame table / the global confusion matrix --------
     __syncthreads();
-    unsigned long long *fkeys = prm.frame_keys + (size_t)b * kFrameSlots;
-    unsigned *fcnts = prm.frame_cnts + (size_t)b * kFrameSlots;
+    const FrameTable ft = frame_table(prm, b);
     for (int i = tid; i < kSmemSlots; i += kPairThreads) {
         const unsigned long long k = t.keys[i];
-        if (k != kEmptyKey && t.cnts[i]) pair_insert_global(fkeys, fcnts, k, t.cnts[i], prm.status + b);
+        if (k != kEmptyKey && t.cnts[i]) pair_insert_global(ft, k, t.cnts[i]);
     }
     for (int i = tid; i < nd * nd; i += kPairThreads) {
         const unsigned c = t.dense[i];
@@ -513,7 +545,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             const unsigned long long tc = (unsigned)(i / nd), pc = (unsigned)(i % nd);
             const unsigned long long key = (tc << prm.L_shift) * (unsigned long long)prm.offset +
                                            (pc << prm.L_shift);
-            pair_insert_global(fkeys, fcnts, key, c, prm.status + b);
+            pair_insert_global(ft, key, c);
         }
     }
     if (cm_smem)
@@ -523,8 +555,10 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
 
 // ---------------------------------------------------------------------------------------
 struct MatchParams {
-    const unsigned long long *frame_keys;
+    const unsigned long long *frame_keys;   // see FrameTable
     const unsigned *frame_cnts;
+    const unsigned *frame_n;
+    const unsigned short *frame_list;
     int num_categories;
     long long ignored_label, L, offset, void_segment_id;
     int L_shift, O_shift;  // >= 0 when L / offset are powers of two (shifts instead of 64-bit divisions)
@@ -589,7 +623,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     unsigned short *s_gslot = (unsigned short *)(p_matched + kSegSlots);   // [kMaxPairs]
     unsigned short *s_pslot = s_gslot + kMaxPairs;                         // [kMaxPairs]
     unsigned short *s_mcat = s_pslot + kMaxPairs;                          // [kMaxMatched]
-    __shared__ int s_m, s_nm;
+    __shared__ int s_nm;
     __shared__ int s_tp[256], s_fn[256], s_fp[256];
 
     SegTable gt{g_id, g_area, nullptr, nullptr, g_matched};
@@ -599,7 +633,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     const int NC = prm.num_categories;
     const unsigned long long *fkeys = prm.frame_keys + (size_t)b * kFrameSlots;
     const unsigned *fcnts = prm.frame_cnts + (size_t)b * kFrameSlots;
-    if (tid == 0) { s_m = 0; s_nm = 0; }
+    if (tid == 0) s_nm = 0;
     for (int c = tid; c < 256; c += kMatchThreads) { s_tp[c] = 0; s_fn[c] = 0; s_fp[c] = 0; }
     for (int i = tid; i < kSegSlots; i += kMatchThreads) {
         g_id[i] = kEmptyKey; p_id[i] = kEmptyKey;
@@ -607,32 +641,17 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     }
     __syncthreads();
 
-    // (0) gather the frame's pairs (independent loads first: the loop is latency bound)
-    constexpr int kGather = 8;
-    for (int i0 = tid; i0 < kFrameSlots; i0 += kMatchThreads * kGather) {
-        unsigned long long k[kGather];
-#pragma unroll
-        for (int u = 0; u < kGather; ++u) {
-            const int i = i0 + u * kMatchThreads;
-            k[u] = i < kFrameSlots ? fkeys[i] : kEmptyKey;
-        }
-#pragma unroll
-        for (int u = 0; u < kGather; ++u) {
-            if (k[u] != kEmptyKey) {
-                const int slot = atomicAdd(&s_m, 1);
-                if (slot < kMaxPairs) {
-                    s_key[slot] = (long long)k[u];
-                    s_cnt[slot] = fcnts[i0 + u * kMatchThreads];
-                }
-            }
-        }
+    // (0) the frame's pairs, through the slot list the pixel pass left behind
+    const unsigned n_pairs = prm.frame_n[b] + 1u;            // the counter starts at -1
+    int m = n_pairs < (unsigned)kMaxPairs ? (int)n_pairs : kMaxPairs;
+    if (n_pairs > (unsigned)kMaxPairs && tid == 0) set_status(prm.status + b, NPB_ERR_CAPACITY);
+    const unsigned short *flist = prm.frame_list + (size_t)b * kMaxPairs;
+    for (int t = tid; t < m; t += kMatchThreads) {
+        const int slot = flist[t];
+        s_key[t] = (long long)fkeys[slot];
+        s_cnt[t] = fcnts[slot] + 1u;                         // stored as pixels - 1
     }
     __syncthreads();
-    int m = s_m;
-    if (m > kMaxPairs) {
-        if (tid == 0) set_status(prm.status + b, NPB_ERR_CAPACITY);
-        m = kMaxPairs;
-    }
 
     // (1) segment tables: areas (pq.py:83-84), void overlap (pq.py:34-43), ignored overlap
     //     (pq.py:47-57); every pair remembers the slots of its two segments
@@ -705,7 +724,9 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
             }
         }
         if (p_id[i] != kEmptyKey && !p_matched[i]) {
-            if (!((double)p_pio[i] / (double)p_area[i] > 0.5)) {
+            // pio / area > 0.5 in float64 (pq.py:172) <=> 2 * pio > area: the quotient of two
+            // integers < 2^32 is never closer to 0.5 than 2^-33 unless it equals 0.5
+            if (!(2ull * p_pio[i] > (unsigned long long)p_area[i])) {
                 const long long cat = div_pow2((long long)p_id[i], prm.L, prm.L_shift);
                 if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
                 else atomicAdd(&s_fp[(int)cat], 1);
@@ -713,36 +734,27 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         }
     }
 
-    // (4) matched pairs in ascending key order (= the reference's visiting order, pq.py:109/119):
-    //     small bitonic sort, then per category the float64 IoU sum in that order
-    int nm = s_nm < kMaxMatched ? s_nm : kMaxMatched;
-    int npad = 1;
-    while (npad < nm) npad <<= 1;
-    for (int i = nm + tid; i < npad; i += kMatchThreads) s_mkey[i] = 0x7fffffffffffffffll;
-    __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < npad; i += kMatchThreads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool up = ((i & k) == 0);
-                    const long long a0 = s_mkey[i], a1 = s_mkey[ixj];
-                    if ((a0 > a1) == up) {
-                        s_mkey[i] = a1; s_mkey[ixj] = a0;
-                        unsigned x = s_mia[i]; s_mia[i] = s_mia[ixj]; s_mia[ixj] = x;
-                        x = s_muni[i]; s_muni[i] = s_muni[ixj]; s_muni[ixj] = x;
-                        const unsigned short cc = s_mcat[i]; s_mcat[i] = s_mcat[ixj]; s_mcat[ixj] = cc;
-                    }
-                }
-            }
-            __syncthreads();
-        }
+    // (4) float64 IoU sums per category with the matched pairs in ascending key order (= the
+    //     reference's visiting order, pq.py:109/119).  Keys are unique, so the rank of a pair is
+    //     the number of smaller keys: every thread ranks its pairs against all others
+    //     (broadcast reads, no barriers) and drops IoU + category at the ranked position.
+    __syncthreads();                                  // phases 2 / 3 done: s_key, s_cnt are free
+    const int nm = s_nm < kMaxMatched ? s_nm : kMaxMatched;
+    double *s_siou = (double *)s_key;                 // [kMaxMatched] sorted IoUs
+    unsigned short *s_scat = (unsigned short *)s_cnt; // [kMaxMatched] their categories
+    for (int i = tid; i < nm; i += kMatchThreads) {
+        const long long key = s_mkey[i];
+        int rank = 0;
+        for (int j = 0; j < nm; ++j) rank += s_mkey[j] < key;
+        s_siou[rank] = (double)s_mia[i] / (double)s_muni[i];              // pq.py:145
+        s_scat[rank] = s_mcat[i];
     }
+    __syncthreads();
     for (int c = tid; c < NC; c += kMatchThreads) {
         double acc = 0.0;
         if (c < 256 && s_tp[c] > 0)
             for (int i = 0; i < nm; ++i)
-                if (s_mcat[i] == c) acc += (double)s_mia[i] / (double)s_muni[i];
+                if (s_scat[i] == c) acc += s_siou[i];
         double *fs = prm.frame_stats + (size_t)b * 4 * NC;
         fs[c] = acc;
         fs[NC + c] = c < 256 ? (double)s_tp[c] : 0.0;
@@ -856,11 +868,17 @@ extern "C" int npb_confmat_update(const void *preds, int preds_dtype, const void
     return record_launch("npb_confmat_update");
 }
 
-// workspace: [frame_keys | frame_cnts | frame_stats]
+// workspace: [frame_keys | frame_cnts | frame_n] (one memset) | frame_list | frame_stats
+static size_t pq_table_bytes(int B)
+{
+    return align256((size_t)B * kFrameSlots * (sizeof(unsigned long long) + sizeof(unsigned)) +
+                    (size_t)B * sizeof(unsigned));
+}
+
 extern "C" size_t npb_pq_update_workspace_bytes(int B, int num_categories)
 {
-    size_t bytes = align256((size_t)B * kFrameSlots * sizeof(unsigned long long));
-    bytes += align256((size_t)B * kFrameSlots * sizeof(unsigned));
+    size_t bytes = pq_table_bytes(B);
+    bytes += align256((size_t)B * kMaxPairs * sizeof(unsigned short));
     bytes += align256((size_t)B * 4 * num_categories * sizeof(double));
     return bytes;
 }
@@ -884,13 +902,15 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
 
     char *ws = (char *)workspace;
     unsigned long long *fkeys = (unsigned long long *)ws;
-    ws += align256((size_t)B * kFrameSlots * sizeof(unsigned long long));
-    unsigned *fcnts = (unsigned *)ws;
-    ws += align256((size_t)B * kFrameSlots * sizeof(unsigned));
+    unsigned *fcnts = (unsigned *)(fkeys + (size_t)B * kFrameSlots);
+    unsigned *fn_entries = fcnts + (size_t)B * kFrameSlots;
+    ws += pq_table_bytes(B);
+    unsigned short *flist = (unsigned short *)ws;
+    ws += align256((size_t)B * kMaxPairs * sizeof(unsigned short));
     double *fstats = frame_stats ? frame_stats : (double *)ws;
 
-    cudaMemsetAsync(fkeys, 0xff, (size_t)B * kFrameSlots * sizeof(unsigned long long), s);
-    cudaMemsetAsync(fcnts, 0, (size_t)B * kFrameSlots * sizeof(unsigned), s);
+    // empty keys, counts and entry counters at -1 (see FrameTable)
+    cudaMemsetAsync(fkeys, 0xff, pq_table_bytes(B), s);
 
     PairParams pp;
     pp.pred = (const long long *)pred; pp.target = (const long long *)target;
@@ -904,7 +924,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     pp.n = confmat ? confmat_n : 0;
     // dense class-pair table: needs `id >> shift` decoding and a table that fits next to the rest
     pp.nd = (pp.L_shift >= 0 && num_categories <= kSmemConfmatMaxN) ? num_categories : 0;
-    pp.frame_keys = fkeys; pp.frame_cnts = fcnts;
+    pp.frame_keys = fkeys; pp.frame_cnts = fcnts; pp.frame_n = fn_entries; pp.frame_list = flist;
     pp.confmat = (unsigned long long *)confmat; pp.status = status;
 
     const bool vec4 = (P % 4 == 0) && (((uintptr_t)pred | (uintptr_t)target) & 15u) == 0 &&
@@ -969,7 +989,8 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     kernel<<<grid, kPairThreads, pc_smem, s>>>(pp);
 
     MatchParams mp;
-    mp.frame_keys = fkeys; mp.frame_cnts = fcnts; mp.num_categories = num_categories;
+    mp.frame_keys = fkeys; mp.frame_cnts = fcnts; mp.frame_n = fn_entries; mp.frame_list = flist;
+    mp.num_categories = num_categories;
     mp.ignored_label = ignored_label; mp.L = max_instances_per_category; mp.offset = offset;
     mp.void_segment_id = void_segment_id; mp.frame_stats = fstats;
     mp.L_shift = pp.L_shift; mp.O_shift = pp.O_shift;
