@@ -27,8 +27,7 @@ namespace npb {
 
 constexpr int kPairThreads = 256;
 constexpr int kSmemSlots = 2048;       // per-CTA pair hash table (instance pairs; class pairs go dense)
-constexpr int kFrameSlots = 8192;      // per-frame global pair hash table (<= kMaxPairs entries)
-constexpr int kMaxPairs = 4096;        // pairs per frame handled by the matcher
+constexpr int kMaxPairs = 4096;        // distinct pairs per frame handled by the matcher
 constexpr int kMatchThreads = 512;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kSmemConfmatMaxN = 96;   // n*n*4 B <= 36 KB privatised in shared memory
@@ -62,41 +61,30 @@ __device__ __forceinline__ bool table_add(unsigned long long *keys, unsigned *cn
     return false;
 }
 
-// The per-frame global table (flush target, and overflow of the CTA table).  ONE memset of 0xff
-// prepares all of it: an empty key is ~0, a pixel count starts at 0xffffffff (= -1, so the
-// stored value is count - 1), and so does the number of entries.  Every newly claimed slot is
-// appended to the frame's slot list, which lets the matcher read the (few hundred) pairs of a
-// frame directly instead of scanning the table.
-struct FrameTable {
-    unsigned long long *keys;   // [kFrameSlots]
-    unsigned *cnts;             // [kFrameSlots] pixels - 1
-    unsigned short *list;       // [kMaxPairs] claimed slots, in claim order
-    unsigned *n;                // entries - 1
+// Hand-over from the pixel pass to the matcher: a per-frame LIST of (pair key, pixels) entries.
+// Every CTA appends the contents of its tables with plain stores after reserving a range with
+// one atomic; the same pair may appear once per CTA (and once more per overflow of a CTA
+// table), the matcher merges duplicates in shared memory.  No global hash table, no
+// compare-and-swap round trips, and only the B entry counters need clearing per launch.
+struct FrameEntries {
+    unsigned long long *keys;   // [cap]
+    unsigned *cnts;             // [cap]
+    unsigned *n;                // entries appended so far (may exceed cap: then the frame failed)
+    unsigned cap;
     int32_t *status;
 };
 
-// out of line: it is the rare path and the pixel loop should stay small in the instruction cache
-__device__ __noinline__ void pair_insert_global(const FrameTable ft, unsigned long long key,
-                                                unsigned cnt)
+// single entry straight to the list (a CTA table overflowed); out of line: it is the rare path
+// and the pixel loop should stay small in the instruction cache
+__device__ __noinline__ void emit_entry(const FrameEntries fe, unsigned long long key, unsigned cnt)
 {
-    unsigned h = hash64(key) & (unsigned)(kFrameSlots - 1);
-    for (int probe = 0; probe < kFrameSlots; ++probe) {
-        unsigned long long k = ft.keys[h];
-        if (k == kEmptyKey) {
-            k = atomicCAS(ft.keys + h, kEmptyKey, key);
-            if (k == kEmptyKey) {                           // this thread claimed the slot
-                const unsigned idx = atomicAdd(ft.n, 1u) + 1u;
-                if (idx < (unsigned)kMaxPairs) ft.list[idx] = (unsigned short)h;
-                else set_status(ft.status, NPB_ERR_CAPACITY);
-            }
-        }
-        if (k == kEmptyKey || k == key) {
-            atomicAdd(ft.cnts + h, cnt);
-            return;
-        }
-        h = (h + 1) & (unsigned)(kFrameSlots - 1);
+    const unsigned idx = atomicAdd(fe.n, 1u);
+    if (idx < fe.cap) {
+        fe.keys[idx] = key;
+        fe.cnts[idx] = cnt;
+    } else {
+        set_status(fe.status, NPB_ERR_CAPACITY);
     }
-    set_status(ft.status, NPB_ERR_CAPACITY);
 }
 
 struct PairParams {
@@ -109,10 +97,10 @@ struct PairParams {
     int O_shift;                // >= 0 when offset is a power of two
     int n;                      // confusion-matrix size (0 = no confmat)
     int nd;                     // side of the dense class-pair table (0 = disabled)
-    unsigned long long *frame_keys;  // [B][kFrameSlots]   (see FrameTable)
-    unsigned *frame_cnts;            // [B][kFrameSlots]
-    unsigned *frame_n;               // [B]
-    unsigned short *frame_list;      // [B][kMaxPairs]
+    unsigned long long *entry_keys;  // [B][entry_cap]   (see FrameEntries)
+    unsigned *entry_cnts;            // [B][entry_cap]
+    unsigned *entry_n;               // [B], zeroed before the launch
+    unsigned entry_cap;
     unsigned long long *confmat;     // [n][n] int64, accumulated
     int32_t *status;                 // [B]
 };
@@ -123,10 +111,11 @@ struct PairParams {
 //               (stuff / void / misclassified single pixels): no hashing, no probing
 //   cm        : privatised confusion matrix
 //   q_*       : one work queue per warp (see pair_count_kernel)
-__device__ __forceinline__ FrameTable frame_table(const PairParams &prm, int b)
+__device__ __forceinline__ FrameEntries frame_entries(const PairParams &prm, int b)
 {
-    return FrameTable{prm.frame_keys + (size_t)b * kFrameSlots, prm.frame_cnts + (size_t)b * kFrameSlots,
-                      prm.frame_list + (size_t)b * kMaxPairs, prm.frame_n + b, prm.status + b};
+    return FrameEntries{prm.entry_keys + (size_t)b * prm.entry_cap,
+                        prm.entry_cnts + (size_t)b * prm.entry_cap, prm.entry_n + b, prm.entry_cap,
+                        prm.status + b};
 }
 
 struct PairTables {
@@ -168,7 +157,7 @@ __device__ __forceinline__ void pair_consume(const PairTables &t, const PairPara
         }
     }
     if (!dense && !table_add(t.keys, t.cnts, kSmemSlots, 8, key, cnt))
-        pair_insert_global(frame_table(prm, b), key, cnt);
+        emit_entry(frame_entries(prm, b), key, cnt);
     if (CONFMAT) {
         if (pc < 0 || pc >= prm.n || st >= prm.n) {
             set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
@@ -203,7 +192,7 @@ __device__ __forceinline__ void pair_consume_std(const PairTables &t, const Pair
     if (!dense) {
         const unsigned long long key = ((unsigned long long)(hi & 0xffffu) << 32) | lo;
         if (!table_add(t.keys, t.cnts, kSmemSlots, 8, key, cnt))
-            pair_insert_global(frame_table(prm, b), key, cnt);
+            emit_entry(frame_entries(prm, b), key, cnt);
     }
     if (CONFMAT) {
         if (pc >= (unsigned)prm.n || st >= (unsigned)prm.n) {
@@ -532,12 +521,32 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
 
     }
 
-    // ---- flush the CTA tables into the per-frame table / the global confusion matrix --------
+    // ---- flush: append the CTA tables to the frame's entry list, add the confusion matrix ----
+    // count, reserve a range of the list with ONE global atomic, then store
+    __shared__ unsigned s_total, s_base, s_cursor;
+    if (tid == 0) { s_total = 0; s_cursor = 0; }
     __syncthreads();
-    const FrameTable ft = frame_table(prm, b);
+    unsigned mine = 0;
+    for (int i = tid; i < kSmemSlots; i += kPairThreads) mine += (t.keys[i] != kEmptyKey && t.cnts[i]) ? 1u : 0u;
+    for (int i = tid; i < nd * nd; i += kPairThreads) mine += t.dense[i] ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFullMask, mine, o);
+    if (lane == 0 && mine) atomicAdd(&s_total, mine);
+    __syncthreads();
+    const FrameEntries fe = frame_entries(prm, b);
+    if (tid == 0) {
+        s_base = s_total ? atomicAdd(fe.n, s_total) : 0u;
+        if (s_total && s_base + s_total > fe.cap) set_status(fe.status, NPB_ERR_CAPACITY);
+    }
+    __syncthreads();
+    const unsigned base = s_base;
     for (int i = tid; i < kSmemSlots; i += kPairThreads) {
         const unsigned long long k = t.keys[i];
-        if (k != kEmptyKey && t.cnts[i]) pair_insert_global(ft, k, t.cnts[i]);
+        const unsigned c = t.cnts[i];
+        if (k != kEmptyKey && c) {
+            const unsigned idx = base + atomicAdd(&s_cursor, 1u);
+            if (idx < fe.cap) { fe.keys[idx] = k; fe.cnts[idx] = c; }
+        }
     }
     for (int i = tid; i < nd * nd; i += kPairThreads) {
         const unsigned c = t.dense[i];
@@ -545,7 +554,8 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             const unsigned long long tc = (unsigned)(i / nd), pc = (unsigned)(i % nd);
             const unsigned long long key = (tc << prm.L_shift) * (unsigned long long)prm.offset +
                                            (pc << prm.L_shift);
-            pair_insert_global(ft, key, c);
+            const unsigned idx = base + atomicAdd(&s_cursor, 1u);
+            if (idx < fe.cap) { fe.keys[idx] = key; fe.cnts[idx] = c; }
         }
     }
     if (cm_smem)
@@ -555,10 +565,10 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
 
 // ---------------------------------------------------------------------------------------
 struct MatchParams {
-    const unsigned long long *frame_keys;   // see FrameTable
-    const unsigned *frame_cnts;
-    const unsigned *frame_n;
-    const unsigned short *frame_list;
+    const unsigned long long *entry_keys;   // see FrameEntries
+    const unsigned *entry_cnts;
+    const unsigned *entry_n;
+    unsigned entry_cap;
     int num_categories;
     long long ignored_label, L, offset, void_segment_id;
     int L_shift, O_shift;  // >= 0 when L / offset are powers of two (shifts instead of 64-bit divisions)
@@ -570,9 +580,11 @@ struct MatchParams {
 };
 
 // ---- matcher: one CTA per frame ------------------------------------------------------------
-// Segment tables (distinct gt ids / pred ids of the frame) are shared-memory hash tables filled
-// from the frame's pair table with atomics; only the matched pairs (one per matched gt segment
-// at most) are sorted, because only their float64 IoU sum depends on the visiting order.
+// The frame's entry list is merged into a shared-memory pair table (pair -> pixels); segment
+// tables (distinct gt ids / pred ids of the frame) are shared-memory hash tables filled from
+// the pairs with atomics; only the matched pairs (one per matched gt segment at most) are
+// ordered, because only their float64 IoU sum depends on the visiting order.
+constexpr int kPairSlots = 2 * kMaxPairs;   // pair table of the matcher (load factor <= 0.5)
 constexpr int kSegSlots = 2048;       // distinct gt (and pred) segments per frame: <= 1536
 constexpr int kMaxMatched = 1024;
 
@@ -581,7 +593,7 @@ struct SegTable {
     unsigned *area;           // [kSegSlots] pixels of the segment
     unsigned *aux;            // gt: unused; pred: pixels inside the gt void segment
     unsigned *pio;            // pred: pixels inside ignored gt segments
-    unsigned *matched;        // 1 once the segment took part in a match
+    unsigned char *matched;   // 1 once the segment took part in a match
 };
 
 __device__ __forceinline__ long long div_pow2(long long v, long long d, int shift)
@@ -605,25 +617,25 @@ __device__ __forceinline__ int seg_slot(SegTable &tb, unsigned long long id)
 __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const MatchParams prm)
 {
     extern __shared__ unsigned char smem_raw[];
-    // pairs of the frame
-    long long *s_key = (long long *)smem_raw;                       // [kMaxPairs]
+    // pair table of the frame
+    unsigned long long *t_key = (unsigned long long *)smem_raw;     // [kPairSlots]
     // matched pairs: key, intersection, union
-    long long *s_mkey = s_key + kMaxPairs;                          // [kMaxMatched]
+    long long *s_mkey = (long long *)(t_key + kPairSlots);          // [kMaxMatched]
     unsigned long long *g_id = (unsigned long long *)(s_mkey + kMaxMatched);   // [kSegSlots]
     unsigned long long *p_id = g_id + kSegSlots;                    // [kSegSlots]
-    unsigned *s_cnt = (unsigned *)(p_id + kSegSlots);               // [kMaxPairs]
-    unsigned *s_mia = s_cnt + kMaxPairs;                            // [kMaxMatched]
+    unsigned *t_cnt = (unsigned *)(p_id + kSegSlots);               // [kPairSlots]
+    unsigned *s_mia = t_cnt + kPairSlots;                           // [kMaxMatched]
     unsigned *s_muni = s_mia + kMaxMatched;                         // [kMaxMatched]
     unsigned *g_area = s_muni + kMaxMatched;                        // [kSegSlots] ...
-    unsigned *g_matched = g_area + kSegSlots;
-    unsigned *p_area = g_matched + kSegSlots;
+    unsigned *p_area = g_area + kSegSlots;
     unsigned *p_void = p_area + kSegSlots;
     unsigned *p_pio = p_void + kSegSlots;
-    unsigned *p_matched = p_pio + kSegSlots;
-    unsigned short *s_gslot = (unsigned short *)(p_matched + kSegSlots);   // [kMaxPairs]
-    unsigned short *s_pslot = s_gslot + kMaxPairs;                         // [kMaxPairs]
-    unsigned short *s_mcat = s_pslot + kMaxPairs;                          // [kMaxMatched]
-    __shared__ int s_nm;
+    unsigned short *t_gslot = (unsigned short *)(p_pio + kSegSlots);       // [kPairSlots]
+    unsigned short *t_pslot = t_gslot + kPairSlots;                        // [kPairSlots]
+    unsigned short *s_mcat = t_pslot + kPairSlots;                         // [kMaxMatched]
+    unsigned char *g_matched = (unsigned char *)(s_mcat + kMaxMatched);    // [kSegSlots]
+    unsigned char *p_matched = g_matched + kSegSlots;                      // [kSegSlots]
+    __shared__ int s_m, s_nm;
     __shared__ int s_tp[256], s_fn[256], s_fp[256];
 
     SegTable gt{g_id, g_area, nullptr, nullptr, g_matched};
@@ -631,40 +643,73 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int NC = prm.num_categories;
-    const unsigned long long *fkeys = prm.frame_keys + (size_t)b * kFrameSlots;
-    const unsigned *fcnts = prm.frame_cnts + (size_t)b * kFrameSlots;
-    if (tid == 0) s_nm = 0;
+    if (tid == 0) { s_m = 0; s_nm = 0; }
     for (int c = tid; c < 256; c += kMatchThreads) { s_tp[c] = 0; s_fn[c] = 0; s_fp[c] = 0; }
+    for (int i = tid; i < kPairSlots; i += kMatchThreads) { t_key[i] = kEmptyKey; t_cnt[i] = 0; }
     for (int i = tid; i < kSegSlots; i += kMatchThreads) {
         g_id[i] = kEmptyKey; p_id[i] = kEmptyKey;
         g_area[i] = 0; g_matched[i] = 0; p_area[i] = 0; p_void[i] = 0; p_pio[i] = 0; p_matched[i] = 0;
     }
     __syncthreads();
 
-    // (0) the frame's pairs, through the slot list the pixel pass left behind
-    const unsigned n_pairs = prm.frame_n[b] + 1u;            // the counter starts at -1
-    int m = n_pairs < (unsigned)kMaxPairs ? (int)n_pairs : kMaxPairs;
-    if (n_pairs > (unsigned)kMaxPairs && tid == 0) set_status(prm.status + b, NPB_ERR_CAPACITY);
-    const unsigned short *flist = prm.frame_list + (size_t)b * kMaxPairs;
-    for (int t = tid; t < m; t += kMatchThreads) {
-        const int slot = flist[t];
-        s_key[t] = (long long)fkeys[slot];
-        s_cnt[t] = fcnts[slot] + 1u;                         // stored as pixels - 1
+    // (0) merge the frame's entry list (one entry per pair and CTA of the pixel pass) into the
+    //     pair table; independent loads first, the loop is latency bound
+    {
+        const unsigned n_raw = prm.entry_n[b];
+        const unsigned n_ent = n_raw < prm.entry_cap ? n_raw : prm.entry_cap;   // overflow: flagged by the writer
+        const unsigned long long *ekeys = prm.entry_keys + (size_t)b * prm.entry_cap;
+        const unsigned *ecnts = prm.entry_cnts + (size_t)b * prm.entry_cap;
+        constexpr int kBatch = 4;
+        for (unsigned e0 = tid; e0 < n_ent; e0 += kMatchThreads * kBatch) {
+            unsigned long long k[kBatch];
+            unsigned c[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const unsigned e = e0 + u * kMatchThreads;
+                k[u] = e < n_ent ? ekeys[e] : kEmptyKey;
+                c[u] = e < n_ent ? ecnts[e] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (c[u] == 0u) continue;
+                unsigned h = hash64(k[u]) & (unsigned)(kPairSlots - 1);
+                bool done = false;
+                for (int probe = 0; probe < kPairSlots && !done; ++probe) {
+                    unsigned long long cur = t_key[h];
+                    if (cur == kEmptyKey) {
+                        cur = atomicCAS(t_key + h, kEmptyKey, k[u]);
+                        if (cur == kEmptyKey && atomicAdd(&s_m, 1) >= kMaxPairs)
+                            set_status(prm.status + b, NPB_ERR_CAPACITY);
+                    }
+                    if (cur == kEmptyKey || cur == k[u]) {
+                        atomicAdd(t_cnt + h, c[u]);
+                        done = true;
+                    }
+                    h = (h + 1) & (unsigned)(kPairSlots - 1);
+                }
+                if (!done) set_status(prm.status + b, NPB_ERR_CAPACITY);
+            }
+        }
     }
     __syncthreads();
 
     // (1) segment tables: areas (pq.py:83-84), void overlap (pq.py:34-43), ignored overlap
     //     (pq.py:47-57); every pair remembers the slots of its two segments
-    for (int t = tid; t < m; t += kMatchThreads) {
-        const long long key = s_key[t];
-        const unsigned cnt = s_cnt[t];
+    for (int t = tid; t < kPairSlots; t += kMatchThreads) {
+        const long long key = (long long)t_key[t];
+        if ((unsigned long long)key == kEmptyKey) continue;
+        const unsigned cnt = t_cnt[t];
         const long long g = div_pow2(key, prm.offset, prm.O_shift);
         const long long p = key - g * prm.offset;
         const int gs = seg_slot(gt, (unsigned long long)g);
         const int ps = seg_slot(pt, (unsigned long long)p);
-        if (gs < 0 || ps < 0) { set_status(prm.status + b, NPB_ERR_CAPACITY); continue; }
-        s_gslot[t] = (unsigned short)gs;
-        s_pslot[t] = (unsigned short)ps;
+        if (gs < 0 || ps < 0) {
+            set_status(prm.status + b, NPB_ERR_CAPACITY);
+            t_key[t] = kEmptyKey;           // later phases skip the pair (its frame failed anyway)
+            continue;
+        }
+        t_gslot[t] = (unsigned short)gs;
+        t_pslot[t] = (unsigned short)ps;
         atomicAdd(g_area + gs, cnt);
         atomicAdd(p_area + ps, cnt);
         if (g == prm.void_segment_id) p_void[ps] = cnt;     // key == void*offset + p, unique
@@ -673,19 +718,20 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     __syncthreads();
 
     // (2) IoU + match decision per intersecting pair                       pq.py:119-152
-    for (int t = tid; t < m; t += kMatchThreads) {
-        const long long key = s_key[t];
+    for (int t = tid; t < kPairSlots; t += kMatchThreads) {
+        const long long key = (long long)t_key[t];
+        if ((unsigned long long)key == kEmptyKey) continue;
         if (key == prm.void_segment_id) continue;                          // pq.py:120
         const long long g = div_pow2(key, prm.offset, prm.O_shift), p = key - g * prm.offset;
         const long long gcat = div_pow2(g, prm.L, prm.L_shift), pcat = div_pow2(p, prm.L, prm.L_shift);
         if (gcat != pcat) continue;                                        // pq.py:128
-        const int gs = s_gslot[t], ps = s_pslot[t];
-        const long long ia = s_cnt[t];
+        const int gs = t_gslot[t], ps = t_pslot[t];
+        const long long ia = t_cnt[t];
         const long long uni = (long long)g_area[gs] + (long long)p_area[ps] - ia -
                               (long long)p_void[ps];                       // pq.py:143
         if (uni == 0) { set_status(prm.status + b, NPB_ERR_ZERO_DIVISION); continue; }
-        const double iou = (double)ia / (double)uni;                       // pq.py:145
-        if (iou > 0.5) {
+        // iou = ia / uni > 0.5 in float64 (pq.py:145-146) <=> 2 * ia > uni (integers < 2^33)
+        if (2 * ia > uni) {
             if (gcat < 0 || gcat >= NC || gcat >= 256) { set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE); continue; }
             g_matched[gs] = 1;
             p_matched[ps] = 1;
@@ -738,10 +784,9 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     //     reference's visiting order, pq.py:109/119).  Keys are unique, so the rank of a pair is
     //     the number of smaller keys: every thread ranks its pairs against all others
     //     (broadcast reads, no barriers) and drops IoU + category at the ranked position.
-    __syncthreads();                                  // phases 2 / 3 done: s_key, s_cnt are free
-    const int nm = s_nm < kMaxMatched ? s_nm : kMaxMatched;
-    double *s_siou = (double *)s_key;                 // [kMaxMatched] sorted IoUs
-    unsigned short *s_scat = (unsigned short *)s_cnt; // [kMaxMatched] their categories
+    const int nm = s_nm < kMaxMatched ? s_nm : kMaxMatched;     // stable since the last barrier
+    double *s_siou = (double *)t_gslot;                         // [kMaxMatched] sorted IoUs; the
+    unsigned short *s_scat = (unsigned short *)(s_siou + kMaxMatched);   // slot arrays are free
     for (int i = tid; i < nm; i += kMatchThreads) {
         const long long key = s_mkey[i];
         int rank = 0;
@@ -841,8 +886,8 @@ confmat_kernel(const void *__restrict__ preds, int pd, const void *__restrict__ 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t match_smem_bytes()
 {
-    return (size_t)kMaxPairs * (8 + 4 + 2 + 2) + (size_t)kMaxMatched * (8 + 4 + 4 + 2) +
-           (size_t)kSegSlots * (8 + 8 + 6 * 4) + 16;
+    return (size_t)kPairSlots * (8 + 4 + 2 + 2) + (size_t)kMaxMatched * (8 + 4 + 4 + 2) +
+           (size_t)kSegSlots * (8 + 8 + 4 * 4 + 2) + 16;
 }
 
 }  // namespace npb
@@ -868,17 +913,36 @@ extern "C" int npb_confmat_update(const void *preds, int preds_dtype, const void
     return record_launch("npb_confmat_update");
 }
 
-// workspace: [frame_keys | frame_cnts | frame_n] (one memset) | frame_list | frame_stats
-static size_t pq_table_bytes(int B)
+// Entries per frame of the list between pixel pass and matcher: every CTA of the pixel pass
+// contributes at most its distinct pairs; the fewer frames, the more CTAs work on one frame.
+static int device_sm_count()
 {
-    return align256((size_t)B * kFrameSlots * (sizeof(unsigned long long) + sizeof(unsigned)) +
-                    (size_t)B * sizeof(unsigned));
+    static int n_sm_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &n = n_sm_dev[dev & 63];
+    if (n == 0) {
+        n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
 }
 
+constexpr int kMaxPairCtasPerSm = 8;
+
+static unsigned pq_entry_cap(int B)
+{
+    const long long ctas_per_frame = ((long long)device_sm_count() * kMaxPairCtasPerSm + B - 1) / B;
+    return (unsigned)(4 * kMaxPairs + 128 * ctas_per_frame);
+}
+
+// workspace: [entry_keys | entry_cnts | entry_n | frame_stats]
 extern "C" size_t npb_pq_update_workspace_bytes(int B, int num_categories)
 {
-    size_t bytes = pq_table_bytes(B);
-    bytes += align256((size_t)B * kMaxPairs * sizeof(unsigned short));
+    const size_t cap = pq_entry_cap(B);
+    size_t bytes = align256((size_t)B * cap * sizeof(unsigned long long));
+    bytes += align256((size_t)B * cap * sizeof(unsigned));
+    bytes += align256((size_t)B * sizeof(unsigned));
     bytes += align256((size_t)B * 4 * num_categories * sizeof(double));
     return bytes;
 }
@@ -900,17 +964,17 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     if (matches && (match_cap < 1 || !n_matches)) return NPB_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
 
+    const unsigned entry_cap = pq_entry_cap(B);
     char *ws = (char *)workspace;
-    unsigned long long *fkeys = (unsigned long long *)ws;
-    unsigned *fcnts = (unsigned *)(fkeys + (size_t)B * kFrameSlots);
-    unsigned *fn_entries = fcnts + (size_t)B * kFrameSlots;
-    ws += pq_table_bytes(B);
-    unsigned short *flist = (unsigned short *)ws;
-    ws += align256((size_t)B * kMaxPairs * sizeof(unsigned short));
+    unsigned long long *ekeys = (unsigned long long *)ws;
+    ws += align256((size_t)B * entry_cap * sizeof(unsigned long long));
+    unsigned *ecnts = (unsigned *)ws;
+    ws += align256((size_t)B * entry_cap * sizeof(unsigned));
+    unsigned *en = (unsigned *)ws;
+    ws += align256((size_t)B * sizeof(unsigned));
     double *fstats = frame_stats ? frame_stats : (double *)ws;
 
-    // empty keys, counts and entry counters at -1 (see FrameTable)
-    cudaMemsetAsync(fkeys, 0xff, pq_table_bytes(B), s);
+    cudaMemsetAsync(en, 0, (size_t)B * sizeof(unsigned), s);
 
     PairParams pp;
     pp.pred = (const long long *)pred; pp.target = (const long long *)target;
@@ -924,7 +988,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     pp.n = confmat ? confmat_n : 0;
     // dense class-pair table: needs `id >> shift` decoding and a table that fits next to the rest
     pp.nd = (pp.L_shift >= 0 && num_categories <= kSmemConfmatMaxN) ? num_categories : 0;
-    pp.frame_keys = fkeys; pp.frame_cnts = fcnts; pp.frame_n = fn_entries; pp.frame_list = flist;
+    pp.entry_keys = ekeys; pp.entry_cnts = ecnts; pp.entry_n = en; pp.entry_cap = entry_cap;
     pp.confmat = (unsigned long long *)confmat; pp.status = status;
 
     const bool vec4 = (P % 4 == 0) && (((uintptr_t)pred | (uintptr_t)target) & 15u) == 0 &&
@@ -949,7 +1013,6 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     const PairKernel kernel = kernels[variant];
     // one process may drive several devices: function attributes and the SM count are per device
     static bool pc_attr_set_dev[64] = {false};
-    static int n_sm_dev[64];
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     const int dslot = cur_dev & 63;
@@ -958,11 +1021,9 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
             cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(match_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)match_smem_bytes());
-        n_sm_dev[dslot] = 148;
-        cudaDeviceGetAttribute(&n_sm_dev[dslot], cudaDevAttrMultiProcessorCount, cur_dev);
         pc_attr_set_dev[dslot] = true;
     }
-    const int n_sm = n_sm_dev[dslot];
+    const int n_sm = device_sm_count();
     // persistent CTAs: the whole batch in ONE wave (a second, partial wave would leave most SMs
     // idle for the length of a CTA), every CTA of a frame gets the same number of chunks
     static size_t occ_smem_dev[64][8] = {{0}};
@@ -982,6 +1043,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
         env_cap = e ? atoi(e) : 0;
     }
     if (env_cap > 0 && per_sm > env_cap) per_sm = env_cap;
+    if (per_sm > kMaxPairCtasPerSm) per_sm = kMaxPairCtasPerSm;     // pq_entry_cap() assumes it
     long long bx = ((long long)n_sm * per_sm) / B;
     if (bx < 1) bx = 1;
     if (bx > n_chunks) bx = n_chunks;
@@ -989,7 +1051,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     kernel<<<grid, kPairThreads, pc_smem, s>>>(pp);
 
     MatchParams mp;
-    mp.frame_keys = fkeys; mp.frame_cnts = fcnts; mp.frame_n = fn_entries; mp.frame_list = flist;
+    mp.entry_keys = ekeys; mp.entry_cnts = ecnts; mp.entry_n = en; mp.entry_cap = entry_cap;
     mp.num_categories = num_categories;
     mp.ignored_label = ignored_label; mp.L = max_instances_per_category; mp.offset = offset;
     mp.void_segment_id = void_segment_id; mp.frame_stats = fstats;

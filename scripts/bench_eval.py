@@ -3,7 +3,7 @@
 confusion-matrix / PQ all-reduce at compute(), on 1..8 GPUs (torchrun).  Evaluation only:
 17 algorithmic bytes per pixel (int64 prediction, int64 target, uint8 semantic target).
 
-    python scripts/bench_eval.py [--frames 50000] [--batch 256]
+    python scripts/bench_eval.py [--frames 50000] [--batch 256] [--height 480 --width 640 --classes 40]
     python -m torch.distributed.run --nproc-per-node N ... scripts/bench_eval.py
 """
 import argparse
@@ -20,6 +20,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=int, default=50000)
     ap.add_argument('--batch', type=int, default=256)
+    ap.add_argument('--height', type=int, default=480)
+    ap.add_argument('--width', type=int, default=640)
+    ap.add_argument('--classes', type=int, default=40)
+    ap.add_argument('--instances', type=int, default=12)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -36,7 +40,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    C, H, W, K, B = 40, 480, 640, 12, args.batch
+    C, H, W, K, B = args.classes, args.height, args.width, args.instances, args.batch
     L, OFF = 1 << 16, 256 ** 3
     is_thing = testing.default_is_thing(C)
     post = get_postprocessing_class(
@@ -87,7 +91,7 @@ def main():
     if rank == 0:
         fps = frames / (ms * 1e-3)
         print(json.dumps({
-            'metric': 'mIoU+PQ accumulation frames/s @480x640', 'value': fps, 'unit': 'frames/s',
+            'metric': f'mIoU+PQ accumulation frames/s @{H}x{W}', 'value': fps, 'unit': 'frames/s',
             'n_gpus': world, 'frames': frames, 'steps': steps, 'batch_per_gpu': B, 'ms_total': ms,
             'roofline': {'bound': 'hbm', 'bytes_per_frame': 17 * H * W,
                          'achieved': fps / world * 17 * H * W / 1e9, 'peak': peak, 'unit': 'GB/s',
