@@ -13,7 +13,9 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libnicr_panoptic_b200.so')
+# NPB_LIB_PATH: an alternative build of the same ABI (A/B measurements); the default is the
+# in-tree library next to the sources
+LIB_PATH = os.environ.get('NPB_LIB_PATH') or os.path.join(_HERE, 'csrc', 'libnicr_panoptic_b200.so')
 
 MAX_INST = 256
 

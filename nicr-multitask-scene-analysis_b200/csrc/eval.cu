@@ -61,11 +61,15 @@ __device__ __forceinline__ bool table_add(unsigned long long *keys, unsigned *cn
     return false;
 }
 
-// Hand-over from the pixel pass to the matcher: a per-frame LIST of (pair key, pixels) entries.
-// Every CTA appends the contents of its tables with plain stores after reserving a range with
-// one atomic; the same pair may appear once per CTA (and once more per overflow of a CTA
-// table), the matcher merges duplicates in shared memory.  No global hash table, no
-// compare-and-swap round trips, and only the B entry counters need clearing per launch.
+// Hand-over from the pixel pass to the matcher.
+//   * pairs of two instance-free segments (class, class): a dense per-frame table [nd][nd] that
+//     every CTA adds to with fire-and-forget reductions (RED, nothing to wait for);
+//   * pairs that involve an instance: a per-frame LIST of (pair key, pixels) entries.  Every
+//     CTA appends its hash table with plain stores after reserving a range with one atomic;
+//     the same pair may appear once per CTA (and once more per overflow of a CTA table), the
+//     matcher merges the duplicates in shared memory.
+// No global hash table and no compare-and-swap round trips; the entry counters and the dense
+// tables are cleared by one memset per launch.
 struct FrameEntries {
     unsigned long long *keys;   // [cap]
     unsigned *cnts;             // [cap]
@@ -101,6 +105,7 @@ struct PairParams {
     unsigned *entry_cnts;            // [B][entry_cap]
     unsigned *entry_n;               // [B], zeroed before the launch
     unsigned entry_cap;
+    unsigned *frame_dense;           // [B][nd][nd] class-pair pixels of the frame, zeroed before the launch
     unsigned long long *confmat;     // [n][n] int64, accumulated
     int32_t *status;                 // [B]
 };
@@ -526,9 +531,16 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     __shared__ unsigned s_total, s_base, s_cursor;
     if (tid == 0) { s_total = 0; s_cursor = 0; }
     __syncthreads();
+    // class pairs first: reductions without a return value, their latency is never waited for
+    if (nd > 0) {
+        unsigned *fd = prm.frame_dense + (size_t)b * nd * nd;
+        for (int i = tid; i < nd * nd; i += kPairThreads) {
+            const unsigned c = t.dense[i];
+            if (c) atomicAdd(fd + i, c);
+        }
+    }
     unsigned mine = 0;
     for (int i = tid; i < kSmemSlots; i += kPairThreads) mine += (t.keys[i] != kEmptyKey && t.cnts[i]) ? 1u : 0u;
-    for (int i = tid; i < nd * nd; i += kPairThreads) mine += t.dense[i] ? 1u : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFullMask, mine, o);
     if (lane == 0 && mine) atomicAdd(&s_total, mine);
@@ -539,23 +551,15 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
         if (s_total && s_base + s_total > fe.cap) set_status(fe.status, NPB_ERR_CAPACITY);
     }
     __syncthreads();
-    const unsigned base = s_base;
-    for (int i = tid; i < kSmemSlots; i += kPairThreads) {
-        const unsigned long long k = t.keys[i];
-        const unsigned c = t.cnts[i];
-        if (k != kEmptyKey && c) {
-            const unsigned idx = base + atomicAdd(&s_cursor, 1u);
-            if (idx < fe.cap) { fe.keys[idx] = k; fe.cnts[idx] = c; }
-        }
-    }
-    for (int i = tid; i < nd * nd; i += kPairThreads) {
-        const unsigned c = t.dense[i];
-        if (c) {
-            const unsigned long long tc = (unsigned)(i / nd), pc = (unsigned)(i % nd);
-            const unsigned long long key = (tc << prm.L_shift) * (unsigned long long)prm.offset +
-                                           (pc << prm.L_shift);
-            const unsigned idx = base + atomicAdd(&s_cursor, 1u);
-            if (idx < fe.cap) { fe.keys[idx] = key; fe.cnts[idx] = c; }
+    if (s_total) {
+        const unsigned base = s_base;
+        for (int i = tid; i < kSmemSlots; i += kPairThreads) {
+            const unsigned long long k = t.keys[i];
+            const unsigned c = t.cnts[i];
+            if (k != kEmptyKey && c) {
+                const unsigned idx = base + atomicAdd(&s_cursor, 1u);
+                if (idx < fe.cap) { fe.keys[idx] = k; fe.cnts[idx] = c; }
+            }
         }
     }
     if (cm_smem)
@@ -569,6 +573,8 @@ struct MatchParams {
     const unsigned *entry_cnts;
     const unsigned *entry_n;
     unsigned entry_cap;
+    const unsigned *frame_dense;            // [B][nd][nd] or null
+    int nd;
     int num_categories;
     long long ignored_label, L, offset, void_segment_id;
     int L_shift, O_shift;  // >= 0 when L / offset are powers of two (shifts instead of 64-bit divisions)
@@ -633,7 +639,8 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     unsigned short *t_gslot = (unsigned short *)(p_pio + kSegSlots);       // [kPairSlots]
     unsigned short *t_pslot = t_gslot + kPairSlots;                        // [kPairSlots]
     unsigned short *s_mcat = t_pslot + kPairSlots;                         // [kMaxMatched]
-    unsigned char *g_matched = (unsigned char *)(s_mcat + kMaxMatched);    // [kSegSlots]
+    unsigned short *s_idx = s_mcat + kMaxMatched;                          // [kMaxPairs] used slots
+    unsigned char *g_matched = (unsigned char *)(s_idx + kMaxPairs);       // [kSegSlots]
     unsigned char *p_matched = g_matched + kSegSlots;                      // [kSegSlots]
     __shared__ int s_m, s_nm;
     __shared__ int s_tp[256], s_fn[256], s_fp[256];
@@ -652,8 +659,50 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     }
     __syncthreads();
 
-    // (0) merge the frame's entry list (one entry per pair and CTA of the pixel pass) into the
-    //     pair table; independent loads first, the loop is latency bound
+    // (0) the frame's pairs -> pair table.  Every used slot is remembered in s_idx, so the later
+    //     phases walk the (few hundred) pairs, not the table.
+    auto add_pair = [&](unsigned long long key, unsigned cnt) {
+        unsigned h = hash64(key) & (unsigned)(kPairSlots - 1);
+        for (int probe = 0; probe < kPairSlots; ++probe) {
+            unsigned long long cur = t_key[h];
+            if (cur == kEmptyKey) {
+                cur = atomicCAS(t_key + h, kEmptyKey, key);
+                if (cur == kEmptyKey) {                      // this thread claimed the slot
+                    const int idx = atomicAdd(&s_m, 1);
+                    if (idx < kMaxPairs) s_idx[idx] = (unsigned short)h;
+                    else set_status(prm.status + b, NPB_ERR_CAPACITY);
+                }
+            }
+            if (cur == kEmptyKey || cur == key) {
+                atomicAdd(t_cnt + h, cnt);
+                return;
+            }
+            h = (h + 1) & (unsigned)(kPairSlots - 1);
+        }
+        set_status(prm.status + b, NPB_ERR_CAPACITY);
+    };
+    // class pairs: dense per-frame table, every pair exactly once (independent loads first)
+    if (prm.frame_dense) {
+        const int nd = prm.nd, nd2 = nd * nd;
+        const unsigned *fd = prm.frame_dense + (size_t)b * nd2;
+        constexpr int kBatch = 4;
+        for (int i0 = tid; i0 < nd2; i0 += kMatchThreads * kBatch) {
+            unsigned c[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int i = i0 + u * kMatchThreads;
+                c[u] = i < nd2 ? fd[i] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (c[u] == 0u) continue;
+                const int i = i0 + u * kMatchThreads;
+                const unsigned long long tc = (unsigned)(i / nd), pc = (unsigned)(i % nd);
+                add_pair((tc << prm.L_shift) * (unsigned long long)prm.offset + (pc << prm.L_shift), c[u]);
+            }
+        }
+    }
+    // instance pairs: the entry list (one entry per pair and CTA of the pixel pass)
     {
         const unsigned n_raw = prm.entry_n[b];
         const unsigned n_ent = n_raw < prm.entry_cap ? n_raw : prm.entry_cap;   // overflow: flagged by the writer
@@ -670,34 +719,18 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
                 c[u] = e < n_ent ? ecnts[e] : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                if (c[u] == 0u) continue;
-                unsigned h = hash64(k[u]) & (unsigned)(kPairSlots - 1);
-                bool done = false;
-                for (int probe = 0; probe < kPairSlots && !done; ++probe) {
-                    unsigned long long cur = t_key[h];
-                    if (cur == kEmptyKey) {
-                        cur = atomicCAS(t_key + h, kEmptyKey, k[u]);
-                        if (cur == kEmptyKey && atomicAdd(&s_m, 1) >= kMaxPairs)
-                            set_status(prm.status + b, NPB_ERR_CAPACITY);
-                    }
-                    if (cur == kEmptyKey || cur == k[u]) {
-                        atomicAdd(t_cnt + h, c[u]);
-                        done = true;
-                    }
-                    h = (h + 1) & (unsigned)(kPairSlots - 1);
-                }
-                if (!done) set_status(prm.status + b, NPB_ERR_CAPACITY);
-            }
+            for (int u = 0; u < kBatch; ++u)
+                if (c[u] != 0u) add_pair(k[u], c[u]);
         }
     }
     __syncthreads();
+    const int m = s_m < kMaxPairs ? s_m : kMaxPairs;
 
     // (1) segment tables: areas (pq.py:83-84), void overlap (pq.py:34-43), ignored overlap
     //     (pq.py:47-57); every pair remembers the slots of its two segments
-    for (int t = tid; t < kPairSlots; t += kMatchThreads) {
+    for (int i = tid; i < m; i += kMatchThreads) {
+        const int t = s_idx[i];
         const long long key = (long long)t_key[t];
-        if ((unsigned long long)key == kEmptyKey) continue;
         const unsigned cnt = t_cnt[t];
         const long long g = div_pow2(key, prm.offset, prm.O_shift);
         const long long p = key - g * prm.offset;
@@ -705,7 +738,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         const int ps = seg_slot(pt, (unsigned long long)p);
         if (gs < 0 || ps < 0) {
             set_status(prm.status + b, NPB_ERR_CAPACITY);
-            t_key[t] = kEmptyKey;           // later phases skip the pair (its frame failed anyway)
+            t_key[t] = kEmptyKey;           // phase 2 skips the pair (its frame failed anyway)
             continue;
         }
         t_gslot[t] = (unsigned short)gs;
@@ -718,7 +751,8 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     __syncthreads();
 
     // (2) IoU + match decision per intersecting pair                       pq.py:119-152
-    for (int t = tid; t < kPairSlots; t += kMatchThreads) {
+    for (int i = tid; i < m; i += kMatchThreads) {
+        const int t = s_idx[i];
         const long long key = (long long)t_key[t];
         if ((unsigned long long)key == kEmptyKey) continue;
         if (key == prm.void_segment_id) continue;                          // pq.py:120
@@ -887,7 +921,7 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t match_smem_bytes()
 {
     return (size_t)kPairSlots * (8 + 4 + 2 + 2) + (size_t)kMaxMatched * (8 + 4 + 4 + 2) +
-           (size_t)kSegSlots * (8 + 8 + 4 * 4 + 2) + 16;
+           (size_t)kMaxPairs * 2 + (size_t)kSegSlots * (8 + 8 + 4 * 4 + 2) + 16;
 }
 
 }  // namespace npb
@@ -936,13 +970,28 @@ static unsigned pq_entry_cap(int B)
     return (unsigned)(4 * kMaxPairs + 128 * ctas_per_frame);
 }
 
-// workspace: [entry_keys | entry_cnts | entry_n | frame_stats]
+// side of the dense class-pair table: it needs `id >> shift` decoding and has to fit into the
+// shared memory of the pixel pass next to the other tables
+static int pq_dense_side(int num_categories, int64_t max_instances_per_category)
+{
+    const bool pow2 = (max_instances_per_category & (max_instances_per_category - 1)) == 0 &&
+                      max_instances_per_category < (1ll << 62);
+    return (pow2 && num_categories <= kSmemConfmatMaxN) ? num_categories : 0;
+}
+
+// workspace: [entry_keys | entry_cnts | (entry_n | frame_dense: one memset) | frame_stats]
+static size_t pq_cleared_bytes(int B)
+{
+    return align256((size_t)B * sizeof(unsigned)) +
+           align256((size_t)B * kSmemConfmatMaxN * kSmemConfmatMaxN * sizeof(unsigned));
+}
+
 extern "C" size_t npb_pq_update_workspace_bytes(int B, int num_categories)
 {
     const size_t cap = pq_entry_cap(B);
     size_t bytes = align256((size_t)B * cap * sizeof(unsigned long long));
     bytes += align256((size_t)B * cap * sizeof(unsigned));
-    bytes += align256((size_t)B * sizeof(unsigned));
+    bytes += pq_cleared_bytes(B);
     bytes += align256((size_t)B * 4 * num_categories * sizeof(double));
     return bytes;
 }
@@ -971,10 +1020,12 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     unsigned *ecnts = (unsigned *)ws;
     ws += align256((size_t)B * entry_cap * sizeof(unsigned));
     unsigned *en = (unsigned *)ws;
-    ws += align256((size_t)B * sizeof(unsigned));
+    unsigned *fdense = (unsigned *)(ws + align256((size_t)B * sizeof(unsigned)));
+    ws += pq_cleared_bytes(B);
     double *fstats = frame_stats ? frame_stats : (double *)ws;
 
-    cudaMemsetAsync(en, 0, (size_t)B * sizeof(unsigned), s);
+    const int nd = pq_dense_side(num_categories, max_instances_per_category);
+    cudaMemsetAsync(en, 0, align256((size_t)B * sizeof(unsigned)) + (size_t)B * nd * nd * sizeof(unsigned), s);
 
     PairParams pp;
     pp.pred = (const long long *)pred; pp.target = (const long long *)target;
@@ -986,8 +1037,8 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
         if ((1ll << sh) == offset) pp.O_shift = sh;
     }
     pp.n = confmat ? confmat_n : 0;
-    // dense class-pair table: needs `id >> shift` decoding and a table that fits next to the rest
-    pp.nd = (pp.L_shift >= 0 && num_categories <= kSmemConfmatMaxN) ? num_categories : 0;
+    pp.nd = nd;
+    pp.frame_dense = nd > 0 ? fdense : nullptr;
     pp.entry_keys = ekeys; pp.entry_cnts = ecnts; pp.entry_n = en; pp.entry_cap = entry_cap;
     pp.confmat = (unsigned long long *)confmat; pp.status = status;
 
@@ -1052,6 +1103,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
 
     MatchParams mp;
     mp.entry_keys = ekeys; mp.entry_cnts = ecnts; mp.entry_n = en; mp.entry_cap = entry_cap;
+    mp.frame_dense = pp.frame_dense; mp.nd = nd;
     mp.num_categories = num_categories;
     mp.ignored_label = ignored_label; mp.L = max_instances_per_category; mp.offset = offset;
     mp.void_segment_id = void_segment_id; mp.frame_stats = fstats;
