@@ -28,7 +28,7 @@ namespace npb {
 constexpr int kPairThreads = 256;
 constexpr int kSmemSlots = 2048;       // per-CTA pair hash table (instance pairs; class pairs go dense)
 constexpr int kMaxPairs = 4096;        // distinct pairs per frame handled by the matcher
-constexpr int kMatchThreads = 512;
+constexpr int kMatchThreads = 1024;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kSmemConfmatMaxN = 96;   // n*n*4 B <= 36 KB privatised in shared memory
 
