@@ -363,15 +363,17 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             // push: minors as single pixels, then one entry per group leader
             const unsigned q_tail = q_base + 8u * (unsigned)q_len;
             if (act && n_minor > 0) {
-                unsigned a = q_tail + 8u * (unsigned)(__popc(b1 & lt_mask) + 2 * __popc(b2 & lt_mask) +
-                                                      3 * __popc(b3 & lt_mask));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (!((member >> j) & 1u)) {
-                        sts_entry(a, klo[j], khi[j] | (1u << 24));
-                        a += 8u;
-                    }
-                }
+                // one address register per store: a store still in flight keeps reading its own
+                const unsigned mm = ~member & 15u;              // bit j: pixel j is a minor
+                const unsigned a0 = q_tail + 8u * (unsigned)(__popc(b1 & lt_mask) + 2 * __popc(b2 & lt_mask) +
+                                                             3 * __popc(b3 & lt_mask));
+                const unsigned a1 = a0 + 8u * (mm & 1u);
+                const unsigned a2 = a0 + 8u * (unsigned)__popc(mm & 3u);
+                const unsigned a3 = a0 + 8u * (unsigned)__popc(mm & 7u);
+                if (mm & 1u) sts_entry(a0, klo[0], khi[0] | (1u << 24));
+                if (mm & 2u) sts_entry(a1, klo[1], khi[1] | (1u << 24));
+                if (mm & 4u) sts_entry(a2, klo[2], khi[2] | (1u << 24));
+                if (mm & 8u) sts_entry(a3, klo[3], khi[3] | (1u << 24));
             }
             if (leader)
                 sts_entry(q_tail + 8u * (unsigned)(total_minor + __popc(leader_mask & lt_mask)), lk_lo,
