@@ -11,14 +11,15 @@
 // contingency table per frame (pair -> pixel count) carries all three area tables
 // (gt area = sum over pairs of that gt id, pred area likewise).  The pixel pass
 // (pair_count_kernel) streams pred / target once (17 B/px with the fused semantic target),
-// counts pairs in a per-CTA shared-memory hash table after warp-level aggregation
-// (neighbouring pixels nearly always share the pair) and flushes it into a small per-frame
-// global hash table.  match_frames_kernel (one CTA per frame) builds the per-segment tables
-// (areas, void / ignored overlap) in shared-memory hash tables straight from the pairs
-// (O(m)), does the matching, and sorts only the MATCHED pairs by `target*offset + pred` --
-// the reference's visiting order, which fixes the float64 summation order;
-// accumulate_frames_kernel adds the frames to the running state in frame order.  Both float64 orders equal the reference's, so the
-// states are bit-identical, not merely close.
+// counts pairs in per-CTA shared-memory tables after warp-level aggregation (neighbouring pixels
+// nearly always share the pair) and hands them to the matcher through a dense per-frame
+// class-pair table (RED) and a per-frame entry list (plain stores).  match_frames_kernel (one
+// CTA per frame) merges them into a shared-memory pair table, builds the per-segment tables
+// (areas, void / ignored overlap) in shared-memory hash tables straight from the pairs (O(m)),
+// does the matching, and orders only the MATCHED pairs by `target*offset + pred` -- the
+// reference's visiting order, which fixes the float64 summation order;
+// accumulate_frames_kernel adds the frames to the running state in frame order.  Both float64
+// orders equal the reference's, so the states are bit-identical, not merely close.
 #include <stdlib.h>
 
 #include "common.cuh"
