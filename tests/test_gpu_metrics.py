@@ -174,6 +174,52 @@ def test_pq_wide_target_ids_standard_geometry(cuda_device):
     assert sorted([list(x) for x in m]) == sorted([list(x) for x in ref[4]])
 
 
+def _many_pairs_frame(seed, n_gt, n_pred, side=60):
+    """side*side pixels, (nearly) every one a different (gt segment, pred segment) pair."""
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randperm(side * side, generator=g).reshape(side, side)
+    L = 1 << 16
+    tgt = 1 * L + (idx % n_gt) + 1
+    pred = 1 * L + (idx % n_pred) + 1
+    return pred, tgt
+
+
+@pytest.mark.parametrize('frames', [2, 600])
+def test_pq_thousands_of_pairs_per_frame(frames, cuda_device):
+    """~3400 distinct pairs in a 3600-pixel frame (997 gt x 241 pred segments): far beyond the
+    2048-slot table of a CTA of the pixel pass.  With 600 frames in the batch one CTA owns a whole
+    frame, so its table overflows and single entries go straight to the frame's list."""
+    from nicr_mt_scene_analysis_b200.metric import PanopticQuality
+    L, OFF, NC = 1 << 16, 256 ** 3, 3
+    distinct = [_many_pairs_frame(s, 997, 241) for s in range(3)]
+    pred = torch.stack([distinct[b % 3][0] for b in range(frames)])
+    tgt = torch.stack([distinct[b % 3][1] for b in range(frames)])
+    pq = PanopticQuality(NC, 0, L, OFF, [False, True, True], device=cuda_device)
+    pq.update(pred.to(cuda_device), tgt.to(cuda_device))
+    pq.check_status()
+    per_frame = [oracle.pq_compare_and_accumulate(p.numpy(), t.numpy(), NC, 0, L, OFF, 0)[:4]
+                 for p, t in distinct]
+    state = np.zeros((4, NC))
+    for b in range(frames):
+        for s, v in zip(state, per_frame[b % 3]):
+            s += v
+    assert np.array_equal(np.stack(_states(pq)), state)
+    assert state[2].sum() > 0 and state[3].sum() > 0        # the case is not trivial
+
+
+def test_pq_too_many_pairs_is_a_capacity_error(cuda_device):
+    """More than 4096 distinct pairs in one frame: reported, never silently wrong."""
+    from nicr_mt_scene_analysis_b200._lib import ERR_CAPACITY, NpbError
+    from nicr_mt_scene_analysis_b200.metric import PanopticQuality
+    L, OFF = 1 << 16, 256 ** 3
+    pred, tgt = _many_pairs_frame(5, 1499, 1013, side=80)       # ~6300 distinct pairs
+    pq = PanopticQuality(3, 0, L, OFF, [False, True, True], device=cuda_device)
+    pq.update(pred[None].to(cuda_device), tgt[None].to(cuda_device))
+    with pytest.raises(NpbError) as err:
+        pq.compute()
+    assert err.value.code == ERR_CAPACITY
+
+
 @pytest.mark.parametrize('bad', ['pred_negative', 'pred_ge_offset', 'target_negative'])
 def test_pq_id_range_errors_standard_geometry(bad, cuda_device):
     from nicr_mt_scene_analysis_b200._lib import NpbError
