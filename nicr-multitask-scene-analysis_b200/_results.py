@@ -100,6 +100,7 @@ class InstanceTables:
         self.dev = storage if storage is not None else \
             torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
         self._np = None
+        self._host = None           # (pinned copy, event) once prefetch() ran
         self._where = 'panoptic post-processing'
 
     def dptr(self, name: str):
@@ -113,9 +114,24 @@ class InstanceTables:
         v = self.dev[off:off + nbytes].view(tdt)
         return v.view(self.B, per_frame) if per_frame > 1 else v
 
+    def prefetch(self) -> 'InstanceTables':
+        """Start the device->host copy of the tables on the CURRENT stream into pinned memory;
+        `wait()` then only waits for this copy, not for whatever was enqueued afterwards."""
+        pinned = torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(self.dev, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(self.device))
+        self._host = (pinned, event)
+        self._np = None
+        return self
+
     def wait(self) -> 'InstanceTables':
         if self._np is None:
-            raw = self.dev.cpu().numpy()        # blocks until the producing kernels are done
+            if self._host is not None:
+                self._host[1].synchronize()
+                raw = self._host[0].numpy()
+            else:
+                raw = self.dev.cpu().numpy()    # blocks until the producing kernels are done
             self._np = {}
             for name, (off, nbytes, dt, per_frame) in self._offsets.items():
                 a = raw[off:off + nbytes].view(dt)
@@ -129,6 +145,7 @@ class InstanceTables:
     def invalidate(self) -> None:
         """Forget the host copy: the device buffer was rewritten (CUDA-graph replay)."""
         self._np = None
+        self._host = None
 
     # ---- python structures of the reference API ------------------------------------------
     def centers_list(self) -> List[torch.Tensor]:

@@ -7,7 +7,9 @@ tensors (model/postprocessing/panoptic.py:143-152) and whose metrics run on the 
 The batch is cut into chunks of a few frames; host->device copies of chunk i+1 run on a
 copy stream while chunk i is post-processed (and evaluated) on the compute stream and its
 dense results are copied back, so the PCIe transfers -- the end-to-end bound of this path --
-overlap the kernels.
+overlap the kernels.  `run()` only enqueues work and `finish()` waits for that batch alone, so
+a caller can enqueue batch k+1 before building the python structures of batch k (with a second
+set of `out` buffers) and keep the host->device link busy across batches.
 """
 from typing import Dict, Optional
 
@@ -68,8 +70,10 @@ class PanopticHostPipeline:
         inst_h = out['panoptic_segmentation_deeplab_instance_idx']
         tables = []
         h2d = d2h = 0
+        # the kernels are ordered after the caller's stream (metric states may have been reset
+        # there) and the caller's stream after this batch; the copy stream only moves host
+        # buffers into staging slots guarded by their own events, so it is free to run ahead
         cur = torch.cuda.current_stream(self.device)
-        self._copy_stream.wait_stream(cur)
         self._compute_stream.wait_stream(cur)
         for i, lo in enumerate(range(0, B, self.chunk)):
             hi = min(lo + self.chunk, B)
@@ -92,6 +96,7 @@ class PanopticHostPipeline:
                     self.evaluation.update(pan, slot['_tgt_pan'][:n], slot['_tgt_sem'][:n])
                 pan_h[lo:hi].copy_(pan, non_blocking=True)
                 inst_h[lo:hi].copy_(inst, non_blocking=True)
+                tab.prefetch()                  # per-instance tables -> pinned host memory
                 d2h += pan.numel() * 8 + inst.numel() + tab.nbytes
                 done = torch.cuda.Event()
                 done.record(self._compute_stream)
@@ -100,14 +105,15 @@ class PanopticHostPipeline:
                 for t in (sem, inst, pan, pan_sem):
                     t.record_stream(self._compute_stream)
             tables.append(tab)
-        cur.wait_stream(self._compute_stream)
+        cur.wait_event(done)
         self.h2d_bytes, self.d2h_bytes = h2d, d2h
         out['_tables'] = tables
+        out['_done'] = done                     # everything of this batch has landed after it
         return out
 
     @staticmethod
     def finish(out: Dict[str, object], with_orientation: bool = True) -> Dict[str, object]:
-        """Block until the copies have landed and build the python structures."""
+        """Block until the copies of THIS batch have landed and build the python structures."""
         ids, meta, orientations = [], [], []
         for tab in out.pop('_tables'):
             tab: InstanceTables
@@ -115,7 +121,7 @@ class PanopticHostPipeline:
             meta += tab.meta()
             if with_orientation:
                 orientations += tab.orientations()
-        torch.cuda.current_stream().synchronize()
+        out.pop('_done').synchronize()
         out['panoptic_segmentation_deeplab_ids'] = ids
         out['panoptic_segmentation_deeplab_instance_meta'] = meta
         if with_orientation:

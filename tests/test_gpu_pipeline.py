@@ -110,3 +110,28 @@ def test_graph_replay_equals_eager(cuda_device):
                         ('iou_per_class', 'tp_per_class', 'fn_per_class', 'fp_per_class')])
         assert np.array_equal(got, state)
         assert np.array_equal(ev.miou.confmat.cpu().numpy(), cm)
+
+
+def test_host_pipeline_overlapped_batches(cuda_device):
+    """Two batches enqueued back to back, finished afterwards (each with its own result
+    buffers): `finish` waits for its own batch only and both results are right."""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.pipeline import PanopticHostPipeline
+    B, C, H, W, K = 5, 9, 80, 112, 4
+    post, ev, is_thing, has_ori = _setup(C, cuda_device, async_results=True)
+    pipe = PanopticHostPipeline(post, None, chunk_frames=2, device=cuda_device)
+    batches, refs, pending = [], [], []
+    for seed in (31, 32, 33):
+        data = testing.make_batch(B, C, H, W, K, seed=seed)
+        refs.append(oracle.panoptic_postprocess(*(data[k].numpy() for k in
+                                                  ('logits', 'heat', 'offset', 'orientation')),
+                                                is_thing, has_ori))
+        batches.append({k: v.pin_memory() for k, v in data.items()})
+    for pinned in batches:                       # enqueue everything first
+        pending.append(pipe.run(pinned, testing.make_batch_dict(B, H, W)))
+    for out, ref in zip(pending, refs):
+        out = PanopticHostPipeline.finish(out)
+        assert np.array_equal(out['panoptic_segmentation_deeplab'].numpy(), ref['panoptic'])
+        assert np.array_equal(out['panoptic_segmentation_deeplab_instance_idx'].numpy(),
+                              ref['instance_idx'])
+        assert out['panoptic_segmentation_deeplab_ids'] == ref['ids']
