@@ -234,17 +234,25 @@ def run_ours(args):
     r0 = post.postprocess(raw, batch, is_training=False)
     tgt_pan, tgt_sem = testing.make_eval_targets(r0['panoptic_segmentation_deeplab'], L)
     del r0
-    KERNELS_PER_STEP = 8     # nms, select, group, finalize, write, pair_count, match, accumulate
+    # default: the kernel that writes the panoptic ids also evaluates them (one launch less, the
+    # ids are not read back); --no-fuse runs post-processing and evaluation as separate calls
+    fused = not args.no_fuse
+    if fused:
+        post.fuse_evaluation(evaluation)
+    batch_gt = dict(batch, panoptic_fullres=tgt_pan, semantic_fullres=tgt_sem) if fused else batch
+    # nms, select, group, finalize, write (+) pair_count, match, accumulate
+    KERNELS_PER_STEP = 7 if fused else 8
 
     def eager_step():
-        r = post.postprocess(raw, batch, is_training=False)
-        evaluation.update(r['panoptic_segmentation_deeplab'], tgt_pan, tgt_sem)
+        r = post.postprocess(raw, batch_gt, is_training=False)
+        if not r.get('_panoptic_evaluation_fused'):
+            evaluation.update(r['panoptic_segmentation_deeplab'], tgt_pan, tgt_sem)
         return r
 
     launch_mode = 'eager'
     step = eager_step
     if not args.no_graph:
-        # the step is 8 short kernels: capture them once, replay with one launch per step
+        # the step is 7-8 short kernels: capture them once, replay with one launch per step
         from nicr_mt_scene_analysis_b200.graph import CapturedStep
         try:
             step = CapturedStep(eager_step, warmup=3, device=dev).replay
@@ -388,7 +396,9 @@ def run_ours(args):
                                       'all-reduced at compute()',
                        'l2_policy': f'inputs ({B * bytes_post_per_frame(C, H, W, ORI) / 1e9:.1f} GB per step) '
                                     'larger than L2, no flush needed',
-                       'launch': launch_mode},
+                       'launch': launch_mode,
+                       'evaluation': 'fused into the kernel that writes the panoptic ids' if fused
+                       else 'separate call on the written ids'},
             'clocks': clocks.summary(region0, region1),
             'e2e': e2e,
             'gpu_launches': KERNELS_PER_STEP * args.steps,
@@ -422,6 +432,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='issue every step from Python')
+    ap.add_argument('--no-fuse', action='store_true',
+                    help='post-processing and evaluation as separate calls (8 kernels per step)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     WORKLOAD.clear()

@@ -302,6 +302,53 @@ int npb_pq_update(const int64_t *pred, const int64_t *target, const uint8_t *sem
                   int64_t *confmat, int confmat_n, double *frame_stats, int64_t *matches,
                   int match_cap, int32_t *n_matches, int32_t *status, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Fused validation step: panoptic ids written AND evaluated in one pass.
+ * Replaces: the tail of PanopticPostprocessing._postprocess_inference (panoptic.py:139-167)
+ *           followed by PanopticTaskHelper.validation_step (task_helper/panoptic.py:104-126),
+ *           which reads the freshly written ids back (8 B/px) for PQ and mIoU.
+ * `npb_eval_args` carries the evaluation half: the arguments of npb_pq_update without `pred`
+ * (the prediction is produced on the fly).  The fused kernel needs the reference's id geometry
+ * (max_instances_per_category = 65536, offset = 256^3) and H*W % 4 == 0; otherwise the call runs
+ * npb_write_panoptic followed by npb_pq_update -- the results are identical either way.
+ * ------------------------------------------------------------------------- */
+typedef struct npb_eval_args {
+    const int64_t *target;      /* (B,H,W) panoptic target ids                              */
+    const uint8_t *sem_target;  /* (B,H,W) semantic target, nullable together with confmat  */
+    int num_categories;
+    int confmat_n;
+    int64_t ignored_label;
+    int64_t offset;
+    int64_t void_segment_id;
+    void *workspace;            /* npb_pq_update_workspace_bytes(B, num_categories)         */
+    double *iou, *tp, *fn, *fp; /* [num_categories] accumulated states                      */
+    int64_t *confmat;           /* [confmat_n][confmat_n] accumulated, nullable             */
+    double *frame_stats;        /* nullable */
+    int64_t *matches;           /* nullable */
+    int match_cap;
+    int32_t *n_matches;         /* nullable */
+    int32_t *status;            /* [B] status words of the evaluation                       */
+} npb_eval_args;
+
+int npb_write_panoptic_eval(const uint8_t *sem, const uint8_t *inst, const int64_t *inst_pan_id,
+                            const int32_t *inst_class, int B, int C, int H, int W,
+                            const uint8_t *h_thing_lut, int64_t max_instances_per_category,
+                            int64_t *pan_out, uint8_t *pan_sem_out, const npb_eval_args *eval,
+                            void *stream);
+
+/* npb_panoptic_forward with npb_write_panoptic_eval as its last stage. */
+int npb_panoptic_forward_eval(const float *logits, const float *heat, const float *offset,
+                              const float *orientation, int B, int C, int H, int W,
+                              const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
+                              float threshold, int nms_kernel_size, int top_k, int apply_fg_mask,
+                              int normalized_offset, int use_distance_threshold,
+                              float distance_threshold, int64_t max_instances_per_category,
+                              void *workspace, uint8_t *sem_out, uint8_t *inst_out,
+                              int64_t *pan_out, uint8_t *pan_sem_out, int32_t *centers_yx,
+                              int32_t *n_centers, float *center_score, int32_t *inst_class,
+                              int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle,
+                              int32_t *status, const npb_eval_args *eval, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

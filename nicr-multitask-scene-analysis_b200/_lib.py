@@ -28,6 +28,20 @@ _DTYPE_CODES = {torch.uint8: U8, torch.int16: I16, torch.int32: I32, torch.int64
                 torch.bool: BOOL}
 
 _P = c_void_p
+
+
+class EvalArgs(ctypes.Structure):
+    """`npb_eval_args` of include/nicr_panoptic_b200.h (evaluation half of the fused calls)."""
+    _fields_ = [('target', _P), ('sem_target', _P), ('num_categories', c_int),
+                ('confmat_n', c_int), ('ignored_label', c_int64), ('offset', c_int64),
+                ('void_segment_id', c_int64), ('workspace', _P), ('iou', _P), ('tp', _P),
+                ('fn', _P), ('fp', _P), ('confmat', _P), ('frame_stats', _P), ('matches', _P),
+                ('match_cap', c_int), ('n_matches', _P), ('status', _P)]
+
+
+_FORWARD_ARGS = [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_float,
+                 c_int, c_int, c_int, c_int, c_int, c_float, c_int64, _P, _P,
+                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]
 _SIGNATURES = {
     'npb_abi_version': (c_int, []),
     'npb_error_string': (c_char_p, [c_int]),
@@ -52,9 +66,10 @@ _SIGNATURES = {
     'npb_write_panoptic': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P,
                                    _P, _P]),
     'npb_panoptic_forward_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
-    'npb_panoptic_forward': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_float,
-                                     c_int, c_int, c_int, c_int, c_int, c_float, c_int64, _P, _P,
-                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'npb_panoptic_forward': (c_int, _FORWARD_ARGS + [_P]),
+    'npb_panoptic_forward_eval': (c_int, _FORWARD_ARGS + [POINTER(EvalArgs), _P]),
+    'npb_write_panoptic_eval': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64,
+                                        _P, _P, POINTER(EvalArgs), _P]),
     'npb_panoptic_scores': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,
                                     _P, _P, _P, _P]),
     'npb_deeplab_merge_workspace_bytes': (c_size_t, [c_int, c_int]),

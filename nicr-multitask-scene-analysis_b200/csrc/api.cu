@@ -22,7 +22,7 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 using namespace npb;
 
-extern "C" int npb_abi_version(void) { return 1; }
+extern "C" int npb_abi_version(void) { return 2; }
 
 extern "C" const char *npb_last_cuda_error(void) { return g_last_cuda_error; }
 
@@ -50,14 +50,15 @@ extern "C" size_t npb_panoptic_forward_workspace_bytes(int B, int C, int H, int 
     return bytes;
 }
 
-extern "C" int npb_panoptic_forward(
+static int panoptic_forward_impl(
     const float *logits, const float *heat, const float *offset, const float *orientation, int B,
     int C, int H, int W, const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
     float threshold, int nms_kernel_size, int top_k, int apply_fg_mask, int normalized_offset,
     int use_distance_threshold, float distance_threshold, int64_t max_instances_per_category,
     void *workspace, uint8_t *sem_out, uint8_t *inst_out, int64_t *pan_out, uint8_t *pan_sem_out,
     int32_t *centers_yx, int32_t *n_centers, float *center_score, int32_t *inst_class,
-    int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle, int32_t *status, void *stream)
+    int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle, int32_t *status,
+    const npb_eval_args *eval, void *stream)
 {
     if (!logits || !heat || !offset || !workspace || !sem_out || !inst_out || !pan_out ||
         !centers_yx || !n_centers || !center_score || !inst_class || !inst_pan_id || !inst_area ||
@@ -101,6 +102,46 @@ extern "C" int npb_panoptic_forward(
                                 0, h_orientation_lut, inst_class, inst_pan_id, inst_area,
                                 inst_angle, stream);
     if (rc != NPB_OK) return rc;
+    if (eval)       // ids written and evaluated in one pass
+        return npb_write_panoptic_eval(sem_out, inst_out, inst_pan_id, inst_class, B, C, H, W,
+                                       h_thing_lut, max_instances_per_category, pan_out, pan_sem_out,
+                                       eval, stream);
     return npb_write_panoptic(sem_out, inst_out, inst_pan_id, inst_class, B, C, H, W, h_thing_lut,
                               max_instances_per_category, pan_out, pan_sem_out, stream);
+}
+
+extern "C" int npb_panoptic_forward(
+    const float *logits, const float *heat, const float *offset, const float *orientation, int B,
+    int C, int H, int W, const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
+    float threshold, int nms_kernel_size, int top_k, int apply_fg_mask, int normalized_offset,
+    int use_distance_threshold, float distance_threshold, int64_t max_instances_per_category,
+    void *workspace, uint8_t *sem_out, uint8_t *inst_out, int64_t *pan_out, uint8_t *pan_sem_out,
+    int32_t *centers_yx, int32_t *n_centers, float *center_score, int32_t *inst_class,
+    int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle, int32_t *status, void *stream)
+{
+    return panoptic_forward_impl(logits, heat, offset, orientation, B, C, H, W, h_thing_lut,
+                                 h_orientation_lut, threshold, nms_kernel_size, top_k, apply_fg_mask,
+                                 normalized_offset, use_distance_threshold, distance_threshold,
+                                 max_instances_per_category, workspace, sem_out, inst_out, pan_out,
+                                 pan_sem_out, centers_yx, n_centers, center_score, inst_class,
+                                 inst_pan_id, inst_area, inst_angle, status, nullptr, stream);
+}
+
+extern "C" int npb_panoptic_forward_eval(
+    const float *logits, const float *heat, const float *offset, const float *orientation, int B,
+    int C, int H, int W, const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
+    float threshold, int nms_kernel_size, int top_k, int apply_fg_mask, int normalized_offset,
+    int use_distance_threshold, float distance_threshold, int64_t max_instances_per_category,
+    void *workspace, uint8_t *sem_out, uint8_t *inst_out, int64_t *pan_out, uint8_t *pan_sem_out,
+    int32_t *centers_yx, int32_t *n_centers, float *center_score, int32_t *inst_class,
+    int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle, int32_t *status,
+    const npb_eval_args *eval, void *stream)
+{
+    if (!eval) return NPB_ERR_ARG;
+    return panoptic_forward_impl(logits, heat, offset, orientation, B, C, H, W, h_thing_lut,
+                                 h_orientation_lut, threshold, nms_kernel_size, top_k, apply_fg_mask,
+                                 normalized_offset, use_distance_threshold, distance_threshold,
+                                 max_instances_per_category, workspace, sem_out, inst_out, pan_out,
+                                 pan_sem_out, centers_yx, n_centers, center_score, inst_class,
+                                 inst_pan_id, inst_area, inst_angle, status, eval, stream);
 }

@@ -93,7 +93,14 @@ __device__ __noinline__ void emit_entry(const FrameEntries fe, unsigned long lon
 }
 
 struct PairParams {
-    const long long *pred;
+    const long long *pred;      // null in the fused variant
+    // fused variant (panoptic ids produced on the fly, see write_panoptic_kernel in merge.cu)
+    const uint8_t *sem_map;     // (B,P) network class per pixel
+    const uint8_t *inst_map;    // (B,P) raw instance id per pixel
+    const long long *inst_pan_id;   // [B][kMaxInst] panoptic id of every instance
+    ClassSet thing;
+    long long *pan_out;         // (B,P)
+    uint8_t *pan_sem_out;       // (B,P) nullable
     const long long *target;
     const uint8_t *sem_target;  // nullable
     long long P;
@@ -230,9 +237,19 @@ __device__ __forceinline__ uint2 lds_entry(unsigned addr)
 // emits ONE entry for all pixels of the group, the remaining pixels are emitted singly.  Entries
 // go to a per-warp shared-memory queue and are consumed 32 at a time, one entry per lane, so
 // the table updates (the expensive, divergent part) always run with a full warp.
-template <int VEC, bool CONFMAT, bool STD>
+template <int VEC, bool CONFMAT, bool STD, bool FUSED = false>
 __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairParams prm)
 {
+    static_assert(!FUSED || (STD && VEC == 4), "the fused variant exists for the standard geometry only");
+    // fused variant: panoptic id of an instance / of a stuff class (0 for thing classes: a thing
+    // pixel without instance stays void, panoptic_merge.py:213-224)
+    __shared__ unsigned s_pan32[FUSED ? kMaxInst : 1];
+    __shared__ unsigned s_stuff[FUSED ? 256 : 1];
+    if (FUSED) {
+        static_assert(kPairThreads == kMaxInst, "one table entry per thread");
+        s_pan32[threadIdx.x] = (unsigned)prm.inst_pan_id[(size_t)blockIdx.y * kMaxInst + threadIdx.x];
+        s_stuff[threadIdx.x] = prm.thing.has((int)threadIdx.x) ? 0u : ((unsigned)threadIdx.x + 1u) << 16;
+    }
     extern __shared__ unsigned long long s_dyn[];
     PairTables t;
     t.keys = s_dyn;                                           // [kSmemSlots]
@@ -268,21 +285,30 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
         // same confusion cell" at once.
         const long long stride = (long long)gridDim.x * chunk;
         long long q_next = (long long)blockIdx.x * chunk + (long long)tid * 4;   // next pixel to fetch
-        const long long *pred_b = prm.pred + (size_t)b * P;
+        const long long *pred_b = FUSED ? nullptr : prm.pred + (size_t)b * P;
         const long long *target_b = prm.target + (size_t)b * P;
         const uint8_t *sem_b = CONFMAT ? prm.sem_target + (size_t)b * P : nullptr;
+        const uint8_t *csem_b = FUSED ? prm.sem_map + (size_t)b * P : nullptr;
+        const uint8_t *cinst_b = FUSED ? prm.inst_map + (size_t)b * P : nullptr;
         const unsigned q_base = (unsigned)__cvta_generic_to_shared(q_key);   // this warp's queue
         uint4 n_p0, n_p1, n_t0, n_t1;
-        unsigned n_sw;
+        unsigned n_sw, n_cw = 0u, n_iw = 0u;
         // software pipeline: the loads of the next chunk are issued before the current chunk is
         // processed, so their DRAM latency hides behind the (instruction bound) table updates
         auto fetch = [&]() {
             n_p0 = n_p1 = n_t0 = n_t1 = make_uint4(0u, 0u, 0u, 0u);
             n_sw = 0u;
+            n_cw = n_iw = 0u;
             if (q_next < P) {
-                const uint4 *pp = (const uint4 *)(pred_b + q_next);
+                if (FUSED) {
+                    // class / instance maps were written by the grouping kernel just before: L2
+                    n_cw = *(const unsigned *)(csem_b + q_next);
+                    n_iw = *(const unsigned *)(cinst_b + q_next);
+                } else {
+                    const uint4 *pp = (const uint4 *)(pred_b + q_next);
+                    n_p0 = __ldcs(pp); n_p1 = __ldcs(pp + 1);
+                }
                 const uint4 *tp = (const uint4 *)(target_b + q_next);
-                n_p0 = __ldcs(pp); n_p1 = __ldcs(pp + 1);
                 n_t0 = __ldcs(tp); n_t1 = __ldcs(tp + 1);
                 if (CONFMAT) n_sw = __ldcs((const unsigned *)(sem_b + q_next));
             }
@@ -292,6 +318,27 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
         for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
             bool act = q_next - stride < P;
             const unsigned sw = n_sw;
+            if (FUSED) {
+                // the prediction of these 4 pixels: instance id -> its panoptic id, otherwise the
+                // stuff id of the class; written out here and evaluated from registers
+                unsigned v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned c = (n_cw >> (8 * j)) & 255u, ii = (n_iw >> (8 * j)) & 255u;
+                    v[j] = ii ? s_pan32[ii] : s_stuff[c];
+                }
+                n_p0 = make_uint4(v[0], 0u, v[1], 0u);
+                n_p1 = make_uint4(v[2], 0u, v[3], 0u);
+                if (act) {
+                    const size_t fq = (size_t)b * P + (size_t)(q_next - stride);
+                    uint4 *o = (uint4 *)(prm.pan_out + fq);
+                    __stcs(o, n_p0);
+                    __stcs(o + 1, n_p1);
+                    if (prm.pan_sem_out)        // pan // 65536, one byte per pixel
+                        *(unsigned *)(prm.pan_sem_out + fq) =
+                            __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+                }
+            }
             const unsigned hi_or = n_p0.y | n_p0.w | n_p1.y | n_p1.w | n_t0.y | n_t0.w | n_t1.y | n_t1.w;
             const unsigned p_or = n_p0.x | n_p0.z | n_p1.x | n_p1.z;
             const unsigned t_or = n_t0.x | n_t0.z | n_t1.x | n_t1.z;
@@ -999,15 +1046,34 @@ extern "C" size_t npb_pq_update_workspace_bytes(int B, int num_categories)
     return bytes;
 }
 
-extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const uint8_t *sem_target,
-                             int B, int64_t P, int num_categories, int64_t ignored_label,
-                             int64_t max_instances_per_category, int64_t offset,
-                             int64_t void_segment_id, void *workspace, double *iou, double *tp,
-                             double *fn, double *fp, int64_t *confmat, int confmat_n,
-                             double *frame_stats, int64_t *matches, int match_cap,
-                             int32_t *n_matches, int32_t *status, void *stream)
+// panoptic ids produced inside the pixel pass (npb_write_panoptic_eval) instead of read from `pred`
+struct FusedWrite {
+    const uint8_t *sem, *inst;
+    const int64_t *inst_pan_id;
+    ClassSet thing;
+    int64_t *pan_out;
+    uint8_t *pan_sem_out;
+};
+
+// the fused pixel pass exists for the reference's id geometry and 4-pixel alignment only
+static bool fused_write_supported(int64_t P, int64_t max_instances_per_category, int64_t offset,
+                                  const FusedWrite &fw, const void *target, const void *sem_target)
 {
-    if (!pred || !target || !workspace || !iou || !tp || !fn || !fp || !status) return NPB_ERR_ARG;
+    return max_instances_per_category == (1ll << 16) && offset == (1ll << 24) && P % 4 == 0 &&
+           (((uintptr_t)fw.pan_out | (uintptr_t)target) & 15u) == 0 &&
+           (((uintptr_t)fw.sem | (uintptr_t)fw.inst | (uintptr_t)fw.pan_sem_out |
+             (uintptr_t)sem_target) & 3u) == 0;
+}
+
+static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64_t *target,
+                          const uint8_t *sem_target, int B, int64_t P, int num_categories,
+                          int64_t ignored_label, int64_t max_instances_per_category, int64_t offset,
+                          int64_t void_segment_id, void *workspace, double *iou, double *tp,
+                          double *fn, double *fp, int64_t *confmat, int confmat_n,
+                          double *frame_stats, int64_t *matches, int match_cap,
+                          int32_t *n_matches, int32_t *status, void *stream)
+{
+    if ((!pred && !fw) || !target || !workspace || !iou || !tp || !fn || !fp || !status) return NPB_ERR_ARG;
     if (B < 1 || B > 65535 || P < 1 || num_categories < 1 || num_categories > 256 ||
         max_instances_per_category < 1 || offset < 1)
         return NPB_ERR_ARG;
@@ -1032,6 +1098,14 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
 
     PairParams pp;
     pp.pred = (const long long *)pred; pp.target = (const long long *)target;
+    pp.sem_map = nullptr; pp.inst_map = nullptr; pp.inst_pan_id = nullptr;
+    pp.pan_out = nullptr; pp.pan_sem_out = nullptr;
+    for (int i = 0; i < 8; ++i) pp.thing.w[i] = 0;
+    if (fw) {
+        pp.sem_map = fw->sem; pp.inst_map = fw->inst;
+        pp.inst_pan_id = (const long long *)fw->inst_pan_id; pp.thing = fw->thing;
+        pp.pan_out = (long long *)fw->pan_out; pp.pan_sem_out = fw->pan_sem_out;
+    }
     pp.sem_target = sem_target; pp.P = P; pp.offset = offset; pp.L = max_instances_per_category;
     pp.L_shift = -1;
     pp.O_shift = -1;
@@ -1045,8 +1119,9 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     pp.entry_keys = ekeys; pp.entry_cnts = ecnts; pp.entry_n = en; pp.entry_cap = entry_cap;
     pp.confmat = (unsigned long long *)confmat; pp.status = status;
 
-    const bool vec4 = (P % 4 == 0) && (((uintptr_t)pred | (uintptr_t)target) & 15u) == 0 &&
-                      ((uintptr_t)sem_target & 3u) == 0;
+    const bool vec4 = fw != nullptr ||     // checked by fused_write_supported()
+                      ((P % 4 == 0) && (((uintptr_t)pred | (uintptr_t)target) & 15u) == 0 &&
+                       ((uintptr_t)sem_target & 3u) == 0);
     const int vec = vec4 ? 4 : 1;
     const long long n_chunks = (P + (long long)kPairThreads * vec - 1) / ((long long)kPairThreads * vec);
     // [hash keys | queue keys | hash counts | dense | confmat (if privatised) | queue meta]
@@ -1058,12 +1133,15 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     // specialisation for the reference's id geometry (offset = 256^3, L = 65536)
     const bool std_geom = pp.O_shift == 24 && pp.L_shift == 16;
     typedef void (*PairKernel)(const PairParams);
-    static const PairKernel kernels[8] = {
+    constexpr int kVariants = 10;
+    static const PairKernel kernels[kVariants] = {
         pair_count_kernel<1, false, false>, pair_count_kernel<4, false, false>,
         pair_count_kernel<1, true, false>,  pair_count_kernel<4, true, false>,
         pair_count_kernel<1, false, true>,  pair_count_kernel<4, false, true>,
-        pair_count_kernel<1, true, true>,   pair_count_kernel<4, true, true>};
-    const int variant = (std_geom ? 4 : 0) + (confmat ? 2 : 0) + (vec4 ? 1 : 0);
+        pair_count_kernel<1, true, true>,   pair_count_kernel<4, true, true>,
+        pair_count_kernel<4, false, true, true>, pair_count_kernel<4, true, true, true>};
+    const int variant = fw ? 8 + (confmat ? 1 : 0)
+                           : (std_geom ? 4 : 0) + (confmat ? 2 : 0) + (vec4 ? 1 : 0);
     const PairKernel kernel = kernels[variant];
     // one process may drive several devices: function attributes and the SM count are per device
     static bool pc_attr_set_dev[64] = {false};
@@ -1071,7 +1149,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     cudaGetDevice(&cur_dev);
     const int dslot = cur_dev & 63;
     if (!pc_attr_set_dev[dslot]) {
-        for (int v = 0; v < 8; ++v)
+        for (int v = 0; v < kVariants; ++v)
             cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(match_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)match_smem_bytes());
@@ -1080,8 +1158,8 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     const int n_sm = device_sm_count();
     // persistent CTAs: the whole batch in ONE wave (a second, partial wave would leave most SMs
     // idle for the length of a CTA), every CTA of a frame gets the same number of chunks
-    static size_t occ_smem_dev[64][8] = {{0}};
-    static int occ_blocks_dev[64][8] = {{0}};
+    static size_t occ_smem_dev[64][kVariants] = {{0}};
+    static int occ_blocks_dev[64][kVariants] = {{0}};
     int per_sm = occ_blocks_dev[dslot][variant];
     if (per_sm == 0 || occ_smem_dev[dslot][variant] != pc_smem) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPairThreads, pc_smem);
@@ -1117,4 +1195,47 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     accumulate_frames_kernel<<<(4 * num_categories * 32 + 127) / 128, 128, 0, s>>>(fstats, B, num_categories,
                                                                          iou, tp, fn, fp);
     return record_launch("npb_pq_update");
+}
+
+extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const uint8_t *sem_target,
+                             int B, int64_t P, int num_categories, int64_t ignored_label,
+                             int64_t max_instances_per_category, int64_t offset,
+                             int64_t void_segment_id, void *workspace, double *iou, double *tp,
+                             double *fn, double *fp, int64_t *confmat, int confmat_n,
+                             double *frame_stats, int64_t *matches, int match_cap,
+                             int32_t *n_matches, int32_t *status, void *stream)
+{
+    if (!pred) return NPB_ERR_ARG;
+    return pq_update_impl(pred, nullptr, target, sem_target, B, P, num_categories, ignored_label,
+                          max_instances_per_category, offset, void_segment_id, workspace, iou, tp,
+                          fn, fp, confmat, confmat_n, frame_stats, matches, match_cap, n_matches,
+                          status, stream);
+}
+
+extern "C" int npb_write_panoptic_eval(const uint8_t *sem, const uint8_t *inst,
+                                       const int64_t *inst_pan_id, const int32_t *inst_class, int B,
+                                       int C, int H, int W, const uint8_t *h_thing_lut,
+                                       int64_t max_instances_per_category, int64_t *pan_out,
+                                       uint8_t *pan_sem_out, const npb_eval_args *ev, void *stream)
+{
+    if (!sem || !inst || !inst_pan_id || !pan_out || !h_thing_lut || !ev) return NPB_ERR_ARG;
+    if (C < 1 || C > 255 || B < 1 || H < 1 || W < 1) return NPB_ERR_ARG;
+    const int64_t P = (int64_t)H * W;
+    FusedWrite fw{sem, inst, inst_pan_id, make_class_set(h_thing_lut, C), pan_out, pan_sem_out};
+    if (fused_write_supported(P, max_instances_per_category, ev->offset, fw, ev->target,
+                              ev->sem_target))
+        return pq_update_impl(nullptr, &fw, ev->target, ev->sem_target, B, P, ev->num_categories,
+                              ev->ignored_label, max_instances_per_category, ev->offset,
+                              ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
+                              ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches,
+                              ev->match_cap, ev->n_matches, ev->status, stream);
+    // other id geometries / unaligned maps: the two passes one after the other (same results)
+    const int rc = npb_write_panoptic(sem, inst, inst_pan_id, inst_class, B, C, H, W, h_thing_lut,
+                                      max_instances_per_category, pan_out, pan_sem_out, stream);
+    if (rc != NPB_OK) return rc;
+    return pq_update_impl(pan_out, nullptr, ev->target, ev->sem_target, B, P, ev->num_categories,
+                          ev->ignored_label, max_instances_per_category, ev->offset,
+                          ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
+                          ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches, ev->match_cap,
+                          ev->n_matches, ev->status, stream);
 }

@@ -35,6 +35,16 @@ class PanopticEvaluation:
             confmat=self.miou.confmat, want_matches=want_matches)
         return (matches, n_matches) if want_matches else None
 
+    def eval_args(self, panoptic_targets: torch.Tensor, semantic_targets: torch.Tensor,
+                  want_matches: bool = False):
+        """Evaluation half of a fused post-processing + evaluation call
+        (`PanopticPostprocessing.fuse_evaluation`): returns (`_lib.EvalArgs`, tensors to keep
+        alive until the call has been issued; 'matches' / 'n_matches' when requested)."""
+        if semantic_targets.dtype != torch.uint8:
+            semantic_targets = semantic_targets.to(torch.uint8)
+        return self.pq._eval_args(panoptic_targets, sem_target=semantic_targets,
+                                  confmat=self.miou.confmat, want_matches=want_matches)
+
     def update_with_orientation(self, panoptic_preds: torch.Tensor, orientation_preds,
                                 panoptic_preds_id_dicts, panoptic_target: torch.Tensor,
                                 orientation_target, panoptic_target_id_dicts,
@@ -49,10 +59,17 @@ class PanopticEvaluation:
         out = self.update(panoptic_preds, panoptic_target, semantic_target, want_matches=with_mae)
         if not with_mae:
             return
-        matches, n_matches = out
+        self.update_mae_from_matches(out, orientation_preds, panoptic_preds_id_dicts,
+                                     orientation_target, panoptic_target_id_dicts)
+
+    def update_mae_from_matches(self, matches, orientation_preds, panoptic_preds_id_dicts,
+                                orientation_target, panoptic_target_id_dicts) -> None:
+        """MAAE part of an update whose PQ part already ran: `matches` = (pairs, counts) device
+        tensors of that launch (mae.py:113-127)."""
+        pairs_d, n_matches = matches
         self.pq.check_status()
         counts = n_matches.cpu().tolist()
-        pairs = matches.cpu()
+        pairs = pairs_d.cpu()
         for b, n in enumerate(counts):
             self.pq.update_mae(orientation_preds[b], panoptic_preds_id_dicts[b],
                                orientation_target[b], panoptic_target_id_dicts[b],

@@ -40,20 +40,17 @@ class _PQKernel:
         return cls._scratch[key]
 
     @staticmethod
-    def run(pred: torch.Tensor, target: torch.Tensor, num_categories: int, ignored_label: int,
-            max_instances_per_category: int, offset: int, void_segment_id: int,
-            iou, tp, fn, fp, sem_target: Optional[torch.Tensor] = None,
-            confmat: Optional[torch.Tensor] = None, want_matches: bool = False,
-            want_frame_stats: bool = False, status: Optional[torch.Tensor] = None):
+    def prepare(target: torch.Tensor, num_categories: int, ignored_label: int, offset: int,
+                void_segment_id: int, iou, tp, fn, fp, sem_target: Optional[torch.Tensor] = None,
+                confmat: Optional[torch.Tensor] = None, want_matches: bool = False,
+                want_frame_stats: bool = False, status: Optional[torch.Tensor] = None):
+        """Everything of an update except the prediction: validated targets, scratch, optional
+        outputs.  Returns (`_lib.EvalArgs`, dict of the tensors it points into)."""
         dev = iou.device
         if not dev.type == 'cuda':
             raise RuntimeError('PanopticQuality.update needs its states on a CUDA device')
-        pred = _lib.require_cuda(pred.to(dev).to(torch.int64), 'preds', ndim=3)
         target = _lib.require_cuda(target.to(dev).to(torch.int64), 'targets', ndim=3)
-        assert target.shape == pred.shape
-        B = pred.shape[0]
-        P = pred.shape[1] * pred.shape[2]
-        L = _lib.lib()
+        B = target.shape[0]
         ws = _PQKernel._workspace(dev, B, num_categories)
         if status is None or status.numel() < B:
             status = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -66,15 +63,40 @@ class _PQKernel:
         n_cm = 0
         if confmat is not None:
             sem_target = _lib.require_cuda(sem_target.to(dev), 'semantic target', torch.uint8, 3)
+            assert sem_target.shape == target.shape
             n_cm = confmat.shape[0]
-        _lib.check(L.npb_pq_update(
-            _lib.ptr(pred), _lib.ptr(target), _lib.ptr(sem_target), c_int(B), c_int64(P),
+        else:
+            sem_target = None
+        p = lambda t: None if t is None else t.data_ptr()
+        args = _lib.EvalArgs(
+            target=p(target), sem_target=p(sem_target), num_categories=num_categories,
+            confmat_n=n_cm, ignored_label=ignored_label, offset=offset,
+            void_segment_id=void_segment_id, workspace=p(ws), iou=p(iou), tp=p(tp), fn=p(fn),
+            fp=p(fp), confmat=p(confmat), frame_stats=p(frame_stats), matches=p(matches),
+            match_cap=MATCH_CAP, n_matches=p(n_matches), status=p(status))
+        keep = dict(target=target, sem_target=sem_target, workspace=ws, status=status,
+                    matches=matches, n_matches=n_matches, frame_stats=frame_stats)
+        return args, keep
+
+    @staticmethod
+    def run(pred: torch.Tensor, target: torch.Tensor, num_categories: int, ignored_label: int,
+            max_instances_per_category: int, offset: int, void_segment_id: int,
+            iou, tp, fn, fp, **kw):
+        a, keep = _PQKernel.prepare(target, num_categories, ignored_label, offset,
+                                    void_segment_id, iou, tp, fn, fp, **kw)
+        dev = iou.device
+        pred = _lib.require_cuda(pred.to(dev).to(torch.int64), 'preds', ndim=3)
+        target = keep['target']
+        assert target.shape == pred.shape
+        B = pred.shape[0]
+        P = pred.shape[1] * pred.shape[2]
+        _lib.check(_lib.lib().npb_pq_update(
+            _lib.ptr(pred), a.target, a.sem_target, c_int(B), c_int64(P),
             c_int(num_categories), c_int64(ignored_label), c_int64(max_instances_per_category),
-            c_int64(offset), c_int64(void_segment_id), _lib.ptr(ws), _lib.ptr(iou), _lib.ptr(tp),
-            _lib.ptr(fn), _lib.ptr(fp), _lib.ptr(confmat), c_int(n_cm), _lib.ptr(frame_stats),
-            _lib.ptr(matches), c_int(MATCH_CAP), _lib.ptr(n_matches), _lib.ptr(status),
-            _lib.stream_ptr(dev)), 'npb_pq_update')
-        return status, matches, n_matches, frame_stats
+            c_int64(offset), c_int64(void_segment_id), a.workspace, a.iou, a.tp, a.fn, a.fp,
+            a.confmat, c_int(a.confmat_n), a.frame_stats, a.matches, c_int(MATCH_CAP),
+            a.n_matches, a.status, _lib.stream_ptr(dev)), 'npb_pq_update')
+        return keep['status'], keep['matches'], keep['n_matches'], keep['frame_stats']
 
 
 def compare_and_accumulate(
@@ -130,20 +152,31 @@ class PanopticQuality(MetricState):
         self._status: Dict[int, torch.Tensor] = {}
 
     # ---- update --------------------------------------------------------------------------
-    def _launch(self, preds, targets, **kw):
-        assert preds.ndim == 3
-        assert targets.shape == preds.shape
-        B = preds.shape[0]
+    def _status_for(self, B: int) -> torch.Tensor:
         status = self._status.get(B)
         if status is None or status.device != self.iou_per_class.device:
             status = torch.zeros(B, dtype=torch.int32, device=self.iou_per_class.device)
             self._status[B] = status
+        return status
+
+    def _launch(self, preds, targets, **kw):
+        assert preds.ndim == 3
+        assert targets.shape == preds.shape
         _, matches, n_matches, frame_stats = _PQKernel.run(
             preds, targets, self.num_categories, self.ignored_label,
             self.max_instances_per_category, self.offset, self.void_segment_id,
             self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
-            status=status, **kw)
+            status=self._status_for(preds.shape[0]), **kw)
         return matches, n_matches, frame_stats
+
+    def _eval_args(self, targets, **kw):
+        """`npb_eval_args` of an update whose prediction is produced by a fused kernel
+        (model/postprocessing/panoptic.py); same keyword arguments as `_launch`."""
+        assert targets.ndim == 3
+        return _PQKernel.prepare(
+            targets, self.num_categories, self.ignored_label, self.offset, self.void_segment_id,
+            self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
+            status=self._status_for(targets.shape[0]), **kw)
 
     def update(self, preds: torch.Tensor, targets: torch.Tensor) -> None:
         """preds, targets: (B,H,W) panoptic ids (class * max_instances + instance).

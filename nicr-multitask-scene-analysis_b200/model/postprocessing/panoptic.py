@@ -56,6 +56,7 @@ class PanopticPostprocessing(DensePostprocessingBase):
         self._max_instances_per_category = 1 << 16
         self._async_results = bool(kwargs.get('async_results', False))
         self._ws = {}
+        self._fused_evaluation = None       # see fuse_evaluation()
 
     @property
     def max_instances_per_category(self):
@@ -68,7 +69,7 @@ class PanopticPostprocessing(DensePostprocessingBase):
         return {**r_sem, **r_ins}
 
     # ------------------------------------------------------------------ fused kernel chain
-    def _forward_kernels(self, logits, heat, offset, orientation):
+    def _forward_kernels(self, logits, heat, offset, orientation, eval_args=None):
         post = self._instance_postprocessing
         logits = _lib.require_cuda(logits, 'semantic logits', torch.float32, 4)
         dev = logits.device
@@ -105,7 +106,7 @@ class PanopticPostprocessing(DensePostprocessingBase):
         inst = buf[o + u8_bytes:o + u8_bytes + B * P].view(B, H, W)
         pan_sem = buf[o + 2 * u8_bytes:o + 2 * u8_bytes + B * P].view(B, H, W)
         use_thr = post._offset_distance_threshold is not None
-        _lib.check(L.npb_panoptic_forward(
+        args = (
             _lib.ptr(logits), _lib.ptr(heat), _lib.ptr(offset), _lib.ptr(orientation),
             c_int(B), c_int(C), c_int(H), c_int(W),
             _lib.host_lut(self._is_thing, C), _lib.host_lut(self._has_orientation, C),
@@ -115,9 +116,38 @@ class PanopticPostprocessing(DensePostprocessingBase):
             c_int64(self._max_instances_per_category), _lib.ptr(ws), _lib.ptr(sem), _lib.ptr(inst),
             _lib.ptr(pan), _lib.ptr(pan_sem), tables.dptr('centers_yx'), tables.dptr('n_centers'),
             tables.dptr('center_score'), tables.dptr('inst_class'), tables.dptr('inst_pan_id'),
-            tables.dptr('inst_area'), tables.dptr('inst_angle'), tables.dptr('status'),
-            _lib.stream_ptr(dev)), 'npb_panoptic_forward')
+            tables.dptr('inst_area'), tables.dptr('inst_angle'), tables.dptr('status'))
+        if eval_args is None:
+            _lib.check(L.npb_panoptic_forward(*args, _lib.stream_ptr(dev)), 'npb_panoptic_forward')
+        else:       # the last stage also evaluates the ids it writes
+            import ctypes
+            _lib.check(L.npb_panoptic_forward_eval(*args, ctypes.byref(eval_args),
+                                                   _lib.stream_ptr(dev)),
+                       'npb_panoptic_forward_eval')
         return sem, inst, pan, pan_sem, tables
+
+    # ------------------------------------------------------------------ fused evaluation
+    def fuse_evaluation(self, evaluation) -> None:
+        """Attach a `metric.PanopticEvaluation` (or None to detach).  When the batch handed to
+        `postprocess` carries the ground truth (`panoptic_fullres`, `semantic_fullres`) at the
+        resolution of the network outputs, the kernel that writes the panoptic ids also feeds
+        PQ and mIoU (task_helper/panoptic.py:104-126) -- the ids are not read back.  The result
+        dict then carries `_panoptic_evaluation_fused` (and `_panoptic_matches` when the batch
+        has orientations) so that the task helper skips its own update."""
+        self._fused_evaluation = evaluation
+
+    def _fused_eval_args(self, batch, logits):
+        ev = getattr(self, '_fused_evaluation', None)
+        if ev is None:
+            return None
+        pan_t, sem_t = batch.get(fullres_key('panoptic')), batch.get(fullres_key('semantic'))
+        if not isinstance(pan_t, torch.Tensor) or not isinstance(sem_t, torch.Tensor):
+            return None
+        shape = (logits.shape[0],) + tuple(logits.shape[-2:])
+        if tuple(pan_t.shape) != shape or tuple(sem_t.shape) != shape:
+            return None         # evaluation happens at dataset resolution: not the same maps
+        want_matches = 'orientations_present' in batch and hasattr(ev.pq, 'update_mae')
+        return ev.eval_args(pan_t, sem_t, want_matches=want_matches)
 
     def _thing_mask(self, sem_u8: torch.Tensor) -> torch.Tensor:
         """panoptic.py:123-127 `isin(semantic idx, thing ids)` -> bool (B,H,W)."""
@@ -134,8 +164,10 @@ class PanopticPostprocessing(DensePostprocessingBase):
         center_heatmap, center_offset = i_output[0], i_output[1]
         orientation = i_output[2] if with_orientation else None
 
+        fused = self._fused_eval_args(batch, s_output)
         sem, inst, pan, pan_sem, tables = self._forward_kernels(
-            s_output, center_heatmap, center_offset, orientation)
+            s_output, center_heatmap, center_offset, orientation,
+            eval_args=fused[0] if fused else None)
 
         # semantic + instance entries (panoptic.py:86-94); the class map is shared
         r = ResultDict(semantic_output=s_output, semantic_side_outputs=s_side_outputs)
@@ -150,6 +182,11 @@ class PanopticPostprocessing(DensePostprocessingBase):
         r.defer('panoptic_segmentation_deeplab_semantic_idx', lambda: widen_u8(pan_sem))
         r['panoptic_segmentation_deeplab_instance_idx'] = inst
         r['_panoptic_instance_tables'] = tables
+        if fused:
+            # PQ / mIoU states already hold this batch; a task helper must not add it again
+            r['_panoptic_evaluation_fused'] = True
+            if fused[1].get('matches') is not None:
+                r['_panoptic_matches'] = (fused[1]['matches'], fused[1]['n_matches'])
         if self._async_results:
             r.defer('panoptic_segmentation_deeplab_ids', tables.panoptic_ids)
             r.defer('panoptic_segmentation_deeplab_instance_meta', lambda: self._meta(r, tables))

@@ -44,6 +44,11 @@ class PanopticTaskHelper(TaskHelperBase):
         self._metric_iou.reset()
         self._evaluation = PanopticEvaluation(self._mae_pq_deeplab, self._metric_iou)
 
+    @property
+    def evaluation(self) -> PanopticEvaluation:
+        """The PQ + mIoU pair of this helper, e.g. for `PanopticPostprocessing.fuse_evaluation`."""
+        return self._evaluation
+
     def validation_step(self, batch: Dict[str, Any], batch_idx: int,
                         predictions_post: Dict[str, Any]) -> Tuple[Dict, Dict]:
         return self._timed('panoptic_step_time', self._validation_step, batch, batch_idx,
@@ -56,6 +61,17 @@ class PanopticTaskHelper(TaskHelperBase):
             orientations_targets = batch['orientations_present']
         else:
             orientations_results = orientations_targets = None
+
+        if predictions_post.get('_panoptic_evaluation_fused'):
+            # the post-processing kernel already fed PQ + mIoU (PanopticPostprocessing.
+            # fuse_evaluation); only the MAAE loop over the matched instances is left
+            matches = predictions_post.get('_panoptic_matches')
+            if self._with_orientation and matches is not None:
+                self._evaluation.update_mae_from_matches(
+                    matches, orientations_results,
+                    predictions_post['panoptic_segmentation_deeplab_ids'], orientations_targets,
+                    batch.get('panoptic_ids_to_instance_dict'))
+            return {}, {}
 
         panoptic_targets = self._dev(get_fullres(batch, 'panoptic'))
         panoptic_preds = predictions_post[fullres_key('panoptic_segmentation_deeplab')]

@@ -1,0 +1,154 @@
+"""Fused validation step: the kernel that writes the panoptic ids also feeds PQ + mIoU
+(`PanopticPostprocessing.fuse_evaluation`, `npb_panoptic_forward_eval`).  Everything must be
+identical to post-processing followed by `PanopticEvaluation.update`, and to the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+L, OFF = 1 << 16, 256 ** 3
+
+
+def _make(C, dev, offset=OFF, with_mae=False):
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, PanopticEvaluation,
+                                                    PanopticQuality,
+                                                    PanopticQualityWithOrientationMAE)
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    is_thing = testing.default_is_thing(C)
+    has_ori = tuple(bool(t and c % 4 == 1) for c, t in enumerate(is_thing))
+    post = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+        instance_postprocessing=get_postprocessing_class('instance')(),
+        semantic_classes_is_thing=is_thing, semantic_class_has_orientation=has_ori)()
+    cls = PanopticQualityWithOrientationMAE if with_mae else PanopticQuality
+    pq = cls(C + 1, 0, L, offset, (False,) + is_thing, device=dev)
+    miou = MeanIntersectionOverUnion(C + 1, ignore_first_class=True, device=dev)
+    return post, PanopticEvaluation(pq, miou), is_thing, has_ori
+
+
+def _states(ev):
+    return np.stack([getattr(ev.pq, n).cpu().numpy() for n in
+                     ('iou_per_class', 'tp_per_class', 'fn_per_class', 'fp_per_class')])
+
+
+def _raw(data, dev):
+    d = {k: v.to(dev) for k, v in data.items()}
+    return ((d['logits'], (d['heat'], d['offset'], d['orientation'])), (None, None))
+
+
+@pytest.mark.parametrize('shape,offset', [((3, 96, 132), OFF),      # fused kernel
+                                          ((2, 75, 91), OFF),       # H*W % 4 != 0: two passes
+                                          ((2, 64, 80), 2 ** 25)])  # other offset: two passes
+def test_fused_equals_separate_and_oracle(shape, offset, cuda_device):
+    from nicr_mt_scene_analysis_b200 import testing
+    B, H, W = shape
+    C, K = 11, 5
+    data = testing.make_batch(B, C, H, W, K, seed=B * H + W)
+    post_f, ev_f, is_thing, has_ori = _make(C, cuda_device, offset)
+    post_s, ev_s, _, _ = _make(C, cuda_device, offset)
+    ref = oracle.panoptic_postprocess(*(data[k].numpy() for k in
+                                        ('logits', 'heat', 'offset', 'orientation')),
+                                      is_thing, has_ori)
+    tgt = np.roll(ref['panoptic'], 5, axis=-1)
+    tgt_sem = (tgt // L).astype(np.uint8)
+    batch = testing.make_batch_dict(B, H, W)
+    gt = dict(batch, panoptic_fullres=torch.from_numpy(tgt).to(cuda_device),
+              semantic_fullres=torch.from_numpy(tgt_sem).to(cuda_device))
+
+    post_f.fuse_evaluation(ev_f)
+    for _ in range(2):                                   # two batches accumulate
+        r_f = post_f.postprocess(_raw(data, cuda_device), gt, is_training=False)
+        r_s = post_s.postprocess(_raw(data, cuda_device), batch, is_training=False)
+        assert r_f.get('_panoptic_evaluation_fused') is True
+        assert '_panoptic_evaluation_fused' not in r_s
+        ev_s.update(r_s['panoptic_segmentation_deeplab'], gt['panoptic_fullres'], gt['semantic_fullres'])
+        for key in ('panoptic_segmentation_deeplab', 'panoptic_segmentation_deeplab_instance_idx',
+                    'panoptic_segmentation_deeplab_semantic_idx'):
+            assert torch.equal(r_f[key], r_s[key]), key
+        assert r_f['panoptic_segmentation_deeplab_ids'] == r_s['panoptic_segmentation_deeplab_ids']
+    assert np.array_equal(r_f['panoptic_segmentation_deeplab'].cpu().numpy(), ref['panoptic'])
+    ev_f.pq.check_status()
+    ev_s.pq.check_status()
+    assert np.array_equal(_states(ev_f), _states(ev_s))                  # bit-exact float64
+    assert np.array_equal(ev_f.miou.confmat.cpu().numpy(), ev_s.miou.confmat.cpu().numpy())
+    # ... and both equal the oracle (2 identical batches)
+    state = np.zeros((4, C + 1))
+    for _ in range(2):
+        for b in range(B):
+            out = oracle.pq_compare_and_accumulate(ref['panoptic'][b], tgt[b], C + 1, 0, L, offset, 0)
+            for s, v in zip(state, out[:4]):
+                s += v
+    assert np.array_equal(_states(ev_f), state)
+    assert np.array_equal(ev_f.miou.confmat.cpu().numpy(),
+                          2 * oracle.confmat(ref['panoptic'] // L, tgt_sem, C + 1))
+    assert int(ev_f.miou.confmat.sum()) == 2 * B * H * W
+
+
+def test_fusion_needs_ground_truth_at_network_resolution(cuda_device):
+    """No ground truth in the batch, or at another resolution: plain post-processing, the
+    metric states stay untouched."""
+    from nicr_mt_scene_analysis_b200 import testing
+    B, C, H, W = 2, 7, 64, 80
+    data = testing.make_batch(B, C, H, W, 4, seed=5)
+    post, ev, _, _ = _make(C, cuda_device)
+    post.fuse_evaluation(ev)
+    batch = testing.make_batch_dict(B, H, W)
+    r = post.postprocess(_raw(data, cuda_device), batch, is_training=False)
+    assert '_panoptic_evaluation_fused' not in r
+    other = dict(batch, panoptic_fullres=torch.zeros((B, 2 * H, 2 * W), dtype=torch.int64),
+                 semantic_fullres=torch.zeros((B, 2 * H, 2 * W), dtype=torch.uint8))
+    r = post.postprocess(_raw(data, cuda_device), other, is_training=False)
+    assert '_panoptic_evaluation_fused' not in r
+    assert float(ev.pq.tp_per_class.sum() + ev.pq.fn_per_class.sum() + ev.pq.fp_per_class.sum()) == 0.0
+    assert int(ev.miou.confmat.sum()) == 0
+
+
+def test_fused_validation_step_with_orientation(cuda_device):
+    """Task helper + fused post-processing: PQ, mIoU and MAAE equal the unfused validation step."""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.task_helper import PanopticTaskHelper
+    B, C, H, W, K = 3, 9, 96, 128, 5
+    data = testing.make_batch(B, C, H, W, K, seed=77)
+    post_f, _, is_thing, has_ori = _make(C, cuda_device)
+    post_s, _, _, _ = _make(C, cuda_device)
+    ref = oracle.panoptic_postprocess(*(data[k].numpy() for k in
+                                        ('logits', 'heat', 'offset', 'orientation')),
+                                      is_thing, has_ori)
+    tgt = np.roll(ref['panoptic'], 3, axis=-1)
+    tgt_ids = [{int(v): int(v) % L for v in np.unique(t) if int(v) % L} for t in tgt]
+    ori_t = [{i: 0.3 * i - 1.0 for i in set(d.values())} for d in tgt_ids]
+    batch = dict(testing.make_batch_dict(B, H, W),
+                 panoptic_fullres=torch.from_numpy(tgt),
+                 semantic_fullres=torch.from_numpy((tgt // L).astype(np.uint8)),
+                 panoptic_ids_to_instance_dict=tgt_ids, orientations_present=ori_t)
+    dev_batch = dict(batch, panoptic_fullres=batch['panoptic_fullres'].to(cuda_device),
+                     semantic_fullres=batch['semantic_fullres'].to(cuda_device))
+    helpers = []
+    for post, fused in ((post_f, True), (post_s, False)):
+        helper = PanopticTaskHelper(C + 1, (False,) + is_thing)
+        helper.initialize(cuda_device)
+        if fused:
+            post.fuse_evaluation(helper.evaluation)
+        r = post.postprocess(_raw(data, cuda_device), dev_batch, is_training=False)
+        assert bool(r.get('_panoptic_evaluation_fused')) == fused
+        assert ('_panoptic_matches' in r) == fused
+        helper.validation_step(dev_batch, 1, r)
+        helpers.append(helper.validation_epoch_end())
+    (art_f, _, logs_f), (art_s, _, logs_s) = helpers
+    assert set(logs_f) == set(logs_s) and set(art_f) == set(art_s)
+    assert float(logs_f['panoptic_mae_deeplab_rad']) > 0
+    for k in logs_s:
+        if k.endswith('_time'):
+            continue
+        a, b = torch.as_tensor(logs_f[k]).double(), torch.as_tensor(logs_s[k]).double()
+        if 'mae' in k:      # float64 sum of float32 errors in match order (not deterministic)
+            assert torch.allclose(a, b, rtol=1e-12), k
+        else:
+            assert torch.equal(a, b), k
+    for k in art_s:
+        assert torch.equal(torch.as_tensor(art_f[k]).cpu(), torch.as_tensor(art_s[k]).cpu()) or \
+            torch.allclose(torch.as_tensor(art_f[k]).cpu(), torch.as_tensor(art_s[k]).cpu(), equal_nan=True), k
