@@ -49,4 +49,32 @@ __device__ __forceinline__ float warp_sum(float v)
 
 int record_launch(const char *what);  // api.cu: cudaGetLastError -> NPB_ERR_CUDA
 
+// ---- programmatic dependent launch ----------------------------------------------------------
+// A kernel launched with launch_dependent() may start while its predecessor on the stream is
+// still draining: its CTAs are scheduled and run their prologue (shared-memory set-up) early and
+// block in grid_dependency_wait() until the predecessor has completed and its memory is visible.
+// Every kernel launched that way MUST call grid_dependency_wait() before it touches global
+// memory.  (Without the launch attribute the instruction is a no-op.)
+__device__ __forceinline__ void grid_dependency_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                             cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace npb

@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         g_id[i] = kEmptyKey; p_id[i] = kEmptyKey;
         g_area[i] = 0; g_matched[i] = 0; p_area[i] = 0; p_void[i] = 0; p_pio[i] = 0; p_matched[i] = 0;
     }
+    grid_dependency_wait();       // the pixel pass (launch_dependent: the set-up above overlaps its tail)
     __syncthreads();
 
     // (0) the frame's pairs -> pair table.  Every used slot is remembered in s_idx, so the later
@@ -902,6 +903,7 @@ accumulate_frames_kernel(const double *__restrict__ frame_stats, int B, int NC,
                          double *iou, double *tp, double *fn, double *fp)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    grid_dependency_wait();       // the matcher (this kernel is launched with launch_dependent)
     if (warp >= 4 * NC) return;
     const int stat = warp / NC, c = warp - stat * NC;
     double *dst = stat == 0 ? iou : stat == 1 ? tp : stat == 2 ? fn : fp;
@@ -1191,9 +1193,9 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     mp.L_shift = pp.L_shift; mp.O_shift = pp.O_shift;
     mp.matches = (long long *)matches; mp.match_cap = match_cap; mp.n_matches = n_matches;
     mp.status = status;
-    match_frames_kernel<<<B, kMatchThreads, match_smem_bytes(), s>>>(mp);
-    accumulate_frames_kernel<<<(4 * num_categories * 32 + 127) / 128, 128, 0, s>>>(fstats, B, num_categories,
-                                                                         iou, tp, fn, fp);
+    launch_dependent(match_frames_kernel, dim3(B), dim3(kMatchThreads), match_smem_bytes(), s, mp);
+    launch_dependent(accumulate_frames_kernel, dim3((4 * num_categories * 32 + 127) / 128), dim3(128), 0, s,
+                     (const double *)fstats, B, num_categories, iou, tp, fn, fp);
     return record_launch("npb_pq_update");
 }
 
