@@ -22,6 +22,8 @@
 // orders equal the reference's, so the states are bit-identical, not merely close.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace npb {
@@ -1004,6 +1006,8 @@ extern "C" int npb_confmat_update(const void *preds, int preds_dtype, const void
 static int device_sm_count()
 {
     static int n_sm_dev[64] = {0};
+    static std::mutex guard;
+    std::lock_guard<std::mutex> lock(guard);
     int dev = 0;
     cudaGetDevice(&dev);
     int &n = n_sm_dev[dev & 63];
@@ -1018,8 +1022,10 @@ constexpr int kMaxPairCtasPerSm = 8;
 
 static unsigned pq_entry_cap(int B)
 {
+    // every CTA of the pixel pass appends at most its hash table; the rest is head room for
+    // single entries of overflowing CTA tables
     const long long ctas_per_frame = ((long long)device_sm_count() * kMaxPairCtasPerSm + B - 1) / B;
-    return (unsigned)(4 * kMaxPairs + 128 * ctas_per_frame);
+    return (unsigned)(4 * kMaxPairs + (long long)kSmemSlots * ctas_per_frame);
 }
 
 // side of the dense class-pair table: it needs `id >> shift` decoding and has to fit into the
@@ -1146,6 +1152,9 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
                            : (std_geom ? 4 : 0) + (confmat ? 2 : 0) + (vec4 ? 1 : 0);
     const PairKernel kernel = kernels[variant];
     // one process may drive several devices: function attributes and the SM count are per device
+    // (host threads may call concurrently: the per-device caches below are guarded)
+    static std::mutex cache_guard;
+    std::unique_lock<std::mutex> cache_lock(cache_guard);
     static bool pc_attr_set_dev[64] = {false};
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
@@ -1176,6 +1185,7 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
         const char *e = getenv("NPB_PAIR_CTAS_PER_SM");
         env_cap = e ? atoi(e) : 0;
     }
+    cache_lock.unlock();
     if (env_cap > 0 && per_sm > env_cap) per_sm = env_cap;
     if (per_sm > kMaxPairCtasPerSm) per_sm = kMaxPairCtasPerSm;     // pq_entry_cap() assumes it
     long long bx = ((long long)n_sm * per_sm) / B;

@@ -325,3 +325,32 @@ def test_pq_with_orientation_mae(cuda_device):
     want = (0.25 + (2 * math.pi - 6.0)) / 2
     assert float(r['mae_deeplab_rad']) == pytest.approx(want, rel=1e-6)
     assert 'all_deeplab_pq' in r and 'mae_deeplab_deg' in r
+
+
+@pytest.mark.parametrize('frames', [1, 8])
+def test_pq_noise_ids_few_frames(frames, cuda_device):
+    """Few frames per launch = many CTAs of the pixel pass per frame, and random ids = nearly
+    every pixel of a CTA is its own pair: the hand-over list takes the most entries here
+    (an untrained network's output looks like this)."""
+    from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion, PanopticEvaluation, PanopticQuality
+    L, OFF, NC = 1 << 16, 256 ** 3, 9
+    g = torch.Generator().manual_seed(100 + frames)
+    H, W = 240, 320
+    cat_t = torch.randint(0, NC, (frames, H, W), generator=g)
+    cat_p = torch.randint(0, NC, (frames, H, W), generator=g)
+    is_thing = [False] + [bool(c % 2) for c in range(1, NC)]
+    it = torch.tensor(is_thing)
+    tgt = cat_t * L + torch.where(it[cat_t], torch.randint(1, 8, (frames, H, W), generator=g), 0)
+    pred = cat_p * L + torch.where(it[cat_p], torch.randint(1, 20, (frames, H, W), generator=g), 0)
+    pq = PanopticQuality(NC, 0, L, OFF, is_thing, device=cuda_device)
+    miou = MeanIntersectionOverUnion(NC, True, device=cuda_device)
+    PanopticEvaluation(pq, miou).update(pred.to(cuda_device), tgt.to(cuda_device),
+                                        cat_t.to(torch.uint8).to(cuda_device))
+    pq.check_status()
+    state = np.zeros((4, NC))
+    for b in range(frames):
+        out = oracle.pq_compare_and_accumulate(pred[b].numpy(), tgt[b].numpy(), NC, 0, L, OFF, 0)
+        for s, v in zip(state, out[:4]):
+            s += v
+    assert np.array_equal(np.stack(_states(pq)), state)
+    assert np.array_equal(miou.confmat.cpu().numpy(), oracle.confmat((pred // L).numpy(), cat_t.numpy(), NC))
