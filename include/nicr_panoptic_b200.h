@@ -303,6 +303,23 @@ int npb_pq_update(const int64_t *pred, const int64_t *target, const uint8_t *sem
                   int match_cap, int32_t *n_matches, int32_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Fall-back of npb_pq_update for ONE frame that exceeded the fixed capacities of the
+ * shared-memory matcher (status NPB_ERR_CAPACITY: more than 4096 distinct (gt, pred) pairs or
+ * 1536 segments, e.g. per-pixel random ids of an untrained network).  Such a frame contributed
+ * nothing to the states; this call evaluates it with every table in global memory (up to one
+ * pair per pixel, ~100 000 segments per side, 65536 matches) and adds its result.
+ * Same arguments as npb_pq_update for B = 1, without the confusion matrix (npb_pq_update has
+ * already counted the frame there).
+ * ------------------------------------------------------------------------- */
+size_t npb_pq_update_big_frame_workspace_bytes(int64_t P, int num_categories);
+int npb_pq_update_big_frame(const int64_t *pred, const int64_t *target, int64_t P,
+                            int num_categories, int64_t ignored_label,
+                            int64_t max_instances_per_category, int64_t offset,
+                            int64_t void_segment_id, void *workspace, double *iou, double *tp,
+                            double *fn, double *fp, int64_t *matches, int match_cap,
+                            int32_t *n_matches, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Fused validation step: panoptic ids written AND evaluated in one pass.
  * Replaces: the tail of PanopticPostprocessing._postprocess_inference (panoptic.py:139-167)
  *           followed by PanopticTaskHelper.validation_step (task_helper/panoptic.py:104-126),

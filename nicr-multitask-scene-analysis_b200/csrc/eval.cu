@@ -638,20 +638,39 @@ struct MatchParams {
 };
 
 // ---- matcher: one CTA per frame ------------------------------------------------------------
-// The frame's entry list is merged into a shared-memory pair table (pair -> pixels); segment
-// tables (distinct gt ids / pred ids of the frame) are shared-memory hash tables filled from
-// the pairs with atomics; only the matched pairs (one per matched gt segment at most) are
+// The frame's hand-over tables are merged into a shared-memory pair table (pair -> pixels);
+// segment tables (distinct gt ids / pred ids of the frame) are shared-memory hash tables filled
+// from the pairs with atomics; only the matched pairs (one per matched gt segment at most) are
 // ordered, because only their float64 IoU sum depends on the visiting order.
+// The phases after the merge are shared with the fall-back for frames that do not fit
+// (match_big_frame_kernel: the same tables in global memory, larger).
 constexpr int kPairSlots = 2 * kMaxPairs;   // pair table of the matcher (load factor <= 0.5)
 constexpr int kSegSlots = 2048;       // distinct gt (and pred) segments per frame: <= 1536
 constexpr int kMaxMatched = 1024;
 
-struct SegTable {
-    unsigned long long *id;   // [kSegSlots], kEmptyKey = free
-    unsigned *area;           // [kSegSlots] pixels of the segment
-    unsigned *aux;            // gt: unused; pred: pixels inside the gt void segment
-    unsigned *pio;            // pred: pixels inside ignored gt segments
-    unsigned char *matched;   // 1 once the segment took part in a match
+// SlotT: index type of segment slots / pair slots (uint16 in shared memory, uint32 in the
+// global-memory fall-back)
+template <typename SlotT>
+struct MatchTables {
+    // pair table: key -> pixels (+ the slots of its two segments, filled by phase 1)
+    unsigned long long *t_key;  // [pair_slots], kEmptyKey = free
+    unsigned *t_cnt;
+    SlotT *t_gslot, *t_pslot;
+    int pair_slots;
+    const SlotT *walk;          // the used pair slots ([n_walk]), or null: walk all pair_slots
+    // segment tables
+    unsigned long long *g_id, *p_id;    // [seg_slots], kEmptyKey = free
+    unsigned *g_area, *p_area;          // pixels of the segment
+    unsigned *p_void;                   // pred: pixels inside the gt void segment
+    unsigned *p_pio;                    // pred: pixels inside ignored gt segments
+    unsigned char *g_matched, *p_matched;
+    int seg_slots;
+    // matched pairs (unordered), then ordered IoUs / categories
+    long long *m_key;
+    unsigned *m_ia, *m_uni;
+    unsigned short *m_cat, *s_cat;
+    double *s_iou;
+    int max_matched;
 };
 
 __device__ __forceinline__ long long div_pow2(long long v, long long d, int shift)
@@ -660,16 +679,153 @@ __device__ __forceinline__ long long div_pow2(long long v, long long d, int shif
 }
 
 // returns the slot of `id` (inserting it), or -1 when the table is full
-__device__ __forceinline__ int seg_slot(SegTable &tb, unsigned long long id)
+__device__ __forceinline__ int seg_slot(unsigned long long *ids, int slots, unsigned long long id)
 {
-    unsigned h = hash64(id) & (unsigned)(kSegSlots - 1);
-    for (int probe = 0; probe < kSegSlots; ++probe) {
-        unsigned long long k = tb.id[h];
-        if (k == kEmptyKey) k = atomicCAS(tb.id + h, kEmptyKey, id);
+    unsigned h = hash64(id) & (unsigned)(slots - 1);
+    for (int probe = 0; probe < slots; ++probe) {
+        unsigned long long k = ids[h];
+        if (k == kEmptyKey) k = atomicCAS(ids + h, kEmptyKey, id);
         if (k == kEmptyKey || k == id) return (int)h;
-        h = (h + 1) & (unsigned)(kSegSlots - 1);
+        h = (h + 1) & (unsigned)(slots - 1);
     }
     return -1;
+}
+
+// counters of one frame, in shared memory of the matching CTA
+struct MatchCounters {
+    int nm;                 // matched pairs
+    int fail;               // a capacity was exceeded: the frame contributes nothing
+    int tp[256], fn[256], fp[256];
+};
+
+// Phases 1-4 of the matcher on a filled pair table.  All threads of the CTA call it; the tables
+// (other than the pair keys / counts) and the counters must be cleared.
+template <typename SlotT>
+__device__ void match_phases(const MatchParams &prm, int b, const MatchTables<SlotT> &T,
+                             int n_walk, MatchCounters &C)
+{
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int NC = prm.num_categories;
+
+    // (1) segment tables: areas (pq.py:83-84), void overlap (pq.py:34-43), ignored overlap
+    //     (pq.py:47-57); every pair remembers the slots of its two segments
+    for (int i = tid; i < n_walk; i += nthreads) {
+        const int t = T.walk ? (int)T.walk[i] : i;
+        const long long key = (long long)T.t_key[t];
+        if ((unsigned long long)key == kEmptyKey) continue;
+        const unsigned cnt = T.t_cnt[t];
+        const long long g = div_pow2(key, prm.offset, prm.O_shift);
+        const long long p = key - g * prm.offset;
+        const int gs = seg_slot(T.g_id, T.seg_slots, (unsigned long long)g);
+        const int ps = seg_slot(T.p_id, T.seg_slots, (unsigned long long)p);
+        if (gs < 0 || ps < 0) {
+            C.fail = 1;
+            T.t_key[t] = kEmptyKey;         // phase 2 skips the pair (its frame failed anyway)
+            continue;
+        }
+        T.t_gslot[t] = (SlotT)gs;
+        T.t_pslot[t] = (SlotT)ps;
+        atomicAdd(T.g_area + gs, cnt);
+        atomicAdd(T.p_area + ps, cnt);
+        if (g == prm.void_segment_id) T.p_void[ps] = cnt;     // key == void*offset + p, unique
+        if (div_pow2(g, prm.L, prm.L_shift) == prm.ignored_label) atomicAdd(T.p_pio + ps, cnt);
+    }
+    __syncthreads();
+
+    // (2) IoU + match decision per intersecting pair                       pq.py:119-152
+    for (int i = tid; i < n_walk; i += nthreads) {
+        const int t = T.walk ? (int)T.walk[i] : i;
+        const long long key = (long long)T.t_key[t];
+        if ((unsigned long long)key == kEmptyKey) continue;
+        if (key == prm.void_segment_id) continue;                          // pq.py:120
+        const long long g = div_pow2(key, prm.offset, prm.O_shift), p = key - g * prm.offset;
+        const long long gcat = div_pow2(g, prm.L, prm.L_shift), pcat = div_pow2(p, prm.L, prm.L_shift);
+        if (gcat != pcat) continue;                                        // pq.py:128
+        const int gs = T.t_gslot[t], ps = T.t_pslot[t];
+        const long long ia = T.t_cnt[t];
+        const long long uni = (long long)T.g_area[gs] + (long long)T.p_area[ps] - ia -
+                              (long long)T.p_void[ps];                     // pq.py:143
+        if (uni == 0) { set_status(prm.status + b, NPB_ERR_ZERO_DIVISION); continue; }
+        // iou = ia / uni > 0.5 in float64 (pq.py:145-146) <=> 2 * ia > uni (integers < 2^33)
+        if (uni > 0 && 2 * ia > uni) {
+            if (gcat < 0 || gcat >= NC || gcat >= 256) { set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE); continue; }
+            T.g_matched[gs] = 1;
+            T.p_matched[ps] = 1;
+            atomicAdd(&C.tp[(int)gcat], 1);
+            const int slot = atomicAdd(&C.nm, 1);
+            if (slot < T.max_matched) {
+                T.m_key[slot] = key;
+                T.m_ia[slot] = (unsigned)ia;
+                T.m_uni[slot] = (unsigned)uni;
+                T.m_cat[slot] = (unsigned short)gcat;
+            } else {
+                C.fail = 1;
+            }
+            if (prm.matches) {
+                if (slot < prm.match_cap) {
+                    long long *o = prm.matches + ((size_t)b * prm.match_cap + slot) * 2;
+                    o[0] = g;
+                    o[1] = p;
+                } else {
+                    C.fail = 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // (3) false negatives: unmatched gt segments outside the ignored label    pq.py:155-163
+    //     false positives: unmatched pred segments, unless more than half of their area lies
+    //     in ignored gt segments                                            pq.py:165-177
+    for (int i = tid; i < T.seg_slots; i += nthreads) {
+        if (T.g_id[i] != kEmptyKey && !T.g_matched[i]) {
+            const long long cat = div_pow2((long long)T.g_id[i], prm.L, prm.L_shift);
+            if (cat != prm.ignored_label) {
+                if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
+                else atomicAdd(&C.fn[(int)cat], 1);
+            }
+        }
+        if (T.p_id[i] != kEmptyKey && !T.p_matched[i]) {
+            // pio / area > 0.5 in float64 (pq.py:172) <=> 2 * pio > area: the quotient of two
+            // integers < 2^32 is never closer to 0.5 than 2^-33 unless it equals 0.5
+            if (!(2ull * T.p_pio[i] > (unsigned long long)T.p_area[i])) {
+                const long long cat = div_pow2((long long)T.p_id[i], prm.L, prm.L_shift);
+                if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
+                else atomicAdd(&C.fp[(int)cat], 1);
+            }
+        }
+    }
+
+    // (4) float64 IoU sums per category with the matched pairs in ascending key order (= the
+    //     reference's visiting order, pq.py:109/119).  Keys are unique, so the rank of a pair is
+    //     the number of smaller keys: every thread ranks its pairs against all others
+    //     (broadcast reads, no barriers) and drops IoU + category at the ranked position.
+    const int nm = C.nm < T.max_matched ? C.nm : T.max_matched;     // stable since the last barrier
+    for (int i = tid; i < nm; i += nthreads) {
+        const long long key = T.m_key[i];
+        int rank = 0;
+        for (int j = 0; j < nm; ++j) rank += T.m_key[j] < key;
+        T.s_iou[rank] = (double)T.m_ia[i] / (double)T.m_uni[i];            // pq.py:145
+        T.s_cat[rank] = T.m_cat[i];
+    }
+    __syncthreads();
+    // a frame beyond the capacities reports it and contributes nothing: the caller may evaluate
+    // it again with npb_pq_update_big_frame
+    const bool failed = C.fail != 0 || prm.status[b] == NPB_ERR_CAPACITY;
+    if (failed && tid == 0) set_status(prm.status + b, NPB_ERR_CAPACITY);
+    for (int c = tid; c < NC; c += nthreads) {
+        double acc = 0.0;
+        if (c < 256 && C.tp[c] > 0)
+            for (int i = 0; i < nm; ++i)
+                if (T.s_cat[i] == c) acc += T.s_iou[i];
+        double *fs = prm.frame_stats + (size_t)b * 4 * NC;
+        fs[c] = failed ? 0.0 : acc;
+        fs[NC + c] = (c < 256 && !failed) ? (double)C.tp[c] : 0.0;
+        fs[2 * NC + c] = (c < 256 && !failed) ? (double)C.fn[c] : 0.0;
+        fs[3 * NC + c] = (c < 256 && !failed) ? (double)C.fp[c] : 0.0;
+    }
+    if (tid == 0 && prm.n_matches)
+        prm.n_matches[b] = failed ? 0 : (C.nm < prm.match_cap ? C.nm : prm.match_cap);
 }
 
 __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const MatchParams prm)
@@ -694,16 +850,12 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     unsigned short *s_idx = s_mcat + kMaxMatched;                          // [kMaxPairs] used slots
     unsigned char *g_matched = (unsigned char *)(s_idx + kMaxPairs);       // [kSegSlots]
     unsigned char *p_matched = g_matched + kSegSlots;                      // [kSegSlots]
-    __shared__ int s_m, s_nm;
-    __shared__ int s_tp[256], s_fn[256], s_fp[256];
-
-    SegTable gt{g_id, g_area, nullptr, nullptr, g_matched};
-    SegTable pt{p_id, p_area, p_void, p_pio, p_matched};
+    __shared__ int s_m;
+    __shared__ MatchCounters C;
 
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int NC = prm.num_categories;
-    if (tid == 0) { s_m = 0; s_nm = 0; }
-    for (int c = tid; c < 256; c += kMatchThreads) { s_tp[c] = 0; s_fn[c] = 0; s_fp[c] = 0; }
+    if (tid == 0) { s_m = 0; C.nm = 0; C.fail = 0; }
+    for (int c = tid; c < 256; c += kMatchThreads) { C.tp[c] = 0; C.fn[c] = 0; C.fp[c] = 0; }
     for (int i = tid; i < kPairSlots; i += kMatchThreads) { t_key[i] = kEmptyKey; t_cnt[i] = 0; }
     for (int i = tid; i < kSegSlots; i += kMatchThreads) {
         g_id[i] = kEmptyKey; p_id[i] = kEmptyKey;
@@ -723,7 +875,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
                 if (cur == kEmptyKey) {                      // this thread claimed the slot
                     const int idx = atomicAdd(&s_m, 1);
                     if (idx < kMaxPairs) s_idx[idx] = (unsigned short)h;
-                    else set_status(prm.status + b, NPB_ERR_CAPACITY);
+                    else C.fail = 1;
                 }
             }
             if (cur == kEmptyKey || cur == key) {
@@ -732,7 +884,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
             }
             h = (h + 1) & (unsigned)(kPairSlots - 1);
         }
-        set_status(prm.status + b, NPB_ERR_CAPACITY);
+        C.fail = 1;
     };
     // class pairs: dense per-frame table, every pair exactly once (independent loads first)
     if (prm.frame_dense) {
@@ -779,121 +931,70 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     __syncthreads();
     const int m = s_m < kMaxPairs ? s_m : kMaxPairs;
 
-    // (1) segment tables: areas (pq.py:83-84), void overlap (pq.py:34-43), ignored overlap
-    //     (pq.py:47-57); every pair remembers the slots of its two segments
-    for (int i = tid; i < m; i += kMatchThreads) {
-        const int t = s_idx[i];
-        const long long key = (long long)t_key[t];
-        const unsigned cnt = t_cnt[t];
-        const long long g = div_pow2(key, prm.offset, prm.O_shift);
-        const long long p = key - g * prm.offset;
-        const int gs = seg_slot(gt, (unsigned long long)g);
-        const int ps = seg_slot(pt, (unsigned long long)p);
-        if (gs < 0 || ps < 0) {
-            set_status(prm.status + b, NPB_ERR_CAPACITY);
-            t_key[t] = kEmptyKey;           // phase 2 skips the pair (its frame failed anyway)
-            continue;
-        }
-        t_gslot[t] = (unsigned short)gs;
-        t_pslot[t] = (unsigned short)ps;
-        atomicAdd(g_area + gs, cnt);
-        atomicAdd(p_area + ps, cnt);
-        if (g == prm.void_segment_id) p_void[ps] = cnt;     // key == void*offset + p, unique
-        if (div_pow2(g, prm.L, prm.L_shift) == prm.ignored_label) atomicAdd(p_pio + ps, cnt);
-    }
-    __syncthreads();
+    MatchTables<unsigned short> T;
+    T.t_key = t_key; T.t_cnt = t_cnt; T.t_gslot = t_gslot; T.t_pslot = t_pslot;
+    T.pair_slots = kPairSlots; T.walk = s_idx;
+    T.g_id = g_id; T.p_id = p_id; T.g_area = g_area; T.p_area = p_area; T.p_void = p_void;
+    T.p_pio = p_pio; T.g_matched = g_matched; T.p_matched = p_matched; T.seg_slots = kSegSlots;
+    T.m_key = s_mkey; T.m_ia = s_mia; T.m_uni = s_muni; T.m_cat = s_mcat;
+    // ordered IoUs / categories reuse the slot arrays of the pair table (free after phase 2)
+    T.s_iou = (double *)t_gslot;
+    T.s_cat = (unsigned short *)((double *)t_gslot + kMaxMatched);
+    T.max_matched = kMaxMatched;
+    match_phases(prm, b, T, m, C);
+}
 
-    // (2) IoU + match decision per intersecting pair                       pq.py:119-152
-    for (int i = tid; i < m; i += kMatchThreads) {
-        const int t = s_idx[i];
-        const long long key = (long long)t_key[t];
-        if ((unsigned long long)key == kEmptyKey) continue;
-        if (key == prm.void_segment_id) continue;                          // pq.py:120
-        const long long g = div_pow2(key, prm.offset, prm.O_shift), p = key - g * prm.offset;
-        const long long gcat = div_pow2(g, prm.L, prm.L_shift), pcat = div_pow2(p, prm.L, prm.L_shift);
-        if (gcat != pcat) continue;                                        // pq.py:128
-        const int gs = t_gslot[t], ps = t_pslot[t];
-        const long long ia = t_cnt[t];
-        const long long uni = (long long)g_area[gs] + (long long)p_area[ps] - ia -
-                              (long long)p_void[ps];                       // pq.py:143
-        if (uni == 0) { set_status(prm.status + b, NPB_ERR_ZERO_DIVISION); continue; }
-        // iou = ia / uni > 0.5 in float64 (pq.py:145-146) <=> 2 * ia > uni (integers < 2^33)
-        if (2 * ia > uni) {
-            if (gcat < 0 || gcat >= NC || gcat >= 256) { set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE); continue; }
-            g_matched[gs] = 1;
-            p_matched[ps] = 1;
-            atomicAdd(&s_tp[(int)gcat], 1);
-            const int slot = atomicAdd(&s_nm, 1);
-            if (slot < kMaxMatched) {
-                s_mkey[slot] = key;
-                s_mia[slot] = (unsigned)ia;
-                s_muni[slot] = (unsigned)uni;
-                s_mcat[slot] = (unsigned short)gcat;
-            } else {
-                set_status(prm.status + b, NPB_ERR_CAPACITY);
-            }
-            if (prm.matches) {
-                if (slot < prm.match_cap) {
-                    long long *o = prm.matches + ((size_t)b * prm.match_cap + slot) * 2;
-                    o[0] = g;
-                    o[1] = p;
-                } else {
-                    set_status(prm.status + b, NPB_ERR_CAPACITY);
-                }
-            }
-        }
-    }
-    __syncthreads();
+// ---- fall-back for frames beyond the shared-memory capacities ---------------------------------
+// One frame per call, every table in global memory (npb_pq_update_big_frame): a plain pixel pass
+// into one large hash table (pair -> pixels), then the phases of the matcher above on it.  Slow
+// (one CTA matches), but it takes a frame of per-pixel random ids.
+struct BigParams {
+    const long long *pred, *target;
+    long long P, offset;
+    int O_shift;
+    unsigned long long *t_key;
+    unsigned *t_cnt;
+    int pair_slots;
+    int32_t *status;
+};
 
-    // (3) false negatives: unmatched gt segments outside the ignored label    pq.py:155-163
-    //     false positives: unmatched pred segments, unless more than half of their area lies
-    //     in ignored gt segments                                            pq.py:165-177
-    for (int i = tid; i < kSegSlots; i += kMatchThreads) {
-        if (g_id[i] != kEmptyKey && !g_matched[i]) {
-            const long long cat = div_pow2((long long)g_id[i], prm.L, prm.L_shift);
-            if (cat != prm.ignored_label) {
-                if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
-                else atomicAdd(&s_fn[(int)cat], 1);
-            }
-        }
-        if (p_id[i] != kEmptyKey && !p_matched[i]) {
-            // pio / area > 0.5 in float64 (pq.py:172) <=> 2 * pio > area: the quotient of two
-            // integers < 2^32 is never closer to 0.5 than 2^-33 unless it equals 0.5
-            if (!(2ull * p_pio[i] > (unsigned long long)p_area[i])) {
-                const long long cat = div_pow2((long long)p_id[i], prm.L, prm.L_shift);
-                if (cat < 0 || cat >= NC || cat >= 256) set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
-                else atomicAdd(&s_fp[(int)cat], 1);
-            }
-        }
-    }
+constexpr int kBigRun = 8;      // consecutive pixels per thread (equal neighbours are merged)
 
-    // (4) float64 IoU sums per category with the matched pairs in ascending key order (= the
-    //     reference's visiting order, pq.py:109/119).  Keys are unique, so the rank of a pair is
-    //     the number of smaller keys: every thread ranks its pairs against all others
-    //     (broadcast reads, no barriers) and drops IoU + category at the ranked position.
-    const int nm = s_nm < kMaxMatched ? s_nm : kMaxMatched;     // stable since the last barrier
-    double *s_siou = (double *)t_gslot;                         // [kMaxMatched] sorted IoUs; the
-    unsigned short *s_scat = (unsigned short *)(s_siou + kMaxMatched);   // slot arrays are free
-    for (int i = tid; i < nm; i += kMatchThreads) {
-        const long long key = s_mkey[i];
-        int rank = 0;
-        for (int j = 0; j < nm; ++j) rank += s_mkey[j] < key;
-        s_siou[rank] = (double)s_mia[i] / (double)s_muni[i];              // pq.py:145
-        s_scat[rank] = s_mcat[i];
+__global__ void __launch_bounds__(256) big_pair_kernel(const BigParams prm)
+{
+    for (long long p0 = ((long long)blockIdx.x * 256 + threadIdx.x) * kBigRun; p0 < prm.P;
+         p0 += (long long)gridDim.x * 256 * kBigRun) {
+        unsigned long long run_key = kEmptyKey;
+        unsigned run = 0;
+        for (int j = 0; j < kBigRun && p0 + j < prm.P; ++j) {
+            const long long pv = prm.pred[p0 + j], tv = prm.target[p0 + j];
+            if (pv < 0 || tv < 0 || pv >= prm.offset) {
+                set_status(prm.status, NPB_ERR_CATEGORY_RANGE);
+                continue;
+            }
+            const unsigned long long key =
+                prm.O_shift >= 0 ? (((unsigned long long)tv << prm.O_shift) | (unsigned long long)pv)
+                                 : (unsigned long long)tv * (unsigned long long)prm.offset + (unsigned long long)pv;
+            if (key == run_key) { ++run; continue; }
+            if (run && !table_add(prm.t_key, prm.t_cnt, prm.pair_slots, prm.pair_slots, run_key, run))
+                set_status(prm.status, NPB_ERR_CAPACITY);
+            run_key = key;
+            run = 1;
+        }
+        if (run && !table_add(prm.t_key, prm.t_cnt, prm.pair_slots, prm.pair_slots, run_key, run))
+            set_status(prm.status, NPB_ERR_CAPACITY);
     }
+}
+
+__global__ void __launch_bounds__(kMatchThreads)
+match_big_frame_kernel(const MatchParams prm, const MatchTables<unsigned> T)
+{
+    __shared__ MatchCounters C;
+    const int tid = threadIdx.x;
+    if (tid == 0) { C.nm = 0; C.fail = 0; }
+    for (int c = tid; c < 256; c += kMatchThreads) { C.tp[c] = 0; C.fn[c] = 0; C.fp[c] = 0; }
     __syncthreads();
-    for (int c = tid; c < NC; c += kMatchThreads) {
-        double acc = 0.0;
-        if (c < 256 && s_tp[c] > 0)
-            for (int i = 0; i < nm; ++i)
-                if (s_scat[i] == c) acc += s_siou[i];
-        double *fs = prm.frame_stats + (size_t)b * 4 * NC;
-        fs[c] = acc;
-        fs[NC + c] = c < 256 ? (double)s_tp[c] : 0.0;
-        fs[2 * NC + c] = c < 256 ? (double)s_fn[c] : 0.0;
-        fs[3 * NC + c] = c < 256 ? (double)s_fp[c] : 0.0;
-    }
-    if (tid == 0 && prm.n_matches) prm.n_matches[b] = s_nm < prm.match_cap ? s_nm : prm.match_cap;
+    match_phases(prm, 0, T, T.pair_slots, C);
 }
 
 // state += frame result, frames in order (PanopticQuality.update, pq.py:298-303).
@@ -1250,4 +1351,109 @@ extern "C" int npb_write_panoptic_eval(const uint8_t *sem, const uint8_t *inst,
                           ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
                           ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches, ev->match_cap,
                           ev->n_matches, ev->status, stream);
+}
+
+// ---- fall-back entry point -----------------------------------------------------------------------
+static int big_pow2_at_least(long long v, int lo, int hi)
+{
+    int sh = lo;
+    while (sh < hi && (1ll << sh) < v) ++sh;
+    return sh;
+}
+
+struct BigLayout {
+    int pair_slots, seg_slots, max_matched;
+    size_t ff_bytes;        // [t_key | g_id | p_id]: cleared to 0xff
+    size_t zero_bytes;      // everything else that must start at zero
+    size_t total;
+};
+
+static BigLayout big_layout(int64_t P, int num_categories)
+{
+    BigLayout l;
+    l.pair_slots = 1 << big_pow2_at_least(2 * P, 12, 23);           // distinct pairs <= pixels
+    l.seg_slots = 1 << big_pow2_at_least(2 * (P < 65536 ? P : 65536), 12, 17);
+    l.max_matched = 65536;
+    l.ff_bytes = align256((size_t)l.pair_slots * 8) + align256((size_t)l.seg_slots * 8) * 2;
+    l.zero_bytes = align256((size_t)l.pair_slots * 4) * 3 + align256((size_t)l.seg_slots * 4) * 4 +
+                   align256((size_t)l.seg_slots) * 2;
+    l.total = l.ff_bytes + l.zero_bytes +
+              align256((size_t)l.max_matched * 8) * 2 + align256((size_t)l.max_matched * 4) * 2 +
+              align256((size_t)l.max_matched * 2) * 2 + align256((size_t)4 * num_categories * sizeof(double));
+    return l;
+}
+
+extern "C" size_t npb_pq_update_big_frame_workspace_bytes(int64_t P, int num_categories)
+{
+    return big_layout(P < 1 ? 1 : P, num_categories < 1 ? 1 : num_categories).total;
+}
+
+extern "C" int npb_pq_update_big_frame(const int64_t *pred, const int64_t *target, int64_t P,
+                                       int num_categories, int64_t ignored_label,
+                                       int64_t max_instances_per_category, int64_t offset,
+                                       int64_t void_segment_id, void *workspace, double *iou,
+                                       double *tp, double *fn, double *fp, int64_t *matches,
+                                       int match_cap, int32_t *n_matches, int32_t *status,
+                                       void *stream)
+{
+    if (!pred || !target || !workspace || !iou || !tp || !fn || !fp || !status) return NPB_ERR_ARG;
+    if (P < 1 || num_categories < 1 || num_categories > 256 || max_instances_per_category < 1 ||
+        offset < 1)
+        return NPB_ERR_ARG;
+    if (matches && (match_cap < 1 || !n_matches)) return NPB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const BigLayout l = big_layout(P, num_categories);
+    char *ws = (char *)workspace;
+    auto take = [&](size_t bytes) { char *p = ws; ws += align256(bytes); return p; };
+
+    MatchTables<unsigned> T;
+    T.t_key = (unsigned long long *)take((size_t)l.pair_slots * 8);
+    T.g_id = (unsigned long long *)take((size_t)l.seg_slots * 8);
+    T.p_id = (unsigned long long *)take((size_t)l.seg_slots * 8);
+    char *zero0 = ws;
+    T.t_cnt = (unsigned *)take((size_t)l.pair_slots * 4);
+    T.t_gslot = (unsigned *)take((size_t)l.pair_slots * 4);
+    T.t_pslot = (unsigned *)take((size_t)l.pair_slots * 4);
+    T.g_area = (unsigned *)take((size_t)l.seg_slots * 4);
+    T.p_area = (unsigned *)take((size_t)l.seg_slots * 4);
+    T.p_void = (unsigned *)take((size_t)l.seg_slots * 4);
+    T.p_pio = (unsigned *)take((size_t)l.seg_slots * 4);
+    T.g_matched = (unsigned char *)take((size_t)l.seg_slots);
+    T.p_matched = (unsigned char *)take((size_t)l.seg_slots);
+    T.m_key = (long long *)take((size_t)l.max_matched * 8);
+    T.s_iou = (double *)take((size_t)l.max_matched * 8);
+    T.m_ia = (unsigned *)take((size_t)l.max_matched * 4);
+    T.m_uni = (unsigned *)take((size_t)l.max_matched * 4);
+    T.m_cat = (unsigned short *)take((size_t)l.max_matched * 2);
+    T.s_cat = (unsigned short *)take((size_t)l.max_matched * 2);
+    double *fstats = (double *)take((size_t)4 * num_categories * sizeof(double));
+    T.pair_slots = l.pair_slots; T.seg_slots = l.seg_slots; T.max_matched = l.max_matched;
+    T.walk = nullptr;
+    cudaMemsetAsync(workspace, 0xff, l.ff_bytes, s);
+    cudaMemsetAsync(zero0, 0, l.zero_bytes, s);
+
+    BigParams bp;
+    bp.pred = (const long long *)pred; bp.target = (const long long *)target;
+    bp.P = P; bp.offset = offset; bp.O_shift = -1;
+    MatchParams mp;
+    mp.L_shift = -1; mp.O_shift = -1;
+    for (int sh = 0; sh < 62; ++sh) {
+        if ((1ll << sh) == max_instances_per_category) mp.L_shift = sh;
+        if ((1ll << sh) == offset) { mp.O_shift = sh; bp.O_shift = sh; }
+    }
+    bp.t_key = T.t_key; bp.t_cnt = T.t_cnt; bp.pair_slots = l.pair_slots; bp.status = status;
+    long long blocks = (P + 256 * kBigRun - 1) / (256 * kBigRun);
+    if (blocks > 4096) blocks = 4096;
+    big_pair_kernel<<<(unsigned)blocks, 256, 0, s>>>(bp);
+
+    mp.entry_keys = nullptr; mp.entry_cnts = nullptr; mp.entry_n = nullptr; mp.entry_cap = 0;
+    mp.frame_dense = nullptr; mp.nd = 0;
+    mp.num_categories = num_categories; mp.ignored_label = ignored_label;
+    mp.L = max_instances_per_category; mp.offset = offset; mp.void_segment_id = void_segment_id;
+    mp.frame_stats = fstats; mp.matches = (long long *)matches; mp.match_cap = match_cap;
+    mp.n_matches = n_matches; mp.status = status;
+    match_big_frame_kernel<<<1, kMatchThreads, 0, s>>>(mp, T);
+    accumulate_frames_kernel<<<(4 * num_categories * 32 + 127) / 128, 128, 0, s>>>(fstats, 1, num_categories,
+                                                                        iou, tp, fn, fp);
+    return record_launch("npb_pq_update_big_frame");
 }

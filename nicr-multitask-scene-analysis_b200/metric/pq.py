@@ -99,6 +99,30 @@ class _PQKernel:
         return keep['status'], keep['matches'], keep['n_matches'], keep['frame_stats']
 
 
+def _evaluate_big_frame(pred: torch.Tensor, target: torch.Tensor, num_categories: int,
+                        ignored_label: int, max_instances_per_category: int, offset: int,
+                        void_segment_id: int, iou, tp, fn, fp, matches_row=None,
+                        n_matches_row=None, where: str = 'PanopticQuality.update') -> None:
+    """`npb_pq_update_big_frame`: one frame (H,W) that exceeded the capacities of the
+    shared-memory matcher (it contributed nothing there), every table in global memory.
+    Synchronous: the frame's own status word is read back before returning."""
+    dev = iou.device
+    pred = _lib.require_cuda(pred.to(dev).to(torch.int64), 'preds', ndim=2)
+    target = _lib.require_cuda(target.to(dev).to(torch.int64), 'targets', ndim=2)
+    P = pred.numel()
+    L = _lib.lib()
+    ws = torch.empty(L.npb_pq_update_big_frame_workspace_bytes(P, num_categories),
+                     dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.npb_pq_update_big_frame(
+        _lib.ptr(pred), _lib.ptr(target), c_int64(P), c_int(num_categories),
+        c_int64(ignored_label), c_int64(max_instances_per_category), c_int64(offset),
+        c_int64(void_segment_id), _lib.ptr(ws), _lib.ptr(iou), _lib.ptr(tp), _lib.ptr(fn),
+        _lib.ptr(fp), _lib.ptr(matches_row), c_int(MATCH_CAP), _lib.ptr(n_matches_row),
+        _lib.ptr(status), _lib.stream_ptr(dev)), 'npb_pq_update_big_frame')
+    _lib.raise_for_status(status.cpu().tolist(), where + ' (large-frame path)')
+
+
 def compare_and_accumulate(
     pred: torch.Tensor,
     target: torch.Tensor,
@@ -117,7 +141,14 @@ def compare_and_accumulate(
     status, matches, n_matches, _ = _PQKernel.run(
         pred[None], target[None], num_categories, ignored_label, max_instances_per_category,
         offset, void_segment_id, *state, want_matches=True)
-    _lib.raise_for_status(status.cpu().tolist(), 'compare_and_accumulate')
+    codes = status.cpu().tolist()
+    if codes[0] == _lib.ERR_CAPACITY:       # beyond the shared-memory matcher: large-frame path
+        _evaluate_big_frame(pred, target, num_categories, ignored_label,
+                            max_instances_per_category, offset, void_segment_id, *state,
+                            matches_row=matches[0], n_matches_row=n_matches[0:1],
+                            where='compare_and_accumulate')
+    else:
+        _lib.raise_for_status(codes, 'compare_and_accumulate')
     n = int(n_matches[0].item())
     pairs = {(int(g), int(p)) for g, p in matches[0, :n].cpu().tolist()}
     iou, tp, fn, fp = (s.cpu() for s in state)
@@ -148,35 +179,94 @@ class PanopticQuality(MetricState):
         for name in ('iou_per_class', 'tp_per_class', 'fn_per_class', 'fp_per_class'):
             self.add_state(name, torch.zeros(num_categories, dtype=torch.float64),
                            dist_reduce_fx='sum')
-        # one status buffer per batch size, shared by all updates (errors merge by atomicMin)
+        # status words.  Eager updates get their own [B] buffer and stay in `_pending` until it has
+        # been read: a frame that reports NPB_ERR_CAPACITY is evaluated again on the large-frame
+        # path (its tensors are kept alive for that).  Updates recorded into a CUDA graph cannot
+        # be followed up per replay; they share one buffer per batch size (errors merge by
+        # atomicMin) and a capacity overflow stays an error.
         self._status: Dict[int, torch.Tensor] = {}
+        self._pending: List[Dict] = []
 
     # ---- update --------------------------------------------------------------------------
-    def _status_for(self, B: int) -> torch.Tensor:
+    def _status_for(self, B: int) -> Tuple[torch.Tensor, bool]:
+        """(status buffer, whether this update can be followed up)"""
+        dev = self.iou_per_class.device
+        if not torch.cuda.is_current_stream_capturing():
+            return torch.zeros(B, dtype=torch.int32, device=dev), True
         status = self._status.get(B)
-        if status is None or status.device != self.iou_per_class.device:
-            status = torch.zeros(B, dtype=torch.int32, device=self.iou_per_class.device)
-            self._status[B] = status
-        return status
+        if status is None or status.device != dev:
+            raise RuntimeError('PanopticQuality: run one update outside of the graph capture first '
+                               '(its status buffer cannot be allocated while capturing)')
+        return status, False
+
+    def _shared_status(self, B: int) -> None:
+        dev = self.iou_per_class.device
+        status = self._status.get(B)
+        if status is None or status.device != dev:
+            self._status[B] = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    def _follow_up(self, status, preds, targets, matches=None, n_matches=None) -> None:
+        """Remember an eager update until its status has been read; older ones are resolved
+        now (their kernels have long finished, so this does not stall the device)."""
+        # the status words travel to pinned memory right behind the update's kernels; waiting for
+        # THAT copy later does not wait for anything enqueued after it
+        host = torch.empty(status.shape, dtype=status.dtype, pin_memory=True)
+        host.copy_(status, non_blocking=True)
+        landed = torch.cuda.Event()
+        landed.record(torch.cuda.current_stream(status.device))
+        older, self._pending = self._pending, [dict(status=status, host=host, landed=landed,
+                                                    preds=preds, targets=targets, matches=matches,
+                                                    n_matches=n_matches)]
+        for entry in older:
+            self._resolve(entry)
+
+    def _resolve(self, entry: Dict) -> None:
+        entry['landed'].synchronize()
+        codes = entry['host'].tolist()
+        big = [b for b, c in enumerate(codes) if c == _lib.ERR_CAPACITY]
+        _lib.raise_for_status([c for c in codes if c != _lib.ERR_CAPACITY],
+                              type(self).__name__ + '.update')
+        for b in big:
+            m, n = entry['matches'], entry['n_matches']
+            _evaluate_big_frame(
+                entry['preds'][b], entry['targets'][b], self.num_categories, self.ignored_label,
+                self.max_instances_per_category, self.offset, self.void_segment_id,
+                self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
+                matches_row=None if m is None else m[b],
+                n_matches_row=None if n is None else n[b:b + 1],
+                where=type(self).__name__ + '.update')
 
     def _launch(self, preds, targets, **kw):
         assert preds.ndim == 3
         assert targets.shape == preds.shape
+        self._shared_status(preds.shape[0])
+        status, eager = self._status_for(preds.shape[0])
         _, matches, n_matches, frame_stats = _PQKernel.run(
             preds, targets, self.num_categories, self.ignored_label,
             self.max_instances_per_category, self.offset, self.void_segment_id,
             self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
-            status=self._status_for(preds.shape[0]), **kw)
+            status=status, **kw)
+        if eager:
+            self._follow_up(status, preds, targets, matches, n_matches)
         return matches, n_matches, frame_stats
 
     def _eval_args(self, targets, **kw):
         """`npb_eval_args` of an update whose prediction is produced by a fused kernel
-        (model/postprocessing/panoptic.py); same keyword arguments as `_launch`."""
+        (model/postprocessing/panoptic.py); same keyword arguments as `_launch`.  The caller
+        hands the produced prediction to `_fused_issued` once the call has been issued."""
         assert targets.ndim == 3
-        return _PQKernel.prepare(
+        self._shared_status(targets.shape[0])
+        status, eager = self._status_for(targets.shape[0])
+        args, keep = _PQKernel.prepare(
             targets, self.num_categories, self.ignored_label, self.offset, self.void_segment_id,
             self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
-            status=self._status_for(targets.shape[0]), **kw)
+            status=status, **kw)
+        keep['eager'] = eager
+        return args, keep
+
+    def _fused_issued(self, keep: Dict, preds: torch.Tensor) -> None:
+        if keep.get('eager'):
+            self._follow_up(keep['status'], preds, keep['target'], keep['matches'], keep['n_matches'])
 
     def update(self, preds: torch.Tensor, targets: torch.Tensor) -> None:
         """preds, targets: (B,H,W) panoptic ids (class * max_instances + instance).
@@ -184,6 +274,9 @@ class PanopticQuality(MetricState):
         self._launch(preds, targets)
 
     def check_status(self) -> None:
+        pending, self._pending = self._pending, []
+        for entry in pending:
+            self._resolve(entry)
         for status in self._status.values():
             codes = status.cpu().tolist()
             status.zero_()
@@ -191,6 +284,7 @@ class PanopticQuality(MetricState):
 
     def reset(self) -> None:
         super().reset()
+        self._pending = []
         for status in self._status.values():
             status.zero_()
 

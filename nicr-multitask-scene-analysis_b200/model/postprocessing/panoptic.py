@@ -147,7 +147,7 @@ class PanopticPostprocessing(DensePostprocessingBase):
         if tuple(pan_t.shape) != shape or tuple(sem_t.shape) != shape:
             return None         # evaluation happens at dataset resolution: not the same maps
         want_matches = 'orientations_present' in batch and hasattr(ev.pq, 'update_mae')
-        return ev.eval_args(pan_t, sem_t, want_matches=want_matches)
+        return ev.eval_args(pan_t, sem_t, want_matches=want_matches) + (ev,)
 
     def _thing_mask(self, sem_u8: torch.Tensor) -> torch.Tensor:
         """panoptic.py:123-127 `isin(semantic idx, thing ids)` -> bool (B,H,W)."""
@@ -183,6 +183,7 @@ class PanopticPostprocessing(DensePostprocessingBase):
         r['panoptic_segmentation_deeplab_instance_idx'] = inst
         r['_panoptic_instance_tables'] = tables
         if fused:
+            fused[2].pq._fused_issued(fused[1], pan)
             # PQ / mIoU states already hold this batch; a task helper must not add it again
             r['_panoptic_evaluation_fused'] = True
             if fused[1].get('matches') is not None:

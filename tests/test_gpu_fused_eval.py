@@ -152,3 +152,37 @@ def test_fused_validation_step_with_orientation(cuda_device):
     for k in art_s:
         assert torch.equal(torch.as_tensor(art_f[k]).cpu(), torch.as_tensor(art_s[k]).cpu()) or \
             torch.allclose(torch.as_tensor(art_f[k]).cpu(), torch.as_tensor(art_s[k]).cpu(), equal_nan=True), k
+
+
+def test_fused_step_with_overflowing_frames(cuda_device):
+    """Ground truth of per-pixel random ids (far more than 4096 pairs per frame): the fused step
+    defers those frames to the large-frame path, which reads the ids the step has written."""
+    from nicr_mt_scene_analysis_b200 import testing
+    B, C, H, W, K = 2, 11, 96, 128, 6
+    data = testing.make_batch(B, C, H, W, K, seed=909)
+    post, ev, is_thing, has_ori = _make(C, cuda_device)
+    ref = oracle.panoptic_postprocess(*(data[k].numpy() for k in
+                                        ('logits', 'heat', 'offset', 'orientation')),
+                                      is_thing, has_ori)
+    g = torch.Generator().manual_seed(3)
+    tgt_cat = torch.randint(1, C + 1, (B, H, W), generator=g)
+    tgt = (tgt_cat * L + torch.randint(0, 60, (B, H, W), generator=g)).numpy()
+    tgt_sem = tgt_cat.to(torch.uint8).numpy()
+    gt = dict(testing.make_batch_dict(B, H, W), panoptic_fullres=torch.from_numpy(tgt).to(cuda_device),
+              semantic_fullres=torch.from_numpy(tgt_sem).to(cuda_device))
+    post.fuse_evaluation(ev)
+    r = post.postprocess(_raw(data, cuda_device), gt, is_training=False)
+    assert r['_panoptic_evaluation_fused']
+    ev.pq.check_status()                                 # runs the large-frame path
+    state = np.zeros((4, C + 1))
+    n_pairs = 0
+    for b in range(B):
+        out = oracle.pq_compare_and_accumulate(ref['panoptic'][b], tgt[b], C + 1, 0, L, OFF, 0)
+        n_pairs = max(n_pairs, len(np.unique(tgt[b].astype(np.int64) * OFF + ref['panoptic'][b])))
+        for s, v in zip(state, out[:4]):
+            s += v
+    assert n_pairs > 4096                                # the case really overflows
+    got = _states(ev)
+    assert np.array_equal(got[1:], state[1:])
+    np.testing.assert_allclose(got[0], state[0], rtol=1e-14)
+    assert np.array_equal(ev.miou.confmat.cpu().numpy(), oracle.confmat(ref['panoptic'] // L, tgt_sem, C + 1))

@@ -207,14 +207,56 @@ def test_pq_thousands_of_pairs_per_frame(frames, cuda_device):
     assert state[2].sum() > 0 and state[3].sum() > 0        # the case is not trivial
 
 
-def test_pq_too_many_pairs_is_a_capacity_error(cuda_device):
-    """More than 4096 distinct pairs in one frame: reported, never silently wrong."""
+def test_pq_large_frame_path(cuda_device):
+    """A frame beyond the shared-memory matcher (~6300 distinct pairs, 1499 gt / 1013 pred
+    segments) between two ordinary ones: it contributes nothing in the batched pass and is
+    evaluated again with the global-memory tables -- the states equal the oracle's (the IoU sums
+    up to the order in which the frames are added)."""
+    from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, PanopticEvaluation,
+                                                    PanopticQuality, compare_and_accumulate)
+    L, OFF, NC = 1 << 16, 256 ** 3, 3
+    small = _many_pairs_frame(1, 31, 17, side=80)
+    big = _many_pairs_frame(5, 1499, 1013, side=80)
+    pred = torch.stack([small[0], big[0], small[0]])
+    tgt = torch.stack([small[1], big[1], small[1]])
+    pq = PanopticQuality(NC, 0, L, OFF, [False, True, True], device=cuda_device)
+    miou = MeanIntersectionOverUnion(NC, True, device=cuda_device)
+    sem_t = (tgt // L).to(torch.uint8)
+    PanopticEvaluation(pq, miou).update(pred.to(cuda_device), tgt.to(cuda_device), sem_t.to(cuda_device))
+    pq.update(pred.to(cuda_device), tgt.to(cuda_device))      # resolves the first update on the way
+    pq.check_status()
+    state = np.zeros((4, NC))
+    frames = [oracle.pq_compare_and_accumulate(pred[b].numpy(), tgt[b].numpy(), NC, 0, L, OFF, 0)
+              for b in range(3)]
+    for _ in range(2):
+        for out in frames:
+            for s, v in zip(state, out[:4]):
+                s += v
+    got = np.stack(_states(pq))
+    assert np.array_equal(got[1:], state[1:])                       # tp / fn / fp
+    np.testing.assert_allclose(got[0], state[0], rtol=1e-14)        # IoU sums (frame order differs)
+    assert np.array_equal(miou.confmat.cpu().numpy(), oracle.confmat((pred // L).numpy(), sem_t.numpy(), NC))
+    # single-frame API: same path, same float64 order as the reference -> bit-exact, with matches
+    iou, tp, fn, fp, m = compare_and_accumulate(big[0].to(cuda_device), big[1].to(cuda_device),
+                                                NC, 0, L, OFF, 0)
+    for a, b in zip((iou, tp, fn, fp), frames[1][:4]):
+        assert np.array_equal(a.numpy(), b)
+    assert m == frames[1][4]
+
+
+def test_pq_capacity_error_inside_a_cuda_graph(cuda_device):
+    """Updates replayed from a CUDA graph cannot be followed up: an overflowing frame stays an
+    error there (never a silently wrong result)."""
     from nicr_mt_scene_analysis_b200._lib import ERR_CAPACITY, NpbError
+    from nicr_mt_scene_analysis_b200.graph import CapturedStep
     from nicr_mt_scene_analysis_b200.metric import PanopticQuality
     L, OFF = 1 << 16, 256 ** 3
-    pred, tgt = _many_pairs_frame(5, 1499, 1013, side=80)       # ~6300 distinct pairs
+    pred, tgt = _many_pairs_frame(5, 1499, 1013, side=80)
+    pred, tgt = pred[None].to(cuda_device), tgt[None].to(cuda_device)
     pq = PanopticQuality(3, 0, L, OFF, [False, True, True], device=cuda_device)
-    pq.update(pred[None].to(cuda_device), tgt[None].to(cuda_device))
+    step = CapturedStep(lambda: pq.update(pred, tgt), warmup=1, device=cuda_device)
+    pq.reset()
+    step.replay()
     with pytest.raises(NpbError) as err:
         pq.compute()
     assert err.value.code == ERR_CAPACITY
@@ -330,8 +372,8 @@ def test_pq_with_orientation_mae(cuda_device):
 @pytest.mark.parametrize('frames', [1, 8])
 def test_pq_noise_ids_few_frames(frames, cuda_device):
     """Few frames per launch = many CTAs of the pixel pass per frame, and random ids = nearly
-    every pixel of a CTA is its own pair: the hand-over list takes the most entries here
-    (an untrained network's output looks like this)."""
+    every pixel of a CTA is its own pair (~5300 distinct pairs per frame: an untrained network's
+    output looks like this).  The frames overflow the batched pass and take the large-frame path."""
     from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion, PanopticEvaluation, PanopticQuality
     L, OFF, NC = 1 << 16, 256 ** 3, 9
     g = torch.Generator().manual_seed(100 + frames)
@@ -341,7 +383,7 @@ def test_pq_noise_ids_few_frames(frames, cuda_device):
     is_thing = [False] + [bool(c % 2) for c in range(1, NC)]
     it = torch.tensor(is_thing)
     tgt = cat_t * L + torch.where(it[cat_t], torch.randint(1, 8, (frames, H, W), generator=g), 0)
-    pred = cat_p * L + torch.where(it[cat_p], torch.randint(1, 20, (frames, H, W), generator=g), 0)
+    pred = cat_p * L + torch.where(it[cat_p], torch.randint(1, 40, (frames, H, W), generator=g), 0)
     pq = PanopticQuality(NC, 0, L, OFF, is_thing, device=cuda_device)
     miou = MeanIntersectionOverUnion(NC, True, device=cuda_device)
     PanopticEvaluation(pq, miou).update(pred.to(cuda_device), tgt.to(cuda_device),
@@ -352,5 +394,7 @@ def test_pq_noise_ids_few_frames(frames, cuda_device):
         out = oracle.pq_compare_and_accumulate(pred[b].numpy(), tgt[b].numpy(), NC, 0, L, OFF, 0)
         for s, v in zip(state, out[:4]):
             s += v
-    assert np.array_equal(np.stack(_states(pq)), state)
+    got = np.stack(_states(pq))
+    assert np.array_equal(got[1:], state[1:])
+    np.testing.assert_allclose(got[0], state[0], rtol=1e-14)
     assert np.array_equal(miou.confmat.cpu().numpy(), oracle.confmat((pred // L).numpy(), cat_t.numpy(), NC))
