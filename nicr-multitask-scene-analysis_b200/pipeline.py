@@ -21,6 +21,8 @@ from .model.postprocessing.panoptic import PanopticPostprocessing
 
 
 class PanopticHostPipeline:
+    N_SLOTS = 3
+
     def __init__(self, postprocessing: PanopticPostprocessing,
                  evaluation: Optional[PanopticEvaluation] = None, chunk_frames: int = 8,
                  device=None):
@@ -32,16 +34,23 @@ class PanopticHostPipeline:
         self._copy_stream = torch.cuda.Stream(self.device)
         self._compute_stream = torch.cuda.Stream(self.device)
         self._slots = None
+        self._chunks_issued = 0
+        self._prev_slot = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
     def _staging(self, like: Dict[str, torch.Tensor]):
         key = tuple((k, tuple(v.shape[1:]), v.dtype) for k, v in like.items())
         if self._slots is None or self._slots[0] != key:
+            # three staging slots, used round robin ACROSS calls: a slot is released by the
+            # chunk after its own (whose metric update may still re-read the previous chunk's
+            # targets on the large-frame path), and by then the third slot is being filled
             slots = [{k: torch.empty((self.chunk,) + tuple(v.shape[1:]), dtype=v.dtype,
                                      device=self.device) for k, v in like.items()}
-                     for _ in range(2)]
-            self._slots = (key, slots, [None, None])
+                     for _ in range(self.N_SLOTS)]
+            self._slots = (key, slots, [None] * self.N_SLOTS)
+            self._chunks_issued = 0
+            self._prev_slot = None
         return self._slots[1], self._slots[2]
 
     @staticmethod
@@ -78,7 +87,9 @@ class PanopticHostPipeline:
         for i, lo in enumerate(range(0, B, self.chunk)):
             hi = min(lo + self.chunk, B)
             n = hi - lo
-            slot, s = slots[i % 2], i % 2
+            s = self._chunks_issued % self.N_SLOTS
+            self._chunks_issued += 1
+            slot = slots[s]
             with torch.cuda.stream(self._copy_stream):
                 if slot_free[s] is not None:
                     self._copy_stream.wait_event(slot_free[s])     # previous user is done
@@ -100,7 +111,9 @@ class PanopticHostPipeline:
                 d2h += pan.numel() * 8 + inst.numel() + tab.nbytes
                 done = torch.cuda.Event()
                 done.record(self._compute_stream)
-                slot_free[s] = done
+                if self._prev_slot is not None:
+                    slot_free[self._prev_slot] = done   # the previous chunk's slot, see _staging
+                self._prev_slot = s
                 # keep the chunk's device tensors alive until the stream has consumed them
                 for t in (sem, inst, pan, pan_sem):
                     t.record_stream(self._compute_stream)
