@@ -74,7 +74,16 @@ static int panoptic_forward_impl(
     ws += align256((size_t)B * kMaxInst * C * sizeof(uint32_t));
     double *ori_sum = orientation ? (double *)ws : nullptr;
 
-    cudaMemsetAsync(status, 0, (size_t)B * sizeof(int32_t), s);
+    // ONE memset for the scratch of all stages: the candidate counters are the last block of the
+    // centres workspace, the vote histograms and orientation sums follow it; the status words
+    // are started by the centre selection (their only writer in this chain)
+    {
+        const size_t cnt_block = align256((size_t)B * sizeof(int32_t));
+        char *first = (char *)vote_hist - cnt_block;
+        const size_t bytes = cnt_block + align256((size_t)B * kMaxInst * C * sizeof(uint32_t)) +
+                             (orientation ? (size_t)B * kMaxInst * 2 * sizeof(double) : 0);
+        cudaMemsetAsync(first, 0, bytes, s);
+    }
     int rc;
     const uint8_t *fg = nullptr;
     const float *group_logits = logits;
@@ -90,13 +99,14 @@ static int panoptic_forward_impl(
         group_logits = nullptr;
         group_sem = sem_out;
     }
-    rc = npb_instance_centers(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
-                              ws_centers, centers_yx, n_centers, center_score, status, stream);
+    rc = instance_centers_impl(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
+                               ws_centers, centers_yx, n_centers, center_score, status, true, true,
+                               stream);
     if (rc != NPB_OK) return rc;
-    rc = npb_group_pixels(group_logits, group_sem, nullptr, offset, orientation, B, C, H, W,
-                          h_thing_lut, centers_yx, n_centers, normalized_offset,
-                          use_distance_threshold, distance_threshold, sem_out, inst_out, vote_hist,
-                          ori_sum, stream);
+    rc = group_pixels_impl(group_logits, group_sem, nullptr, offset, orientation, B, C, H, W,
+                           h_thing_lut, centers_yx, n_centers, normalized_offset,
+                           use_distance_threshold, distance_threshold, sem_out, inst_out, vote_hist,
+                           ori_sum, true, stream);
     if (rc != NPB_OK) return rc;
     rc = npb_finalize_instances(vote_hist, ori_sum, n_centers, B, C, 1, max_instances_per_category,
                                 0, h_orientation_lut, inst_class, inst_pan_id, inst_area,

@@ -224,7 +224,8 @@ select_centers_kernel(const uint2 *__restrict__ cand, int cap,
                       const int32_t *__restrict__ cand_cnt, const float *__restrict__ heat,
                       const uint8_t *__restrict__ fg, int H, int W, int top_k,
                       int32_t *__restrict__ centers_yx, int32_t *__restrict__ n_centers,
-                      float *__restrict__ center_score, int32_t *__restrict__ status)
+                      float *__restrict__ center_score, int32_t *__restrict__ status,
+                      int reset_status)
 {
     __shared__ unsigned hist[256];
     __shared__ unsigned s_prefix, s_remaining;
@@ -235,6 +236,9 @@ select_centers_kernel(const uint2 *__restrict__ cand, int cap,
     const int tid = threadIdx.x;
     const size_t P = (size_t)H * W;
     const uint2 *cb = cand + (size_t)b * cap;
+    // this kernel is the only writer of the frame's status word in the forward chain: it may
+    // start it from NPB_OK itself (saves the chain a memset); thread 0 also does the first write
+    if (reset_status && tid == 0) status[b] = NPB_OK;
     int S = cand_cnt[b];
     if (S > cap) {  // cannot happen (cap is the independent-set bound); be loud if it does
         if (tid == 0) set_status(status + b, NPB_ERR_CAPACITY);
@@ -323,11 +327,13 @@ extern "C" size_t npb_instance_centers_workspace_bytes(int B, int H, int W, int 
     return bytes;
 }
 
-extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, float threshold,
-                                    int nms_kernel_size, int top_k, const uint8_t *fg,
-                                    int apply_fg_mask, void *workspace, int32_t *centers_yx,
-                                    int32_t *n_centers, float *center_score, int32_t *status,
-                                    void *stream)
+// internal form: `cleared` = the caller has already zeroed the candidate counters (they are
+// the last 256-byte aligned block of the workspace); `reset_status` = status starts at NPB_OK
+int npb::instance_centers_impl(const float *heat, int B, int H, int W, float threshold,
+                               int nms_kernel_size, int top_k, const uint8_t *fg, int apply_fg_mask,
+                               void *workspace, int32_t *centers_yx, int32_t *n_centers,
+                               float *center_score, int32_t *status, bool cleared,
+                               bool reset_status, void *stream)
 {
     if (!heat || !workspace || !centers_yx || !n_centers || !center_score || !status)
         return NPB_ERR_ARG;
@@ -344,7 +350,7 @@ extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, floa
     size_t off = ((size_t)B * cap * sizeof(uint2) + 255) & ~(size_t)255;
     int32_t *cand_cnt = (int32_t *)((char *)workspace + off);
 
-    cudaMemsetAsync(cand_cnt, 0, (size_t)B * sizeof(int32_t), s);
+    if (!cleared) cudaMemsetAsync(cand_cnt, 0, (size_t)B * sizeof(int32_t), s);
     if (nms_kernel_size <= 3) {
         // small window: per-pixel early out beats staging tiles (see kernel comment)
         const int P = H * W;
@@ -366,6 +372,18 @@ extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, floa
     }
     select_centers_kernel<<<B, kSelThreads, 0, s>>>(cand, cap, cand_cnt, heat,
                                                     apply_fg_mask ? fg : nullptr, H, W, top_k,
-                                                    centers_yx, n_centers, center_score, status);
+                                                    centers_yx, n_centers, center_score, status,
+                                                    reset_status ? 1 : 0);
     return record_launch("npb_instance_centers");
+}
+
+extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, float threshold,
+                                    int nms_kernel_size, int top_k, const uint8_t *fg,
+                                    int apply_fg_mask, void *workspace, int32_t *centers_yx,
+                                    int32_t *n_centers, float *center_score, int32_t *status,
+                                    void *stream)
+{
+    return instance_centers_impl(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
+                                 workspace, centers_yx, n_centers, center_score, status, false,
+                                 false, stream);
 }

@@ -49,6 +49,20 @@ __device__ __forceinline__ float warp_sum(float v)
 
 int record_launch(const char *what);  // api.cu: cudaGetLastError -> NPB_ERR_CUDA
 
+// internal forms of npb_instance_centers / npb_group_pixels for npb_panoptic_forward, which clears
+// the scratch of both stages with ONE memset (centers.cu, group.cu)
+int instance_centers_impl(const float *heat, int B, int H, int W, float threshold,
+                          int nms_kernel_size, int top_k, const uint8_t *fg, int apply_fg_mask,
+                          void *workspace, int32_t *centers_yx, int32_t *n_centers,
+                          float *center_score, int32_t *status, bool cleared, bool reset_status,
+                          void *stream);
+int group_pixels_impl(const float *logits, const uint8_t *sem_in, const uint8_t *fg_in,
+                      const float *offset, const float *orientation, int B, int C, int H, int W,
+                      const uint8_t *h_thing_lut, const int32_t *centers_yx,
+                      const int32_t *n_centers, int normalized_offset, int use_distance_threshold,
+                      float distance_threshold, uint8_t *sem_out, uint8_t *inst_out,
+                      uint32_t *vote_hist, double *ori_sum, bool cleared, void *stream);
+
 // ---- programmatic dependent launch ----------------------------------------------------------
 // A kernel launched with launch_dependent() may start while its predecessor on the stream is
 // still draining: its CTAs are scheduled and run their prologue (shared-memory set-up) early and

@@ -387,13 +387,14 @@ using namespace npb;
 
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
-extern "C" int npb_group_pixels(const float *logits, const uint8_t *sem_in, const uint8_t *fg_in,
-                                const float *offset, const float *orientation, int B, int C,
-                                int H, int W, const uint8_t *h_thing_lut,
-                                const int32_t *centers_yx, const int32_t *n_centers,
-                                int normalized_offset, int use_distance_threshold,
-                                float distance_threshold, uint8_t *sem_out, uint8_t *inst_out,
-                                uint32_t *vote_hist, double *ori_sum, void *stream)
+// internal form: `cleared` = the caller has already zeroed vote_hist and ori_sum
+int npb::group_pixels_impl(const float *logits, const uint8_t *sem_in, const uint8_t *fg_in,
+                           const float *offset, const float *orientation, int B, int C, int H, int W,
+                           const uint8_t *h_thing_lut, const int32_t *centers_yx,
+                           const int32_t *n_centers, int normalized_offset,
+                           int use_distance_threshold, float distance_threshold, uint8_t *sem_out,
+                           uint8_t *inst_out, uint32_t *vote_hist, double *ori_sum, bool cleared,
+                           void *stream)
 {
     const int n_src = (logits != nullptr) + (sem_in != nullptr) + (fg_in != nullptr);
     if (n_src != 1 || !offset || !centers_yx || !n_centers || !inst_out || !vote_hist)
@@ -419,8 +420,10 @@ extern "C" int npb_group_pixels(const float *logits, const uint8_t *sem_in, cons
     prm.thing = make_class_set(h_thing_lut, fg_in ? 0 : C);
 
     const int CH = fg_in ? 1 : C;
-    cudaMemsetAsync(vote_hist, 0, (size_t)B * kMaxInst * CH * sizeof(uint32_t), s);
-    if (ori_sum) cudaMemsetAsync(ori_sum, 0, (size_t)B * kMaxInst * 2 * sizeof(double), s);
+    if (!cleared) {
+        cudaMemsetAsync(vote_hist, 0, (size_t)B * kMaxInst * CH * sizeof(uint32_t), s);
+        if (ori_sum) cudaMemsetAsync(ori_sum, 0, (size_t)B * kMaxInst * 2 * sizeof(double), s);
+    }
 
     const bool vec4 = (prm.P % 4 == 0) && W >= 4 && aligned16(logits) && aligned16(offset) &&
                       aligned16(orientation) && (((uintptr_t)sem_in | (uintptr_t)fg_in |
@@ -437,4 +440,17 @@ extern "C" int npb_group_pixels(const float *logits, const uint8_t *sem_in, cons
         else launch_group<1, kFromFgMask>(prm, B, ori, s);
     }
     return record_launch("npb_group_pixels");
+}
+
+extern "C" int npb_group_pixels(const float *logits, const uint8_t *sem_in, const uint8_t *fg_in,
+                                const float *offset, const float *orientation, int B, int C,
+                                int H, int W, const uint8_t *h_thing_lut,
+                                const int32_t *centers_yx, const int32_t *n_centers,
+                                int normalized_offset, int use_distance_threshold,
+                                float distance_threshold, uint8_t *sem_out, uint8_t *inst_out,
+                                uint32_t *vote_hist, double *ori_sum, void *stream)
+{
+    return group_pixels_impl(logits, sem_in, fg_in, offset, orientation, B, C, H, W, h_thing_lut,
+                             centers_yx, n_centers, normalized_offset, use_distance_threshold,
+                             distance_threshold, sem_out, inst_out, vote_hist, ori_sum, false, stream);
 }
