@@ -292,7 +292,10 @@ int npb_confmat_update(const void *preds, int preds_dtype, const void *target, i
  * State (accumulated in place): iou/tp/fn/fp [num_categories] f64, confmat [n][n] i64.
  * Per-frame outputs (nullable): frame_stats [B][4][num_categories] f64,
  *   matches [B][match_cap][2] i64 (gt_id, pred_id), n_matches [B].
- * status [B]: NPB_ERR_ZERO_DIVISION / _CATEGORY_RANGE / _CAPACITY per frame.
+ * status [B]: NPB_ERR_ZERO_DIVISION / _CATEGORY_RANGE / _CAPACITY per frame; must be zero on
+ *   entry.  A frame that reports NPB_ERR_CAPACITY (more than 4096 distinct (gt, pred) pairs,
+ *   1536 segments on one side or 1024 matches) has added NOTHING to iou/tp/fn/fp (its pixels are
+ *   in confmat): evaluate it with npb_pq_update_big_frame.
  * ------------------------------------------------------------------------- */
 size_t npb_pq_update_workspace_bytes(int B, int num_categories);
 int npb_pq_update(const int64_t *pred, const int64_t *target, const uint8_t *sem_target, int B,
