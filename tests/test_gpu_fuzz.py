@@ -1,5 +1,7 @@
 """Seeded random sweep: the whole CUDA path (post-processing + evaluation) against the oracle
 on many small, odd-shaped, tie-heavy configurations.  Everything integer bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -7,6 +9,8 @@ import torch
 import oracle
 
 pytestmark = pytest.mark.gpu
+
+N_SEEDS = int(os.environ.get('NPB_FUZZ_SEEDS', '40'))      # a longer sweep on request
 
 
 def _cfg(rng):
@@ -22,7 +26,7 @@ def _cfg(rng):
         with_orientation=bool(rng.integers(0, 2)))
 
 
-@pytest.mark.parametrize('seed', range(40))
+@pytest.mark.parametrize('seed', range(N_SEEDS))
 def test_random_configuration(seed, cuda_device):
     from nicr_mt_scene_analysis_b200 import testing
     from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, PanopticEvaluation,
@@ -95,7 +99,19 @@ def test_random_configuration(seed, cuda_device):
     pq2 = PanopticQuality(C + 1, int(rng.integers(0, C + 1)), 1 << 16, 3 * 10 ** 7,
                           (False,) + is_thing, device=dev)        # offset not a power of two
     pq2.update(pred, tgt)
-    for metric in (pq, pq2):
+    # the same batch through the fused step (ids written and evaluated by one kernel)
+    pq3 = PanopticQuality(C + 1, 0, 1 << 16, 256 ** 3, (False,) + is_thing, device=dev)
+    miou3 = MeanIntersectionOverUnion(C + 1, ignore_first_class=True, device=dev)
+    pan.fuse_evaluation(PanopticEvaluation(pq3, miou3))
+    rf = pan.postprocess(((data['logits'].to(dev), inst_out), (None, None)),
+                         dict(testing.make_batch_dict(B, H, W), panoptic_fullres=tgt,
+                              semantic_fullres=tgt_sem), is_training=False)
+    assert rf['_panoptic_evaluation_fused']
+    assert torch.equal(rf['panoptic_segmentation_deeplab'], pred), c
+    assert torch.equal(rf['panoptic_segmentation_deeplab_semantic_idx'],
+                       r['panoptic_segmentation_deeplab_semantic_idx']), c
+    assert torch.equal(miou3.confmat, miou.confmat), c
+    for metric in (pq, pq2, pq3):
         state = np.zeros((4, C + 1))
         zero_division = False
         for b in range(B):
