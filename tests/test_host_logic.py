@@ -216,3 +216,24 @@ def test_task_helper_requires_cuda_device():
         helper.initialize(torch.device('cpu'))
     with pytest.raises(RuntimeError):
         helper.device
+
+
+def test_eval_args_struct_layout_matches_the_header(tmp_path):
+    """`_lib.EvalArgs` (ctypes) must mirror `npb_eval_args` of include/nicr_panoptic_b200.h
+    field by field: compile a C probe against the header and compare sizes and offsets."""
+    import ctypes
+    import subprocess
+    from nicr_mt_scene_analysis_b200 import _lib
+    names = [f[0] for f in _lib.EvalArgs._fields_]
+    src = tmp_path / 'probe.c'
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "nicr_panoptic_b200.h"\n'
+        'int main(void) {\n  printf("%zu\\n", sizeof(npb_eval_args));\n' +
+        ''.join(f'  printf("%zu\\n", offsetof(npb_eval_args, {n}));\n' for n in names) +
+        '  return 0;\n}\n')
+    exe = tmp_path / 'probe'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True,
+                                          text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.EvalArgs)
+    assert out[1:] == [getattr(_lib.EvalArgs, n).offset for n in names]
