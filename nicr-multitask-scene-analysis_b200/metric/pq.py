@@ -205,8 +205,10 @@ class PanopticQuality(MetricState):
         if status is None or status.device != dev:
             self._status[B] = torch.zeros(B, dtype=torch.int32, device=dev)
 
+    FOLLOW_UP_DEPTH = 3     # eager updates whose status words have not been read yet
+
     def _follow_up(self, status, preds, targets, matches=None, n_matches=None) -> None:
-        """Remember an eager update until its status has been read; older ones are resolved
+        """Remember an eager update until its status has been read; the oldest ones are resolved
         now (their kernels have long finished, so this does not stall the device)."""
         # the status words travel to pinned memory right behind the update's kernels; waiting for
         # THAT copy later does not wait for anything enqueued after it
@@ -214,11 +216,11 @@ class PanopticQuality(MetricState):
         host.copy_(status, non_blocking=True)
         landed = torch.cuda.Event()
         landed.record(torch.cuda.current_stream(status.device))
-        older, self._pending = self._pending, [dict(status=status, host=host, landed=landed,
-                                                    preds=preds, targets=targets, matches=matches,
-                                                    n_matches=n_matches)]
-        for entry in older:
-            self._resolve(entry)
+        self._pending.append(dict(status=status, host=host, landed=landed, preds=preds,
+                                  targets=targets, matches=matches, n_matches=n_matches))
+        # a few updates may be in flight: the host never waits for the batch it has just issued
+        while len(self._pending) > self.FOLLOW_UP_DEPTH:
+            self._resolve(self._pending.pop(0))
 
     def _resolve(self, entry: Dict) -> None:
         entry['landed'].synchronize()

@@ -21,7 +21,7 @@ from .model.postprocessing.panoptic import PanopticPostprocessing
 
 
 class PanopticHostPipeline:
-    N_SLOTS = 3
+    N_SLOTS = 2     # staging slots, used round robin across calls
 
     def __init__(self, postprocessing: PanopticPostprocessing,
                  evaluation: Optional[PanopticEvaluation] = None, chunk_frames: int = 8,
@@ -35,22 +35,17 @@ class PanopticHostPipeline:
         self._compute_stream = torch.cuda.Stream(self.device)
         self._slots = None
         self._chunks_issued = 0
-        self._prev_slot = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
     def _staging(self, like: Dict[str, torch.Tensor]):
         key = tuple((k, tuple(v.shape[1:]), v.dtype) for k, v in like.items())
         if self._slots is None or self._slots[0] != key:
-            # three staging slots, used round robin ACROSS calls: a slot is released by the
-            # chunk after its own (whose metric update may still re-read the previous chunk's
-            # targets on the large-frame path), and by then the third slot is being filled
             slots = [{k: torch.empty((self.chunk,) + tuple(v.shape[1:]), dtype=v.dtype,
                                      device=self.device) for k, v in like.items()}
                      for _ in range(self.N_SLOTS)]
             self._slots = (key, slots, [None] * self.N_SLOTS)
             self._chunks_issued = 0
-            self._prev_slot = None
         return self._slots[1], self._slots[2]
 
     @staticmethod
@@ -104,16 +99,18 @@ class PanopticHostPipeline:
                 sem, inst, pan, pan_sem, tab = self.post._forward_kernels(
                     slot['logits'][:n], slot['heat'][:n], slot['offset'][:n], ori)
                 if targets is not None and self.evaluation is not None:
-                    self.evaluation.update(pan, slot['_tgt_pan'][:n], slot['_tgt_sem'][:n])
+                    # private copies (28 MB per 8 frames, nothing next to the PCIe time): the
+                    # metric may re-read the targets of a frame a few updates later (large-frame
+                    # path), when the staging slot already holds another chunk
+                    self.evaluation.update(pan, slot['_tgt_pan'][:n].clone(),
+                                           slot['_tgt_sem'][:n].clone())
                 pan_h[lo:hi].copy_(pan, non_blocking=True)
                 inst_h[lo:hi].copy_(inst, non_blocking=True)
                 tab.prefetch()                  # per-instance tables -> pinned host memory
                 d2h += pan.numel() * 8 + inst.numel() + tab.nbytes
                 done = torch.cuda.Event()
                 done.record(self._compute_stream)
-                if self._prev_slot is not None:
-                    slot_free[self._prev_slot] = done   # the previous chunk's slot, see _staging
-                self._prev_slot = s
+                slot_free[s] = done
                 # keep the chunk's device tensors alive until the stream has consumed them
                 for t in (sem, inst, pan, pan_sem):
                     t.record_stream(self._compute_stream)

@@ -223,7 +223,7 @@ def test_pq_large_frame_path(cuda_device):
     miou = MeanIntersectionOverUnion(NC, True, device=cuda_device)
     sem_t = (tgt // L).to(torch.uint8)
     PanopticEvaluation(pq, miou).update(pred.to(cuda_device), tgt.to(cuda_device), sem_t.to(cuda_device))
-    pq.update(pred.to(cuda_device), tgt.to(cuda_device))      # resolves the first update on the way
+    pq.update(pred.to(cuda_device), tgt.to(cuda_device))      # both updates are followed up below
     pq.check_status()
     state = np.zeros((4, NC))
     frames = [oracle.pq_compare_and_accumulate(pred[b].numpy(), tgt[b].numpy(), NC, 0, L, OFF, 0)
