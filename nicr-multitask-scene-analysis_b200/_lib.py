@@ -6,7 +6,7 @@ live on a CUDA device, the call raises.  Torch is used for device memory and str
 """
 import ctypes
 import os
-from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
+from ctypes import (POINTER, c_char_p, c_float, c_int, c_int64, c_size_t,
                     c_void_p)
 from typing import Optional, Sequence
 

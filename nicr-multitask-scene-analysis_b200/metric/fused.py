@@ -10,7 +10,6 @@ is read twice and `pred // L` is materialised as an int64 tensor in between.
 (17 bytes per pixel: int64 prediction, int64 panoptic target, uint8 semantic target); the
 states it leaves in the two metric objects are identical to those of the two separate calls.
 """
-from typing import Optional
 
 import torch
 

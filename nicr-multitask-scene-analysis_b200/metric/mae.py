@@ -3,7 +3,6 @@
 metric/mae.py:16-172).  The PQ part runs in `npb_pq_update`; the MAAE loop works on the
 matched (gt id, pred id) pairs the kernel returns and on python dicts, exactly like the
 reference (O(#instances) host work)."""
-import math
 from typing import Dict, List, Tuple
 
 import torch
