@@ -1289,6 +1289,9 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     cache_lock.unlock();
     if (env_cap > 0 && per_sm > env_cap) per_sm = env_cap;
     if (per_sm > kMaxPairCtasPerSm) per_sm = kMaxPairCtasPerSm;     // pq_entry_cap() assumes it
+    // few frames: every CTA only gets a handful of chunks, so its fixed cost (table set-up, flush)
+    // and the duplicates it hands to the matcher weigh more than the extra residency
+    if (B <= 32 && per_sm > 2) per_sm = 2;
     long long bx = ((long long)n_sm * per_sm) / B;
     if (bx < 1) bx = 1;
     if (bx > n_chunks) bx = n_chunks;
