@@ -43,6 +43,7 @@ struct GroupParams {
     double *ori_sum;
     int C, H, W, P;
     float fH, fW;
+    float inv_W;                // 1 / W rounded to nearest (row estimate, see kernel)
     int normalized, use_thr;
     float dist_thr;
     ClassSet thing;
@@ -96,6 +97,10 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
 {
     // centres of the frame as (cy, cy, cx, cx): one LDS.128 feeds two packed f32x2 operands
     __shared__ float4 s_centers[kMaxInst];
+    // thing flag per class: one LDS.U8 per pixel instead of an indexed constant load + shifts
+    __shared__ unsigned char s_thing[256];
+    static_assert(kGroupThreads == 256, "one class flag per thread");
+    s_thing[threadIdx.x] = prm.thing.has((int)threadIdx.x) ? 1 : 0;
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
             for (int j = 0; j < VEC; ++j) fg[j] = (m[j] != 0);
         } else {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) fg[j] = prm.thing.has(cls[j]);
+            for (int j = 0; j < VEC; ++j) fg[j] = s_thing[cls[j] & 255] != 0;
         }
     }
 
@@ -200,13 +205,24 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
             PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + p0, oc, true);
             PixVec<VEC>::loadf(prm.orientation + (size_t)b * 2 * P + P + p0, os, true);
         }
-        int y = p0 / W, x = p0 - y * W;
+        // row / column of the first pixel: float estimate of p0 / W, corrected by at most one
+        // (exact for p0 < 2^24; larger frames take the integer division)
+        int y, x;
+        if (P <= (1 << 24) && W >= 4) {
+            y = __float2int_rd(__fmul_rn((float)p0, prm.inv_W));
+            x = p0 - y * W;
+            if (x < 0) { x += W; --y; } else if (x >= W) { x -= W; ++y; }
+        } else {
+            y = p0 / W;
+            x = p0 - y * W;
+        }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float dy = oy[j], dx = ox[j];
             if (prm.normalized) { dy = __fmul_rn(dy, prm.fH); dx = __fmul_rn(dx, prm.fW); }
-            nly[j] = -__fadd_rn((float)y, dy);
-            nlx[j] = -__fadd_rn((float)x, dx);
+            // -(y + dy) == (-y) + (-dy) exactly (IEEE negation is symmetric)
+            nly[j] = __fadd_rn(-(float)y, -dy);
+            nlx[j] = __fadd_rn(-(float)x, -dx);
             if (++x == W) { x = 0; ++y; }
         }
     }
@@ -415,6 +431,7 @@ int npb::group_pixels_impl(const float *logits, const uint8_t *sem_in, const uin
     prm.vote_hist = vote_hist; prm.ori_sum = ori_sum;
     prm.C = C; prm.H = H; prm.W = W; prm.P = H * W;
     prm.fH = (float)H; prm.fW = (float)W;
+    prm.inv_W = 1.0f / (float)W;
     prm.normalized = normalized_offset; prm.use_thr = use_distance_threshold;
     prm.dist_thr = distance_threshold;
     prm.thing = make_class_set(h_thing_lut, fg_in ? 0 : C);
