@@ -388,7 +388,8 @@ def run_ours(args):
         bpf = bytes_post_per_frame(C, H, W, ORI) + bytes_eval_per_frame(H, W)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': n_warm, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'warmup': args.warmup, 'warmup_steps_run': n_warm,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': w['name'], 'frames_per_gpu_per_step': B, 'classes': C,
                        'height': H, 'width': W, 'instances_per_frame': K,

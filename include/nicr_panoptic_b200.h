@@ -281,6 +281,18 @@ int npb_confmat_update(const void *preds, int preds_dtype, const void *target, i
                        int64_t N, int n_classes, int64_t *confmat, int32_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * The same for the validation step of the semantic task: elements whose target is 0 (void)
+ * are skipped, the others count as confmat[target - 1][pred]; no masked copies of the maps.
+ * Replaces: mask = target != 0; preds[mask]; target[mask] - 1; MeanIntersectionOverUnion.update
+ *           of SemanticTaskHelper.validation_step, task_helper/semantic.py:126-131.
+ * status [1] : NPB_ERR_CATEGORY_RANGE if pred or target - 1 of a non-void element lies
+ *              outside [0, n_classes) (predictions at void elements are not looked at).
+ * ------------------------------------------------------------------------- */
+int npb_confmat_update_nonvoid(const void *preds, int preds_dtype, const void *target,
+                               int target_dtype, int64_t N, int n_classes, int64_t *confmat,
+                               int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------------------
  * PQ segment matching + accumulation for a batch of frames (and, fused, the mIoU
  * confusion matrix of `pred // L` against a semantic target when confmat != NULL).
  * Replaces: compare_and_accumulate metric/pq.py:60-179 and the accumulation of

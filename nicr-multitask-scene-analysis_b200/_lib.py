@@ -84,6 +84,7 @@ _SIGNATURES = {
     'npb_instance_orientation': (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P,
                                          _P, _P]),
     'npb_confmat_update': (c_int, [_P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P]),
+    'npb_confmat_update_nonvoid': (c_int, [_P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P]),
     'npb_pq_update_workspace_bytes': (c_size_t, [c_int, c_int]),
     'npb_pq_update_big_frame_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'npb_pq_update_big_frame': (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int64, c_int64, _P,

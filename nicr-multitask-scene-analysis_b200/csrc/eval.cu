@@ -22,6 +22,7 @@
 // orders equal the reference's, so the states are bit-identical, not merely close.
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -1031,6 +1032,8 @@ __device__ __forceinline__ long long load_int(const void *p, int dtype, size_t i
     }
 }
 
+// Generic form: one element per thread and round, any dtype / alignment, any n.
+template <bool SKIP_VOID>
 __global__ void __launch_bounds__(256)
 confmat_kernel(const void *__restrict__ preds, int pd, const void *__restrict__ target, int td,
                long long N, int n, unsigned long long *__restrict__ confmat,
@@ -1049,9 +1052,12 @@ confmat_kernel(const void *__restrict__ preds, int pd, const void *__restrict__ 
         int key = -1;
         if (i < N) {
             const long long p = load_int(preds, pd, (size_t)i);
-            const long long t = load_int(target, td, (size_t)i);
-            if (p < 0 || p >= n || t < 0 || t >= n) set_status(status, NPB_ERR_CATEGORY_RANGE);
-            else key = (int)(t * n + p);
+            long long t = load_int(target, td, (size_t)i);
+            if (!SKIP_VOID || t != 0) {
+                if (SKIP_VOID) t -= 1;
+                if (p < 0 || p >= n || t < 0 || t >= n) set_status(status, NPB_ERR_CATEGORY_RANGE);
+                else key = (int)(t * n + p);
+            }
         }
         unsigned pending = __ballot_sync(kFullMask, key >= 0);
         while (pending) {
@@ -1072,6 +1078,155 @@ confmat_kernel(const void *__restrict__ preds, int pd, const void *__restrict__ 
     }
 }
 
+// Streaming form (n <= kSmemConfmatMaxN, 16-byte aligned maps).  A warp takes 512 consecutive
+// elements per round.  Loads: 8 rows of 64 elements, lane l owns the elements 64 j + 2 l, + 1 of
+// row j, so every load instruction of the warp covers one contiguous, fully used range (int64
+// predictions: 512 B per LDG.128 = 4 lines); all 16 loads of a thread are issued before the
+// first use (136 B in flight per thread for int64 + uint8).  Counting: the keys (16 bit, two
+// per word) are transposed through a 1 KB shared-memory tile per warp so that every lane holds
+// 16 CONSECUTIVE elements.  Class maps are piecewise constant: the elements of a lane that
+// agree with its first one are counted together, adjacent lanes with the same first key are
+// merged into runs (inclusive scan of the counts with shuffles, one ballot for the run heads)
+// and each run costs ONE shared-memory atomic; the (few) other elements are added singly.
+// Measured alternatives on B200 (256 frames 480x640, int64 + uint8, fraction of the HBM peak):
+// 16 consecutive elements per lane loaded directly (32 lines per LDG.128) + MATCH.ANY / REDUX
+// 0.65; row layout with one MATCH.ANY + per-group REDUX per row 0.40-0.54.
+constexpr int kCmRows = 8;
+constexpr int kCmChunk = 256 * 2 * kCmRows;      // elements per CTA and round
+
+// two adjacent elements of a map as 32-bit words; `wide`: the value does not fit (a 64-bit
+// element with a non-zero high word: negative or >= 2^32, never a valid class).  Negative
+// 16 / 32-bit values become large unsigned numbers and fail the range check the same way.
+template <typename T> struct CmPair;
+template <> struct CmPair<uint8_t> {
+    typedef unsigned short raw;
+    static __device__ __forceinline__ void split(raw r, unsigned &a, unsigned &b, bool &wa, bool &wb)
+    { a = r & 0xffu; b = r >> 8; wa = wb = false; }
+};
+template <> struct CmPair<int16_t> {
+    typedef int raw;
+    static __device__ __forceinline__ void split(raw r, unsigned &a, unsigned &b, bool &wa, bool &wb)
+    { a = (unsigned)(int)(short)(r & 0xffff); b = (unsigned)(r >> 16); wa = wb = false; }
+};
+template <> struct CmPair<int32_t> {
+    typedef int2 raw;
+    static __device__ __forceinline__ void split(raw r, unsigned &a, unsigned &b, bool &wa, bool &wb)
+    { a = (unsigned)r.x; b = (unsigned)r.y; wa = wb = false; }
+};
+template <> struct CmPair<long long> {
+    typedef uint4 raw;
+    static __device__ __forceinline__ void split(raw r, unsigned &a, unsigned &b, bool &wa, bool &wb)
+    { a = r.x; wa = r.y != 0u; b = r.z; wb = r.w != 0u; }
+};
+
+// key = target * n + pred (16 bit), 0xffff for an element that is not counted
+template <bool SKIP_VOID>
+__device__ __forceinline__ unsigned confmat_key(unsigned p, bool p_wide, unsigned t, bool t_wide,
+                                                unsigned n, bool &bad)
+{
+    const bool skip = SKIP_VOID && t == 0u && !t_wide;
+    if (SKIP_VOID) t -= 1u;                                  // void wraps to 0xffffffff
+    const bool ok = p < n && t < n && !p_wide && !t_wide;
+    bad |= !ok && !skip;
+    return ok ? t * n + p : 0xffffu;
+}
+
+template <bool SKIP_VOID, typename PT, typename TT>
+__device__ __forceinline__ unsigned confmat_key_at(const PT *preds, const TT *target, long long i,
+                                                   long long N, unsigned n, bool &bad)
+{
+    if (i >= N) return 0xffffu;
+    const long long p = (long long)preds[i], t = (long long)target[i];
+    return confmat_key<SKIP_VOID>((unsigned)p, (unsigned long long)p >> 32 != 0ull, (unsigned)t,
+                                  (unsigned long long)t >> 32 != 0ull, n, bad);
+}
+
+template <typename PT, typename TT, bool SKIP_VOID>
+__global__ void __launch_bounds__(256, 4)
+confmat_stream_kernel(const PT *__restrict__ preds, const TT *__restrict__ target, long long N,
+                      int n, unsigned long long *__restrict__ confmat,
+                      int32_t *__restrict__ status)
+{
+    typedef typename CmPair<PT>::raw PRaw;
+    typedef typename CmPair<TT>::raw TRaw;
+    extern __shared__ unsigned s_cm[];
+    __shared__ __align__(16) unsigned s_tile[8][32 * kCmRows];     // per warp: [row][lane]
+    for (int i = threadIdx.x; i < n * n; i += 256) s_cm[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned *tile = s_tile[warp];
+    const long long n_chunks = (N + kCmChunk - 1) / kCmChunk;
+    bool bad = false;
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        // first element of this lane in row 0 of its warp's 512 elements
+        const long long i0 = c * kCmChunk + warp * (64 * kCmRows) + 2 * lane;
+        if (c * kCmChunk + kCmChunk <= N) {
+            PRaw pr[kCmRows];
+            TRaw tr[kCmRows];
+#pragma unroll
+            for (int j = 0; j < kCmRows; ++j) pr[j] = __ldcs((const PRaw *)(preds + i0 + 64 * j));
+#pragma unroll
+            for (int j = 0; j < kCmRows; ++j) tr[j] = __ldcs((const TRaw *)(target + i0 + 64 * j));
+#pragma unroll
+            for (int j = 0; j < kCmRows; ++j) {
+                unsigned pa, pb, ta, tb;
+                bool wpa, wpb, wta, wtb;
+                CmPair<PT>::split(pr[j], pa, pb, wpa, wpb);
+                CmPair<TT>::split(tr[j], ta, tb, wta, wtb);
+                const unsigned ka = confmat_key<SKIP_VOID>(pa, wpa, ta, wta, (unsigned)n, bad);
+                const unsigned kb = confmat_key<SKIP_VOID>(pb, wpb, tb, wtb, (unsigned)n, bad);
+                tile[32 * j + lane] = ka | (kb << 16);
+            }
+        } else {
+            // the last, partial chunk of the map
+#pragma unroll 1
+            for (int j = 0; j < kCmRows; ++j) {
+                const long long i = i0 + 64 * j;
+                const unsigned ka = confmat_key_at<SKIP_VOID>(preds, target, i, N, (unsigned)n, bad);
+                const unsigned kb = confmat_key_at<SKIP_VOID>(preds, target, i + 1, N, (unsigned)n, bad);
+                tile[32 * j + lane] = ka | (kb << 16);
+            }
+        }
+        __syncwarp();
+        // 16 consecutive elements of this lane: words 8 lane .. 8 lane + 7
+        const uint4 w0 = *(const uint4 *)(tile + 8 * lane);
+        const uint4 w1 = *(const uint4 *)(tile + 8 * lane + 4);
+        __syncwarp();
+        const unsigned w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const unsigned lead = w[0] & 0xffffu;           // 0xffff: not counted
+        const unsigned lead2 = lead * 0x10001u;
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const unsigned x = w[i] ^ lead2;
+            if (x == 0u) { cnt += 2; continue; }
+            const unsigned a = w[i] & 0xffffu, b = w[i] >> 16;
+            if ((x & 0xffffu) == 0u) cnt += 1;
+            else if (a != 0xffffu) atomicAdd(s_cm + a, 1u);
+            if ((x >> 16) == 0u) cnt += 1;
+            else if (b != 0xffffu) atomicAdd(s_cm + b, 1u);
+        }
+        if (lead == 0xffffu) cnt = 0;
+        // runs of adjacent lanes with the same first key
+        const unsigned prev = __shfl_up_sync(kFullMask, lead, 1);
+        const unsigned heads = __ballot_sync(kFullMask, lane == 0 || prev != lead);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const unsigned above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);   // heads after this lane
+        const int last = above ? __ffs(above) - 2 : 31;                          // last lane of my run
+        const int run = __shfl_sync(kFullMask, incl, last) - (incl - cnt);
+        if (((heads >> lane) & 1u) && run > 0) atomicAdd(s_cm + lead, (unsigned)run);
+    }
+    if (bad) set_status(status, NPB_ERR_CATEGORY_RANGE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * n; i += 256)
+        if (s_cm[i]) atomicAdd(confmat + i, (unsigned long long)s_cm[i]);
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t match_smem_bytes()
 {
@@ -1082,25 +1237,6 @@ static size_t match_smem_bytes()
 }  // namespace npb
 
 using namespace npb;
-
-extern "C" int npb_confmat_update(const void *preds, int preds_dtype, const void *target,
-                                  int target_dtype, int64_t N, int n_classes, int64_t *confmat,
-                                  int32_t *status, void *stream)
-{
-    if (!preds || !target || !confmat || !status) return NPB_ERR_ARG;
-    if (N < 0 || n_classes < 1 || n_classes > 46340) return NPB_ERR_ARG;
-    if (preds_dtype < NPB_U8 || preds_dtype > NPB_BOOL || target_dtype < NPB_U8 ||
-        target_dtype > NPB_BOOL)
-        return NPB_ERR_ARG;
-    if (N == 0) return NPB_OK;
-    long long blocks = (N + 256 * 16 - 1) / (256 * 16);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    const size_t smem = n_classes <= kSmemConfmatMaxN ? (size_t)n_classes * n_classes * 4 : 0;
-    confmat_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(
-        preds, preds_dtype, target, target_dtype, (long long)N, n_classes,
-        (unsigned long long *)confmat, status);
-    return record_launch("npb_confmat_update");
-}
 
 // Entries per frame of the list between pixel pass and matcher: every CTA of the pixel pass
 // contributes at most its distinct pairs; the fewer frames, the more CTAs work on one frame.
@@ -1117,6 +1253,120 @@ static int device_sm_count()
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     }
     return n;
+}
+
+template <typename PT, typename TT>
+static void launch_confmat_stream(const void *preds, const void *target, long long N, int n,
+                                  bool skip_void, int64_t *confmat, int32_t *status,
+                                  cudaStream_t stream)
+{
+    long long blocks = (N + kCmChunk - 1) / kCmChunk;
+    const size_t smem = (size_t)n * n * 4;
+    // one wave of persistent CTAs (occupancy of the instance, normally 4 per SM)
+    static std::atomic<int> ctas_per_sm_skip{0}, ctas_per_sm_all{0};
+    std::atomic<int> &cached = skip_void ? ctas_per_sm_skip : ctas_per_sm_all;
+    int per_sm = cached.load(std::memory_order_relaxed);
+    if (per_sm == 0) {
+        per_sm = 3;
+        if (skip_void)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &per_sm, confmat_stream_kernel<PT, TT, true>, 256, kSmemConfmatMaxN * kSmemConfmatMaxN * 4);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &per_sm, confmat_stream_kernel<PT, TT, false>, 256, kSmemConfmatMaxN * kSmemConfmatMaxN * 4);
+        if (per_sm < 1) per_sm = 1;
+        cached.store(per_sm, std::memory_order_relaxed);
+    }
+    const long long wave = (long long)device_sm_count() * per_sm;
+    if (blocks > wave) blocks = wave;
+    if (skip_void)
+        confmat_stream_kernel<PT, TT, true><<<(int)blocks, 256, smem, stream>>>(
+            (const PT *)preds, (const TT *)target, N, n, (unsigned long long *)confmat, status);
+    else
+        confmat_stream_kernel<PT, TT, false><<<(int)blocks, 256, smem, stream>>>(
+            (const PT *)preds, (const TT *)target, N, n, (unsigned long long *)confmat, status);
+}
+
+template <typename PT>
+static void launch_confmat_stream_p(const void *preds, const void *target, int td, long long N,
+                                    int n, bool skip_void, int64_t *confmat, int32_t *status,
+                                    cudaStream_t stream)
+{
+    switch (td) {
+        case NPB_U8: case NPB_BOOL:
+            launch_confmat_stream<PT, uint8_t>(preds, target, N, n, skip_void, confmat, status, stream);
+            break;
+        case NPB_I16:
+            launch_confmat_stream<PT, int16_t>(preds, target, N, n, skip_void, confmat, status, stream);
+            break;
+        case NPB_I32:
+            launch_confmat_stream<PT, int32_t>(preds, target, N, n, skip_void, confmat, status, stream);
+            break;
+        default:
+            launch_confmat_stream<PT, long long>(preds, target, N, n, skip_void, confmat, status, stream);
+    }
+}
+
+static int confmat_update(const void *preds, int preds_dtype, const void *target, int target_dtype,
+                          int64_t N, int n_classes, bool skip_void, int64_t *confmat,
+                          int32_t *status, void *stream, const char *what)
+{
+    if (!preds || !target || !confmat || !status) return NPB_ERR_ARG;
+    if (N < 0 || n_classes < 1 || n_classes > 46340) return NPB_ERR_ARG;
+    if (preds_dtype < NPB_U8 || preds_dtype > NPB_BOOL || target_dtype < NPB_U8 ||
+        target_dtype > NPB_BOOL)
+        return NPB_ERR_ARG;
+    if (N == 0) return NPB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (((uintptr_t)preds | (uintptr_t)target) & 15u) == 0;
+    if (aligned && n_classes <= kSmemConfmatMaxN) {
+        switch (preds_dtype) {
+            case NPB_U8: case NPB_BOOL:
+                launch_confmat_stream_p<uint8_t>(preds, target, target_dtype, N, n_classes,
+                                                 skip_void, confmat, status, st);
+                break;
+            case NPB_I16:
+                launch_confmat_stream_p<int16_t>(preds, target, target_dtype, N, n_classes,
+                                                 skip_void, confmat, status, st);
+                break;
+            case NPB_I32:
+                launch_confmat_stream_p<int32_t>(preds, target, target_dtype, N, n_classes,
+                                                 skip_void, confmat, status, st);
+                break;
+            default:
+                launch_confmat_stream_p<long long>(preds, target, target_dtype, N, n_classes,
+                                                   skip_void, confmat, status, st);
+        }
+        return record_launch(what);
+    }
+    long long blocks = (N + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const size_t smem = n_classes <= kSmemConfmatMaxN ? (size_t)n_classes * n_classes * 4 : 0;
+    if (skip_void)
+        confmat_kernel<true><<<(int)blocks, 256, smem, st>>>(
+            preds, preds_dtype, target, target_dtype, (long long)N, n_classes,
+            (unsigned long long *)confmat, status);
+    else
+        confmat_kernel<false><<<(int)blocks, 256, smem, st>>>(
+            preds, preds_dtype, target, target_dtype, (long long)N, n_classes,
+            (unsigned long long *)confmat, status);
+    return record_launch(what);
+}
+
+extern "C" int npb_confmat_update(const void *preds, int preds_dtype, const void *target,
+                                  int target_dtype, int64_t N, int n_classes, int64_t *confmat,
+                                  int32_t *status, void *stream)
+{
+    return confmat_update(preds, preds_dtype, target, target_dtype, N, n_classes, false, confmat,
+                          status, stream, "npb_confmat_update");
+}
+
+extern "C" int npb_confmat_update_nonvoid(const void *preds, int preds_dtype, const void *target,
+                                          int target_dtype, int64_t N, int n_classes,
+                                          int64_t *confmat, int32_t *status, void *stream)
+{
+    return confmat_update(preds, preds_dtype, target, target_dtype, N, n_classes, true, confmat,
+                          status, stream, "npb_confmat_update_nonvoid");
 }
 
 constexpr int kMaxPairCtasPerSm = 8;

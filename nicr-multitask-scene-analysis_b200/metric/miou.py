@@ -1,7 +1,7 @@
 # -*- coding: utf-8 -*-
 """Mean intersection over union from an int64 confusion matrix kept on the GPU
 (API of metric/miou.py:9-94).  `update` is one launch of `npb_confmat_update`
-(csrc/eval.cu: warp-aggregated, shared-memory privatised histogram)."""
+(csrc/eval.cu: 128-bit streaming loads, warp-aggregated, shared-memory privatised histogram)."""
 from ctypes import c_int, c_int64
 
 import torch
@@ -27,6 +27,15 @@ class MeanIntersectionOverUnion(MetricState):
     def update(self, preds: torch.Tensor, target: torch.Tensor) -> None:
         """confmat[target, pred] += 1 for every element (rows = target, miou.py:50-56).
         Any integer dtype; values must lie in [0, n_classes)."""
+        self._update(preds, target, 'npb_confmat_update')
+
+    def update_nonvoid(self, preds: torch.Tensor, target: torch.Tensor) -> None:
+        """`update(preds[target != 0], target[target != 0] - 1)` without the masked copies:
+        the call of SemanticTaskHelper.validation_step (task_helper/semantic.py:126-131).
+        `preds` in [0, n_classes) at the non-void elements, `target` in [0, n_classes]."""
+        self._update(preds, target, 'npb_confmat_update_nonvoid')
+
+    def _update(self, preds: torch.Tensor, target: torch.Tensor, entry: str) -> None:
         if not self.confmat.is_cuda:
             raise RuntimeError('MeanIntersectionOverUnion.update needs its state on a CUDA device')
         dev = self.confmat.device
@@ -35,10 +44,10 @@ class MeanIntersectionOverUnion(MetricState):
         if preds.numel() != target.numel():
             raise ValueError('preds and target differ in size')
         status = self._status_word()
-        _lib.check(_lib.lib().npb_confmat_update(
+        _lib.check(getattr(_lib.lib(), entry)(
             _lib.ptr(preds), c_int(_lib.dtype_code(preds)), _lib.ptr(target),
             c_int(_lib.dtype_code(target)), c_int64(preds.numel()), c_int(self._n_classes),
-            _lib.ptr(self.confmat), _lib.ptr(status), _lib.stream_ptr(dev)), 'npb_confmat_update')
+            _lib.ptr(self.confmat), _lib.ptr(status), _lib.stream_ptr(dev)), entry)
 
     def check_status(self) -> None:
         if self._status is not None:

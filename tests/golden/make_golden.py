@@ -438,6 +438,48 @@ def run_task_helpers():
           'mae_gt', ins_out['logs/orientation_mae_gt_rad'])
 
 
+def run_semantic_helper():
+    """Validation path of the reference's SemanticTaskHelper (task_helper/semantic.py:111-163):
+    three validation steps + epoch end.  Predictions are network classes 0..C-1 (int64), the
+    target is uint8 with 0 = void; the helper masks the void pixels and shifts the target.
+    batch_idx != 0 skips the visualisation examples; the loss (not on the evaluated path) is
+    bypassed by overriding `_compute_losses`."""
+    from nicr_mt_scene_analysis.task_helper.semantic import SemanticTaskHelper
+
+    class SemanticHelperNoLoss(SemanticTaskHelper):
+        def _compute_losses(self, batch, batch_idx, predictions_post):
+            return {}
+
+    g = torch.Generator().manual_seed(31)
+    B, H, W, C = 3, 75, 101, 9          # 75*101 is odd: the last group of the map is partial
+    helper = SemanticHelperNoLoss(n_classes=C)
+    helper.initialize(torch.device('cpu'))
+    arrays = {'n_classes': C, 'n_steps': 3}
+    for step in range(3):
+        target = blocky(g, B, H, W, C + 1, 12)               # 0 = void
+        target[:, :, -7:] = 0                                # a void border (invalid region)
+        clean = (target - 1).clamp(min=0)
+        noisy = torch.rand(B, H, W, generator=g) < 0.15
+        preds = torch.where(noisy, torch.randint(0, C, (B, H, W), generator=g), clean)
+        if step == 2:
+            target = target[:1].clone(); preds = preds[:1].clone()
+            target[0, :40] = 0                               # class C-1 may lose its ground truth
+            target[target == C] = 1
+        batch = {'semantic_fullres': target.to(torch.uint8)}
+        post = {'semantic_segmentation_idx_fullres': preds}
+        helper.validation_step(batch, 1 + step, post)
+        arrays[f'step{step}/target'] = target.to(torch.uint8).numpy()
+        arrays[f'step{step}/preds'] = preds.numpy()
+    artifacts, examples, logs = helper.validation_epoch_end()
+    assert examples == {}
+    arrays['artifacts/semantic_cm'] = artifacts['semantic_cm'].numpy()
+    arrays['artifacts/semantic_ious_per_class'] = artifacts['semantic_ious_per_class'].numpy()
+    arrays['logs/semantic_miou'] = logs['semantic_miou'].numpy()
+    np.savez_compressed(os.path.join(HERE, 'semantic_helper.npz'), **arrays)
+    print('semantic helper: miou', float(logs['semantic_miou']),
+          'pixels counted', int(artifacts['semantic_cm'].sum()))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(1)
     if len(sys.argv) > 1:       # regenerate selected fixtures only: make_golden.py task_helpers pq
@@ -461,3 +503,4 @@ if __name__ == '__main__':
     run_miou()
     run_orientation()
     run_task_helpers()
+    run_semantic_helper()

@@ -308,6 +308,73 @@ def test_miou_out_of_range_raises(cuda_device):
         m.compute()
 
 
+_TORCH_INT = {'u8': torch.uint8, 'i16': torch.int16, 'i32': torch.int32, 'i64': torch.int64}
+
+
+@pytest.mark.parametrize('pd', ['u8', 'i16', 'i32', 'i64'])
+@pytest.mark.parametrize('td', ['u8', 'i16', 'i32', 'i64'])
+def test_miou_dtypes_alignment_and_tails(pd, td, cuda_device):
+    """Every dtype pair through the streaming kernel (aligned maps, whole and partial groups of
+    16 elements) and the generic kernel (maps that start at an odd element; n > 96), with and
+    without the void skip, against the oracle's confusion matrix."""
+    from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion
+    g = torch.Generator().manual_seed(len(pd) * 7 + len(td))
+    for n, N in ((5, 1), (19, 15), (41, 16), (41, 4096 + 17), (96, 3 * 4096 * 16 + 5), (97, 70001)):
+        low = torch.randint(0, n + 1, (N // 50 + 2,), generator=g)
+        target = low.repeat_interleave(50)[:N + 1].contiguous()           # runs of equal labels
+        clean = (target - 1).clamp(min=0)
+        preds = torch.where(torch.rand(N + 1, generator=g) < 0.2,
+                            torch.randint(0, n, (N + 1,), generator=g), clean)
+        p_dev = preds.to(_TORCH_INT[pd]).to(cuda_device)
+        t_dev = target.to(_TORCH_INT[td]).to(cuda_device)
+        for first in (0, 1):                     # first = 1: the maps start at an odd element
+            p, t = preds[first:first + N], target[first:first + N]
+            keep = t != 0
+            m = MeanIntersectionOverUnion(n_classes=n, device=cuda_device)
+            m.update_nonvoid(p_dev[first:first + N], t_dev[first:first + N])
+            m.check_status()
+            assert np.array_equal(m.confmat.cpu().numpy(),
+                                  oracle.confmat(p[keep].numpy(), (t[keep] - 1).numpy(), n)), (n, N, first)
+            m = MeanIntersectionOverUnion(n_classes=n + 1, device=cuda_device)
+            m.update(p_dev[first:first + N], t_dev[first:first + N])
+            m.update(p_dev[first:first + N], t_dev[first:first + N])      # accumulates
+            m.check_status()
+            assert np.array_equal(m.confmat.cpu().numpy(),
+                                  2 * oracle.confmat(p.numpy(), t.numpy(), n + 1)), (n, N, first)
+
+
+def test_miou_nonvoid_full_size_and_range(cuda_device):
+    """480x640 x 8 frames: sum of the matrix == number of non-void pixels, rows / columns ==
+    bincounts; predictions at void pixels are not range checked, the others are."""
+    from nicr_mt_scene_analysis_b200 import _lib
+    from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion
+    C = 40
+    g = torch.Generator().manual_seed(3)
+    low = torch.randint(0, C + 1, (8, 15, 20), generator=g)
+    target = low.repeat_interleave(32, 1).repeat_interleave(32, 2).to(torch.uint8).to(cuda_device)
+    preds = torch.randint(0, C, (8, 480, 640), generator=g).to(cuda_device)
+    preds[target == 0] = 1000                                    # garbage below void
+    m = MeanIntersectionOverUnion(n_classes=C, device=cuda_device)
+    m.update_nonvoid(preds, target)
+    m.check_status()
+    cm = m.confmat.cpu()
+    keep = (target != 0).cpu()
+    assert int(cm.sum()) == int(keep.sum())
+    assert torch.equal(cm.sum(1), torch.bincount(target.cpu()[keep].long() - 1, minlength=C))
+    assert torch.equal(cm.sum(0), torch.bincount(preds.cpu()[keep], minlength=C))
+    preds[0, 0, :16] = C                                          # out of range at non-void pixels
+    target[0, 0, :16] = 3
+    m.update_nonvoid(preds, target)
+    with pytest.raises(_lib.NpbError):
+        m.compute()
+    m = MeanIntersectionOverUnion(n_classes=C, device=cuda_device)
+    target[0, 0, :16] = C + 1                                     # target - 1 out of range
+    preds[0, 0, :16] = 0
+    m.update_nonvoid(preds, target)
+    with pytest.raises(_lib.NpbError):
+        m.compute()
+
+
 @pytest.mark.parametrize('shape', [(3, 120, 160), (2, 97, 131), (2, 530, 730)])
 def test_fused_evaluation_against_oracle(shape, cuda_device):
     """PanopticEvaluation (one pixel pass) == separate PQ + mIoU updates == oracle."""

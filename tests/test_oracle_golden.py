@@ -247,3 +247,20 @@ def test_task_helper_epoch_results():
             kind = 'artifacts' if np.ndim(v) else 'logs'
             np.testing.assert_allclose(np.float64(v), z[f'{prefix}/{kind}/{prefix}_{k}'],
                                        rtol=1e-14, err_msg=k)
+
+
+def test_semantic_task_helper_epoch_results():
+    """The oracle's confusion matrix over the non-void pixels (target - 1) reproduces what the
+    reference's SemanticTaskHelper logs (tests/golden/semantic_helper.npz)."""
+    z = load_golden('semantic_helper')
+    C = int(z['n_classes'])
+    cm = np.zeros((C, C), np.int64)
+    for i in range(int(z['n_steps'])):
+        t, p = z[f'step{i}/target'], z[f'step{i}/preds']
+        keep = t != 0
+        cm += oracle.confmat(p[keep], t[keep].astype(np.int64) - 1, C)
+    assert np.array_equal(cm, z['artifacts/semantic_cm'])
+    miou, ious = oracle.miou_from_confmat(cm, False)
+    np.testing.assert_allclose(miou, z['logs/semantic_miou'], rtol=1e-6)
+    np.testing.assert_allclose(ious, z['artifacts/semantic_ious_per_class'], rtol=1e-6,
+                               equal_nan=True)
