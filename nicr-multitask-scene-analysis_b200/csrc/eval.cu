@@ -1311,12 +1311,12 @@ static int confmat_update(const void *preds, int preds_dtype, const void *target
                           int64_t N, int n_classes, bool skip_void, int64_t *confmat,
                           int32_t *status, void *stream, const char *what)
 {
-    if (!preds || !target || !confmat || !status) return NPB_ERR_ARG;
     if (N < 0 || n_classes < 1 || n_classes > 46340) return NPB_ERR_ARG;
     if (preds_dtype < NPB_U8 || preds_dtype > NPB_BOOL || target_dtype < NPB_U8 ||
         target_dtype > NPB_BOOL)
         return NPB_ERR_ARG;
-    if (N == 0) return NPB_OK;
+    if (N == 0) return NPB_OK;          // empty maps (their pointers may be null) add nothing
+    if (!preds || !target || !confmat || !status) return NPB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const bool aligned = (((uintptr_t)preds | (uintptr_t)target) & 15u) == 0;
     if (aligned && n_classes <= kSmemConfmatMaxN) {

@@ -273,6 +273,9 @@ class PanopticQuality(MetricState):
     def update(self, preds: torch.Tensor, targets: torch.Tensor) -> None:
         """preds, targets: (B,H,W) panoptic ids (class * max_instances + instance).
         Asynchronous; data-dependent errors surface at `compute()` / `check_status()`."""
+        if preds.shape[0] == 0:          # an empty batch adds nothing (the loop of pq.py:276-303)
+            assert targets.shape == preds.shape
+            return
         self._launch(preds, targets)
 
     def check_status(self) -> None:
