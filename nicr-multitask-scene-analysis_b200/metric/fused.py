@@ -66,13 +66,8 @@ class PanopticEvaluation:
         """MAAE part of an update whose PQ part already ran: `matches` = (pairs, counts) device
         tensors of that launch (mae.py:113-127)."""
         pairs_d, n_matches = matches
-        self.pq.check_status()
-        counts = n_matches.cpu().tolist()
-        pairs = pairs_d.cpu()
-        for b, n in enumerate(counts):
-            self.pq.update_mae(orientation_preds[b], panoptic_preds_id_dicts[b],
-                               orientation_target[b], panoptic_target_id_dicts[b],
-                               [tuple(p) for p in pairs[b, :n].tolist()])
+        self.pq.update_mae_batch(pairs_d, n_matches, orientation_preds, panoptic_preds_id_dicts,
+                                 orientation_target, panoptic_target_id_dicts)
 
     def reset(self) -> None:
         self.pq.reset()

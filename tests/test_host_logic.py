@@ -196,6 +196,29 @@ def test_mean_absolute_angular_error_host_logic():
     assert int(m.n_elements) == 0 and float(m.sum_angular_error) == 0.0
 
 
+def test_batched_angular_errors_equal_the_per_pair_loop():
+    """The MAAE update evaluates the errors of a batch with one float32 vector operation; every
+    element must equal the reference's scalar form `abs_angle_error_rad(torch.tensor(p),
+    torch.tensor(t))` (mae.py:157-160) bit for bit, and the float64 state the sequential sum."""
+    import math
+    import random
+    from nicr_mt_scene_analysis_b200.metric import MeanAbsoluteAngularError
+    from nicr_mt_scene_analysis_b200.metric.mae import abs_angle_error_rad
+    rnd = random.Random(5)
+    preds = [rnd.uniform(-10, 10) for _ in range(500)] + [0.0, math.pi, -math.pi, 2 * math.pi, 7.5]
+    targets = [rnd.uniform(-10, 10) for _ in range(500)] + [2 * math.pi, -math.pi, math.pi, 0.0, 7.5]
+    vec = abs_angle_error_rad(torch.tensor(preds), torch.tensor(targets))
+    total = torch.tensor(0, dtype=torch.float64)
+    for i, (p, t) in enumerate(zip(preds, targets)):
+        e = abs_angle_error_rad(torch.tensor(p), torch.tensor(t))
+        assert e.dtype == torch.float32 and float(e) == float(vec[i]), i
+        total += e
+    m = MeanAbsoluteAngularError(device='cpu')
+    m.update([dict(enumerate(preds))], [dict(enumerate(targets))])
+    assert int(m.n_elements) == len(preds)
+    assert float(m.sum_angular_error) == float(total)
+
+
 def test_instance_tables_layout_is_aligned():
     from nicr_mt_scene_analysis_b200._results import InstanceTables
     for B in (1, 3, 64):
