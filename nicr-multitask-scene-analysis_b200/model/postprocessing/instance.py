@@ -165,10 +165,12 @@ class InstancePostprocessing(DensePostprocessingBase):
             _lib.ptr(ori), _lib.ptr(seg), c_int(_lib.dtype_code(seg)), _lib.ptr(mask), c_int(B),
             c_int64(P), c_int(max_id), _lib.ptr(count), _lib.ptr(angle), _lib.ptr(sums),
             _lib.ptr(status), _lib.stream_ptr(dev)), 'npb_instance_orientation')
-        count_h, angle_h = count.cpu(), angle.cpu()
+        # python lists (float32 values as python floats): tensor elements read one by one
+        # cost microseconds each
+        count_h, angle_h = count.cpu().tolist(), angle.cpu().tolist()
         _lib.raise_for_status(status.cpu().tolist(), 'instance orientation')
-        return [{i: float(angle_h[b, i]) for i in range(1, max_id + 1) if count_h[b, i] > 0}
-                for b in range(B)]
+        return [{i: angle_b[i] for i in range(1, max_id + 1) if count_b[i] > 0}
+                for count_b, angle_b in zip(count_h, angle_h)]
 
     # ------------------------------------------------------------------ postprocess
     def _postprocess_training(self, data, batch):

@@ -50,10 +50,11 @@ def deeplab_merge_batch(
         c_int64(max_instances_per_category), lut, c_int64(void_label), _lib.ptr(ws),
         _lib.ptr(pan), _lib.ptr(inst_class), _lib.ptr(inst_pan), _lib.ptr(inst_area),
         _lib.ptr(status), _lib.stream_ptr(dev)), 'deeplab_merge_batch')
-    cls_h, pan_h, status_h = inst_class.cpu(), inst_pan.cpu(), status.cpu()
+    # python lists: indexing tensor elements one by one costs microseconds each
+    cls_h, pan_h, status_h = inst_class.cpu().tolist(), inst_pan.cpu().tolist(), status.cpu()
     _lib.raise_for_status(status_h.tolist(), 'deeplab_merge_batch')
-    ids = [{int(pan_h[b, i]): i for i in range(1, _lib.MAX_INST) if cls_h[b, i] >= 0}
-           for b in range(B)]
+    ids = [{pan_b[i]: i for i in range(1, _lib.MAX_INST) if cls_b[i] >= 0}
+           for cls_b, pan_b in zip(cls_h, pan_h)]
     return pan, ids
 
 
@@ -96,7 +97,9 @@ def naive_merge_semantic_and_instance_batch(
         _lib.ptr(part_keys), _lib.ptr(part_pan), _lib.ptr(n_parts), _lib.ptr(status),
         _lib.stream_ptr(dev)), 'npb_naive_merge')
     _lib.raise_for_status(status.cpu().tolist(), 'naive_merge_semantic_and_instance_batch')
-    n_h, keys_h, pan_h = n_parts.cpu().tolist(), part_keys.cpu(), part_pan.cpu()
-    ids = [{int(pan_h[b, t]): (int(keys_h[b, t]) >> 16) & 0xffff for t in range(n_h[b])}
+    n_h = n_parts.cpu().tolist()
+    n_max = max(n_h, default=0)
+    keys_h, pan_h = part_keys[:, :n_max].cpu().tolist(), part_pan[:, :n_max].cpu().tolist()
+    ids = [{pan_h[b][t]: (keys_h[b][t] >> 16) & 0xffff for t in range(n_h[b])}
            for b in range(B)]
     return pan, ids
