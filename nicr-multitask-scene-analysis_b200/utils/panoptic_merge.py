@@ -6,6 +6,7 @@ pass instead, see model/postprocessing/panoptic.py.)"""
 from ctypes import c_int, c_int64
 from typing import Dict, List, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -50,11 +51,13 @@ def deeplab_merge_batch(
         c_int64(max_instances_per_category), lut, c_int64(void_label), _lib.ptr(ws),
         _lib.ptr(pan), _lib.ptr(inst_class), _lib.ptr(inst_pan), _lib.ptr(inst_area),
         _lib.ptr(status), _lib.stream_ptr(dev)), 'deeplab_merge_batch')
-    # python lists: indexing tensor elements one by one costs microseconds each
-    cls_h, pan_h, status_h = inst_class.cpu().tolist(), inst_pan.cpu().tolist(), status.cpu()
+    # numpy on the host copies: indexing tensor elements one by one costs microseconds each
+    cls_h, pan_h, status_h = inst_class.cpu().numpy(), inst_pan.cpu().numpy(), status.cpu()
     _lib.raise_for_status(status_h.tolist(), 'deeplab_merge_batch')
-    ids = [{pan_b[i]: i for i in range(1, _lib.MAX_INST) if cls_b[i] >= 0}
-           for cls_b, pan_b in zip(cls_h, pan_h)]
+    ids = []
+    for b in range(B):
+        used = np.flatnonzero(cls_h[b, 1:] >= 0) + 1          # ascending instance id
+        ids.append(dict(zip(pan_h[b, used].tolist(), used.tolist())))
     return pan, ids
 
 
