@@ -73,6 +73,9 @@ resize_bilinear_kernel(const float *__restrict__ src, ResizeGeom g, float *__res
     dst[(size_t)plane * g.Hout * g.Wout + o] = bilerp(src + (size_t)plane * g.Hin * g.Win, g, cy, cx);
 }
 
+// The four taps of an output pixel are the same offsets in every class plane: they are computed
+// once as four pointers that advance by one plane per class: a plane costs four pointer
+// increments + four loads instead of the 64-bit row / column arithmetic of bilerp() per tap.
 template <bool SCORE>
 __global__ void __launch_bounds__(256)
 argmax_bilinear_kernel(const float *__restrict__ logits, int C, ResizeGeom g,
@@ -85,17 +88,27 @@ argmax_bilinear_kernel(const float *__restrict__ logits, int C, ResizeGeom g,
     const LinCoord cy = lin_coord(oy, g.sy, g.Hc), cx = lin_coord(ox, g.sx, g.Wc);
     const size_t plane = (size_t)g.Hin * g.Win;
     const float *lp = logits + (size_t)b * C * plane;
-    float best = bilerp(lp, g, cy, cx), sum = 1.0f;
+    const float *r0 = lp + (size_t)(g.y0 + cy.i0) * g.Win + g.x0;
+    const float *r1 = lp + (size_t)(g.y0 + cy.i1) * g.Win + g.x0;
+    const float *p00 = r0 + cx.i0, *p01 = r0 + cx.i1, *p10 = r1 + cx.i0, *p11 = r1 + cx.i1;
+    auto tap = [&]() {          // same operation order as bilerp()
+        const float top = __fadd_rn(__fmul_rn(__ldg(p00), cx.w0), __fmul_rn(__ldg(p01), cx.w1));
+        const float bot = __fadd_rn(__fmul_rn(__ldg(p10), cx.w0), __fmul_rn(__ldg(p11), cx.w1));
+        p00 += plane; p01 += plane; p10 += plane; p11 += plane;
+        return __fadd_rn(__fmul_rn(top, cy.w0), __fmul_rn(bot, cy.w1));
+    };
+    float best = tap(), sum = 1.0f;
     int cls = 0;
     for (int c = 1; c < C; ++c) {
-        const float v = bilerp(lp + (size_t)c * plane, g, cy, cx);
-        if (v > best) {
-            if (SCORE) sum = sum * __expf(best - v) + 1.0f;
-            best = v;
-            cls = c;
-        } else if (SCORE) {
-            sum += __expf(v - best);
+        const float v = tap();
+        const bool gt = v > best;
+        if (SCORE) {
+            // online soft-max, branch free: exp(best - v) if v is the new maximum, else exp(v - best)
+            const float e = __expf(gt ? best - v : v - best);
+            sum = gt ? sum * e + 1.0f : sum + e;
         }
+        best = gt ? v : best;
+        cls = gt ? c : cls;
     }
     const size_t q = (size_t)b * g.Hout * g.Wout + o;
     sem_out[q] = (uint8_t)cls;
