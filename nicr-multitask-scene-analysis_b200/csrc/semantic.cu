@@ -38,13 +38,14 @@ semantic_argmax_kernel(const float *__restrict__ logits, int C, int P,
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            if (v[j] > best[j]) {
-                if (SCORE) sum[j] = sum[j] * __expf(best[j] - v[j]) + 1.0f;
-                best[j] = v[j];
-                cls[j] = c;
-            } else if (SCORE) {
-                sum[j] += __expf(v[j] - best[j]);
+            const bool gt = v[j] > best[j];
+            if (SCORE) {
+                // online soft-max, branch free: exp(best - v) for a new maximum, else exp(v - best)
+                const float e = __expf(gt ? best[j] - v[j] : v[j] - best[j]);
+                sum[j] = gt ? sum[j] * e + 1.0f : sum[j] + e;
             }
+            best[j] = gt ? v[j] : best[j];
+            cls[j] = gt ? c : cls[j];
         }
     }
     const size_t fb = (size_t)b * P + p0;
