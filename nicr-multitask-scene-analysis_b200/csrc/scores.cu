@@ -15,6 +15,10 @@
 
 namespace npb {
 
+// VEC = 4: four consecutive pixels per thread (128-bit loads, 8 planes in flight, branch-free
+// online soft-max -- the loop of semantic_argmax_kernel<4, true>); VEC = 1 for maps whose size or
+// alignment rules that out.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 semantic_score_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ pan_sem,
                       const uint8_t *__restrict__ inst, int C, int P,
@@ -22,35 +26,85 @@ semantic_score_kernel(const float *__restrict__ logits, const uint8_t *__restric
 {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * 256 + threadIdx.x;
-    const bool act = p < P;
-    float score = 0.0f;
-    int ii = 0;
+    const int p = (blockIdx.x * 256 + threadIdx.x) * VEC;
+    const bool act = p < P;         // P % VEC == 0 is guaranteed by the launcher
+    float score[VEC];
+    int ii[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { score[j] = 0.0f; ii[j] = 0; }
     if (act) {
         const size_t q = (size_t)b * P + p;
-        const int want = (int)pan_sem[q] - 1;       // network class of the panoptic label
-        ii = inst[q];
-        const float *lp = logits + (size_t)b * C * P + p;
-        float mx = ld_stream_f1(lp), sum = 1.0f, sel = mx;
-        for (int c = 1; c < C; ++c) {
-            const float v = ld_stream_f1(lp + (size_t)c * P);
-            if (c == want) sel = v;
-            if (v > mx) { sum = sum * __expf(mx - v) + 1.0f; mx = v; }
-            else sum += __expf(v - mx);
+        int want[VEC];              // network class of the panoptic label (-1: void)
+        if (VEC == 4) {
+            const uint32_t w = *(const uint32_t *)(pan_sem + q), i4 = *(const uint32_t *)(inst + q);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                want[j] = (int)((w >> (8 * j)) & 255u) - 1;
+                ii[j] = (int)((i4 >> (8 * j)) & 255u);
+            }
+        } else {
+            want[0] = (int)pan_sem[q] - 1;
+            ii[0] = inst[q];
         }
-        score = want >= 0 ? __expf(sel - mx) / sum : 0.0f;     // void has no valid score
-        sem_score[q] = score;
+        const float *lp = logits + (size_t)b * C * P + p;
+        float mx[VEC], sum[VEC], sel[VEC];
+        auto load = [&](int c, float (&v)[VEC]) {
+            if (VEC == 4) {
+                const float4 t = ld_stream_f4((const float4 *)(lp + (size_t)c * P));
+                v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+            } else {
+                v[0] = ld_stream_f1(lp + (size_t)c * P);
+            }
+        };
+        load(0, mx);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { sum[j] = 1.0f; sel[j] = mx[j]; }
+        if (VEC == 4) {
+#pragma unroll 8
+            for (int c = 1; c < C; ++c) {
+                float v[VEC];
+                load(c, v);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    sel[j] = (c == want[j]) ? v[j] : sel[j];
+                    const bool gt = v[j] > mx[j];
+                    const float e = __expf(gt ? mx[j] - v[j] : v[j] - mx[j]);
+                    sum[j] = gt ? sum[j] * e + 1.0f : sum[j] + e;
+                    mx[j] = gt ? v[j] : mx[j];
+                }
+            }
+        } else {
+            for (int c = 1; c < C; ++c) {
+                float v[VEC];
+                load(c, v);
+                if (c == want[0]) sel[0] = v[0];
+                if (v[0] > mx[0]) { sum[0] = sum[0] * __expf(mx[0] - v[0]) + 1.0f; mx[0] = v[0]; }
+                else sum[0] += __expf(v[0] - mx[0]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)       // void has no valid score
+            score[j] = want[j] >= 0 ? __expf(sel[j] - mx[j]) / sum[j] : 0.0f;
+        if (VEC == 4) *(float4 *)(sem_score + q) = make_float4(score[0], score[1 % VEC], score[2 % VEC], score[3 % VEC]);
+        else sem_score[q] = score[0];
     }
-    // per-instance sums: loop over the distinct instances of the warp
-    unsigned pending = __ballot_sync(kFullMask, act && ii > 0);
+    // per-instance sums: one round per distinct instance of the warp; a round adds EVERY pixel
+    // of that instance in the warp (lane-local sum, f32 shuffle tree, one f64 RED) and retires them
     double *sums = inst_sum + (size_t)b * kMaxInst;
-    while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const int cur = __shfl_sync(kFullMask, ii, leader);
-        const bool mine = act && ii == cur;
-        const float s = warp_sum(mine ? score : 0.0f);
-        if (lane == leader) atomicAdd(sums + cur, (double)s);
-        pending &= ~__ballot_sync(kFullMask, mine);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        unsigned pending = __ballot_sync(kFullMask, ii[k] > 0);
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const int cur = __shfl_sync(kFullMask, ii[k], leader);
+            float mine = 0.0f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (ii[j] == cur) { mine += score[j]; ii[j] = 0; }
+            const float s = warp_sum(mine);
+            if (lane == leader) atomicAdd(sums + cur, (double)s);
+            pending = __ballot_sync(kFullMask, ii[k] > 0);
+        }
     }
 }
 
@@ -108,7 +162,13 @@ extern "C" int npb_panoptic_scores(const float *logits, const uint8_t *pan_sem, 
     cudaStream_t s = (cudaStream_t)stream;
     cudaMemsetAsync(inst_sum, 0, (size_t)B * kMaxInst * sizeof(double), s);
     dim3 grid((P + 255) / 256, B);
-    semantic_score_kernel<<<grid, 256, 0, s>>>(logits, pan_sem, inst, C, P, sem_score, inst_sum);
+    const bool vec4 = P % 4 == 0 && (((uintptr_t)logits | (uintptr_t)sem_score) & 15u) == 0 &&
+                      (((uintptr_t)pan_sem | (uintptr_t)inst) & 3u) == 0;
+    if (vec4)
+        semantic_score_kernel<4><<<dim3((P / 4 + 255) / 256, B), 256, 0, s>>>(logits, pan_sem, inst, C, P,
+                                                                          sem_score, inst_sum);
+    else
+        semantic_score_kernel<1><<<grid, 256, 0, s>>>(logits, pan_sem, inst, C, P, sem_score, inst_sum);
     instance_panoptic_score_kernel<<<grid, 256, 0, s>>>(sem_score, inst, inst_class, inst_area,
                                                         center_score, inst_sum, P, inst_score,
                                                         pan_score, inst_mean_sem, inst_pan_score);

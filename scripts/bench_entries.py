@@ -79,6 +79,26 @@ def main():
         ('naive_merge_semantic_and_instance_batch',
          lambda: naive_merge_semantic_and_instance_batch(sem_u8, inst_i32, 1 << 16, thing_ids, 0), P * (1 + 4 + 8)),
     ]
+    post_async = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+        instance_postprocessing=get_postprocessing_class('instance')(),
+        semantic_classes_is_thing=is_thing, semantic_class_has_orientation=has_ori,
+        async_results=True)()
+    post_scores = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+        instance_postprocessing=get_postprocessing_class('instance')(),
+        semantic_classes_is_thing=is_thing, semantic_class_has_orientation=has_ori,
+        compute_scores=True, async_results=True)()
+    raw = ((data['logits'], (data['heat'], data['offset'], data['orientation'])), (None, None))
+    bdict = testing.make_batch_dict(B, H, W)
+    bytes_post = bench.bytes_post_per_frame(C, H, W, True)
+    entries += [
+        ('postprocess (async results)', lambda: post_async.postprocess(raw, bdict, is_training=False),
+         bytes_post),
+        ('postprocess with compute_scores (async results; + logits again, 3 score maps)',
+         lambda: post_scores.postprocess(raw, bdict, is_training=False),
+         bytes_post + P * (4 * C + 2 + 12 + 4)),
+    ]
     out = {'frames': B, 'height': H, 'width': W, 'classes': C, 'peak_GBs': peak}
     for name, fn, bytes_per_frame in entries:
         try:

@@ -92,3 +92,49 @@ def test_postprocess_frame_without_things_and_void_only_target(cuda_device):
     for b in range(B):
         out = oracle.pq_compare_and_accumulate(pan[b], np.zeros((H, W), np.int64), C + 1, 0, L, OFF, 0)
         assert all(float(v.sum()) == 0.0 for v in out[:4])
+
+
+@pytest.mark.parametrize('hw', [(75, 91), (64, 96)])      # odd map size: scalar kernels; 4 px / thread
+def test_score_maps_against_a_torch_restatement(hw, cuda_device):
+    """compute_scores=True (panoptic.py:171-239): semantic score = soft-max probability of the
+    pixel's panoptic class (0 for void), instance score = heat-map value at the instance's centre,
+    panoptic score = mean semantic score of the instance x instance score (things) or the
+    semantic score (stuff); restated with torch fp32 on the kernel's own label maps, 1e-5."""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    H, W = hw
+    B, C, K = 2, 7, 4
+    d = testing.make_batch(B, C, H, W, K, seed=23, with_orientation=False, device=cuda_device,
+                           quantize='q10')
+    is_thing = testing.default_is_thing(C)
+    post = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+        instance_postprocessing=get_postprocessing_class('instance')(),
+        semantic_classes_is_thing=is_thing, semantic_class_has_orientation=(False,) * C,
+        compute_scores=True)()
+    r = post.postprocess(((d['logits'], (d['heat'], d['offset'])), (None, None)),
+                         testing.make_batch_dict(B, H, W), is_training=False)
+    pan_sem = r['panoptic_segmentation_deeplab_semantic_idx'].cpu()           # 0 = void
+    inst = r['panoptic_segmentation_deeplab_instance_idx'].cpu().long()
+    probs = torch.softmax(d['logits'].cpu(), dim=1)
+    want = (pan_sem - 1).clamp(min=0)
+    sem_score = torch.gather(probs, 1, want[:, None])[:, 0] * (pan_sem > 0)
+    np.testing.assert_allclose(r['panoptic_segmentation_deeplab_semantic_score'].cpu().numpy(),
+                               sem_score.numpy(), rtol=1e-5, atol=1e-7)
+    pan_score = sem_score.clone()
+    inst_score = torch.zeros_like(sem_score)
+    meta = r['panoptic_segmentation_deeplab_instance_meta']
+    ids = r['panoptic_segmentation_deeplab_ids']
+    for b in range(B):
+        kept = set(ids[b].values())                  # instances that survived the merge
+        for i, m in meta[b].items():
+            mask = inst[b] == i
+            if not bool(mask.any()):
+                continue
+            if i in kept:       # instances dropped by the merge keep 0 / the semantic score
+                inst_score[b][mask] = m['score']
+                pan_score[b][mask] = sem_score[b][mask].double().mean().float() * m['score']
+    np.testing.assert_allclose(r['panoptic_segmentation_deeplab_instance_score'].cpu().numpy(),
+                               inst_score.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(r['panoptic_segmentation_deeplab_panoptic_score'].cpu().numpy(),
+                               pan_score.numpy(), rtol=1e-5, atol=1e-7)
