@@ -138,3 +138,24 @@ def test_score_maps_against_a_torch_restatement(hw, cuda_device):
                                inst_score.numpy(), rtol=1e-6)
     np.testing.assert_allclose(r['panoptic_segmentation_deeplab_panoptic_score'].cpu().numpy(),
                                pan_score.numpy(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('C,hw', [(1, (5, 7)), (19, (33, 40)), (40, (31, 37)), (64, (8, 12)), (70, (16, 20)),
+                                  (70, (15, 21))])
+def test_softmax_scores_all_kernels(C, hw, cuda_device):
+    """`semantic_softmax_scores` (two passes, 4 px / thread and the scalar form for odd map sizes)
+    against torch.softmax, 1e-5 relative; -inf and NaN logits behave like the reference's."""
+    from nicr_mt_scene_analysis_b200.model.postprocessing.semantic import softmax_scores
+    g = torch.Generator().manual_seed(C)
+    logits = (torch.randn((2, C) + hw, generator=g) * 4).to(cuda_device)
+    if C > 1:
+        logits[0, 0, 0, 0] = float('-inf')
+    got = softmax_scores(logits)
+    ref = torch.softmax(logits.cpu(), dim=1)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(got.sum(1).cpu().numpy(), 1.0, rtol=1e-5)
+    if C > 1:       # a NaN logit poisons its column like the reference's soft-max
+        logits[1, 1, 2, 3] = float('nan')
+        got = softmax_scores(logits)
+        assert bool(torch.isnan(got[1, :, 2, 3]).all())
+        assert not bool(torch.isnan(got[1, :, 2, 4]).any())
