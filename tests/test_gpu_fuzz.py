@@ -111,6 +111,18 @@ def test_random_configuration(seed, cuda_device):
     assert torch.equal(rf['panoptic_segmentation_deeplab_semantic_idx'],
                        r['panoptic_segmentation_deeplab_semantic_idx']), c
     assert torch.equal(miou3.confmat, miou.confmat), c
+    # the stand-alone confusion-matrix kernels on the same maps (int64 predictions, uint8 targets):
+    # all pixels, and the semantic task helper's form (void skipped, target - 1)
+    miou4 = MeanIntersectionOverUnion(C + 1, ignore_first_class=True, device=dev)
+    miou4.update(r['panoptic_segmentation_deeplab_semantic_idx'], tgt_sem)
+    miou4.check_status()
+    assert torch.equal(miou4.confmat, miou.confmat), c
+    miou5 = MeanIntersectionOverUnion(C, device=dev)
+    miou5.update_nonvoid(r['semantic_segmentation_idx'], tgt_sem)
+    miou5.check_status()
+    keep = (tgt_sem != 0).cpu().numpy()
+    assert np.array_equal(miou5.confmat.cpu().numpy(),
+                          oracle.confmat(ref['semantic_idx'][keep], tgt_sem.cpu().numpy()[keep].astype(np.int64) - 1, C)), c
     for metric in (pq, pq2, pq3):
         state = np.zeros((4, C + 1))
         zero_division = False
