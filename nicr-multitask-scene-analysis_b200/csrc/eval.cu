@@ -248,11 +248,10 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     // pixel without instance stays void, panoptic_merge.py:213-224)
     __shared__ unsigned s_pan32[FUSED ? kMaxInst : 1];
     __shared__ unsigned s_stuff[FUSED ? 256 : 1];
-    if (FUSED) {
-        static_assert(kPairThreads == kMaxInst, "one table entry per thread");
-        s_pan32[threadIdx.x] = (unsigned)prm.inst_pan_id[(size_t)blockIdx.y * kMaxInst + threadIdx.x];
-        s_stuff[threadIdx.x] = prm.thing.has((int)threadIdx.x) ? 0u : ((unsigned)threadIdx.x + 1u) << 16;
-    }
+    static_assert(!FUSED || kPairThreads == kMaxInst, "one table entry per thread");
+    // issued first, stored after the tables below have been cleared: the clearing hides its latency
+    unsigned my_pan32 = 0u;
+    if (FUSED) my_pan32 = (unsigned)prm.inst_pan_id[(size_t)blockIdx.y * kMaxInst + threadIdx.x];
     extern __shared__ unsigned long long s_dyn[];
     PairTables t;
     t.keys = s_dyn;                                           // [kSmemSlots]
@@ -272,6 +271,10 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     for (int i = tid; i < nd * nd; i += kPairThreads) t.dense[i] = 0;
     if (cm_smem)
         for (int i = tid; i < n * n; i += kPairThreads) t.cm[i] = 0;
+    if (FUSED) {
+        s_pan32[tid] = my_pan32;
+        s_stuff[tid] = prm.thing.has(tid) ? 0u : ((unsigned)tid + 1u) << 16;
+    }
     __syncthreads();
 
     const long long P = prm.P;
