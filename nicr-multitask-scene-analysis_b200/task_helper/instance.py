@@ -1,6 +1,6 @@
 # -*- coding: utf-8 -*-
 """`InstanceTaskHelper`: stand-alone evaluation of the instance segmentation
-(task_helper/instance.py:289-446 without losses and visualisation examples).
+(task_helper/instance.py:289-436 without losses and visualisation examples).
 
 The predicted instances (grouped inside the ground-truth foreground) are merged with the
 ground-truth semantic map by `deeplab_merge_batch` and scored with PQ against the panoptic

@@ -1,6 +1,6 @@
 # -*- coding: utf-8 -*-
 """`PanopticTaskHelper`: validation of the merged panoptic prediction
-(task_helper/panoptic.py:28-213 without the visualisation examples).
+(task_helper/panoptic.py:28-212 without the visualisation examples).
 
 The reference's step moves prediction and target to the CPU, runs
 `PanopticQualityWithOrientationMAE.update` (process pool) and then

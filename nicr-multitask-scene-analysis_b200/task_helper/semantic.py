@@ -1,6 +1,6 @@
 # -*- coding: utf-8 -*-
 """`SemanticTaskHelper`: validation of the semantic segmentation
-(task_helper/semantic.py:21-163 without losses and visualisation examples).
+(task_helper/semantic.py:21-161 without losses and visualisation examples).
 
 The reference's step builds `mask = target != 0`, the masked copies `preds[mask]` and
 `target[mask] - 1`, moves both to the CPU and calls `MeanIntersectionOverUnion.update`

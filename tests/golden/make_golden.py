@@ -344,7 +344,7 @@ def run_orientation():
 
 def run_task_helpers():
     """Validation path of the reference's task helpers (task_helper/panoptic.py:87-212,
-    task_helper/instance.py:289-446): two validation steps + epoch end on random blocky
+    task_helper/instance.py:289-436): two validation steps + epoch end on random blocky
     batches.  batch_idx != 0 skips the visualisation examples; the instance helper's loss
     computation (not on the evaluated path) is bypassed by overriding `_compute_losses`."""
     from types import SimpleNamespace
@@ -439,7 +439,7 @@ def run_task_helpers():
 
 
 def run_semantic_helper():
-    """Validation path of the reference's SemanticTaskHelper (task_helper/semantic.py:111-163):
+    """Validation path of the reference's SemanticTaskHelper (task_helper/semantic.py:111-161):
     three validation steps + epoch end.  Predictions are network classes 0..C-1 (int64), the
     target is uint8 with 0 = void; the helper masks the void pixels and shifts the target.
     batch_idx != 0 skips the visualisation examples; the loss (not on the evaluated path) is

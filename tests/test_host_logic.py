@@ -260,3 +260,33 @@ def test_eval_args_struct_layout_matches_the_header(tmp_path):
                                           text=True).stdout.split()]
     assert out[0] == ctypes.sizeof(_lib.EvalArgs)
     assert out[1:] == [getattr(_lib.EvalArgs, n).offset for n in names]
+
+
+def test_reference_citations_resolve():
+    """Every `file.py:first-last` citation of the C header, the design / integration notes, the
+    host package, the kernels and the oracle names a file of the reference that has that many
+    lines (checked where /root/reference exists; the GPU box has no reference)."""
+    import glob
+    import re
+    ref_root = '/root/reference'
+    if not os.path.isdir(ref_root):
+        pytest.skip('reference sources not present')
+    files = glob.glob(os.path.join(ref_root, '**', '*.py'), recursive=True)
+    n_lines = {f: sum(1 for _ in open(f, encoding='utf-8', errors='replace')) for f in files}
+    pkg = os.path.join(ROOT, 'nicr-multitask-scene-analysis_b200')
+    sources = [os.path.join(ROOT, p) for p in ('include/nicr_panoptic_b200.h', 'DESIGN.md',
+                                               'INTEGRATION.md', 'oracle/panoptic_oracle.c',
+                                               'oracle/__init__.py')]
+    sources += glob.glob(os.path.join(pkg, '**', '*.py'), recursive=True)
+    sources += glob.glob(os.path.join(pkg, 'csrc', '*.cu*'))
+    total = 0
+    for src in sources:
+        for name, first, last in re.findall(r'([A-Za-z_/+]+\.py):(\d+)(?:-(\d+))?', open(src).read()):
+            total += 1
+            last = int(last or first)
+            candidates = [f for f in files if f.endswith('/' + name)]
+            where = f'{os.path.relpath(src, ROOT)}: {name}:{first}-{last}'
+            assert candidates, where + ' (no such file in the reference)'
+            assert any(n_lines[f] >= last for f in candidates), where + ' (beyond the end of the file)'
+            assert int(first) <= last, where
+    assert total >= 200
