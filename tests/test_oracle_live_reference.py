@@ -112,3 +112,76 @@ def test_oracle_equals_live_reference(seed, ref):
     m.reset()
     m.update(preds=pred // L, target=(tgt // L).to(torch.uint8))
     assert np.array_equal(m.confmat.numpy(), oracle.confmat((pred // L).numpy(), (tgt // L).numpy(), C + 1)), c
+
+
+def _blocky(rng, B, H, W, n_values, block):
+    low = rng.integers(0, n_values, (B, (H + block - 1) // block, (W + block - 1) // block))
+    return np.repeat(np.repeat(low, block, 1), block, 2)[:, :H, :W].copy()
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_merges_equal_live_reference(seed, ref):
+    """Stand-alone merges on random noisy maps: deeplab_merge_batch (panoptic_merge.py:18-40,
+    majority votes with close calls and ties, a foreground mask that disagrees with the
+    semantic map, odd id geometries) and naive_merge_semantic_and_instance_np
+    (panoptic_merge.py:43-107, uint16 instance ids, instances spanning several classes)."""
+    from nicr_mt_scene_analysis.utils.panoptic_merge import (deeplab_merge_batch,
+                                                             naive_merge_semantic_and_instance_np)
+    rng = np.random.default_rng(8100 + seed)
+    B, H, W = int(rng.integers(1, 4)), int(rng.integers(20, 70)), int(rng.integers(20, 90))
+    n_sem = int(rng.integers(3, 12))
+    sem = _blocky(rng, B, H, W, n_sem, int(rng.integers(4, 12)))
+    noise = rng.integers(0, n_sem, (B, H, W))
+    sem = np.where(rng.random((B, H, W)) < 0.3, noise, sem)                    # 0 = void
+    ins = _blocky(rng, B, H, W, int(rng.integers(2, 12)), int(rng.integers(5, 16))).astype(np.uint8)
+    fg = _blocky(rng, B, H, W, 4, int(rng.integers(3, 9))) > 0
+    thing_ids = np.flatnonzero(rng.integers(0, 2, n_sem))
+    thing_ids = thing_ids[thing_ids > 0]
+    L = int(rng.choice([1 << 16, 1000, 256]))
+    void = int(rng.choice([0, 0, int(rng.integers(0, n_sem))]))
+    want, want_ids = deeplab_merge_batch(torch.from_numpy(sem), torch.from_numpy(ins),
+                                         torch.from_numpy(fg), L, thing_ids, void)
+    have, have_ids = oracle.deeplab_merge_batch(sem, ins, fg, L, thing_ids.tolist(), void)
+    assert np.array_equal(have, want.numpy())
+    assert have_ids == [{int(k): int(v) for k, v in d.items()} for d in want_ids]
+
+    ins16 = _blocky(rng, B, H, W, 12, int(rng.integers(6, 16))).astype(np.uint16)
+    ins16[ins16 == 7] = 40000
+    ins16[ins16 == 11] = 65535
+    sem8 = sem.astype(np.uint8)
+    have, have_ids = oracle.naive_merge_batch(sem8, ins16.astype(np.int32), 1 << 16,
+                                              thing_ids.tolist(), 0)
+    for b in range(B):
+        want, d = naive_merge_semantic_and_instance_np(sem8[b], ins16[b], 1 << 16, thing_ids, 0)
+        assert np.array_equal(have[b], want.astype(np.int64))
+        assert have_ids[b] == {int(k): int(v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_instance_targets_equal_live_reference(seed, ref):
+    """InstanceTargetGenerator (data/preprocessing/instance.py:97-286) on random ground truth:
+    float32 centre heat-maps bit for bit, offsets (normalised and in pixels), masks."""
+    from nicr_mt_scene_analysis.data.preprocessing.instance import InstanceTargetGenerator
+    rng = np.random.default_rng(8200 + seed)
+    H, W = int(rng.integers(30, 80)), int(rng.integers(30, 110))
+    sigma = int(rng.choice([3, 5, 8]))
+    n_cls = int(rng.integers(3, 8))
+    is_thing = (False,) + tuple(bool(x) for x in rng.integers(0, 2, n_cls - 1))
+    ins = _blocky(rng, 1, H, W, 9, int(rng.integers(7, 16)))[0].astype(np.uint16)
+    ins[ins == 5] = 51234
+    sem = np.zeros((H, W), np.uint8)
+    for i in np.unique(ins):
+        sem[ins == i] = int(rng.integers(1, n_cls))
+    noise = rng.random((H, W)) < 0.2
+    sem[noise] = rng.integers(0, n_cls, int(noise.sum())).astype(np.uint8)
+    # the reference asserts that no stuff pixel carries an instance id
+    ins[~np.asarray(is_thing)[sem]] = 0
+    for norm in (True, False):
+        gen = InstanceTargetGenerator(sigma=sigma, semantic_classes_is_thing=is_thing,
+                                      normalized_offset=norm)
+        want = gen({'semantic': sem.copy(), 'instance': ins.copy()})
+        have = oracle.instance_targets(sem[None], ins[None].astype(np.int32), sigma, list(is_thing), norm)
+        assert np.array_equal(have['instance_center'][0], want['instance_center'])
+        assert np.array_equal(have['instance_offset'][0], want['instance_offset'].transpose(2, 0, 1))
+        assert np.array_equal(have['instance_foreground'][0], want['instance_foreground'])
+        assert np.array_equal(have['instance_center_mask'][0], want['instance_center_mask'])
