@@ -408,7 +408,7 @@ def run_ours(args):
                          'unit': 'GB/s', 'frac': achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
                          # capture of this command (profiles/r01_group_pixels_ncu_raw.csv)
-                         'traffic': 4.0187e9 if args.config == 'sunrgbd' and not args.frames else None,
+                         'traffic': 4.0221e9 if args.config == 'sunrgbd' and not args.frames else None,
                          'kernel_ms': kernel_ms, 'algorithmic_bytes_per_launch': kbytes},
             'roofline_path': {'bytes_per_frame': bpf,
                               'achieved': value / world * bpf / 1e9, 'unit': 'GB/s',
