@@ -6,6 +6,7 @@ live on a CUDA device, the call raises.  Torch is used for device memory and str
 """
 import ctypes
 import os
+import threading
 from ctypes import (POINTER, c_char_p, c_float, c_int, c_int64, c_size_t,
                     c_void_p)
 from typing import Optional, Sequence
@@ -96,6 +97,7 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
+_switched = threading.local()       # devices to switch back to (see stream_ptr / check)
 
 
 class NpbError(RuntimeError):
@@ -128,6 +130,11 @@ def lib():
 
 
 def check(code: int, where: str = '') -> None:
+    """Return code of a library call -> exception.  Also undoes the device switch `stream_ptr`
+    made for that call (see there)."""
+    stack = getattr(_switched, 'stack', None)
+    if stack:
+        torch.cuda.set_device(stack.pop())
     if code != OK:
         raise NpbError(code, where)
 
@@ -162,6 +169,21 @@ def ptr(t: Optional[torch.Tensor]):
 
 
 def stream_ptr(device) -> c_void_p:
+    """Current stream of `device` as the `stream` argument of a library call.
+
+    The kernels launch on the CURRENT device of the calling thread, so for tensors that live on
+    another device of the process (one process driving several GPUs) that device is made current
+    here; `check`, which every call site applies to the return code of the same call, switches
+    back.  With one process per GPU (the usual set-up) nothing is switched."""
+    device = torch.device(device)
+    current = torch.cuda.current_device()
+    index = current if device.index is None else device.index
+    if index != current:
+        stack = getattr(_switched, 'stack', None)
+        if stack is None:
+            stack = _switched.stack = []
+        stack.append(current)
+        torch.cuda.set_device(index)
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

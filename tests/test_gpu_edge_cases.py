@@ -159,3 +159,43 @@ def test_softmax_scores_all_kernels(C, hw, cuda_device):
         got = softmax_scores(logits)
         assert bool(torch.isnan(got[1, :, 2, 3]).all())
         assert not bool(torch.isnan(got[1, :, 2, 4]).any())
+
+
+def test_tensors_on_a_device_that_is_not_current(cuda_device):
+    """One process, several GPUs: post-processing and metrics of tensors on cuda:1 while cuda:0 is
+    the current device give the results of cuda:0 and leave the current device alone."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, PanopticEvaluation,
+                                                    PanopticQuality)
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    B, C, H, W, K = 2, 6, 48, 64, 3
+    d = testing.make_batch(B, C, H, W, K, seed=5, with_orientation=True, quantize='q10')
+    is_thing = testing.default_is_thing(C)
+    results = []
+    torch.cuda.set_device(0)
+    for index in (0, 1):
+        dev = torch.device('cuda', index)
+        post = get_postprocessing_class(
+            'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+            instance_postprocessing=get_postprocessing_class('instance')(),
+            semantic_classes_is_thing=is_thing, semantic_class_has_orientation=is_thing)()
+        r = post.postprocess(((d['logits'].to(dev), (d['heat'].to(dev), d['offset'].to(dev),
+                                                     d['orientation'].to(dev))), (None, None)),
+                             testing.make_batch_dict(B, H, W), is_training=False)
+        pan = r['panoptic_segmentation_deeplab']
+        assert pan.device == dev and torch.cuda.current_device() == 0
+        tgt = torch.roll(pan, 3, -1).contiguous()
+        pq = PanopticQuality(C + 1, 0, L, OFF, (False,) + is_thing, device=dev)
+        miou = MeanIntersectionOverUnion(C + 1, True, device=dev)
+        PanopticEvaluation(pq, miou).update(pan, tgt, (tgt // L).to(torch.uint8))
+        res = pq.compute()
+        assert torch.cuda.current_device() == 0
+        results.append((pan.cpu(), r['panoptic_segmentation_deeplab_ids'], miou.confmat.cpu(),
+                        res['all_pq'], pq.iou_per_class.cpu()))
+    for a, b in zip(*results):
+        if isinstance(a, torch.Tensor):
+            assert torch.equal(a, b)
+        else:
+            assert a == b
