@@ -199,3 +199,52 @@ def test_tensors_on_a_device_that_is_not_current(cuda_device):
             assert torch.equal(a, b)
         else:
             assert a == b
+
+
+def test_memory_formats_and_misaligned_views(cuda_device):
+    """channels_last decoder outputs (NCHW shape, NHWC strides) and contiguous views whose storage
+    starts 4 bytes off a 16-byte boundary give the results of plain contiguous inputs (the
+    kernels fall back to their scalar forms / the host makes one contiguous copy)."""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    B, C, H, W, K = 2, 8, 48, 64, 4
+    d = testing.make_batch(B, C, H, W, K, seed=9, with_orientation=True, device=cuda_device,
+                           quantize='q10')
+    is_thing = testing.default_is_thing(C)
+    post = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+        instance_postprocessing=get_postprocessing_class('instance')(),
+        semantic_classes_is_thing=is_thing, semantic_class_has_orientation=is_thing)()
+
+    def run(t):
+        r = post.postprocess(((t['logits'], (t['heat'], t['offset'], t['orientation'])), (None, None)),
+                             testing.make_batch_dict(B, H, W), is_training=False)
+        return (r['panoptic_segmentation_deeplab'].clone(), r['semantic_segmentation_idx'].clone(),
+                r['panoptic_segmentation_deeplab_instance_idx'].clone(),
+                r['panoptic_segmentation_deeplab_ids'],
+                r['orientations_panoptic_segmentation_deeplab_instance'])
+
+    want = run(d)
+
+    def shifted(x):         # same values, contiguous, storage offset of one element (4 bytes)
+        flat = torch.empty(x.numel() + 1, dtype=x.dtype, device=x.device)
+        flat[1:].copy_(x.reshape(-1))
+        v = flat[1:].view(x.shape)
+        assert v.is_contiguous() and v.data_ptr() % 16 == 4
+        return v
+
+    variants = {
+        'channels_last': {k: v.contiguous(memory_format=torch.channels_last) for k, v in d.items()},
+        'shifted': {k: shifted(v) for k, v in d.items()},
+        'shifted logits only': dict(d, logits=shifted(d['logits'])),
+        'shifted offset only': dict(d, offset=shifted(d['offset'])),
+    }
+    for name, t in variants.items():
+        got = run(t)
+        for a, b in zip(want[:3], got[:3]):
+            assert torch.equal(a, b), name
+        assert want[3] == got[3], name
+        for dw, dg in zip(want[4], got[4]):
+            assert sorted(dw) == sorted(dg), name
+            for k in dw:
+                assert abs(dw[k] - dg[k]) <= 1e-5 * max(1.0, abs(dw[k])), name
