@@ -290,3 +290,28 @@ def test_reference_citations_resolve():
             assert any(n_lines[f] >= last for f in candidates), where + ' (beyond the end of the file)'
             assert int(first) <= last, where
     assert total >= 200
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: C oracle port on the host cores) runs without a
+    GPU and prints ONE JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '0'], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['higher_is_better'] is True and d['scaling'] == 'weak'
+    assert d['unit'] == 'frames/s' and d['value'] > 0 and d['ms_per_step'] > 0
+    assert d['n_gpus'] == 1 and d['steps'] == 1 and d['vs_baseline'] is None
+    assert d['data'] == 'synthetic' and d['dtype'] == 'f32'
+    assert d['config']['workload'] == 'sunrgbd_530x730_c37_b64_orientation'
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}
+    assert d['gpu_launches'] == 0
