@@ -16,6 +16,7 @@ import oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SRC = '/root/reference/src'
+MORE = int(os.environ.get('NPB_LIVE_SEEDS', '0'))      # a longer sweep on request
 
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='reference sources not present')
 
@@ -47,7 +48,7 @@ def _cfg(rng):
         with_orientation=bool(rng.integers(0, 2)))
 
 
-@pytest.mark.parametrize('seed', range(8))
+@pytest.mark.parametrize('seed', range(MORE or 8))
 def test_oracle_equals_live_reference(seed, ref):
     from nicr_mt_scene_analysis_b200 import testing
     rng = np.random.default_rng(7000 + seed)
@@ -119,7 +120,7 @@ def _blocky(rng, B, H, W, n_values, block):
     return np.repeat(np.repeat(low, block, 1), block, 2)[:, :H, :W].copy()
 
 
-@pytest.mark.parametrize('seed', range(6))
+@pytest.mark.parametrize('seed', range(MORE or 6))
 def test_merges_equal_live_reference(seed, ref):
     """Stand-alone merges on random noisy maps: deeplab_merge_batch (panoptic_merge.py:18-40,
     majority votes with close calls and ties, a foreground mask that disagrees with the
@@ -157,7 +158,7 @@ def test_merges_equal_live_reference(seed, ref):
         assert have_ids[b] == {int(k): int(v) for k, v in d.items()}
 
 
-@pytest.mark.parametrize('seed', range(4))
+@pytest.mark.parametrize('seed', range(MORE or 4))
 def test_instance_targets_equal_live_reference(seed, ref):
     """InstanceTargetGenerator (data/preprocessing/instance.py:97-286) on random ground truth:
     float32 centre heat-maps bit for bit, offsets (normalised and in pixels), masks."""
