@@ -101,9 +101,10 @@ def test_oracle_equals_live_reference(seed, ref):
     for b in range(B):
         try:
             want = ref['pq'](pred[b], tgt[b], C + 1, 0, L, OFF, 0)
-        except ZeroDivisionError:
-            with pytest.raises(ZeroDivisionError):
+        except ZeroDivisionError:           # union == 0 (pq.py:145): the oracle reports code -3
+            with pytest.raises(oracle.OracleError) as err:
                 oracle.pq_compare_and_accumulate(pred[b].numpy(), tgt[b].numpy(), C + 1, 0, L, OFF, 0)
+            assert err.value.code == -3
             continue
         have = oracle.pq_compare_and_accumulate(pred[b].numpy(), tgt[b].numpy(), C + 1, 0, L, OFF, 0)
         for w, h in zip(want[:4], have[:4]):
@@ -186,3 +187,41 @@ def test_instance_targets_equal_live_reference(seed, ref):
         assert np.array_equal(have['instance_offset'][0], want['instance_offset'].transpose(2, 0, 1))
         assert np.array_equal(have['instance_foreground'][0], want['instance_foreground'])
         assert np.array_equal(have['instance_center_mask'][0], want['instance_center_mask'])
+
+
+@pytest.mark.parametrize('seed', range(MORE or 10))
+def test_pq_frames_equal_live_reference(seed, ref):
+    """compare_and_accumulate (metric/pq.py:60-179) on random blocky / noisy panoptic maps with
+    odd id geometries: any ignored label, offsets that are not powers of two, predictions inside
+    void and ignored ground truth, thin and single-pixel segments.  float64 bit for bit."""
+    rng = np.random.default_rng(9300 + seed)
+    H, W = int(rng.integers(8, 60)), int(rng.integers(8, 80))
+    NC = int(rng.integers(2, 12))
+    L = int(rng.choice([1 << 16, 1000, 37]))
+    n_inst = int(rng.integers(1, min(L, 9)))
+    ignored = int(rng.integers(0, NC))
+    offset = int(rng.choice([256 ** 3, 3 * 10 ** 7, NC * L + 1]))
+    assert offset > NC * L
+
+    def random_map():
+        cat = _blocky(rng, 1, H, W, NC, int(rng.integers(2, 12)))[0]
+        ins = _blocky(rng, 1, H, W, n_inst, int(rng.integers(2, 9)))[0]
+        noise = rng.random((H, W)) < rng.choice([0.0, 0.05, 0.3])
+        cat = np.where(noise, rng.integers(0, NC, (H, W)), cat)
+        return (cat * L + ins).astype(np.int64)
+
+    tgt = random_map()
+    pred = np.where(rng.random((H, W)) < 0.7, tgt, random_map())
+    void_segment_id = ignored * L
+    try:
+        want = ref['pq'](torch.from_numpy(pred), torch.from_numpy(tgt), NC, ignored, L, offset,
+                         void_segment_id)
+    except ZeroDivisionError:               # union == 0 (pq.py:145): the oracle reports code -3
+        with pytest.raises(oracle.OracleError) as err:
+            oracle.pq_compare_and_accumulate(pred, tgt, NC, ignored, L, offset, void_segment_id)
+        assert err.value.code == -3
+        return
+    have = oracle.pq_compare_and_accumulate(pred, tgt, NC, ignored, L, offset, void_segment_id)
+    for w, h in zip(want[:4], have[:4]):
+        assert np.array_equal(np.asarray(w, np.float64), h), (NC, L, ignored, offset)
+    assert {(int(g), int(p)) for g, p in want[4]} == have[4]
