@@ -97,6 +97,11 @@ def test_oracle_equals_live_reference(seed, ref):
     for gm, rm in zip(got['meta'], r['panoptic_segmentation_deeplab_instance_meta']):
         assert {k: (tuple(v['center_yx']), v['area']) for k, v in gm.items()} == \
             {int(k): (tuple(int(x) for x in v['center_yx']), int(v['area'])) for k, v in rm.items()}, c
+    for gm, rm in zip(got['meta'], r['panoptic_segmentation_deeplab_instance_meta']):
+        for k, v in rm.items():             # heat-map value at the centre (instance.py:262)
+            assert gm[int(k)]['score'] == pytest.approx(float(v['score']), rel=1e-6), (c, k)
+    np.testing.assert_allclose(oracle.semantic_score(data['logits'].numpy()),
+                               r['semantic_segmentation_score'].numpy(), rtol=1e-5)
     if c['with_orientation']:
         for dg, dr in zip(got['orientations'], r['orientations_panoptic_segmentation_deeplab_instance']):
             assert sorted(dg) == sorted(int(k) for k in dr), c
