@@ -239,3 +239,48 @@ def test_pq_frames_equal_live_reference(seed, ref):
     for w, h in zip(want[:4], have[:4]):
         assert np.array_equal(np.asarray(w, np.float64), h), (NC, L, ignored, offset)
     assert {(int(g), int(p)) for g, p in want[4]} == have[4]
+
+
+@pytest.mark.parametrize('seed', range(MORE or 6))
+def test_instance_stage_functions_equal_live_reference(seed, ref):
+    """InstancePostprocessing._get_instance_segmentation / _get_instance_orientation called
+    directly with an ARBITRARY foreground mask (the ground-truth foreground path,
+    instance.py:371-449, calls them that way): instance map and meta identical, angles 1e-5."""
+    from nicr_mt_scene_analysis_b200 import testing
+    rng = np.random.default_rng(9400 + seed)
+    B, H, W = int(rng.integers(1, 3)), int(rng.integers(24, 70)), int(rng.integers(24, 90))
+    K = int(rng.integers(1, 7))
+    data = testing.make_batch(B, 4, H, W, K, seed=500 + seed, quantize=str(rng.choice(['q10', 'tie'])),
+                              with_orientation=True)
+    normalized = bool(rng.integers(0, 2))
+    thr, ks, top_k = float(rng.choice([0.1, 0.3])), int(rng.choice([3, 5])), int(rng.integers(1, 9))
+    apply_fg = bool(rng.integers(0, 2))
+    dist_thr = None if rng.integers(0, 2) else int(rng.integers(3, 25))
+    fg = torch.from_numpy(_blocky(rng, B, H, W, 3, int(rng.integers(3, 12))) > 0)
+    offset = data['offset'].clone()
+    if not normalized:
+        offset[:, 0] *= H
+        offset[:, 1] *= W
+    ins = ref['get']('instance', heatmap_threshold=thr, heatmap_nms_kernel_size=ks,
+                     top_k_instances=top_k, heatmap_apply_foreground_mask=apply_fg,
+                     normalized_offset=normalized, offset_distance_threshold=dist_thr)()
+    scaled = offset.clone()                  # the caller de-normalises (panoptic.py:105-111)
+    if normalized:
+        scaled[:, 0] *= H
+        scaled[:, 1] *= W
+    want_seg, want_meta = ins._get_instance_segmentation(data['heat'], scaled, fg)
+    have_seg, have_meta = oracle.instance_segmentation(
+        data['heat'].numpy(), offset.numpy(), fg.numpy(), thr, ks, top_k, apply_fg, normalized, dist_thr)
+    assert np.array_equal(have_seg, want_seg.numpy())
+    for gm, rm in zip(have_meta, want_meta):
+        assert {k: (tuple(v['center_yx']), v['area']) for k, v in gm.items()} == \
+            {int(k): (tuple(int(x) for x in v['center_yx']), int(v['area'])) for k, v in rm.items()}
+    ori_mask = torch.from_numpy(_blocky(rng, B, H, W, 2, int(rng.integers(3, 12))) > 0)
+    for mask in (ori_mask, None):
+        want = ins._get_instance_orientation(data['orientation'], want_seg, mask)
+        have = oracle.instance_orientation(data['orientation'].numpy(), want_seg.numpy(),
+                                           None if mask is None else mask.numpy())
+        assert [sorted(int(k) for k in d) for d in want] == [sorted(d) for d in have]
+        for dw, dh in zip(want, have):
+            for k, v in dw.items():
+                assert abs(dh[int(k)] - v) <= 1e-5 * max(1.0, abs(v)), (k, v, dh[int(k)])
