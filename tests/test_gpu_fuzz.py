@@ -20,7 +20,7 @@ def _cfg(rng):
         B=int(rng.integers(1, 4)), C=int(rng.integers(1, 24)), H=H, W=W,
         K=int(rng.integers(0, 12)), quantize=str(rng.choice(['q10', 'tie'])),
         top_k=int(rng.integers(1, 12)), ks=int(rng.choice([1, 3, 3, 3, 5, 7])),
-        thr=float(rng.choice([0.1, 0.1, 0.3, 0.6])), apply_fg=bool(rng.integers(0, 2)),
+        thr=float(rng.choice([0.1, 0.1, 0.3, 0.6, -0.5])), apply_fg=bool(rng.integers(0, 2)),
         normalized=bool(rng.integers(0, 2)),
         dist_thr=(None if rng.integers(0, 2) else int(rng.integers(2, 30))),
         with_orientation=bool(rng.integers(0, 2)))
