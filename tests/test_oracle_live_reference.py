@@ -284,3 +284,90 @@ def test_instance_stage_functions_equal_live_reference(seed, ref):
         for dw, dh in zip(want, have):
             for k, v in dw.items():
                 assert abs(dh[int(k)] - v) <= 1e-5 * max(1.0, abs(v)), (k, v, dh[int(k)])
+
+
+def test_product_compute_equals_live_reference(ref):
+    """The PRODUCT's host arithmetic (not the oracle): `PanopticQuality.compute` /
+    `result_per_category` and `MeanIntersectionOverUnion.compute` of this package on hand-set
+    states against the reference's own metric objects holding the same states (pq.py:254-361,
+    miou.py:58-94): every key, every value."""
+    from nicr_mt_scene_analysis.metric import PanopticQuality as RefPQ
+    from nicr_mt_scene_analysis_b200.metric import MeanIntersectionOverUnion, PanopticQuality
+    rng = np.random.default_rng(77)
+    for trial in range(12):
+        n = int(rng.integers(2, 14))
+        ignored = int(rng.integers(0, n))
+        is_thing = [bool(x) for x in rng.integers(0, 2, n)]
+        tp = rng.integers(0, 6, n).astype(np.float64) * (rng.random(n) < 0.7)
+        fn = rng.integers(0, 5, n).astype(np.float64) * (rng.random(n) < 0.6)
+        fp = rng.integers(0, 5, n).astype(np.float64) * (rng.random(n) < 0.6)
+        iou = tp * rng.uniform(0.5, 1.0, n)
+        theirs = RefPQ(n, ignored, 1 << 16, 256 ** 3, is_thing, num_workers=1)
+        ours = PanopticQuality(n, ignored, 1 << 16, 256 ** 3, is_thing, device='cpu')
+        for m in (theirs, ours):
+            m.iou_per_class = torch.from_numpy(iou.copy())
+            m.tp_per_class = torch.from_numpy(tp.copy())
+            m.fn_per_class = torch.from_numpy(fn.copy())
+            m.fp_per_class = torch.from_numpy(fp.copy())
+        want, got = theirs.compute(suffix='_s'), ours.compute(suffix='_s')
+        assert set(want) == set(got), trial
+        for k, v in want.items():
+            np.testing.assert_array_equal(np.asarray(torch.as_tensor(got[k]).double()),
+                                          np.asarray(torch.as_tensor(v).double()), err_msg=f'{trial} {k}')
+        want, got = theirs.result_per_category(), ours.result_per_category()
+        assert set(want) == set(got)
+        for k, v in want.items():
+            np.testing.assert_array_equal(got[k].numpy(), v.numpy(), err_msg=f'{trial} {k}')
+        del theirs                                  # terminates its worker pool
+
+        cm = rng.integers(0, 50, (n, n)) * (rng.random((n, n)) < 0.6)
+        cm[int(rng.integers(0, n))] = 0             # a class without ground truth
+        for flag in (False, True):
+            theirs = ref['miou'](n_classes=n, ignore_first_class=flag)
+            ours_m = MeanIntersectionOverUnion(n, ignore_first_class=flag, device='cpu')
+            theirs.confmat = torch.from_numpy(cm.astype(np.int64))
+            ours_m.confmat = torch.from_numpy(cm.astype(np.int64))
+            (w_miou, w_ious), (g_miou, g_ious) = theirs.compute(return_ious=True), ours_m.compute(return_ious=True)
+            np.testing.assert_array_equal(g_ious.numpy(), w_ious.numpy())
+            assert (torch.isnan(w_miou) and torch.isnan(g_miou)) or float(g_miou) == float(w_miou)
+            assert float(ours_m.compute()) == float(theirs.compute()) or torch.isnan(theirs.compute())
+
+
+def test_product_angular_errors_equal_live_reference(ref):
+    """MeanAbsoluteAngularError.update and PanopticQualityWithOrientationMAE.update_mae of this
+    package (one vector operation per batch) against the reference's per-pair loops
+    (mae.py:46-58, 129-162) on random dicts: same element count, float64 sums equal (bit for
+    bit where the visiting order is the same, 1e-12 for the set-ordered matches)."""
+    from nicr_mt_scene_analysis.metric.mae import (MeanAbsoluteAngularError as RefMAE,
+                                                   PanopticQualityWithOrientationMAE as RefPQMAE)
+    from nicr_mt_scene_analysis_b200.metric import (MeanAbsoluteAngularError,
+                                                    PanopticQualityWithOrientationMAE)
+    rng = np.random.default_rng(91)
+    preds = [{int(i): float(rng.uniform(-7, 7)) for i in rng.choice(50, int(rng.integers(0, 20)), replace=False)}
+             for _ in range(6)]
+    targets = [dict({k: float(rng.uniform(-7, 7)) for k in d}, extra=1.0) for d in preds]
+    theirs, ours = RefMAE(), MeanAbsoluteAngularError(device='cpu')
+    theirs.update(preds, targets)
+    ours.update(preds, targets)
+    assert int(ours.n_elements) == int(theirs.n_elements) == sum(len(d) for d in preds)
+    assert float(ours.sum_angular_error) == float(theirs.sum_angular_error)
+    for a, b in zip(ours.compute(), theirs.compute()):
+        assert float(a) == float(b)
+
+    L = 1 << 16
+    theirs = RefPQMAE(4, 0, L, 256 ** 3, [False, True, True, False], num_workers=1)
+    ours = PanopticQualityWithOrientationMAE(4, 0, L, 256 ** 3, [False, True, True, False], device='cpu')
+    for _ in range(5):
+        gt_ids = [int(c * L + i) for c in (1, 2) for i in range(1, 6)]
+        pred_ids = [int(c * L + i) for c in (1, 2) for i in range(1, 7)]
+        matching = {(g, p) for g, p in zip(gt_ids, rng.permutation(pred_ids)[:len(gt_ids)].tolist())}
+        matching |= {(0, 0), (3 * L, 3 * L)}                      # stuff / void pairs
+        tgt_id_dict = {g: g % L + 100 for g in gt_ids if rng.random() < 0.8}
+        pred_id_dict = {p: p % L + 200 for p in pred_ids if rng.random() < 0.8}
+        ori_t = {v: float(rng.uniform(-4, 4)) for v in tgt_id_dict.values() if rng.random() < 0.7}
+        ori_p = {v: float(rng.uniform(-4, 4)) for v in pred_id_dict.values() if rng.random() < 0.7}
+        theirs.update_mae(ori_p, pred_id_dict, ori_t, tgt_id_dict, matching)
+        ours.update_mae(ori_p, pred_id_dict, ori_t, tgt_id_dict, matching)
+    assert int(ours.n_elements) == int(theirs.n_elements) > 0
+    np.testing.assert_allclose(float(ours.sum_angular_error), float(theirs.sum_angular_error), rtol=1e-12)
+    del theirs
