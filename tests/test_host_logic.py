@@ -1,6 +1,7 @@
 """CPU-only tests: the C-ABI library loads and exports what the header declares, host-side
 helpers behave like the reference's, the product package never touches the oracle, and the
 cross-rank metric reduction works with world_size 2 (gloo)."""
+import ctypes
 import os
 import re
 import subprocess
@@ -42,6 +43,14 @@ def test_host_argument_validation_without_gpu():
                                   None) == _lib.ERR_ARG
     assert L.npb_instance_centers_workspace_bytes(2, 480, 640, 3) >= 2 * 240 * 320 * 8
     assert L.npb_pq_update_workspace_bytes(4, 41) > 4 * 16384 * 12
+    one = (ctypes.c_int64 * 1)()
+    for fn in (L.npb_confmat_update, L.npb_confmat_update_nonvoid):
+        # empty maps add nothing (their pointers may be null); bad sizes / dtypes / pointers
+        assert fn(None, _lib.I64, None, _lib.U8, 0, 5, None, None, None) == _lib.OK
+        assert fn(None, _lib.I64, None, _lib.U8, 16, 5, one, one, None) == _lib.ERR_ARG
+        assert fn(one, _lib.I64, one, _lib.U8, 1, 0, one, one, None) == _lib.ERR_ARG
+        assert fn(one, 9, one, _lib.U8, 1, 5, one, one, None) == _lib.ERR_ARG
+        assert fn(one, _lib.I64, one, _lib.U8, -1, 5, one, one, None) == _lib.ERR_ARG
 
 
 def test_product_never_imports_the_oracle():
