@@ -55,6 +55,9 @@ extern "C" {
 int npb_abi_version(void);
 const char *npb_error_string(int code);
 const char *npb_last_cuda_error(void);
+/* "sm_100a pdl=<0|1> debug=<0|1>": programmatic dependent launches on (NPB_NO_PDL=1 in the
+ * environment turns them off), library built with -DNPB_DEBUG (table-bound assertions). */
+const char *npb_build_info(void);
 
 /* ---------------------------------------------------------------------------
  * Semantic arg-max.
@@ -181,8 +184,13 @@ int npb_write_panoptic(const uint8_t *sem, const uint8_t *inst, const int64_t *i
  * Whole post-processing of a batch in one call (centres -> grouping -> table -> ids).
  * Replaces: PanopticPostprocessing._postprocess_inference, panoptic.py:77-167, 294-314.
  * Same arguments as the stage functions above; `status` [B] collects stage errors.
+ * The chain contains no memset (every kernel is a programmatic dependent of its predecessor):
+ * `workspace` must have been prepared ONCE with npb_panoptic_forward_workspace_init for the
+ * same (B, C, H, W, nms_kernel_size); every call leaves it ready for the next one.
  * ------------------------------------------------------------------------- */
 size_t npb_panoptic_forward_workspace_bytes(int B, int C, int H, int W, int nms_kernel_size);
+int npb_panoptic_forward_workspace_init(void *workspace, int B, int C, int H, int W,
+                                        int nms_kernel_size, void *stream);
 int npb_panoptic_forward(const float *logits, const float *heat, const float *offset,
                          const float *orientation, int B, int C, int H, int W,
                          const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,

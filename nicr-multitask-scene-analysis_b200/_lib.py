@@ -47,6 +47,7 @@ _SIGNATURES = {
     'npb_abi_version': (c_int, []),
     'npb_error_string': (c_char_p, [c_int]),
     'npb_last_cuda_error': (c_char_p, []),
+    'npb_build_info': (c_char_p, []),
     'npb_semantic_argmax': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     'npb_softmax': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     'npb_thing_mask': (c_int, [_P, c_int64, c_int, _P, _P, _P]),
@@ -67,6 +68,7 @@ _SIGNATURES = {
     'npb_write_panoptic': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P,
                                    _P, _P]),
     'npb_panoptic_forward_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'npb_panoptic_forward_workspace_init': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P]),
     'npb_panoptic_forward': (c_int, _FORWARD_ARGS + [_P]),
     'npb_panoptic_forward_eval': (c_int, _FORWARD_ARGS + [POINTER(EvalArgs), _P]),
     'npb_write_panoptic_eval': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64,
@@ -122,7 +124,12 @@ def lib():
                 '(nvcc, sm_100a).  There is no CPU / PyTorch fallback for this path.')
         handle = ctypes.CDLL(LIB_PATH)
         for name, (restype, argtypes) in _SIGNATURES.items():
-            fn = getattr(handle, name)     # AttributeError if the ABI lost a symbol
+            try:
+                fn = getattr(handle, name)     # AttributeError if the ABI lost a symbol
+            except AttributeError:
+                if os.environ.get('NPB_LIB_PATH'):      # an older build in an A/B measurement
+                    continue
+                raise
             fn.restype = restype
             fn.argtypes = argtypes
         _lib = handle

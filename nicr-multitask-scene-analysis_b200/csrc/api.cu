@@ -1,12 +1,36 @@
 // api.cu -- C-ABI glue: error strings, launch-error bookkeeping, the one-call pipeline
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "finalize.cuh"
 
 namespace npb {
 
 static thread_local char g_last_cuda_error[256] = "";
+
+bool dependent_launch_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("NPB_NO_PDL");
+        return !(e && e[0] && e[0] != '0');
+    }();
+    return on;
+}
+
+#ifdef NPB_TIMELINE
+TimelineSlot *timeline_buffer()
+{
+    static TimelineSlot *buf = nullptr;
+    if (!buf) {
+        cudaMalloc(&buf, 16 * sizeof(TimelineSlot));
+        TimelineSlot init[16];
+        for (int i = 0; i < 16; ++i) init[i] = TimelineSlot{~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
+        cudaMemcpy(buf, init, sizeof(init), cudaMemcpyHostToDevice);
+    }
+    return buf;
+}
+#endif
 
 int record_launch(const char *what)
 {
@@ -16,15 +40,41 @@ int record_launch(const char *what)
     return NPB_ERR_CUDA;
 }
 
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace npb
 
 using namespace npb;
 
-extern "C" int npb_abi_version(void) { return 2; }
+extern "C" int npb_abi_version(void) { return 3; }
 
 extern "C" const char *npb_last_cuda_error(void) { return g_last_cuda_error; }
+
+#ifdef NPB_TIMELINE
+// debug builds only: copy the 16 x 6 timeline words to the host and reset them (synchronises)
+extern "C" int npb_timeline_read(unsigned long long *h_out)
+{
+    TimelineSlot *buf = timeline_buffer();
+    cudaDeviceSynchronize();
+    cudaMemcpy(h_out, buf, 16 * sizeof(TimelineSlot), cudaMemcpyDeviceToHost);
+    TimelineSlot init[16];
+    for (int i = 0; i < 16; ++i) init[i] = TimelineSlot{~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
+    cudaMemcpy(buf, init, sizeof(init), cudaMemcpyHostToDevice);
+    return NPB_OK;
+}
+#endif
+
+extern "C" const char *npb_build_info(void)
+{
+    static char info[96];
+    snprintf(info, sizeof(info), "sm_100a pdl=%d debug=%d", dependent_launch_enabled() ? 1 : 0,
+#ifdef NPB_DEBUG
+             1
+#else
+             0
+#endif
+    );
+    return info;
+}
 
 extern "C" const char *npb_error_string(int code)
 {
@@ -50,6 +100,15 @@ extern "C" size_t npb_panoptic_forward_workspace_bytes(int B, int C, int H, int 
     return bytes;
 }
 
+extern "C" int npb_panoptic_forward_workspace_init(void *workspace, int B, int C, int H, int W,
+                                                   int nms_kernel_size, void *stream)
+{
+    if (!workspace || B < 1) return NPB_ERR_ARG;
+    cudaMemsetAsync(workspace, 0, npb_panoptic_forward_workspace_bytes(B, C, H, W, nms_kernel_size),
+                    (cudaStream_t)stream);
+    return record_launch("npb_panoptic_forward_workspace_init");
+}
+
 static int panoptic_forward_impl(
     const float *logits, const float *heat, const float *offset, const float *orientation, int B,
     int C, int H, int W, const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
@@ -66,7 +125,6 @@ static int panoptic_forward_impl(
         return NPB_ERR_ARG;
     if (C < 1 || C > 255) return NPB_ERR_ARG;
     if (orientation && (!inst_angle || !h_orientation_lut)) return NPB_ERR_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
     char *ws = (char *)workspace;
     void *ws_centers = ws;
     ws += align256(npb_instance_centers_workspace_bytes(B, H, W, nms_kernel_size));
@@ -74,15 +132,21 @@ static int panoptic_forward_impl(
     ws += align256((size_t)B * kMaxInst * C * sizeof(uint32_t));
     double *ori_sum = orientation ? (double *)ws : nullptr;
 
-    // ONE memset for the scratch of all stages: the candidate counters are the last block of the
-    // centres workspace, the vote histograms and orientation sums follow it; the status words
-    // are started by the centre selection (their only writer in this chain)
-    {
-        const size_t cnt_block = align256((size_t)B * sizeof(int32_t));
-        char *first = (char *)vote_hist - cnt_block;
-        const size_t bytes = cnt_block + align256((size_t)B * kMaxInst * C * sizeof(uint32_t)) +
-                             (orientation ? (size_t)B * kMaxInst * 2 * sizeof(double) : 0);
-        cudaMemsetAsync(first, 0, bytes, s);
+    // No memset in the chain: the counters of the centre detection are left at zero by every
+    // call (npb_panoptic_forward_workspace_init zeroes them once), the vote histograms /
+    // orientation sums and the cleared part of the evaluation workspace are zeroed by the NMS
+    // pass itself -- nothing reads or writes them before that grid has completed.  Every kernel
+    // of the chain is launched as a programmatic dependent of its predecessor (common.cuh).
+    ScratchToClear scratch;
+    scratch.p0 = vote_hist;
+    scratch.bytes0 = align256((size_t)B * kMaxInst * C * sizeof(uint32_t)) +
+                     (orientation ? (size_t)B * kMaxInst * 2 * sizeof(double) : 0);
+    scratch.p1 = nullptr;
+    scratch.bytes1 = 0;
+    if (eval) {
+        if (!eval->workspace) return NPB_ERR_ARG;
+        pq_cleared_range(eval->workspace, B, eval->num_categories, max_instances_per_category,
+                         &scratch.p1, &scratch.bytes1);
     }
     int rc;
     const uint8_t *fg = nullptr;
@@ -101,21 +165,28 @@ static int panoptic_forward_impl(
     }
     rc = instance_centers_impl(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
                                ws_centers, centers_yx, n_centers, center_score, status, true, true,
-                               stream);
+                               &scratch, stream);
     if (rc != NPB_OK) return rc;
     rc = group_pixels_impl(group_logits, group_sem, nullptr, offset, orientation, B, C, H, W,
                            h_thing_lut, centers_yx, n_centers, normalized_offset,
                            use_distance_threshold, distance_threshold, sem_out, inst_out, vote_hist,
                            ori_sum, true, stream);
     if (rc != NPB_OK) return rc;
+    if (eval) {     // instance tables, ids written and evaluated in one pass
+        FinalizeParams f;
+        f.vote_hist = vote_hist; f.ori_sum = ori_sum; f.n_centers = n_centers; f.C = C;
+        f.class_offset = 1; f.L = (long long)max_instances_per_category; f.void_label = 0;
+        f.orient = orientation_class_set(h_orientation_lut, C, 1);
+        f.inst_class = inst_class; f.inst_pan_id = inst_pan_id; f.inst_area = inst_area;
+        f.inst_angle = inst_angle;
+        return write_panoptic_eval_impl(sem_out, inst_out, inst_pan_id, inst_class, B, C, H, W,
+                                        h_thing_lut, max_instances_per_category, pan_out,
+                                        pan_sem_out, eval, &f, true, stream);
+    }
     rc = npb_finalize_instances(vote_hist, ori_sum, n_centers, B, C, 1, max_instances_per_category,
                                 0, h_orientation_lut, inst_class, inst_pan_id, inst_area,
                                 inst_angle, stream);
     if (rc != NPB_OK) return rc;
-    if (eval)       // ids written and evaluated in one pass
-        return npb_write_panoptic_eval(sem_out, inst_out, inst_pan_id, inst_class, B, C, H, W,
-                                       h_thing_lut, max_instances_per_category, pan_out, pan_sem_out,
-                                       eval, stream);
     return npb_write_panoptic(sem_out, inst_out, inst_pan_id, inst_class, B, C, H, W, h_thing_lut,
                               max_instances_per_category, pan_out, pan_sem_out, stream);
 }

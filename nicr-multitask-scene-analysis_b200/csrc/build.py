@@ -28,17 +28,25 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """`defines` / `out`: instrumented variants of the same ABI for measurements and debugging
+    (loaded through NPB_LIB_PATH), e.g. build(force=True, defines=('NPB_TIMELINE',),
+    out='build/timeline/libnicr_panoptic_b200.so')."""
+    if not force and out == LIB and not is_stale():
         return LIB
+    os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     cmd = [NVCC, '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
            '-shared', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'), '-I', HERE]
+    cmd += ['-D' + d for d in defines]
     if verbose:
         cmd += ['-Xptxas', '-v']
-    cmd += sources() + ['-o', LIB]
+    cmd += sources() + ['-o', out]
     subprocess.run(cmd, check=True)
-    return LIB
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith('-D'))
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith('--out=')]
+    print(build(force='--force' in sys.argv or bool(defs), verbose='-v' in sys.argv, defines=defs,
+                out=outs[0] if outs else LIB))

@@ -13,10 +13,13 @@
 // Only survivors with value >= 0 can ever be selected, so only those are materialised
 // ("candidates"); everything else is equivalent to the -1 fill.
 //
-// Kernel 1 (nms_candidates_kernel): shared-memory halo tiles (8 x 128 pixels + halo per CTA,
-//   a warp per tile row), whole-tile early out, warp-aggregated append of the survivors.
-// Kernel 2 (select_centers_kernel): one CTA per frame, exact radix select of the k-th
-//   largest value over the candidate list, compaction, rank sort by pixel index.
+// NMS pass (nms_candidates_kernel for k >= 5: shared-memory halo tiles of 8 x 128 pixels + halo
+//   per CTA, a warp per tile row, whole-tile early out, warp-aggregated append of the survivors;
+//   nms_candidates_direct_kernel for k <= 3).
+// Selection (select_centers_frame): exact radix select of the k-th largest value over the
+//   candidate list of a frame, compaction, rank sort by pixel index.  It runs in the LAST CTA of
+//   the NMS pass that finishes the frame (fence + per-frame counter): the candidate list is a
+//   few dozen entries, a kernel of its own would cost a launch and one CTA per frame of latency.
 #include "common.cuh"
 
 namespace npb {
@@ -24,13 +27,154 @@ namespace npb {
 constexpr int kTileW = 128;   // one warp covers one tile row, 4 consecutive pixels per lane
 constexpr int kTileH = 8;
 constexpr int kNmsThreads = 256;
-constexpr int kSelThreads = 1024;
+
+struct SelectParams {
+    const uint2 *cand;          // [B][cap] (value bits, flat pixel index), written by the NMS pass
+    int cap;
+    int32_t *cand_cnt;          // [B]
+    int32_t *done_cnt;          // [B] CTAs of the NMS pass that finished the frame
+    const float *heat;
+    const uint8_t *fg;          // nullable
+    int H, W, top_k;
+    int32_t *centers_yx;
+    int32_t *n_centers;
+    float *center_score;
+    int32_t *status;
+    int reset_status;
+    // scratch of the LATER stages of the chain, zeroed here by all CTAs (nothing touches it
+    // before this grid has completed): no memset node between the kernels of a step
+    uint32_t *clear0, *clear1;
+    size_t clear0_words, clear1_words;
+    NPB_TL_FIELD
+};
+
+// every CTA of the NMS pass zeroes its share of the downstream scratch
+__device__ __forceinline__ void clear_downstream_scratch(const SelectParams &sp)
+{
+    if (!sp.clear0 && !sp.clear1) return;
+    const size_t total = (size_t)gridDim.x * gridDim.y * gridDim.z * blockDim.x;
+    const size_t gtid = (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) *
+                            blockDim.x + threadIdx.x;
+    for (size_t i = gtid; i < sp.clear0_words; i += total) sp.clear0[i] = 0u;
+    for (size_t i = gtid; i < sp.clear1_words; i += total) sp.clear1[i] = 0u;
+}
+
+// All NT threads of one CTA.  Candidates were written by other CTAs of the same grid: they are
+// read through L2 (__ldcg), after the caller's fence.
+template <int NT>
+__device__ void select_centers_frame(const SelectParams &sp, int b)
+{
+    static_assert(NT >= kMaxInst, "one thread per centre in the rank sort");
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_remaining;
+    __shared__ int s_n;
+    __shared__ unsigned s_idx[kMaxInst];
+
+    const int tid = threadIdx.x;
+    const int W = sp.W, cap = sp.cap, top_k = sp.top_k;
+    const size_t P = (size_t)sp.H * W;
+    const uint2 *cb = sp.cand + (size_t)b * cap;
+    // the selection is the only writer of the frame's status word in the forward chain: it may
+    // start it from NPB_OK itself (saves the chain a memset); thread 0 also does the first write
+    if (sp.reset_status && tid == 0) sp.status[b] = NPB_OK;
+    int S = __ldcg(sp.cand_cnt + b);
+    if (S > cap) {  // cannot happen (cap is the independent-set bound); be loud if it does
+        if (tid == 0) set_status(sp.status + b, NPB_ERR_CAPACITY);
+        S = cap;
+    }
+
+    // exact k-th largest candidate value: 4 passes of an 8-bit radix select on the f32 bits
+    // (all candidate values are >= +0.0, so the unsigned bit pattern is order preserving)
+    unsigned kth_bits = 0u;
+    if (S > top_k) {
+        unsigned prefix = 0u, mask = 0u;
+        if (tid == 0) s_remaining = (unsigned)top_k;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) hist[tid] = 0u;
+            __syncthreads();
+            for (int i = tid; i < S; i += NT) {
+                const unsigned bits = __ldcg(cb + i).x;
+                if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned rem = s_remaining;
+                int d = 255;
+                for (; d > 0; --d) {
+                    if (hist[d] >= rem) break;
+                    rem -= hist[d];
+                }
+                s_prefix = prefix | ((unsigned)d << shift);
+                s_remaining = rem;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            mask |= 0xFFu << shift;
+        }
+        kth_bits = prefix;
+    }
+
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const uint8_t *fgb = sp.fg ? sp.fg + (size_t)b * P : nullptr;
+    for (int i = tid; i < S; i += NT) {
+        const uint2 c = __ldcg(cb + i);
+        if (c.x >= kth_bits && (!fgb || fgb[c.y])) {
+            const int slot = atomicAdd(&s_n, 1);
+            if (slot < kMaxInst) s_idx[slot] = c.y;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    // the counters of the frame go back to zero: the next call on this workspace needs no memset
+    if (tid == 0) { sp.cand_cnt[b] = 0; sp.done_cnt[b] = 0; }
+    if (n > kMaxInst - 1) {
+        if (tid == 0) {
+            set_status(sp.status + b, NPB_ERR_TOO_MANY_CENTERS);
+            sp.n_centers[b] = 0;
+        }
+        return;
+    }
+    if (tid < n) {  // rank sort by flat pixel index = raster (y, x) order of nonzero()
+        const unsigned my = s_idx[tid];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (s_idx[j] < my);
+        const int y = (int)(my / (unsigned)W), x = (int)(my - (unsigned)y * (unsigned)W);
+        int32_t *o = sp.centers_yx + ((size_t)b * kMaxInst + rank) * 2;
+        o[0] = y;
+        o[1] = x;
+        sp.center_score[(size_t)b * kMaxInst + rank] = sp.heat[(size_t)b * P + my];
+    }
+    if (tid == 0) sp.n_centers[b] = n;
+}
+
+// End of an NMS CTA: publish its candidates, count the CTA; the CTA that completes the frame
+// selects the centres.  Every thread of the CTA must call it (barriers inside).
+template <int NT>
+__device__ __forceinline__ void nms_frame_epilogue(const SelectParams &sp, int b, int ctas_per_frame)
+{
+    __shared__ int s_last;
+    __threadfence();            // this thread's candidates are visible before the CTA is counted
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(sp.done_cnt + b, 1) == ctas_per_frame - 1);
+    __syncthreads();
+    NPB_TL(sp, 0, end);
+    if (!s_last) return;
+    __threadfence();
+    select_centers_frame<NT>(sp, b);
+    NPB_TL(sp, 0, end);
+}
 
 __global__ void __launch_bounds__(kNmsThreads)
 nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, int r,
-                      uint2 *__restrict__ cand, int cap, int32_t *__restrict__ cand_cnt)
+                      uint2 *cand, int cap, int32_t *cand_cnt, const SelectParams sp)
 {
     extern __shared__ float tile[];  // (kTileH + 2r) x (kTileW + 2r), thresholded heat + halo
+    NPB_TL(sp, 0, start);
+    grid_launch_dependents();
+    grid_dependency_wait();
+    NPB_TL(sp, 0, wait);
+    clear_downstream_scratch(sp);
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
     const int pitch = kTileW + 2 * r, rows = kTileH + 2 * r;
@@ -55,13 +199,13 @@ nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, i
         }
     }
     // most tiles of a real heat-map hold nothing above the threshold: nothing to do there
-    if (!__syncthreads_or(any)) return;
+    const bool tile_hot = __syncthreads_or(any);
 
     const int ty = warp;                 // kTileH == number of warps
     const int y = y0 + ty;
     const float *center_row = tile + (ty + r) * pitch + r;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 4 && tile_hot; ++j) {
         const int tx = lane * 4 + j;
         const int x = x0 + tx;
         bool surv = false;
@@ -101,6 +245,7 @@ nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, i
             }
         }
     }
+    nms_frame_epilogue<kNmsThreads>(sp, b, (int)(gridDim.x * gridDim.y));
 }
 
 // Direct variant for small windows (k <= 3, the default): 4 consecutive pixels per thread from
@@ -113,8 +258,13 @@ constexpr int kNmsGroups = 4;   // independent 128-bit loads per thread
 template <int VEC>
 __global__ void __launch_bounds__(256)
 nms_candidates_direct_kernel(const float *__restrict__ heat, int H, int W, float thr, int r,
-                             uint2 *__restrict__ cand, int cap, int32_t *__restrict__ cand_cnt)
+                             uint2 *cand, int cap, int32_t *cand_cnt, const SelectParams sp)
 {
+    NPB_TL(sp, 0, start);
+    grid_launch_dependents();
+    grid_dependency_wait();
+    NPB_TL(sp, 0, wait);
+    clear_downstream_scratch(sp);
     const int b = blockIdx.y;
     const int P = H * W;
     const int base = blockIdx.x * (256 * VEC * kNmsGroups) + threadIdx.x * VEC;
@@ -142,9 +292,8 @@ nms_candidates_direct_kernel(const float *__restrict__ heat, int H, int W, float
             v[u][j] = (v[u][j] > thr) ? v[u][j] : -1.0f;
             any |= (v[u][j] >= 0.0f);
         }
-    if (!any) return;
 #pragma unroll
-    for (int u = 0; u < kNmsGroups; ++u) {
+    for (int u = 0; u < kNmsGroups && any; ++u) {
         const int p0 = base + u * 256 * VEC;
         if (p0 >= P) continue;
         bool hot = false;
@@ -217,95 +366,7 @@ nms_candidates_direct_kernel(const float *__restrict__ heat, int H, int W, float
             if (++x == W) { x = 0; ++y; }
         }
     }
-}
-
-__global__ void __launch_bounds__(kSelThreads)
-select_centers_kernel(const uint2 *__restrict__ cand, int cap,
-                      const int32_t *__restrict__ cand_cnt, const float *__restrict__ heat,
-                      const uint8_t *__restrict__ fg, int H, int W, int top_k,
-                      int32_t *__restrict__ centers_yx, int32_t *__restrict__ n_centers,
-                      float *__restrict__ center_score, int32_t *__restrict__ status,
-                      int reset_status)
-{
-    __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix, s_remaining;
-    __shared__ int s_n;
-    __shared__ unsigned s_idx[kMaxInst];
-
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x;
-    const size_t P = (size_t)H * W;
-    const uint2 *cb = cand + (size_t)b * cap;
-    // this kernel is the only writer of the frame's status word in the forward chain: it may
-    // start it from NPB_OK itself (saves the chain a memset); thread 0 also does the first write
-    if (reset_status && tid == 0) status[b] = NPB_OK;
-    int S = cand_cnt[b];
-    if (S > cap) {  // cannot happen (cap is the independent-set bound); be loud if it does
-        if (tid == 0) set_status(status + b, NPB_ERR_CAPACITY);
-        S = cap;
-    }
-
-    // exact k-th largest candidate value: 4 passes of an 8-bit radix select on the f32 bits
-    // (all candidate values are >= +0.0, so the unsigned bit pattern is order preserving)
-    unsigned kth_bits = 0u;
-    if (S > top_k) {
-        unsigned prefix = 0u, mask = 0u;
-        if (tid == 0) s_remaining = (unsigned)top_k;
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            if (tid < 256) hist[tid] = 0u;
-            __syncthreads();
-            for (int i = tid; i < S; i += kSelThreads) {
-                const unsigned bits = cb[i].x;
-                if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned rem = s_remaining;
-                int d = 255;
-                for (; d > 0; --d) {
-                    if (hist[d] >= rem) break;
-                    rem -= hist[d];
-                }
-                s_prefix = prefix | ((unsigned)d << shift);
-                s_remaining = rem;
-            }
-            __syncthreads();
-            prefix = s_prefix;
-            mask |= 0xFFu << shift;
-        }
-        kth_bits = prefix;
-    }
-
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-    const uint8_t *fgb = fg ? fg + (size_t)b * P : nullptr;
-    for (int i = tid; i < S; i += kSelThreads) {
-        const uint2 c = cb[i];
-        if (c.x >= kth_bits && (!fgb || fgb[c.y])) {
-            const int slot = atomicAdd(&s_n, 1);
-            if (slot < kMaxInst) s_idx[slot] = c.y;
-        }
-    }
-    __syncthreads();
-    const int n = s_n;
-    if (n > kMaxInst - 1) {
-        if (tid == 0) {
-            set_status(status + b, NPB_ERR_TOO_MANY_CENTERS);
-            n_centers[b] = 0;
-        }
-        return;
-    }
-    if (tid < n) {  // rank sort by flat pixel index = raster (y, x) order of nonzero()
-        const unsigned my = s_idx[tid];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) rank += (s_idx[j] < my);
-        const int y = (int)(my / (unsigned)W), x = (int)(my - (unsigned)y * (unsigned)W);
-        int32_t *o = centers_yx + ((size_t)b * kMaxInst + rank) * 2;
-        o[0] = y;
-        o[1] = x;
-        center_score[(size_t)b * kMaxInst + rank] = heat[(size_t)b * P + my];
-    }
-    if (tid == 0) n_centers[b] = n;
+    nms_frame_epilogue<256>(sp, b, (int)gridDim.x);
 }
 
 static int cand_capacity(int H, int W, int ks)
@@ -323,18 +384,21 @@ extern "C" size_t npb_instance_centers_workspace_bytes(int B, int H, int W, int 
     const size_t cap = (size_t)cand_capacity(H, W, nms_kernel_size);
     size_t bytes = (size_t)B * cap * sizeof(uint2);
     bytes = (bytes + 255) & ~(size_t)255;
-    bytes += ((size_t)B * sizeof(int32_t) + 255) & ~(size_t)255;
+    bytes += npb::centers_counter_bytes(B);
     return bytes;
 }
 
-// internal form: `cleared` = the caller has already zeroed the candidate counters (they are
-// the last 256-byte aligned block of the workspace); `reset_status` = status starts at NPB_OK
+// internal form: `cleared` = the counters (candidates per frame, finished CTAs per frame: the
+// last centers_counter_bytes(B) of the workspace) are zero -- every call leaves them at zero, so
+// a workspace that was zeroed once stays usable without a memset; `reset_status` = status starts
+// at NPB_OK; `downstream` = scratch of later stages that the NMS pass zeroes on the way
 int npb::instance_centers_impl(const float *heat, int B, int H, int W, float threshold,
                                int nms_kernel_size, int top_k, const uint8_t *fg, int apply_fg_mask,
                                void *workspace, int32_t *centers_yx, int32_t *n_centers,
                                float *center_score, int32_t *status, bool cleared,
-                               bool reset_status, void *stream)
+                               bool reset_status, const ScratchToClear *downstream, void *stream)
 {
+    static_assert(kNmsThreads >= kMaxInst, "the selection needs one thread per centre");
     if (!heat || !workspace || !centers_yx || !n_centers || !center_score || !status)
         return NPB_ERR_ARG;
     if (B < 1 || B > 65535 || H < 1 || W < 1 || (nms_kernel_size & 1) == 0 || nms_kernel_size < 1 ||
@@ -350,30 +414,39 @@ int npb::instance_centers_impl(const float *heat, int B, int H, int W, float thr
     size_t off = ((size_t)B * cap * sizeof(uint2) + 255) & ~(size_t)255;
     int32_t *cand_cnt = (int32_t *)((char *)workspace + off);
 
-    if (!cleared) cudaMemsetAsync(cand_cnt, 0, (size_t)B * sizeof(int32_t), s);
+    int32_t *done_cnt = cand_cnt + B;
+    if (!cleared) cudaMemsetAsync(cand_cnt, 0, 2 * (size_t)B * sizeof(int32_t), s);
+    SelectParams sp;
+    sp.cand = cand; sp.cap = cap; sp.cand_cnt = cand_cnt; sp.done_cnt = done_cnt; sp.heat = heat;
+    sp.fg = apply_fg_mask ? fg : nullptr; sp.H = H; sp.W = W; sp.top_k = top_k;
+    sp.centers_yx = centers_yx; sp.n_centers = n_centers; sp.center_score = center_score;
+    sp.status = status; sp.reset_status = reset_status ? 1 : 0;
+    sp.clear0 = sp.clear1 = nullptr;
+    sp.clear0_words = sp.clear1_words = 0;
+    if (downstream) {
+        sp.clear0 = (uint32_t *)downstream->p0; sp.clear0_words = downstream->bytes0 / 4;
+        sp.clear1 = (uint32_t *)downstream->p1; sp.clear1_words = downstream->bytes1 / 4;
+    }
+    NPB_TL_SET(sp);
     if (nms_kernel_size <= 3) {
         // small window: per-pixel early out beats staging tiles (see kernel comment)
         const int P = H * W;
         if (P % 4 == 0 && W >= 4 && ((uintptr_t)heat & 15u) == 0) {
             dim3 grid((P / 4 + 256 * kNmsGroups - 1) / (256 * kNmsGroups), B);
-            nms_candidates_direct_kernel<4><<<grid, 256, 0, s>>>(heat, H, W, threshold, r, cand,
-                                                                 cap, cand_cnt);
+            launch_dependent(nms_candidates_direct_kernel<4>, grid, dim3(256), 0, s, heat, H, W,
+                             threshold, r, cand, cap, cand_cnt, sp);
         } else {
             dim3 grid((P + 256 * kNmsGroups - 1) / (256 * kNmsGroups), B);
-            nms_candidates_direct_kernel<1><<<grid, 256, 0, s>>>(heat, H, W, threshold, r, cand,
-                                                                 cap, cand_cnt);
+            launch_dependent(nms_candidates_direct_kernel<1>, grid, dim3(256), 0, s, heat, H, W,
+                             threshold, r, cand, cap, cand_cnt, sp);
         }
     } else {
         // large window: shared-memory halo tiles bound the cost per pixel
         dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, B);
         const size_t smem = (size_t)(kTileH + 2 * r) * (kTileW + 2 * r) * sizeof(float);
-        nms_candidates_kernel<<<grid, kNmsThreads, smem, s>>>(heat, H, W, threshold, r, cand, cap,
-                                                              cand_cnt);
+        launch_dependent(nms_candidates_kernel, grid, dim3(kNmsThreads), smem, s, heat, H, W,
+                         threshold, r, cand, cap, cand_cnt, sp);
     }
-    select_centers_kernel<<<B, kSelThreads, 0, s>>>(cand, cap, cand_cnt, heat,
-                                                    apply_fg_mask ? fg : nullptr, H, W, top_k,
-                                                    centers_yx, n_centers, center_score, status,
-                                                    reset_status ? 1 : 0);
     return record_launch("npb_instance_centers");
 }
 
@@ -385,5 +458,5 @@ extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, floa
 {
     return instance_centers_impl(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
                                  workspace, centers_yx, n_centers, center_score, status, false,
-                                 false, stream);
+                                 false, nullptr, stream);
 }

@@ -21,11 +21,12 @@
 // accumulate_frames_kernel adds the frames to the running state in frame order.  Both float64
 // orders equal the reference's, so the states are bit-identical, not merely close.
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <mutex>
 
-#include "common.cuh"
+#include "finalize.cuh"
 
 namespace npb {
 
@@ -101,6 +102,8 @@ struct PairParams {
     const uint8_t *sem_map;     // (B,P) network class per pixel
     const uint8_t *inst_map;    // (B,P) raw instance id per pixel
     const long long *inst_pan_id;   // [B][kMaxInst] panoptic id of every instance
+    int fold_finalize;          // the instance tables are derived here from the vote histograms
+    FinalizeParams fin;         //   (finalize.cuh), CTA 0 of every frame stores them
     ClassSet thing;
     long long *pan_out;         // (B,P)
     uint8_t *pan_sem_out;       // (B,P) nullable
@@ -119,6 +122,7 @@ struct PairParams {
     unsigned *frame_dense;           // [B][nd][nd] class-pair pixels of the frame, zeroed before the launch
     unsigned long long *confmat;     // [n][n] int64, accumulated
     int32_t *status;                 // [B]
+    NPB_TL_FIELD
 };
 
 // Shared-memory state of one CTA of the pixel pass.
@@ -248,10 +252,11 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     // pixel without instance stays void, panoptic_merge.py:213-224)
     __shared__ unsigned s_pan32[FUSED ? kMaxInst : 1];
     __shared__ unsigned s_stuff[FUSED ? 256 : 1];
+    __shared__ int s_fin_cls[FUSED ? kMaxInst : 1];
     static_assert(!FUSED || kPairThreads == kMaxInst, "one table entry per thread");
-    // issued first, stored after the tables below have been cleared: the clearing hides its latency
-    unsigned my_pan32 = 0u;
-    if (FUSED) my_pan32 = (unsigned)prm.inst_pan_id[(size_t)blockIdx.y * kMaxInst + threadIdx.x];
+    NPB_TL(prm, 2, start);
+    grid_launch_dependents();       // the matcher: its CTAs need a whole SM each, they only move in
+                                    // where this grid has left
     extern __shared__ unsigned long long s_dyn[];
     PairTables t;
     t.keys = s_dyn;                                           // [kSmemSlots]
@@ -271,8 +276,17 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     for (int i = tid; i < nd * nd; i += kPairThreads) t.dense[i] = 0;
     if (cm_smem)
         for (int i = tid; i < n * n; i += kPairThreads) t.cm[i] = 0;
+    // everything above touched shared memory only: it overlaps the tail of the predecessor
+    grid_dependency_wait();
+    NPB_TL(prm, 2, wait);
     if (FUSED) {
-        s_pan32[tid] = my_pan32;
+        // panoptic id of every instance of the frame: from the table, or derived right here from
+        // the vote histograms of the grouping kernel (every CTA of the frame repeats the few
+        // hundred loads; CTA 0 stores the tables) -- no finalize launch in between
+        const long long pan = prm.fold_finalize
+                                  ? finalize_frame(prm.fin, b, tid, s_fin_cls, blockIdx.x == 0)
+                                  : prm.inst_pan_id[(size_t)b * kMaxInst + tid];
+        s_pan32[tid] = (unsigned)pan;
         s_stuff[tid] = prm.thing.has(tid) ? 0u : ((unsigned)tid + 1u) << 16;
     }
     __syncthreads();
@@ -280,6 +294,11 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     const long long P = prm.P;
     const long long chunk = (long long)kPairThreads * VEC;
     const long long n_chunks = (P + chunk - 1) / chunk;
+    // every CTA takes a CONTIGUOUS range of chunks (a band of rows): a segment then shows up in
+    // the tables of the few CTAs whose band it crosses instead of in all of them -- fewer entries
+    // per CTA table and far fewer duplicates for the matcher to merge
+    const long long ch_begin = n_chunks * blockIdx.x / gridDim.x;
+    const long long ch_end = n_chunks * (blockIdx.x + 1) / gridDim.x;
     const unsigned lt_mask = (1u << lane) - 1u;
     int q_len = 0;      // warp-uniform
 
@@ -289,8 +308,9 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
         // st << 16, one PRMT each; valid when 0 <= pred, target < 2^24, which one OR over the
         // lane's words checks.  Comparing / MATCHing the 64-bit entry decides "same pair and
         // same confusion cell" at once.
-        const long long stride = (long long)gridDim.x * chunk;
-        long long q_next = (long long)blockIdx.x * chunk + (long long)tid * 4;   // next pixel to fetch
+        const long long stride = chunk;
+        const long long q_end = ch_end * chunk < P ? ch_end * chunk : P;
+        long long q_next = ch_begin * chunk + (long long)tid * 4;   // next pixel to fetch
         const long long *pred_b = FUSED ? nullptr : prm.pred + (size_t)b * P;
         const long long *target_b = prm.target + (size_t)b * P;
         const uint8_t *sem_b = CONFMAT ? prm.sem_target + (size_t)b * P : nullptr;
@@ -305,7 +325,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             n_p0 = n_p1 = n_t0 = n_t1 = make_uint4(0u, 0u, 0u, 0u);
             n_sw = 0u;
             n_cw = n_iw = 0u;
-            if (q_next < P) {
+            if (q_next < q_end) {
                 if (FUSED) {
                     // class / instance maps were written by the grouping kernel just before: L2
                     n_cw = *(const unsigned *)(csem_b + q_next);
@@ -321,7 +341,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             q_next += stride;
         };
         fetch();
-        for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        for (long long ch = ch_begin; ch < ch_end; ++ch) {
             bool act = q_next - stride < P;
             const unsigned sw = n_sw;
             if (FUSED) {
@@ -455,7 +475,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     #pragma unroll
             for (int j = 0; j < VEC; ++j) { n_pv[j] = 0; n_tv[j] = 0; }
             n_sw = 0;
-            if (ch < n_chunks && q0 < P) {
+            if (ch < ch_end && q0 < P) {
                 const size_t fq = (size_t)b * P + q0;
                 if (VEC == 4) {
                     const longlong2 a0 = __ldcs((const longlong2 *)(prm.pred + fq));
@@ -472,9 +492,9 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
                 }
             }
         };
-        fetch(blockIdx.x);
+        fetch(ch_begin);
 
-        for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        for (long long ch = ch_begin; ch < ch_end; ++ch) {
             const long long p0 = ch * chunk + (long long)tid * VEC;
             const bool act = p0 < P;    // P % VEC == 0 guaranteed by the launcher
             unsigned long long key[VEC];
@@ -482,7 +502,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             long long pv[VEC], tv[VEC];
     #pragma unroll
             for (int j = 0; j < VEC; ++j) { key[j] = 0; pv[j] = n_pv[j]; tv[j] = n_tv[j]; }
-            fetch(ch + gridDim.x);
+            fetch(ch + 1);
             if (act) {
                 // ids must satisfy 0 <= pred < offset, 0 <= target (checked on the OR of the lane)
                 long long any_neg = 0;
@@ -621,6 +641,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     if (cm_smem)
         for (int i = tid; i < n * n; i += kPairThreads)
             if (t.cm[i]) atomicAdd(prm.confmat + i, (unsigned long long)t.cm[i]);
+    NPB_TL(prm, 2, end);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -635,10 +656,13 @@ struct MatchParams {
     long long ignored_label, L, offset, void_segment_id;
     int L_shift, O_shift;  // >= 0 when L / offset are powers of two (shifts instead of 64-bit divisions)
     double *frame_stats;   // [B][4][num_categories]
+    unsigned *done_cnt;    // frames matched so far (zeroed before the launch); null: no accumulation
+    double *iou, *tp, *fn, *fp;     // running state [num_categories]
     long long *matches;    // [B][match_cap][2] nullable
     int match_cap;
     int32_t *n_matches;    // [B] nullable
     int32_t *status;       // [B]
+    NPB_TL_FIELD
 };
 
 // ---- matcher: one CTA per frame ------------------------------------------------------------
@@ -651,6 +675,12 @@ struct MatchParams {
 constexpr int kPairSlots = 2 * kMaxPairs;   // pair table of the matcher (load factor <= 0.5)
 constexpr int kSegSlots = 2048;       // distinct gt (and pred) segments per frame: <= 1536
 constexpr int kMaxMatched = 1024;
+
+__host__ __device__ constexpr size_t match_smem_bytes()
+{
+    return (size_t)kPairSlots * (8 + 4 + 2 + 2) + (size_t)kMaxMatched * (8 + 4 + 4 + 2) +
+           (size_t)kMaxPairs * 2 + (size_t)kSegSlots * (8 + 8 + 4 * 4 + 2) + 16;
+}
 
 // SlotT: index type of segment slots / pair slots (uint16 in shared memory, uint32 in the
 // global-memory fall-back)
@@ -735,6 +765,7 @@ __device__ void match_phases(const MatchParams &prm, int b, const MatchTables<Sl
         if (div_pow2(g, prm.L, prm.L_shift) == prm.ignored_label) atomicAdd(T.p_pio + ps, cnt);
     }
     __syncthreads();
+    NPB_TL(prm, 7, wait);
 
     // (2) IoU + match decision per intersecting pair                       pq.py:119-152
     for (int i = tid; i < n_walk; i += nthreads) {
@@ -777,6 +808,7 @@ __device__ void match_phases(const MatchParams &prm, int b, const MatchTables<Sl
         }
     }
     __syncthreads();
+    NPB_TL(prm, 8, wait);
 
     // (3) false negatives: unmatched gt segments outside the ignored label    pq.py:155-163
     //     false positives: unmatched pred segments, unless more than half of their area lies
@@ -815,6 +847,7 @@ __device__ void match_phases(const MatchParams &prm, int b, const MatchTables<Sl
     __syncthreads();
     // a frame beyond the capacities reports it and contributes nothing: the caller may evaluate
     // it again with npb_pq_update_big_frame
+    NPB_TL(prm, 9, wait);
     const bool failed = C.fail != 0 || prm.status[b] == NPB_ERR_CAPACITY;
     if (failed && tid == 0) set_status(prm.status + b, NPB_ERR_CAPACITY);
     for (int c = tid; c < NC; c += nthreads) {
@@ -832,7 +865,7 @@ __device__ void match_phases(const MatchParams &prm, int b, const MatchTables<Sl
         prm.n_matches[b] = failed ? 0 : (C.nm < prm.match_cap ? C.nm : prm.match_cap);
 }
 
-__global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const MatchParams prm)
+__global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const MatchParams prm)
 {
     extern __shared__ unsigned char smem_raw[];
     // pair table of the frame
@@ -858,6 +891,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     __shared__ MatchCounters C;
 
     const int b = blockIdx.x, tid = threadIdx.x;
+    NPB_TL(prm, 3, start);
     if (tid == 0) { s_m = 0; C.nm = 0; C.fail = 0; }
     for (int c = tid; c < 256; c += kMatchThreads) { C.tp[c] = 0; C.fn[c] = 0; C.fp[c] = 0; }
     for (int i = tid; i < kPairSlots; i += kMatchThreads) { t_key[i] = kEmptyKey; t_cnt[i] = 0; }
@@ -866,6 +900,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         g_area[i] = 0; g_matched[i] = 0; p_area[i] = 0; p_void[i] = 0; p_pio[i] = 0; p_matched[i] = 0;
     }
     grid_dependency_wait();       // the pixel pass (launch_dependent: the set-up above overlaps its tail)
+    NPB_TL(prm, 3, wait);
     __syncthreads();
 
     // (0) the frame's pairs -> pair table.  Every used slot is remembered in s_idx, so the later
@@ -890,6 +925,9 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         }
         C.fail = 1;
     };
+    // entries of the frame (loaded first: the dense part below hides the latency)
+    const unsigned n_raw = prm.entry_n[b];
+    const unsigned n_ent = n_raw < prm.entry_cap ? n_raw : prm.entry_cap;   // overflow: flagged by the writer
     // class pairs: dense per-frame table, every pair exactly once (independent loads first)
     if (prm.frame_dense) {
         const int nd = prm.nd, nd2 = nd * nd;
@@ -911,10 +949,9 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
             }
         }
     }
+    NPB_TL(prm, 5, wait);
     // instance pairs: the entry list (one entry per pair and CTA of the pixel pass)
     {
-        const unsigned n_raw = prm.entry_n[b];
-        const unsigned n_ent = n_raw < prm.entry_cap ? n_raw : prm.entry_cap;   // overflow: flagged by the writer
         const unsigned long long *ekeys = prm.entry_keys + (size_t)b * prm.entry_cap;
         const unsigned *ecnts = prm.entry_cnts + (size_t)b * prm.entry_cap;
         constexpr int kBatch = 4;
@@ -933,6 +970,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
         }
     }
     __syncthreads();
+    NPB_TL(prm, 6, wait);       // pair table merged (slot 5 = dense part done)
     const int m = s_m < kMaxPairs ? s_m : kMaxPairs;
 
     MatchTables<unsigned short> T;
@@ -946,6 +984,42 @@ __global__ void __launch_bounds__(kMatchThreads) match_frames_kernel(const Match
     T.s_cat = (unsigned short *)((double *)t_gslot + kMaxMatched);
     T.max_matched = kMaxMatched;
     match_phases(prm, b, T, m, C);
+    NPB_TL(prm, 4, start);      // slot 4: the accumulation tail (start = matching done)
+
+    // state += frame results, frames in order (PanopticQuality.update, pq.py:298-303), by the CTA
+    // that finishes last: the results of `chunk` frames are staged in shared memory (coalesced,
+    // independent loads), then thread (statistic, category) adds them strictly in frame order --
+    // the float64 order of the reference.
+    if (!prm.done_cnt) return;
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(prm.done_cnt, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int NC = prm.num_categories, row = 4 * NC, B = (int)gridDim.x;
+    static_assert(kMatchThreads >= 4 * 256, "one thread per (statistic, category)");
+    double *buf = (double *)smem_raw;
+    const int chunk = (int)(match_smem_bytes() / sizeof(double)) / row;
+    double acc = 0.0;
+    double *dst = nullptr;
+    if (tid < row) {
+        const int stat = tid / NC, c = tid - stat * NC;
+        dst = (stat == 0 ? prm.iou : stat == 1 ? prm.tp : stat == 2 ? prm.fn : prm.fp) + c;
+        acc = *dst;
+    }
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = min(chunk, B - b0);
+        __syncthreads();
+        for (int i = tid; i < nb * row; i += kMatchThreads)
+            buf[i] = __ldcg(prm.frame_stats + (size_t)b0 * row + i);
+        __syncthreads();
+        if (tid < row)
+            for (int j = 0; j < nb; ++j) acc += buf[j * row + tid];
+    }
+    if (tid < row) *dst = acc;
+    NPB_TL(prm, 4, end);
 }
 
 // ---- fall-back for frames beyond the shared-memory capacities ---------------------------------
@@ -1006,7 +1080,7 @@ match_big_frame_kernel(const MatchParams prm, const MatchTables<unsigned> T)
 // independent), lane 0 then adds them strictly in frame order -- the float64 order of the
 // reference -- so the sequential part touches registers only.
 __global__ void __launch_bounds__(128)
-accumulate_frames_kernel(const double *__restrict__ frame_stats, int B, int NC,
+accumulate_frames_kernel(const double *frame_stats, int B, int NC,
                          double *iou, double *tp, double *fn, double *fp)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1230,12 +1304,6 @@ confmat_stream_kernel(const PT *__restrict__ preds, const TT *__restrict__ targe
         if (s_cm[i]) atomicAdd(confmat + i, (unsigned long long)s_cm[i]);
 }
 
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-static size_t match_smem_bytes()
-{
-    return (size_t)kPairSlots * (8 + 4 + 2 + 2) + (size_t)kMaxMatched * (8 + 4 + 4 + 2) +
-           (size_t)kMaxPairs * 2 + (size_t)kSegSlots * (8 + 8 + 4 * 4 + 2) + 16;
-}
 
 }  // namespace npb
 
@@ -1391,11 +1459,57 @@ static int pq_dense_side(int num_categories, int64_t max_instances_per_category)
     return (pow2 && num_categories <= kSmemConfmatMaxN) ? num_categories : 0;
 }
 
-// workspace: [entry_keys | entry_cnts | (entry_n | frame_dense: one memset) | frame_stats]
+// workspace: [entry_keys | entry_cnts | (entry_n, frames done | frame_dense: one memset) | frame_stats]
+static size_t pq_counter_bytes(int B) { return align256((size_t)(B + 1) * sizeof(unsigned)); }
 static size_t pq_cleared_bytes(int B)
 {
-    return align256((size_t)B * sizeof(unsigned)) +
+    return pq_counter_bytes(B) +
            align256((size_t)B * kSmemConfmatMaxN * kSmemConfmatMaxN * sizeof(unsigned));
+}
+
+struct PqWorkspace {
+    unsigned long long *ekeys;
+    unsigned *ecnts;
+    unsigned *en;           // [B] entries per frame, [B] = frames matched
+    unsigned *fdense;
+    double *fstats;
+    unsigned entry_cap;
+};
+
+static PqWorkspace pq_workspace(void *workspace, int B)
+{
+    PqWorkspace w;
+    w.entry_cap = pq_entry_cap(B);
+    char *ws = (char *)workspace;
+    w.ekeys = (unsigned long long *)ws;
+    ws += align256((size_t)B * w.entry_cap * sizeof(unsigned long long));
+    w.ecnts = (unsigned *)ws;
+    ws += align256((size_t)B * w.entry_cap * sizeof(unsigned));
+    w.en = (unsigned *)ws;
+    w.fdense = (unsigned *)(ws + pq_counter_bytes(B));
+    ws += pq_cleared_bytes(B);
+    w.fstats = (double *)ws;
+    return w;
+}
+
+// the one memset of an update (entry counters, frame counter, dense class-pair tables); the
+// forward chain issues it at its head so that no memset separates its kernels
+void npb::pq_cleared_range(void *workspace, int B, int num_categories,
+                           int64_t max_instances_per_category, void **p, size_t *bytes)
+{
+    const PqWorkspace w = pq_workspace(workspace, B);
+    const int nd = pq_dense_side(num_categories, max_instances_per_category);
+    *p = w.en;
+    *bytes = pq_counter_bytes(B) + (size_t)B * nd * nd * sizeof(unsigned);
+}
+
+void npb::pq_clear_workspace(void *workspace, int B, int num_categories,
+                             int64_t max_instances_per_category, void *stream)
+{
+    void *p;
+    size_t bytes;
+    pq_cleared_range(workspace, B, num_categories, max_instances_per_category, &p, &bytes);
+    cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream);
 }
 
 extern "C" size_t npb_pq_update_workspace_bytes(int B, int num_categories)
@@ -1415,6 +1529,7 @@ struct FusedWrite {
     ClassSet thing;
     int64_t *pan_out;
     uint8_t *pan_sem_out;
+    const FinalizeParams *fold;     // non-null: the pixel pass derives the instance tables itself
 };
 
 // the fused pixel pass exists for the reference's id geometry and 4-pixel alignment only
@@ -1433,7 +1548,7 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
                           int64_t void_segment_id, void *workspace, double *iou, double *tp,
                           double *fn, double *fp, int64_t *confmat, int confmat_n,
                           double *frame_stats, int64_t *matches, int match_cap,
-                          int32_t *n_matches, int32_t *status, void *stream)
+                          int32_t *n_matches, int32_t *status, bool cleared, void *stream)
 {
     if ((!pred && !fw) || !target || !workspace || !iou || !tp || !fn || !fp || !status) return NPB_ERR_ARG;
     if (B < 1 || B > 65535 || P < 1 || num_categories < 1 || num_categories > 256 ||
@@ -1444,29 +1559,27 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     if (matches && (match_cap < 1 || !n_matches)) return NPB_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
 
-    const unsigned entry_cap = pq_entry_cap(B);
-    char *ws = (char *)workspace;
-    unsigned long long *ekeys = (unsigned long long *)ws;
-    ws += align256((size_t)B * entry_cap * sizeof(unsigned long long));
-    unsigned *ecnts = (unsigned *)ws;
-    ws += align256((size_t)B * entry_cap * sizeof(unsigned));
-    unsigned *en = (unsigned *)ws;
-    unsigned *fdense = (unsigned *)(ws + align256((size_t)B * sizeof(unsigned)));
-    ws += pq_cleared_bytes(B);
-    double *fstats = frame_stats ? frame_stats : (double *)ws;
+    const PqWorkspace w = pq_workspace(workspace, B);
+    const unsigned entry_cap = w.entry_cap;
+    unsigned long long *ekeys = w.ekeys;
+    unsigned *ecnts = w.ecnts, *en = w.en, *fdense = w.fdense;
+    double *fstats = frame_stats ? frame_stats : w.fstats;
 
     const int nd = pq_dense_side(num_categories, max_instances_per_category);
-    cudaMemsetAsync(en, 0, align256((size_t)B * sizeof(unsigned)) + (size_t)B * nd * nd * sizeof(unsigned), s);
+    if (!cleared) pq_clear_workspace(workspace, B, num_categories, max_instances_per_category, stream);
 
-    PairParams pp;
+    PairParams pp = {};
     pp.pred = (const long long *)pred; pp.target = (const long long *)target;
     pp.sem_map = nullptr; pp.inst_map = nullptr; pp.inst_pan_id = nullptr;
     pp.pan_out = nullptr; pp.pan_sem_out = nullptr;
     for (int i = 0; i < 8; ++i) pp.thing.w[i] = 0;
+    pp.fold_finalize = 0;
+    memset(&pp.fin, 0, sizeof(pp.fin));
     if (fw) {
         pp.sem_map = fw->sem; pp.inst_map = fw->inst;
         pp.inst_pan_id = (const long long *)fw->inst_pan_id; pp.thing = fw->thing;
         pp.pan_out = (long long *)fw->pan_out; pp.pan_sem_out = fw->pan_sem_out;
+        if (fw->fold) { pp.fold_finalize = 1; pp.fin = *fw->fold; }
     }
     pp.sem_target = sem_target; pp.P = P; pp.offset = offset; pp.L = max_instances_per_category;
     pp.L_shift = -1;
@@ -1480,6 +1593,7 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     pp.frame_dense = nd > 0 ? fdense : nullptr;
     pp.entry_keys = ekeys; pp.entry_cnts = ecnts; pp.entry_n = en; pp.entry_cap = entry_cap;
     pp.confmat = (unsigned long long *)confmat; pp.status = status;
+    NPB_TL_SET(pp);
 
     const bool vec4 = fw != nullptr ||     // checked by fused_write_supported()
                       ((P % 4 == 0) && (((uintptr_t)pred | (uintptr_t)target) & 15u) == 0 &&
@@ -1540,6 +1654,7 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
         env_cap = e ? atoi(e) : 0;
     }
     cache_lock.unlock();
+    const int natural_per_sm = per_sm;
     if (env_cap > 0 && per_sm > env_cap) per_sm = env_cap;
     if (per_sm > kMaxPairCtasPerSm) per_sm = kMaxPairCtasPerSm;     // pq_entry_cap() assumes it
     // few frames: every CTA only gets a handful of chunks, so its fixed cost (table set-up, flush)
@@ -1549,9 +1664,18 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     if (bx < 1) bx = 1;
     if (bx > n_chunks) bx = n_chunks;
     dim3 grid((unsigned)bx, B);
-    kernel<<<grid, kPairThreads, pc_smem, s>>>(pp);
+    // The grid is one wave of `per_sm` CTAs per SM.  As a programmatic dependent its CTAs are
+    // placed while the predecessor drains, SM by SM: with room for more than `per_sm` of them the
+    // first free SMs would take four and others none.  Padding the dynamic shared memory makes
+    // `per_sm` the residency limit, so the wave spreads evenly whenever it is placed.
+    size_t launch_smem = pc_smem;
+    if (per_sm < natural_per_sm) {
+        const size_t pad = (size_t)(228 * 1024) / (size_t)(per_sm + 1);
+        if (pad > launch_smem) launch_smem = pad < (size_t)(200 * 1024) ? pad : (size_t)(200 * 1024);
+    }
+    launch_dependent(kernel, grid, dim3(kPairThreads), launch_smem, s, pp);
 
-    MatchParams mp;
+    MatchParams mp = {};
     mp.entry_keys = ekeys; mp.entry_cnts = ecnts; mp.entry_n = en; mp.entry_cap = entry_cap;
     mp.frame_dense = pp.frame_dense; mp.nd = nd;
     mp.num_categories = num_categories;
@@ -1560,9 +1684,9 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     mp.L_shift = pp.L_shift; mp.O_shift = pp.O_shift;
     mp.matches = (long long *)matches; mp.match_cap = match_cap; mp.n_matches = n_matches;
     mp.status = status;
+    mp.done_cnt = en + B; mp.iou = iou; mp.tp = tp; mp.fn = fn; mp.fp = fp;
+    NPB_TL_SET(mp);
     launch_dependent(match_frames_kernel, dim3(B), dim3(kMatchThreads), match_smem_bytes(), s, mp);
-    launch_dependent(accumulate_frames_kernel, dim3((4 * num_categories * 32 + 127) / 128), dim3(128), 0, s,
-                     (const double *)fstats, B, num_categories, iou, tp, fn, fp);
     return record_launch("npb_pq_update");
 }
 
@@ -1578,7 +1702,42 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     return pq_update_impl(pred, nullptr, target, sem_target, B, P, num_categories, ignored_label,
                           max_instances_per_category, offset, void_segment_id, workspace, iou, tp,
                           fn, fp, confmat, confmat_n, frame_stats, matches, match_cap, n_matches,
-                          status, stream);
+                          status, false, stream);
+}
+
+// `fold`: derive the instance tables from the vote histograms inside the fused pass (or, when
+// the fused pass does not apply, with the finalize kernel first); `cleared`: the caller has
+// issued pq_clear_workspace()
+int npb::write_panoptic_eval_impl(const uint8_t *sem, const uint8_t *inst, int64_t *inst_pan_id,
+                                  int32_t *inst_class, int B, int C, int H, int W,
+                                  const uint8_t *h_thing_lut, int64_t max_instances_per_category,
+                                  int64_t *pan_out, uint8_t *pan_sem_out, const npb_eval_args *ev,
+                                  const FinalizeParams *fold, bool cleared, void *stream)
+{
+    if (!sem || !inst || !inst_pan_id || !pan_out || !h_thing_lut || !ev) return NPB_ERR_ARG;
+    if (C < 1 || C > 255 || B < 1 || H < 1 || W < 1) return NPB_ERR_ARG;
+    const int64_t P = (int64_t)H * W;
+    FusedWrite fw{sem, inst, inst_pan_id, make_class_set(h_thing_lut, C), pan_out, pan_sem_out, fold};
+    if (fused_write_supported(P, max_instances_per_category, ev->offset, fw, ev->target,
+                              ev->sem_target))
+        return pq_update_impl(nullptr, &fw, ev->target, ev->sem_target, B, P, ev->num_categories,
+                              ev->ignored_label, max_instances_per_category, ev->offset,
+                              ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
+                              ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches,
+                              ev->match_cap, ev->n_matches, ev->status, cleared, stream);
+    // other id geometries / unaligned maps: the passes one after the other (same results)
+    if (fold) {
+        const int rc0 = launch_finalize(*fold, B, stream);
+        if (rc0 != NPB_OK) return rc0;
+    }
+    const int rc = npb_write_panoptic(sem, inst, inst_pan_id, inst_class, B, C, H, W, h_thing_lut,
+                                      max_instances_per_category, pan_out, pan_sem_out, stream);
+    if (rc != NPB_OK) return rc;
+    return pq_update_impl(pan_out, nullptr, ev->target, ev->sem_target, B, P, ev->num_categories,
+                          ev->ignored_label, max_instances_per_category, ev->offset,
+                          ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
+                          ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches, ev->match_cap,
+                          ev->n_matches, ev->status, cleared, stream);
 }
 
 extern "C" int npb_write_panoptic_eval(const uint8_t *sem, const uint8_t *inst,
@@ -1587,26 +1746,9 @@ extern "C" int npb_write_panoptic_eval(const uint8_t *sem, const uint8_t *inst,
                                        int64_t max_instances_per_category, int64_t *pan_out,
                                        uint8_t *pan_sem_out, const npb_eval_args *ev, void *stream)
 {
-    if (!sem || !inst || !inst_pan_id || !pan_out || !h_thing_lut || !ev) return NPB_ERR_ARG;
-    if (C < 1 || C > 255 || B < 1 || H < 1 || W < 1) return NPB_ERR_ARG;
-    const int64_t P = (int64_t)H * W;
-    FusedWrite fw{sem, inst, inst_pan_id, make_class_set(h_thing_lut, C), pan_out, pan_sem_out};
-    if (fused_write_supported(P, max_instances_per_category, ev->offset, fw, ev->target,
-                              ev->sem_target))
-        return pq_update_impl(nullptr, &fw, ev->target, ev->sem_target, B, P, ev->num_categories,
-                              ev->ignored_label, max_instances_per_category, ev->offset,
-                              ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
-                              ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches,
-                              ev->match_cap, ev->n_matches, ev->status, stream);
-    // other id geometries / unaligned maps: the two passes one after the other (same results)
-    const int rc = npb_write_panoptic(sem, inst, inst_pan_id, inst_class, B, C, H, W, h_thing_lut,
-                                      max_instances_per_category, pan_out, pan_sem_out, stream);
-    if (rc != NPB_OK) return rc;
-    return pq_update_impl(pan_out, nullptr, ev->target, ev->sem_target, B, P, ev->num_categories,
-                          ev->ignored_label, max_instances_per_category, ev->offset,
-                          ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
-                          ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches, ev->match_cap,
-                          ev->n_matches, ev->status, stream);
+    return write_panoptic_eval_impl(sem, inst, (int64_t *)inst_pan_id, (int32_t *)inst_class, B, C,
+                                    H, W, h_thing_lut, max_instances_per_category, pan_out,
+                                    pan_sem_out, ev, nullptr, false, stream);
 }
 
 // ---- fall-back entry point -----------------------------------------------------------------------
@@ -1691,7 +1833,7 @@ extern "C" int npb_pq_update_big_frame(const int64_t *pred, const int64_t *targe
     BigParams bp;
     bp.pred = (const long long *)pred; bp.target = (const long long *)target;
     bp.P = P; bp.offset = offset; bp.O_shift = -1;
-    MatchParams mp;
+    MatchParams mp = {};
     mp.L_shift = -1; mp.O_shift = -1;
     for (int sh = 0; sh < 62; ++sh) {
         if ((1ll << sh) == max_instances_per_category) mp.L_shift = sh;

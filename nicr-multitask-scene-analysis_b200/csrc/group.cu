@@ -47,6 +47,7 @@ struct GroupParams {
     int normalized, use_thr;
     float dist_thr;
     ClassSet thing;
+    NPB_TL_FIELD
 };
 
 template <int VEC>
@@ -100,23 +101,25 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
     // thing flag per class: one LDS.U8 per pixel instead of an indexed constant load + shifts
     __shared__ unsigned char s_thing[256];
     static_assert(kGroupThreads == 256, "one class flag per thread");
+    NPB_TL(prm, 1, start);
+    // the successor (id writer / evaluation pixel pass) is staged while the last wave of this grid
+    // runs; its residency is limited by its (padded) shared memory, so its one wave of CTAs
+    // spreads evenly however early it is placed
+    grid_launch_dependents();
     s_thing[threadIdx.x] = prm.thing.has((int)threadIdx.x) ? 1 : 0;
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int P = prm.P, W = prm.W, C = prm.C;
-    const int n = prm.n_centers[b];
-    for (int i = tid; i < n; i += kGroupThreads) {
-        const int32_t *c = prm.centers_yx + ((size_t)b * kMaxInst + i) * 2;
-        const float cy = (float)c[0], cx = (float)c[1];
-        s_centers[i] = make_float4(cy, cy, cx, cx);
-    }
-    __syncthreads();
 
     const int p0 = (blockIdx.x * kGroupThreads + tid) * VEC;
     const bool active = p0 < P;  // P % VEC == 0 is guaranteed by the launcher
     const size_t fb = (size_t)b * P + p0;
+    // The arg-max over the logits (most of this kernel's bytes) depends on nothing the chain
+    // produces: with a programmatic launch it runs while the centre detection is still busy.
+    // Class / foreground maps of the other modes come from kernels of the chain: wait first.
+    if (MODE != kFromLogits) grid_dependency_wait();
 
     // ---- 1. semantic class ------------------------------------------------------------
     int cls[VEC];
@@ -176,10 +179,21 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
             PixVec<VEC>::loadb(prm.fg_in + fb, m);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) fg[j] = (m[j] != 0);
-        } else {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) fg[j] = s_thing[cls[j] & 255] != 0;
         }
+    }
+    // centres of the frame (the centre detection has completed after this wait)
+    if (MODE == kFromLogits) grid_dependency_wait();
+    NPB_TL(prm, 1, wait);
+    const int n = prm.n_centers[b];
+    for (int i = tid; i < n; i += kGroupThreads) {
+        const int32_t *c = prm.centers_yx + ((size_t)b * kMaxInst + i) * 2;
+        const float cy = (float)c[0], cx = (float)c[1];
+        s_centers[i] = make_float4(cy, cy, cx, cx);
+    }
+    __syncthreads();        // also orders s_thing
+    if (MODE != kFromFgMask) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) fg[j] = active && s_thing[cls[j] & 255] != 0;
     }
 
     // ---- 2. nearest centre ------------------------------------------------------------
@@ -321,6 +335,7 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
         }
     }
     if (active) PixVec<VEC>::storeb(prm.inst_out + fb, inst);
+    NPB_TL(prm, 1, end);
 
     // ---- 3. class votes (warp aggregated: MATCH.ANY + REDUX, one RED per group) -----------
     const int CH = (MODE == kFromFgMask) ? 1 : C;
@@ -392,9 +407,9 @@ static void launch_group(const GroupParams &prm, int B, bool ori, cudaStream_t s
 {
     dim3 grid((prm.P / VEC + kGroupThreads - 1) / kGroupThreads, B);
     if (ori)
-        group_pixels_kernel<VEC, MODE, true><<<grid, kGroupThreads, 0, s>>>(prm);
+        launch_dependent(group_pixels_kernel<VEC, MODE, true>, grid, dim3(kGroupThreads), 0, s, prm);
     else
-        group_pixels_kernel<VEC, MODE, false><<<grid, kGroupThreads, 0, s>>>(prm);
+        launch_dependent(group_pixels_kernel<VEC, MODE, false>, grid, dim3(kGroupThreads), 0, s, prm);
 }
 
 }  // namespace npb
@@ -435,6 +450,7 @@ int npb::group_pixels_impl(const float *logits, const uint8_t *sem_in, const uin
     prm.normalized = normalized_offset; prm.use_thr = use_distance_threshold;
     prm.dist_thr = distance_threshold;
     prm.thing = make_class_set(h_thing_lut, fg_in ? 0 : C);
+    NPB_TL_SET(prm);
 
     const int CH = fg_in ? 1 : C;
     if (!cleared) {

@@ -7,54 +7,16 @@
 // plus the meta areas (instance.py:253) and the orientation angle (instance.py:313,
 // utils/_orientation.py:39-42).  The per-pixel histogram half lives in group.cu (fused path)
 // or in merge_votes_kernel below (stand-alone API).
-#include <math.h>
-
-#include "common.cuh"
+#include "finalize.cuh"
 
 namespace npb {
 
-// one CTA per frame, thread i <-> raw instance id i
-__global__ void __launch_bounds__(kMaxInst)
-finalize_instances_kernel(const uint32_t *__restrict__ vote_hist,
-                          const double *__restrict__ ori_sum,
-                          const int32_t *__restrict__ n_centers, int C, int class_offset,
-                          long long L, long long void_label, ClassSet orient,
-                          int32_t *__restrict__ inst_class, int64_t *__restrict__ inst_pan_id,
-                          int32_t *__restrict__ inst_area, float *__restrict__ inst_angle)
+// one CTA per frame, thread i <-> raw instance id i (finalize.cuh)
+__global__ void __launch_bounds__(kMaxInst) finalize_instances_kernel(const FinalizeParams f)
 {
     __shared__ int s_cls[kMaxInst];
-    const int b = blockIdx.x, i = threadIdx.x;
-    const int n = n_centers ? n_centers[b] : kMaxInst - 1;
-    const uint32_t *row = vote_hist + ((size_t)b * kMaxInst + i) * C;
-
-    int cls = -1;
-    uint32_t best = 0, area = 0;
-    if (i >= 1 && i <= n) {
-        for (int c = 0; c < C; ++c) {
-            const uint32_t h = row[c];
-            area += h;
-            if (h > best) { best = h; cls = c; }  // strict > : smallest class wins ties
-        }
-    }
-    int pcls = (cls >= 0) ? cls + class_offset : -1;
-    if (pcls == 0) pcls = -1;  // majority is void -> instance dropped (panoptic_merge.py:201)
-    s_cls[i] = pcls;
-    __syncthreads();
-    int number = 1;
-    if (pcls >= 0)
-        for (int j = 1; j < i; ++j) number += (s_cls[j] == pcls);
-
-    const size_t o = (size_t)b * kMaxInst + i;
-    inst_class[o] = pcls;
-    inst_pan_id[o] = (pcls >= 0) ? (long long)pcls * L + number : void_label;
-    inst_area[o] = (int32_t)area;
-    float ang = nanf("");
-    if (ori_sum && pcls >= 0 && orient.has(pcls)) {
-        const double sc = ori_sum[2 * o], ss = ori_sum[2 * o + 1];
-        // the reference forms f32 sums and calls atan2 on them (instance.py:310-313)
-        ang = (float)atan2((double)(float)ss, (double)(float)sc);
-    }
-    if (inst_angle) inst_angle[o] = ang;
+    grid_dependency_wait();
+    finalize_frame(f, blockIdx.x, threadIdx.x, s_cls, true);
 }
 
 // 4 pixels per group (32-bit loads of the two uint8 maps, two 128-bit streaming stores of
@@ -63,15 +25,18 @@ constexpr int kWriteGroups = 4;
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
-write_panoptic_kernel(const uint8_t *__restrict__ sem, const uint8_t *__restrict__ inst,
-                      const int64_t *__restrict__ inst_pan_id,
-                      const int32_t *__restrict__ inst_class, int P, long long L,
-                      ClassSet thing, int64_t *__restrict__ pan_out,
-                      uint8_t *__restrict__ pan_sem_out)
+write_panoptic_kernel(const uint8_t *sem, const uint8_t *inst, const int64_t *inst_pan_id,
+                      const int32_t *inst_class, int P, long long L, ClassSet thing,
+                      int64_t *pan_out, uint8_t *pan_sem_out)
 {
+    // NO `const __restrict__` on inputs that a predecessor of the chain produces: such loads
+    // become LDG.CONSTANT (ld.global.nc), which the compiler is free to hoist above
+    // grid_dependency_wait() -- the "memory" clobber does not order read-only loads (seen in
+    // the SASS of this kernel: the table loads sat above ACQBULK and read stale rows).
     __shared__ long long s_pan[kMaxInst];
     __shared__ int s_cls[kMaxInst];
     const int b = blockIdx.y;
+    grid_dependency_wait();
     s_pan[threadIdx.x] = inst_pan_id[(size_t)b * kMaxInst + threadIdx.x];
     if (pan_sem_out) {
         const int c = inst_class[(size_t)b * kMaxInst + threadIdx.x];
@@ -191,6 +156,12 @@ merge_write_kernel(const int64_t *__restrict__ sem, const uint8_t *__restrict__ 
 
 using namespace npb;
 
+int npb::launch_finalize(const FinalizeParams &f, int B, void *stream)
+{
+    launch_dependent(finalize_instances_kernel, dim3(B), dim3(kMaxInst), 0, (cudaStream_t)stream, f);
+    return record_launch("npb_finalize_instances");
+}
+
 extern "C" int npb_finalize_instances(const uint32_t *vote_hist, const double *ori_sum,
                                       const int32_t *n_centers, int B, int C, int class_offset,
                                       int64_t max_instances_per_category, int64_t void_label,
@@ -200,16 +171,14 @@ extern "C" int npb_finalize_instances(const uint32_t *vote_hist, const double *o
 {
     if (!vote_hist || !inst_class || !inst_pan_id || !inst_area) return NPB_ERR_ARG;
     if (B < 1 || C < 1 || C > 65536 || max_instances_per_category < 1) return NPB_ERR_ARG;
-    // the orientation set is indexed by PANOPTIC class (network class + class_offset)
-    uint8_t lut[256] = {0};
-    if (h_orientation_lut)
-        for (int c = 0; c < C && c + class_offset < 256; ++c)
-            if (c + class_offset >= 0) lut[c + class_offset] = h_orientation_lut[c];
-    const ClassSet orient = make_class_set(lut, 256);
-    finalize_instances_kernel<<<B, kMaxInst, 0, (cudaStream_t)stream>>>(
-        vote_hist, ori_sum, n_centers, C, class_offset, (long long)max_instances_per_category,
-        (long long)void_label, orient, inst_class, inst_pan_id, inst_area, inst_angle);
-    return record_launch("npb_finalize_instances");
+    FinalizeParams f;
+    f.vote_hist = vote_hist; f.ori_sum = ori_sum; f.n_centers = n_centers; f.C = C;
+    f.class_offset = class_offset; f.L = (long long)max_instances_per_category;
+    f.void_label = (long long)void_label;
+    f.orient = orientation_class_set(h_orientation_lut, C, class_offset);
+    f.inst_class = inst_class; f.inst_pan_id = inst_pan_id; f.inst_area = inst_area;
+    f.inst_angle = inst_angle;
+    return launch_finalize(f, B, stream);
 }
 
 extern "C" int npb_write_panoptic(const uint8_t *sem, const uint8_t *inst,
@@ -231,14 +200,14 @@ extern "C" int npb_write_panoptic(const uint8_t *sem, const uint8_t *inst,
                       ((uintptr_t)pan_out & 15u) == 0;
     if (vec4) {
         dim3 grid((P / 4 + 256 * kWriteGroups - 1) / (256 * kWriteGroups), B);
-        write_panoptic_kernel<4><<<grid, 256, 0, s>>>(sem, inst, inst_pan_id, inst_class, P,
-                                                      (long long)max_instances_per_category,
-                                                      thing, pan_out, pan_sem_out);
+        launch_dependent(write_panoptic_kernel<4>, grid, dim3(256), 0, s, sem, inst, inst_pan_id,
+                         inst_class, P, (long long)max_instances_per_category, thing, pan_out,
+                         pan_sem_out);
     } else {
         dim3 grid((P + 256 * kWriteGroups - 1) / (256 * kWriteGroups), B);
-        write_panoptic_kernel<1><<<grid, 256, 0, s>>>(sem, inst, inst_pan_id, inst_class, P,
-                                                      (long long)max_instances_per_category,
-                                                      thing, pan_out, pan_sem_out);
+        launch_dependent(write_panoptic_kernel<1>, grid, dim3(256), 0, s, sem, inst, inst_pan_id,
+                         inst_class, P, (long long)max_instances_per_category, thing, pan_out,
+                         pan_sem_out);
     }
     return record_launch("npb_write_panoptic");
 }
@@ -271,10 +240,13 @@ extern "C" int npb_deeplab_merge(const int64_t *sem, const uint8_t *ins, const u
     const int bx = (int)((P + 256 * 8 - 1) / (256 * 8));
     dim3 grid(bx < 1 ? 1 : bx, B);
     merge_votes_kernel<<<grid, 256, 0, s>>>(sem, ins, fg, (long long)P, n_classes, hist, status);
-    const ClassSet none = make_class_set(nullptr, 0);
-    finalize_instances_kernel<<<B, kMaxInst, 0, s>>>(
-        hist, nullptr, nullptr, n_classes, 0, (long long)max_instances_per_category,
-        (long long)void_label, none, inst_class, inst_pan_id, inst_area, nullptr);
+    FinalizeParams f;
+    f.vote_hist = hist; f.ori_sum = nullptr; f.n_centers = nullptr; f.C = n_classes;
+    f.class_offset = 0; f.L = (long long)max_instances_per_category;
+    f.void_label = (long long)void_label; f.orient = make_class_set(nullptr, 0);
+    f.inst_class = inst_class; f.inst_pan_id = inst_pan_id; f.inst_area = inst_area;
+    f.inst_angle = nullptr;
+    finalize_instances_kernel<<<B, kMaxInst, 0, s>>>(f);
     merge_write_kernel<<<grid, 256, 0, s>>>(sem, ins, fg, inst_pan_id, (long long)P, n_classes,
                                             (long long)max_instances_per_category,
                                             (long long)void_label, d_lut, pan_out);

@@ -88,11 +88,19 @@ class PanopticPostprocessing(DensePostprocessingBase):
         # scratch (candidate lists, vote histograms, orientation sums) is reused across calls:
         # the calls are ordered on the stream, nothing in it outlives a call
         # (one scratch buffer per stream: calls on different streams may run concurrently)
-        ws_bytes = L.npb_panoptic_forward_workspace_bytes(B, C, H, W, ks)
-        ws_key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        # (npb_panoptic_forward_workspace_init once per buffer and shape: the chain itself contains
+        # no memset and leaves the workspace ready for the next call)
+        ws_key = (dev, torch.cuda.current_stream(dev).cuda_stream, B, C, H, W, ks)
         ws = self._ws.get(ws_key)
-        if ws is None or ws.numel() < ws_bytes:
-            ws = self._ws[ws_key] = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if ws is None:
+            ws_bytes = L.npb_panoptic_forward_workspace_bytes(B, C, H, W, ks)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.npb_panoptic_forward_workspace_init(
+                _lib.ptr(ws), c_int(B), c_int(C), c_int(H), c_int(W), c_int(ks),
+                _lib.stream_ptr(dev)), 'npb_panoptic_forward_workspace_init')
+            if len(self._ws) >= 8:      # shapes rarely change; do not hoard scratch if they do
+                self._ws.clear()
+            self._ws[ws_key] = ws
         # all outputs of a call live in ONE fresh allocation: [pan i64 | tables | sem | inst | pan_sem]
         P = H * W
         _, tab_bytes = InstanceTables.layout(B)

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), f'{name} declared in the header but not exported'
     assert declared == set(_lib.EXPORTED_SYMBOLS)
-    assert handle.npb_abi_version() == 2
+    assert handle.npb_abi_version() == 3
     assert handle.npb_error_string(-2).decode().startswith('more than 255')
 
 
