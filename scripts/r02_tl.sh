@@ -1,13 +1,10 @@
 #!/bin/bash
+# in-situ timeline of the replayed step (library built with -DNPB_TIMELINE) + ncu launch list
 set -u
-python -m pytest tests -q -m gpu -x 2>&1 | tail -4
-for pdl in 0 1; do
-  NPB_NO_PDL=$pdl python bench.py --config nyuv2 --steps 300 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('nyuv2 NO_PDL=$pdl', round(d['value']), round(d['ms_per_step']*1e3,1),'us', d['quality'])"
-done
-python bench.py --config sunrgbd --steps 300 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('sunrgbd', round(d['value']), round(d['ms_per_step']*1e3,1),'us', d['quality'], d['clocks'])"
-export NPB_LIB_PATH=$PWD/build/timeline/libnicr_panoptic_b200.so
-python scripts/probes/timeline.py --config nyuv2 2>&1 | tail -12
+mkdir -p gpurun_out
+NPB_LIB_PATH=$PWD/build/timeline/libnicr_panoptic_b200.so python scripts/probes/timeline.py --config nyuv2 2>&1 | tail -14
+KERNELS='regex:group_pixels|pair_count|nms_candidates|select_centers|finalize_instances|match_frames|accumulate_frames|write_panoptic'
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -s 40 -c 24 --csv \
+    --log-file gpurun_out/r02_launches_nyuv2.csv python bench.py --config nyuv2 --steps 30 --warmup 5 --no-e2e --no-cpu-baseline \
+    > gpurun_out/r02_ncu_launches.log 2>&1
+tail -12 gpurun_out/r02_launches_nyuv2.csv | cut -d, -f5,9,15 | cut -c1-160

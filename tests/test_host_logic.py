@@ -301,15 +301,13 @@ def test_reference_citations_resolve():
     assert total >= 200
 
 
-def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU arm: C oracle port on the host cores) runs without a
-    GPU and prints ONE JSON line with the keys the driver reads."""
+def _bench_reference_line(*extra):
     import json
     import subprocess
     import sys
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
-                          '--steps', '1', '--warmup', '0'], capture_output=True, text=True,
-                         timeout=600, cwd=ROOT)
+                          '--steps', '1', '--warmup', '0', *extra], capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -318,9 +316,34 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['unit'] == 'frames/s' and d['value'] > 0 and d['ms_per_step'] > 0
     assert d['n_gpus'] == 1 and d['steps'] == 1 and d['vs_baseline'] is None
     assert d['data'] == 'synthetic' and d['dtype'] == 'f32'
-    assert d['config']['workload'] == 'sunrgbd_530x730_c37_b64_orientation'
-    cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    # the configuration the metric is quoted on (BASELINE.json "@480x640")
+    assert d['config']['workload'] == 'nyuv2_480x640_c40_b8'
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
     assert d['gpu_launches'] == 0
+    cb = d['cpu_baseline']
+    assert cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    return d
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs without a GPU and prints ONE JSON line with the keys the
+    driver reads.  Where the reference is installed (baseline/_ref) or present (/root/reference)
+    it is the UNMODIFIED reference that is timed (`kind: "reference"`), on one batch of the
+    headline workload per step."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import reference_arm
+    d = _bench_reference_line()
+    cb = d['cpu_baseline']
+    if reference_arm.available():
+        assert cb['kind'] == 'reference' and 'UNMODIFIED reference' in cb['sample']
+        assert d['config']['sample_frames_per_step'] == 8
+        assert 0.0 < d['quality']['all_pq'] <= 1.0 and 0.0 < d['quality']['miou'] <= 1.0
+    else:
+        assert cb['kind'] == 'port'
+
+
+def test_bench_port_arm_prints_the_contract_line():
+    """`--port`: the C oracle port as the CPU arm (second key of the GPU arm's line)."""
+    d = _bench_reference_line('--port', '--frames', '4')
+    assert d['cpu_baseline']['kind'] == 'port'
