@@ -81,6 +81,14 @@ struct PixVec<1> {
     __device__ static void storeb(uint8_t *p, const int (&v)[1]) { *p = (uint8_t)v[0]; }
 };
 
+// max(a, b), NaN if either is NaN (PTX max.NaN.f32)
+__device__ __forceinline__ float fmax_nan(float a, float b)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
 // exact "does centre i beat the current best" test on squared distances (see header)
 __device__ __forceinline__ void consider_center(float s, int i, float &sbest, int &ibest)
 {
@@ -129,47 +137,48 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
     if (active) {
         if (MODE == kFromLogits) {
             const float *lp = prm.logits + (size_t)b * C * P + p0;
-            float best[VEC];
-            PixVec<VEC>::loadf(lp, best, true);
-            // batches of 8 independent 128-bit loads in flight per thread before the first
-            // compare: the loop is latency bound, bytes in flight are what buys bandwidth
+            // Batches of 8 independent 128-bit loads in flight per thread before the first
+            // compare: the loop is latency bound, bytes in flight are what buys bandwidth.  All
+            // C planes go through ceil(C / 8) batches (plane 0 included, the last batch with its
+            // loads predicated): every batch is one DRAM latency in the life of the CTA.
             constexpr int U = 8;
-            int c = 1;
+            // Non-finite logits: the reference takes the arg-max of softmax(logits), which is NaN
+            // in every class -- index 0 -- as soon as a logit is NaN or +Inf, or all are -Inf
+            // (semantic.py:52-53); -Inf next to finite logits just has probability 0.  The
+            // running maximum is kept with max.NaN (NaN-propagating, same cost as a select): once
+            // a NaN is in, no later logit compares greater and it stays to the end.
+            float best[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) best[j] = __int_as_float(0xff800000);
+            auto consume = [&](const float (&v)[VEC], int c) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if (v[j] > best[j]) cls[j] = c;                 // first maximum wins
+                    best[j] = fmax_nan(best[j], v[j]);
+                }
+            };
+            int c = 0;
             for (; c + U <= C; c += U) {
                 float v[U][VEC];
 #pragma unroll
                 for (int u = 0; u < U; ++u) PixVec<VEC>::loadf(lp + (size_t)(c + u) * P, v[u], true);
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j)
-                        if (v[u][j] > best[j]) { best[j] = v[u][j]; cls[j] = c + u; }
+                for (int u = 0; u < U; ++u) consume(v[u], c + u);
             }
-            if (c + 4 <= C) {   // tail: one batch of 4 ...
-                float v[4][VEC];
+            if (c < C) {        // up to 7 planes, loads of planes >= C predicated off
+                float v[U - 1][VEC];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) PixVec<VEC>::loadf(lp + (size_t)(c + u) * P, v[u], true);
+                for (int u = 0; u < U - 1; ++u) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j)
-                        if (v[u][j] > best[j]) { best[j] = v[u][j]; cls[j] = c + u; }
-                c += 4;
-            }
-            if (c < C) {        // ... and up to 3 planes, loads of planes >= C predicated off
-                float v[3][VEC];
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) v[u][j] = __int_as_float(0xff800000);  // -inf
+                    for (int j = 0; j < VEC; ++j) v[u][j] = __int_as_float(0xff800000);   // -inf: neutral
                     if (c + u < C) PixVec<VEC>::loadf(lp + (size_t)(c + u) * P, v[u], true);
                 }
 #pragma unroll
-                for (int u = 0; u < 3; ++u)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j)
-                        if (v[u][j] > best[j]) { best[j] = v[u][j]; cls[j] = c + u; }
+                for (int u = 0; u < U - 1; ++u) consume(v[u], c + u);
             }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (!(best[j] < __int_as_float(0x7f800000))) cls[j] = 0;    // NaN or +Inf came by
             PixVec<VEC>::storeb(prm.sem_out + fb, cls);
         } else if (MODE == kFromSemMap) {
             PixVec<VEC>::loadb(prm.sem_in + fb, cls);

@@ -98,10 +98,12 @@ argmax_bilinear_kernel(const float *__restrict__ logits, int C, ResizeGeom g,
         return __fadd_rn(__fmul_rn(top, cy.w0), __fmul_rn(bot, cy.w1));
     };
     float best = tap(), sum = 1.0f;
+    float taint = __fmul_rn(best, 0.0f);    // +0 while every resized logit is finite, else NaN
     int cls = 0;
     for (int c = 1; c < C; ++c) {
         const float v = tap();
         const bool gt = v > best;
+        taint = __fmaf_rn(v, 0.0f, taint);
         if (SCORE) {
             // online soft-max, branch free: exp(best - v) if v is the new maximum, else exp(v - best)
             const float e = __expf(gt ? best - v : v - best);
@@ -109,6 +111,30 @@ argmax_bilinear_kernel(const float *__restrict__ logits, int C, ResizeGeom g,
         }
         best = gt ? v : best;
         cls = gt ? c : cls;
+    }
+    if (taint != taint) {
+        // non-finite resized logits (rare path): a NaN or +Inf value, or nothing but -Inf, makes the
+        // reference's soft-max NaN in every class and its arg-max 0 (semantic.py:73-74)
+        const float kInf = __int_as_float(0x7f800000);
+        p00 -= (size_t)C * plane; p01 -= (size_t)C * plane; p10 -= (size_t)C * plane; p11 -= (size_t)C * plane;
+        bool poisoned = false;
+        float mx = -kInf;
+        int arg = 0;
+        for (int k = 0; k < C; ++k) {
+            const float v = tap();
+            poisoned |= (v != v) || v == kInf;
+            if (v > mx) { mx = v; arg = k; }
+        }
+        if (poisoned || mx == -kInf) {
+            cls = 0;
+            sum = __int_as_float(0x7fc00000);
+        } else {
+            cls = arg;
+            p00 -= (size_t)C * plane; p01 -= (size_t)C * plane; p10 -= (size_t)C * plane; p11 -= (size_t)C * plane;
+            float acc = 0.0f;
+            for (int k = 0; k < C; ++k) acc += __expf(tap() - mx);
+            sum = acc;
+        }
     }
     const size_t q = (size_t)b * g.Hout * g.Wout + o;
     sem_out[q] = (uint8_t)cls;

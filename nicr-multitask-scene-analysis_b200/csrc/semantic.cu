@@ -17,7 +17,7 @@ semantic_argmax_kernel(const float *__restrict__ logits, int C, int P,
     const int p0 = (blockIdx.x * 256 + threadIdx.x) * VEC;
     if (p0 >= P) return;
     const float *lp = logits + (size_t)b * C * P + p0;
-    float best[VEC], sum[VEC];
+    float best[VEC], sum[VEC], taint[VEC];
     int cls[VEC];
     if (VEC == 4) {
         const float4 t = ld_stream_f4((const float4 *)lp);
@@ -25,8 +25,9 @@ semantic_argmax_kernel(const float *__restrict__ logits, int C, int P,
     } else {
         best[0] = ld_stream_f1(lp);
     }
+    // taint: +0 while every logit of the pixel is finite, NaN otherwise (x * 0 + taint)
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) { cls[j] = 0; sum[j] = 1.0f; }
+    for (int j = 0; j < VEC; ++j) { cls[j] = 0; sum[j] = 1.0f; taint[j] = __fmul_rn(best[j], 0.0f); }
 #pragma unroll 8
     for (int c = 1; c < C; ++c) {
         float v[VEC];
@@ -39,6 +40,7 @@ semantic_argmax_kernel(const float *__restrict__ logits, int C, int P,
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             const bool gt = v[j] > best[j];
+            taint[j] = __fmaf_rn(v[j], 0.0f, taint[j]);
             if (SCORE) {
                 // online soft-max, branch free: exp(best - v) for a new maximum, else exp(v - best)
                 const float e = __expf(gt ? best[j] - v[j] : v[j] - best[j]);
@@ -46,6 +48,32 @@ semantic_argmax_kernel(const float *__restrict__ logits, int C, int P,
             }
             best[j] = gt ? v[j] : best[j];
             cls[j] = gt ? c : cls[j];
+        }
+    }
+    // Non-finite logits (rare path).  The reference takes max / arg-max of softmax(logits)
+    // (semantic.py:52-53): a NaN or +Inf logit, or nothing but -Inf, makes every probability NaN
+    // and torch.max answers (NaN, index 0); -Inf next to finite logits has probability 0.
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        if (taint[j] != taint[j]) {
+            const float kInf = __int_as_float(0x7f800000);
+            bool poisoned = false;
+            float mx = -kInf;
+            int arg = 0;
+            for (int k = 0; k < C; ++k) {
+                const float v = lp[(size_t)k * P + j];
+                poisoned |= (v != v) || v == kInf;
+                if (v > mx) { mx = v; arg = k; }
+            }
+            if (poisoned || mx == -kInf) {
+                cls[j] = 0;
+                sum[j] = __int_as_float(0x7fc00000);        // score = NaN
+            } else {
+                cls[j] = arg;
+                float acc = 0.0f;
+                for (int k = 0; k < C; ++k) acc += __expf(lp[(size_t)k * P + j] - mx);
+                sum[j] = acc;
+            }
         }
     }
     const size_t fb = (size_t)b * P + p0;

@@ -35,7 +35,9 @@ class _PQKernel:
         # can share it; calls on different streams get their own
         key = (dev, torch.cuda.current_stream(dev).cuda_stream, B, num_categories)
         if key not in cls._scratch:
-            nbytes = _lib.lib().npb_pq_update_workspace_bytes(B, num_categories)
+            # the size depends on the SM count of the device the kernels will run on
+            with torch.cuda.device(dev):
+                nbytes = _lib.lib().npb_pq_update_workspace_bytes(B, num_categories)
             cls._scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         return cls._scratch[key]
 

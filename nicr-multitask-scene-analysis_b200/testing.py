@@ -90,6 +90,39 @@ def make_batch(B: int, C: int, H: int, W: int, K: int, seed: int = 0,
     return {k: torch.stack([f[k] for f in frames]).contiguous() for k in frames[0]}
 
 
+def poison_logits(logits: torch.Tensor, fraction: float, seed: int = 0) -> torch.Tensor:
+    """Overwrite the logits of about `fraction` of the pixels (in place) with the non-finite
+    patterns that matter for `softmax -> max` (semantic.py:52-53): a NaN, a +Inf, +Inf next to
+    -Inf, nothing but -Inf (all of them: every probability NaN, index 0), and -Inf next to finite
+    logits (harmless: probability 0), each at a random class (or the first / the winning one)."""
+    B, C, H, W = logits.shape
+    g = torch.Generator()
+    g.manual_seed(10_000 + seed)
+    n = max(6, int(fraction * B * H * W))
+    bs = torch.randint(0, B, (n,), generator=g)
+    ys = torch.randint(0, H, (n,), generator=g)
+    xs = torch.randint(0, W, (n,), generator=g)
+    cs = torch.randint(0, C, (n,), generator=g)
+    kinds = torch.arange(n) % 6
+    inf = float('inf')
+    for b, y, x, c, kind in zip(bs.tolist(), ys.tolist(), xs.tolist(), cs.tolist(), kinds.tolist()):
+        px = logits[b, :, y, x]
+        if kind == 0:
+            px[c] = float('nan')
+        elif kind == 1:
+            px[c] = inf
+        elif kind == 2:
+            px[c] = inf
+            px[(c + 1) % C] = -inf
+        elif kind == 3:
+            px[:] = -inf
+        elif kind == 4:
+            px[c] = -inf
+        else:       # the winner itself becomes -Inf: the runner-up wins
+            px[int(torch.argmax(torch.nan_to_num(px, nan=-inf)))] = -inf
+    return logits
+
+
 def make_eval_targets(panoptic: torch.Tensor, max_instances_per_category: int = 1 << 16,
                       shift: int = 5):
     """Evaluation targets: panoptic target = prediction rolled

@@ -53,10 +53,16 @@ int orc_semantic_argmax(const float *logits, int B, int C, long P, uint8_t *out)
         for (long p = 0; p < P; ++p) {
             float best = lb[p];
             int arg = 0;
+            /* non-finite logits (semantic.py:52-53): softmax is NaN in every class as soon as
+               a logit is NaN or +Inf (inf - inf) or all are -Inf, and torch.max of an all-NaN
+               row answers index 0; -Inf next to finite logits just has probability 0 */
+            int poisoned = isnan(best) || (isinf(best) && best > 0);
             for (int c = 1; c < C; ++c) {
                 float v = lb[(size_t)c * P + p];
                 if (v > best) { best = v; arg = c; }
+                poisoned |= isnan(v) || (isinf(v) && v > 0);
             }
+            if (poisoned) arg = 0;
             ob[p] = (uint8_t)arg;
         }
     }

@@ -48,9 +48,11 @@ def meta_to_json(meta):
 
 def run_postprocess(name, B, C, H, W, K, seed, quantize, with_orientation=True, top_k=64,
                     ks=3, thr=0.1, apply_fg=False, normalized=True, dist_thr=None,
-                    compute_scores=False):
+                    compute_scores=False, poison=0.0):
     data = testing.make_batch(B, C, H, W, K, seed=seed, with_orientation=with_orientation,
                               quantize=quantize)
+    if poison:      # non-finite logits at a fraction of the pixels (semantic.py:52-53 on NaN / Inf)
+        testing.poison_logits(data['logits'], poison, seed)
     if not normalized:      # offsets in pixels
         data['offset'][:, 0] *= H
         data['offset'][:, 1] *= W
@@ -494,6 +496,7 @@ if __name__ == '__main__':
                     normalized=False, with_orientation=False)
     run_postprocess('scores', B=2, C=6, H=64, W=96, K=4, seed=5, quantize='q10',
                     compute_scores=True)
+    run_postprocess('nonfinite', B=2, C=6, H=48, W=64, K=4, seed=6, quantize='q10', poison=0.05)
     run_fullres()
     run_centers()
     run_merge()

@@ -11,7 +11,7 @@ from conftest import int_keys, jload, load_golden
 
 pytestmark = pytest.mark.gpu
 
-POST_CASES = ['q10', 'tie', 'odd', 'pixel_offsets', 'scores']
+POST_CASES = ['q10', 'tie', 'odd', 'pixel_offsets', 'scores', 'nonfinite']
 
 
 def _build(cfg, is_thing, has_ori, **extra):
@@ -521,3 +521,89 @@ def test_baseline_shapes_full_size(shape, cuda_device):
         got = np.stack([getattr(pq, n).cpu().numpy() for n in
                         ('iou_per_class', 'tp_per_class', 'fn_per_class', 'fp_per_class')])
         assert np.array_equal(got, np.stack(out[:4]))
+
+
+@pytest.mark.parametrize('shape', [(2, 40, 48, 64), (2, 37, 30, 50), (1, 9, 33, 47), (1, 1, 16, 20),
+                                   (2, 8, 24, 32), (1, 13, 20, 28)])
+def test_nonfinite_logits_against_oracle(shape, cuda_device):
+    """NaN / +-Inf logits (semantic.py:52-53: softmax -> max answers class 0 with a NaN score as
+    soon as a NaN or +Inf poisons the soft-max, -Inf next to finite logits is harmless): the fused
+    arg-max of the grouping kernel (4-pixel and scalar path) and the stand-alone semantic
+    post-processing against the oracle, which tests/test_oracle_live_reference.py pins on the
+    live reference for the same poisoning."""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    B, C, H, W = shape
+    for frac in (0.03, 0.5):
+        data = testing.make_batch(B, C, H, W, 3, seed=41, quantize='q10', with_orientation=False)
+        testing.poison_logits(data['logits'], frac, seed=H + W)
+        is_thing = tuple(bool(c % 2 == 0) for c in range(C))
+        pcfg = dict(thr=0.1, ks=3, top_k=64, apply_fg=False, normalized=True, dist_thr=None)
+        _, _, pan = _build(pcfg, is_thing, (False,) * C)
+        r = _run(pan, data['logits'].numpy(), data['heat'].numpy(), data['offset'].numpy(), None,
+                 cuda_device)
+        ref = oracle.panoptic_postprocess(data['logits'].numpy(), data['heat'].numpy(),
+                                          data['offset'].numpy(), None, is_thing, (False,) * C)
+        assert np.array_equal(r['_semantic_segmentation_idx_u8'].cpu().numpy(), ref['semantic_idx'])
+        assert np.array_equal(r['panoptic_segmentation_deeplab'].cpu().numpy(), ref['panoptic'])
+        assert r['panoptic_segmentation_deeplab_ids'] == ref['ids']
+        # score of the winner: NaN exactly where the reference's is, equal elsewhere
+        want = oracle.semantic_score(data['logits'].numpy())
+        np.testing.assert_allclose(r['semantic_segmentation_score'].cpu().numpy(), want, rtol=1e-5)
+        sem = get_postprocessing_class('semantic')()
+        rs = sem.postprocess((data['logits'].to(cuda_device), None), testing.make_batch_dict(B, H, W),
+                             is_training=False)
+        assert np.array_equal(rs['semantic_segmentation_idx'].cpu().numpy(), ref['semantic_idx'])
+        np.testing.assert_allclose(rs['semantic_segmentation_score'].cpu().numpy(), want, rtol=1e-5)
+
+
+def test_nonfinite_logits_through_the_fullres_resize(cuda_device):
+    """the full-resolution class map is the arg-max of the soft-max of the RESIZED logits
+    (semantic.py:68-74): a non-finite tap poisons every output pixel it contributes to."""
+    import torch.nn.functional as F
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    B, C, H, W, FH, FW = 2, 7, 24, 32, 37, 53
+    data = testing.make_batch(B, C, H, W, 2, seed=43, quantize='q10', with_orientation=False)
+    testing.poison_logits(data['logits'], 0.03, seed=5)
+    sem = get_postprocessing_class('semantic')()
+    batch = {'semantic_fullres': torch.zeros(B, FH, FW),
+             '_applied_preprocessing': [[{'type': 'Resize', 'valid_region_slice_y': slice(0, H),
+                                          'valid_region_slice_x': slice(0, W)}]] * B}
+    r = sem.postprocess((data['logits'].to(cuda_device), None), batch, is_training=False)
+    full = F.interpolate(data['logits'], size=(FH, FW), mode='bilinear', align_corners=False)
+    score, idx = torch.max(F.softmax(full, dim=1), dim=1)
+    got = r['semantic_segmentation_idx_fullres'].cpu()
+    finite = torch.isfinite(full).all(1)
+    assert (~finite).any()
+    # pixels touched by a non-finite tap: exactly the reference's rule (class 0 when poisoned)
+    assert torch.equal(got[~finite], idx[~finite])
+    # elsewhere the usual near-tie caveat of the resized logits applies
+    top2 = torch.sort(full, dim=1)[0][:, -2:]
+    differs = (got != idx) & finite
+    assert bool(((top2[:, 1] - top2[:, 0])[differs] < 1e-5).all())
+    got_score = r['semantic_segmentation_score_fullres'].cpu()
+    assert torch.equal(torch.isnan(got_score), torch.isnan(score))
+
+
+def test_unquantised_bench_frames(cuda_device):
+    """bench.py's inputs are NOT quantised: the CUDA path against the oracle on exactly the frames
+    of the bench's headline workload (seeds 1000 + i); the live-reference test
+    test_unquantised_bench_inputs_have_no_softmax_flips shows the oracle == the reference's
+    softmax -> max on the same 4.3 M pixels, so there is no hidden arg-max flip in the bench."""
+    from nicr_mt_scene_analysis_b200 import testing
+    C, H, W, K = 40, 480, 640, 12
+    is_thing = testing.default_is_thing(C)
+    pcfg = dict(thr=0.1, ks=3, top_k=64, apply_fg=False, normalized=True, dist_thr=None)
+    _, _, pan = _build(pcfg, is_thing, (False,) * C)
+    for lo in (0, 7):
+        frames = [testing.make_frame(C, H, W, K, seed=1000 + i, with_orientation=False, quantize=None)
+                  for i in range(lo, lo + 7)]
+        data = {k: torch.stack([f[k] for f in frames]) for k in frames[0]}
+        r = _run(pan, data['logits'].numpy(), data['heat'].numpy(), data['offset'].numpy(), None,
+                 cuda_device)
+        ref = oracle.panoptic_postprocess(data['logits'].numpy(), data['heat'].numpy(),
+                                          data['offset'].numpy(), None, is_thing, (False,) * C)
+        assert np.array_equal(r['_semantic_segmentation_idx_u8'].cpu().numpy(), ref['semantic_idx'])
+        assert np.array_equal(r['panoptic_segmentation_deeplab'].cpu().numpy(), ref['panoptic'])
+        assert r['panoptic_segmentation_deeplab_ids'] == ref['ids']

@@ -8,7 +8,7 @@ import pytest
 import oracle
 from conftest import int_keys, jload, load_golden
 
-POST_CASES = ['q10', 'tie', 'odd', 'pixel_offsets', 'scores']
+POST_CASES = ['q10', 'tie', 'odd', 'pixel_offsets', 'scores', 'nonfinite']
 
 
 def _meta_equal(ref_meta, got_meta, orient=None):

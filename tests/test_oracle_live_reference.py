@@ -371,3 +371,52 @@ def test_product_angular_errors_equal_live_reference(ref):
     assert int(ours.n_elements) == int(theirs.n_elements) > 0
     np.testing.assert_allclose(float(ours.sum_angular_error), float(theirs.sum_angular_error), rtol=1e-12)
     del theirs
+
+
+@pytest.mark.parametrize('seed', range(MORE or 6))
+def test_nonfinite_logits_equal_live_reference(seed, ref):
+    """NaN / +-Inf logits: the reference's `softmax -> max` (semantic.py:52-53) answers class 0
+    wherever a NaN or +Inf poisons the soft-max (or nothing but -Inf is there) and ignores -Inf
+    next to finite logits; the whole panoptic result follows from that class map."""
+    from nicr_mt_scene_analysis_b200 import testing
+    rng = np.random.default_rng(9100 + seed)
+    B, C, H, W, K = int(rng.integers(1, 3)), int(rng.integers(1, 12)), int(rng.integers(16, 56)), \
+        int(rng.integers(16, 72)), int(rng.integers(1, 5))
+    data = testing.make_batch(B, C, H, W, K, seed=500 + seed, quantize='q10', with_orientation=False)
+    testing.poison_logits(data['logits'], float(rng.choice([0.02, 0.2, 0.6])), seed)
+    is_thing = tuple(bool(x) for x in rng.integers(0, 2, C))
+    get = ref['get']
+    pan = get('panoptic', semantic_postprocessing=get('semantic')(),
+              instance_postprocessing=get('instance')(), semantic_classes_is_thing=is_thing,
+              semantic_class_has_orientation=(False,) * C)()
+    r = pan.postprocess(((data['logits'].clone(), (data['heat'].clone(), data['offset'].clone())),
+                         (None, None)), testing.make_batch_dict(B, H, W), is_training=False)
+    want = r['semantic_segmentation_idx'].numpy()
+    assert np.array_equal(oracle.semantic_argmax(data['logits'].numpy()), want)
+    got = oracle.panoptic_postprocess(data['logits'].numpy(), data['heat'].numpy(),
+                                      data['offset'].numpy(), None, is_thing, (False,) * C)
+    assert np.array_equal(got['panoptic'], r['panoptic_segmentation_deeplab'].numpy())
+    assert np.array_equal(got['instance_idx'], r['panoptic_segmentation_deeplab_instance_idx'].numpy())
+    np.testing.assert_allclose(oracle.semantic_score(data['logits'].numpy()),
+                               r['semantic_segmentation_score'].numpy(), rtol=1e-5)
+
+
+UNQUANTISED_FRAMES = 14     # x 480 x 640 = 4.3 M pixels of the bench distribution
+
+
+def test_unquantised_bench_inputs_have_no_softmax_flips(ref):
+    """bench.py feeds UNQUANTISED logits (testing.make_frame(quantize=None), seeds 1000 + i of
+    rank 0).  The product and the oracle take the arg-max of the logits, the reference the arg-max
+    of softmax(logits); they can only differ where two logits are closer than ~2^-23 relative.
+    On 4.3 M pixels of exactly the frames the bench uses there is no such pixel (0 flips);
+    tests/test_gpu_postprocessing.py::test_unquantised_bench_frames checks the CUDA path against
+    the oracle on the same frames."""
+    import torch.nn.functional as F
+    from nicr_mt_scene_analysis_b200 import testing
+    flips = 0
+    for i in range(UNQUANTISED_FRAMES):
+        f = testing.make_frame(40, 480, 640, 12, seed=1000 + i, with_orientation=False, quantize=None)
+        want = torch.max(F.softmax(f['logits'][None], dim=1), dim=1)[1][0].numpy()
+        have = oracle.semantic_argmax(f['logits'][None].numpy())[0]
+        flips += int((want != have).sum())
+    assert flips == 0
