@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
         s_stuff[tid] = prm.thing.has(tid) ? 0u : ((unsigned)tid + 1u) << 16;
     }
     __syncthreads();
+    NPB_TL(prm, 10, wait);      // instance tables of the frame derived
 
     const long long P = prm.P;
     const long long chunk = (long long)kPairThreads * VEC;
@@ -602,6 +603,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
 
     }
 
+    NPB_TL(prm, 11, wait);      // pixel loop done
     // ---- flush: append the CTA tables to the frame's entry list, add the confusion matrix ----
     // count, reserve a range of the list with ONE global atomic, then store
     __shared__ unsigned s_total, s_base, s_cursor;
@@ -992,33 +994,34 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const Ma
     // the float64 order of the reference.
     if (!prm.done_cnt) return;
     __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(prm.done_cnt, 1u) == gridDim.x - 1);
+    __syncthreads();            // the frame results of every thread are issued ...
+    if (tid == 0) {             // ... and made visible by one fence (cumulative over the barrier)
+        __threadfence();
+        s_last = (atomicAdd(prm.done_cnt, 1u) == gridDim.x - 1);
+        if (s_last) __threadfence();
+    }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
     const int NC = prm.num_categories, row = 4 * NC, B = (int)gridDim.x;
     static_assert(kMatchThreads >= 4 * 256, "one thread per (statistic, category)");
-    double *buf = (double *)smem_raw;
-    const int chunk = (int)(match_smem_bytes() / sizeof(double)) / row;
-    double acc = 0.0;
-    double *dst = nullptr;
     if (tid < row) {
         const int stat = tid / NC, c = tid - stat * NC;
-        dst = (stat == 0 ? prm.iou : stat == 1 ? prm.tp : stat == 2 ? prm.fn : prm.fp) + c;
-        acc = *dst;
+        double *dst = (stat == 0 ? prm.iou : stat == 1 ? prm.tp : stat == 2 ? prm.fn : prm.fp) + c;
+        double acc = *dst;
+        // batches of independent loads (adjacent threads read adjacent words), added strictly in
+        // frame order
+        constexpr int kFrames = 8;
+        for (int b0 = 0; b0 < B; b0 += kFrames) {
+            double v[kFrames];
+#pragma unroll
+            for (int j = 0; j < kFrames; ++j)
+                v[j] = b0 + j < B ? __ldcg(prm.frame_stats + (size_t)(b0 + j) * row + tid) : 0.0;
+#pragma unroll
+            for (int j = 0; j < kFrames; ++j)
+                if (b0 + j < B) acc += v[j];
+        }
+        *dst = acc;
     }
-    for (int b0 = 0; b0 < B; b0 += chunk) {
-        const int nb = min(chunk, B - b0);
-        __syncthreads();
-        for (int i = tid; i < nb * row; i += kMatchThreads)
-            buf[i] = __ldcg(prm.frame_stats + (size_t)b0 * row + i);
-        __syncthreads();
-        if (tid < row)
-            for (int j = 0; j < nb; ++j) acc += buf[j * row + tid];
-    }
-    if (tid < row) *dst = acc;
     NPB_TL(prm, 4, end);
 }
 

@@ -39,19 +39,19 @@ __device__ __forceinline__ long long finalize_frame(const FinalizeParams &f, int
     int cls = -1;
     uint32_t best = 0, area = 0;
     if (i >= 1 && i <= n) {
-        int c = 0;
-        for (; c + 4 <= C; c += 4) {     // independent loads, then the ordered compares
-            const uint32_t h0 = row[c], h1 = row[c + 1], h2 = row[c + 2], h3 = row[c + 3];
-            area += h0 + h1 + h2 + h3;
-            if (h0 > best) { best = h0; cls = c; }          // strict > : smallest class wins ties
-            if (h1 > best) { best = h1; cls = c + 1; }
-            if (h2 > best) { best = h2; cls = c + 2; }
-            if (h3 > best) { best = h3; cls = c + 3; }
-        }
-        for (; c < C; ++c) {
-            const uint32_t h = row[c];
-            area += h;
-            if (h > best) { best = h; cls = c; }
+        // batches of 16 independent loads, then the ordered compares: a frame has a dozen
+        // instances, so this is a handful of threads and every batch is one memory latency on
+        // the critical path of the CTA
+        constexpr int U = 16;
+        for (int c0 = 0; c0 < C; c0 += U) {
+            uint32_t h[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) h[u] = (c0 + u < C) ? row[c0 + u] : 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                area += h[u];
+                if (h[u] > best) { best = h[u]; cls = c0 + u; }    // strict > : smallest class wins ties
+            }
         }
     }
     int pcls = (cls >= 0) ? cls + f.class_offset : -1;

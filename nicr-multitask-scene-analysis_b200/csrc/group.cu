@@ -25,7 +25,12 @@
 
 namespace npb {
 
+// CTA sizes of the grouping kernel: 256 threads x 4 resident CTAs per SM, or 128 threads x 9
+// (same 56 registers per thread).  The smaller CTAs make the last, partial wave of a small batch
+// finer grained; the launcher picks the variant whose grid fills its waves best.
 constexpr int kGroupThreads = 256;
+constexpr int kGroupThreadsSmall = 128;
+constexpr int kGroupCtasPerSm = 4, kGroupCtasPerSmSmall = 9;
 
 enum SemSource { kFromLogits = 0, kFromSemMap = 1, kFromFgMask = 2 };
 
@@ -101,27 +106,27 @@ __device__ __forceinline__ void consider_center(float s, int i, float &sbest, in
     }
 }
 
-template <int VEC, int MODE, bool ORI>
-__global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const GroupParams prm)
+template <int VEC, int MODE, bool ORI, int NT = kGroupThreads>
+__global__ void __launch_bounds__(NT, NT == kGroupThreads ? kGroupCtasPerSm : kGroupCtasPerSmSmall)
+group_pixels_kernel(const GroupParams prm)
 {
     // centres of the frame as (cy, cy, cx, cx): one LDS.128 feeds two packed f32x2 operands
     __shared__ float4 s_centers[kMaxInst];
     // thing flag per class: one LDS.U8 per pixel instead of an indexed constant load + shifts
     __shared__ unsigned char s_thing[256];
-    static_assert(kGroupThreads == 256, "one class flag per thread");
     NPB_TL(prm, 1, start);
     // the successor (id writer / evaluation pixel pass) is staged while the last wave of this grid
     // runs; its residency is limited by its (padded) shared memory, so its one wave of CTAs
     // spreads evenly however early it is placed
     grid_launch_dependents();
-    s_thing[threadIdx.x] = prm.thing.has((int)threadIdx.x) ? 1 : 0;
+    for (int c = threadIdx.x; c < 256; c += NT) s_thing[c] = prm.thing.has(c) ? 1 : 0;
 
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int P = prm.P, W = prm.W, C = prm.C;
 
-    const int p0 = (blockIdx.x * kGroupThreads + tid) * VEC;
+    const int p0 = (blockIdx.x * NT + tid) * VEC;
     const bool active = p0 < P;  // P % VEC == 0 is guaranteed by the launcher
     const size_t fb = (size_t)b * P + p0;
     // The arg-max over the logits (most of this kernel's bytes) depends on nothing the chain
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
     if (MODE == kFromLogits) grid_dependency_wait();
     NPB_TL(prm, 1, wait);
     const int n = prm.n_centers[b];
-    for (int i = tid; i < n; i += kGroupThreads) {
+    for (int i = tid; i < n; i += NT) {
         const int32_t *c = prm.centers_yx + ((size_t)b * kMaxInst + i) * 2;
         const float cy = (float)c[0], cx = (float)c[1];
         s_centers[i] = make_float4(cy, cy, cx, cx);
@@ -411,14 +416,49 @@ __global__ void __launch_bounds__(kGroupThreads, 4) group_pixels_kernel(const Gr
     }
 }
 
+static int group_sm_count()
+{
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
+// fraction of the CTA slots of all waves that a grid of `ctas` CTAs keeps busy
+static double wave_fill(long long ctas, long long slots)
+{
+    const long long waves = (ctas + slots - 1) / slots;
+    return (double)ctas / (double)(waves * slots);
+}
+
+template <int VEC, int MODE, bool ORI>
+static void launch_group_nt(const GroupParams &prm, int B, cudaStream_t s)
+{
+    const long long groups = prm.P / VEC;       // threads needed per frame
+    const long long big = (groups + kGroupThreads - 1) / kGroupThreads * B;
+    const long long small = (groups + kGroupThreadsSmall - 1) / kGroupThreadsSmall * B;
+    static int n_sm = group_sm_count();
+    // the 128-thread CTAs only pay where the batch is a handful of waves: their last wave is
+    // finer grained (and 9 x 128 threads are resident per SM instead of 4 x 256)
+    const bool use_small = VEC == 4 && big <= 16ll * n_sm * kGroupCtasPerSm &&
+                           wave_fill(small, (long long)n_sm * kGroupCtasPerSmSmall) >
+                               wave_fill(big, (long long)n_sm * kGroupCtasPerSm) + 0.02;
+    if (use_small) {
+        dim3 grid((unsigned)((groups + kGroupThreadsSmall - 1) / kGroupThreadsSmall), B);
+        launch_dependent(group_pixels_kernel<VEC, MODE, ORI, kGroupThreadsSmall>, grid,
+                         dim3(kGroupThreadsSmall), 0, s, prm);
+    } else {
+        dim3 grid((unsigned)((groups + kGroupThreads - 1) / kGroupThreads), B);
+        launch_dependent(group_pixels_kernel<VEC, MODE, ORI, kGroupThreads>, grid, dim3(kGroupThreads),
+                         0, s, prm);
+    }
+}
+
 template <int VEC, int MODE>
 static void launch_group(const GroupParams &prm, int B, bool ori, cudaStream_t s)
 {
-    dim3 grid((prm.P / VEC + kGroupThreads - 1) / kGroupThreads, B);
-    if (ori)
-        launch_dependent(group_pixels_kernel<VEC, MODE, true>, grid, dim3(kGroupThreads), 0, s, prm);
-    else
-        launch_dependent(group_pixels_kernel<VEC, MODE, false>, grid, dim3(kGroupThreads), 0, s, prm);
+    if (ori) launch_group_nt<VEC, MODE, true>(prm, B, s);
+    else launch_group_nt<VEC, MODE, false>(prm, B, s);
 }
 
 }  // namespace npb

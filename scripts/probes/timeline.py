@@ -20,7 +20,7 @@ from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, Panop
                                                 PanopticQualityWithOrientationMAE)
 from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class  # noqa: E402
 
-NAMES = {0: 'nms+select', 1: 'group', 2: 'pair(+finalize)', 3: 'match', 5: ' m: dense merged', 6: ' m: entries merged',
+NAMES = {0: 'nms+select', 1: 'group', 2: 'pair(+finalize)', 10: ' p: tables derived', 11: ' p: pixel loop done', 3: 'match', 5: ' m: dense merged', 6: ' m: entries merged',
          7: ' m: segment tables', 8: ' m: matched', 9: ' m: fn/fp + ordered', 4: 'accumulate tail'}
 
 
