@@ -389,6 +389,39 @@ int npb_panoptic_forward_eval(const float *logits, const float *heat, const floa
                               int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle,
                               int32_t *status, const npb_eval_args *eval, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Validation LOOP: npb_panoptic_forward_eval with the matcher pipelined over consecutive calls.
+ * Replaces: the same reference code as npb_panoptic_forward_eval; what changes is WHEN the PQ
+ *           matcher of a batch runs (metric/pq.py:264-303 only defines the states after the loop).
+ * The matcher of a batch is 1 CTA per frame of pure latency (hash merges, barriers) that leaves
+ * the other SMs idle at the end of every call.  Here a call issues the pixel pass of ITS batch but
+ * not the matcher; the next call starts with that matcher (`pending`, with its own batch size),
+ * which lets the centre detection + grouping of the new batch run beside it, and the pixel pass of
+ * the new batch is ordered behind it (all on `stream`, a chain of programmatic dependent
+ * launches, capturable).  The states therefore lag one batch behind until npb_pq_match_pending
+ * has been called for the last batch (the Python layer does that before anything reads the
+ * states).  Frame order, and with it every float64 sum, is unchanged.
+ *   eval       evaluation half of THIS batch (its matcher is left pending)
+ *   pending    evaluation half of the previous pipelined call on the same eval->workspace whose
+ *              matcher has not run yet, or NULL; pending_B its batch size
+ * eval->workspace must have been zeroed ONCE by the caller when it was created: the hand-over
+ * tables in it are zero at rest (the matcher cleans up behind itself), no call clears them.
+ * ------------------------------------------------------------------------- */
+int npb_panoptic_forward_eval_pipelined(
+    const float *logits, const float *heat, const float *offset, const float *orientation, int B,
+    int C, int H, int W, const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
+    float threshold, int nms_kernel_size, int top_k, int apply_fg_mask, int normalized_offset,
+    int use_distance_threshold, float distance_threshold, int64_t max_instances_per_category,
+    void *workspace, uint8_t *sem_out, uint8_t *inst_out, int64_t *pan_out, uint8_t *pan_sem_out,
+    int32_t *centers_yx, int32_t *n_centers, float *center_score, int32_t *inst_class,
+    int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle, int32_t *status,
+    const npb_eval_args *eval, const npb_eval_args *pending, int pending_B, void *stream);
+
+/* The matcher + frame accumulation of a batch whose pixel pass was issued by
+ * npb_panoptic_forward_eval_pipelined (call it on a stream ordered after that call). */
+int npb_pq_match_pending(const npb_eval_args *pending, int B, int64_t max_instances_per_category,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,9 @@ _SIGNATURES = {
     'npb_panoptic_forward_workspace_init': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P]),
     'npb_panoptic_forward': (c_int, _FORWARD_ARGS + [_P]),
     'npb_panoptic_forward_eval': (c_int, _FORWARD_ARGS + [POINTER(EvalArgs), _P]),
+    'npb_panoptic_forward_eval_pipelined': (c_int, _FORWARD_ARGS + [POINTER(EvalArgs), POINTER(EvalArgs),
+                                                            c_int, _P]),
+    'npb_pq_match_pending': (c_int, [POINTER(EvalArgs), c_int, c_int64, _P]),
     'npb_write_panoptic_eval': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64,
                                         _P, _P, POINTER(EvalArgs), _P]),
     'npb_panoptic_scores': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,

@@ -117,7 +117,8 @@ static int panoptic_forward_impl(
     void *workspace, uint8_t *sem_out, uint8_t *inst_out, int64_t *pan_out, uint8_t *pan_sem_out,
     int32_t *centers_yx, int32_t *n_centers, float *center_score, int32_t *inst_class,
     int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle, int32_t *status,
-    const npb_eval_args *eval, void *stream)
+    const npb_eval_args *eval, const npb_eval_args *pending, int pending_B, bool pipelined,
+    void *stream)
 {
     if (!logits || !heat || !offset || !workspace || !sem_out || !inst_out || !pan_out ||
         !centers_yx || !n_centers || !center_score || !inst_class || !inst_pan_id || !inst_area ||
@@ -145,10 +146,25 @@ static int panoptic_forward_impl(
     scratch.bytes1 = 0;
     if (eval) {
         if (!eval->workspace) return NPB_ERR_ARG;
-        pq_cleared_range(eval->workspace, B, eval->num_categories, max_instances_per_category,
-                         &scratch.p1, &scratch.bytes1);
+        // pipelined: the hand-over tables are zero at rest (the matcher cleans up behind itself) and
+        // the matcher of the PREVIOUS call may still be reading them while this call's NMS runs
+        if (!pipelined)
+            pq_cleared_range(eval->workspace, B, eval->num_categories, max_instances_per_category,
+                             &scratch.p1, &scratch.bytes1);
     }
     int rc;
+    // Pipelined evaluation: the matcher of the PREVIOUS call (1 CTA per frame of pure latency,
+    // nothing for the other SMs to do) is the first kernel of this chain.  It lets its dependents
+    // start as soon as its own dependency wait has passed, and the NMS pass -- which needs nothing
+    // from it -- then runs beside it and only waits for it at its END, so that "NMS complete"
+    // still implies "matcher complete" for the pixel pass of this call, the next writer of the
+    // hand-over tables.  A plain chain of programmatic dependent launches: eager or captured.
+    bool nms_late_wait = false;
+    if (pending) {
+        rc = pq_match_impl(pending, pending_B, max_instances_per_category, stream);
+        if (rc != NPB_OK) return rc;
+        nms_late_wait = !apply_fg_mask;     // (the arg-max pass of that option is a plain launch)
+    }
     const uint8_t *fg = nullptr;
     const float *group_logits = logits;
     const uint8_t *group_sem = nullptr;
@@ -165,7 +181,7 @@ static int panoptic_forward_impl(
     }
     rc = instance_centers_impl(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
                                ws_centers, centers_yx, n_centers, center_score, status, true, true,
-                               &scratch, stream);
+                               &scratch, nms_late_wait, stream);
     if (rc != NPB_OK) return rc;
     rc = group_pixels_impl(group_logits, group_sem, nullptr, offset, orientation, B, C, H, W,
                            h_thing_lut, centers_yx, n_centers, normalized_offset,
@@ -181,7 +197,7 @@ static int panoptic_forward_impl(
         f.inst_angle = inst_angle;
         return write_panoptic_eval_impl(sem_out, inst_out, inst_pan_id, inst_class, B, C, H, W,
                                         h_thing_lut, max_instances_per_category, pan_out,
-                                        pan_sem_out, eval, &f, true, stream);
+                                        pan_sem_out, eval, &f, true, pipelined, stream);
     }
     rc = npb_finalize_instances(vote_hist, ori_sum, n_centers, B, C, 1, max_instances_per_category,
                                 0, h_orientation_lut, inst_class, inst_pan_id, inst_area,
@@ -205,7 +221,8 @@ extern "C" int npb_panoptic_forward(
                                  normalized_offset, use_distance_threshold, distance_threshold,
                                  max_instances_per_category, workspace, sem_out, inst_out, pan_out,
                                  pan_sem_out, centers_yx, n_centers, center_score, inst_class,
-                                 inst_pan_id, inst_area, inst_angle, status, nullptr, stream);
+                                 inst_pan_id, inst_area, inst_angle, status, nullptr, nullptr, 0, false,
+                                 stream);
 }
 
 extern "C" int npb_panoptic_forward_eval(
@@ -224,5 +241,27 @@ extern "C" int npb_panoptic_forward_eval(
                                  normalized_offset, use_distance_threshold, distance_threshold,
                                  max_instances_per_category, workspace, sem_out, inst_out, pan_out,
                                  pan_sem_out, centers_yx, n_centers, center_score, inst_class,
-                                 inst_pan_id, inst_area, inst_angle, status, eval, stream);
+                                 inst_pan_id, inst_area, inst_angle, status, eval, nullptr, 0, false,
+                                 stream);
+}
+
+extern "C" int npb_panoptic_forward_eval_pipelined(
+    const float *logits, const float *heat, const float *offset, const float *orientation, int B,
+    int C, int H, int W, const uint8_t *h_thing_lut, const uint8_t *h_orientation_lut,
+    float threshold, int nms_kernel_size, int top_k, int apply_fg_mask, int normalized_offset,
+    int use_distance_threshold, float distance_threshold, int64_t max_instances_per_category,
+    void *workspace, uint8_t *sem_out, uint8_t *inst_out, int64_t *pan_out, uint8_t *pan_sem_out,
+    int32_t *centers_yx, int32_t *n_centers, float *center_score, int32_t *inst_class,
+    int64_t *inst_pan_id, int32_t *inst_area, float *inst_angle, int32_t *status,
+    const npb_eval_args *eval, const npb_eval_args *pending, int pending_B, void *stream)
+{
+    if (!eval) return NPB_ERR_ARG;
+    if (pending && pending_B < 1) return NPB_ERR_ARG;
+    return panoptic_forward_impl(logits, heat, offset, orientation, B, C, H, W, h_thing_lut,
+                                 h_orientation_lut, threshold, nms_kernel_size, top_k, apply_fg_mask,
+                                 normalized_offset, use_distance_threshold, distance_threshold,
+                                 max_instances_per_category, workspace, sem_out, inst_out, pan_out,
+                                 pan_sem_out, centers_yx, n_centers, center_score, inst_class,
+                                 inst_pan_id, inst_area, inst_angle, status, eval, pending, pending_B,
+                                 true, stream);
 }

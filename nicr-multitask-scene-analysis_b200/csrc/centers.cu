@@ -41,6 +41,10 @@ struct SelectParams {
     float *center_score;
     int32_t *status;
     int reset_status;
+    // 1: the predecessor on the stream is the matcher of the previous pipelined call, which this
+    // pass does not depend on: the dependency wait moves to the END of the first CTA (completion
+    // of this grid then still implies completion of the matcher, see api.cu)
+    int late_wait;
     // scratch of the LATER stages of the chain, zeroed here by all CTAs (nothing touches it
     // before this grid has completed): no memset node between the kernels of a step
     uint32_t *clear0, *clear1;
@@ -148,6 +152,15 @@ __device__ void select_centers_frame(const SelectParams &sp, int b)
     if (tid == 0) sp.n_centers[b] = n;
 }
 
+// Late dependency wait (SelectParams::late_wait): ONE thread of the grid waits for the predecessor
+// before it exits -- enough for "this grid has completed => the predecessor has completed", and
+// the other CTAs leave their slots to the CTAs behind them instead of idling in them.
+__device__ __forceinline__ void late_dependency_wait(const SelectParams &sp)
+{
+    if (sp.late_wait && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
+        grid_dependency_wait();
+}
+
 // End of an NMS CTA: publish its candidates, count the CTA; the CTA that completes the frame
 // selects the centres.  Every thread of the CTA must call it (barriers inside).
 template <int NT>
@@ -172,7 +185,7 @@ nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, i
     extern __shared__ float tile[];  // (kTileH + 2r) x (kTileW + 2r), thresholded heat + halo
     NPB_TL(sp, 0, start);
     grid_launch_dependents();
-    grid_dependency_wait();
+    if (!sp.late_wait) grid_dependency_wait();
     NPB_TL(sp, 0, wait);
     clear_downstream_scratch(sp);
     const int b = blockIdx.z;
@@ -246,6 +259,7 @@ nms_candidates_kernel(const float *__restrict__ heat, int H, int W, float thr, i
         }
     }
     nms_frame_epilogue<kNmsThreads>(sp, b, (int)(gridDim.x * gridDim.y));
+    late_dependency_wait(sp);
 }
 
 // Direct variant for small windows (k <= 3, the default): 4 consecutive pixels per thread from
@@ -262,7 +276,7 @@ nms_candidates_direct_kernel(const float *__restrict__ heat, int H, int W, float
 {
     NPB_TL(sp, 0, start);
     grid_launch_dependents();
-    grid_dependency_wait();
+    if (!sp.late_wait) grid_dependency_wait();
     NPB_TL(sp, 0, wait);
     clear_downstream_scratch(sp);
     const int b = blockIdx.y;
@@ -367,6 +381,7 @@ nms_candidates_direct_kernel(const float *__restrict__ heat, int H, int W, float
         }
     }
     nms_frame_epilogue<256>(sp, b, (int)gridDim.x);
+    late_dependency_wait(sp);
 }
 
 static int cand_capacity(int H, int W, int ks)
@@ -396,7 +411,8 @@ int npb::instance_centers_impl(const float *heat, int B, int H, int W, float thr
                                int nms_kernel_size, int top_k, const uint8_t *fg, int apply_fg_mask,
                                void *workspace, int32_t *centers_yx, int32_t *n_centers,
                                float *center_score, int32_t *status, bool cleared,
-                               bool reset_status, const ScratchToClear *downstream, void *stream)
+                               bool reset_status, const ScratchToClear *downstream, bool late_wait,
+                               void *stream)
 {
     static_assert(kNmsThreads >= kMaxInst, "the selection needs one thread per centre");
     if (!heat || !workspace || !centers_yx || !n_centers || !center_score || !status)
@@ -421,6 +437,7 @@ int npb::instance_centers_impl(const float *heat, int B, int H, int W, float thr
     sp.fg = apply_fg_mask ? fg : nullptr; sp.H = H; sp.W = W; sp.top_k = top_k;
     sp.centers_yx = centers_yx; sp.n_centers = n_centers; sp.center_score = center_score;
     sp.status = status; sp.reset_status = reset_status ? 1 : 0;
+    sp.late_wait = late_wait ? 1 : 0;
     sp.clear0 = sp.clear1 = nullptr;
     sp.clear0_words = sp.clear1_words = 0;
     if (downstream) {
@@ -458,5 +475,5 @@ extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, floa
 {
     return instance_centers_impl(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
                                  workspace, centers_yx, n_centers, center_score, status, false,
-                                 false, nullptr, stream);
+                                 false, nullptr, false, stream);
 }

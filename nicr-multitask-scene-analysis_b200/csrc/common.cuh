@@ -63,7 +63,7 @@ int instance_centers_impl(const float *heat, int B, int H, int W, float threshol
                           int nms_kernel_size, int top_k, const uint8_t *fg, int apply_fg_mask,
                           void *workspace, int32_t *centers_yx, int32_t *n_centers,
                           float *center_score, int32_t *status, bool cleared, bool reset_status,
-                          const ScratchToClear *downstream, void *stream);
+                          const ScratchToClear *downstream, bool late_wait, void *stream);
 int group_pixels_impl(const float *logits, const uint8_t *sem_in, const uint8_t *fg_in,
                       const float *offset, const float *orientation, int B, int C, int H, int W,
                       const uint8_t *h_thing_lut, const int32_t *centers_yx,
@@ -83,7 +83,10 @@ int write_panoptic_eval_impl(const uint8_t *sem, const uint8_t *inst, int64_t *i
                              int32_t *inst_class, int B, int C, int H, int W,
                              const uint8_t *h_thing_lut, int64_t max_instances_per_category,
                              int64_t *pan_out, uint8_t *pan_sem_out, const npb_eval_args *ev,
-                             const FinalizeParams *fold, bool cleared, void *stream);
+                             const FinalizeParams *fold, bool cleared, bool skip_match,
+                             void *stream);
+// the matcher + frame accumulation of an update whose pixel pass was issued with `skip_match`
+int pq_match_impl(const npb_eval_args *ev, int B, int64_t max_instances_per_category, void *stream);
 // merge.cu: launches finalize_instances_kernel with launch_dependent()
 int launch_finalize(const FinalizeParams &f, int B, void *stream);
 

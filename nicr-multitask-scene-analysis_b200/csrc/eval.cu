@@ -650,15 +650,15 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
 struct MatchParams {
     const unsigned long long *entry_keys;   // see FrameEntries
     const unsigned *entry_cnts;
-    const unsigned *entry_n;
+    unsigned *entry_n;                      // read, then put back to zero
     unsigned entry_cap;
-    const unsigned *frame_dense;            // [B][nd][nd] or null
+    unsigned *frame_dense;                  // [B][nd][nd] or null; every cell read is put back to zero
     int nd;
     int num_categories;
     long long ignored_label, L, offset, void_segment_id;
     int L_shift, O_shift;  // >= 0 when L / offset are powers of two (shifts instead of 64-bit divisions)
     double *frame_stats;   // [B][4][num_categories]
-    unsigned *done_cnt;    // frames matched so far (zeroed before the launch); null: no accumulation
+    unsigned *done_cnt;    // frames matched so far (zero at rest); null: no accumulation
     double *iou, *tp, *fn, *fp;     // running state [num_categories]
     long long *matches;    // [B][match_cap][2] nullable
     int match_cap;
@@ -902,6 +902,10 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const Ma
         g_area[i] = 0; g_matched[i] = 0; p_area[i] = 0; p_void[i] = 0; p_pio[i] = 0; p_matched[i] = 0;
     }
     grid_dependency_wait();       // the pixel pass (launch_dependent: the set-up above overlaps its tail)
+    // Dependents may be staged from here on (not earlier: everything before this grid has
+    // completed now, which is what a successor that does not wait for THIS grid relies on -- the
+    // NMS pass of the next pipelined call, api.cu)
+    grid_launch_dependents();
     NPB_TL(prm, 3, wait);
     __syncthreads();
 
@@ -927,13 +931,18 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const Ma
         }
         C.fail = 1;
     };
+    // The hand-over tables are ZERO AT REST: what the matcher has consumed -- the entry counter of
+    // the frame, the cells of the dense table, the frame counter -- it puts back to zero, so the
+    // pixel pass of the next update finds them clean without a memset in between (and the matcher
+    // of an update may run while the NEXT call's centre detection and grouping are already busy,
+    // npb_panoptic_forward_eval_pipelined).
     // entries of the frame (loaded first: the dense part below hides the latency)
     const unsigned n_raw = prm.entry_n[b];
     const unsigned n_ent = n_raw < prm.entry_cap ? n_raw : prm.entry_cap;   // overflow: flagged by the writer
     // class pairs: dense per-frame table, every pair exactly once (independent loads first)
     if (prm.frame_dense) {
         const int nd = prm.nd, nd2 = nd * nd;
-        const unsigned *fd = prm.frame_dense + (size_t)b * nd2;
+        unsigned *fd = prm.frame_dense + (size_t)b * nd2;
         constexpr int kBatch = 4;
         for (int i0 = tid; i0 < nd2; i0 += kMatchThreads * kBatch) {
             unsigned c[kBatch];
@@ -946,6 +955,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const Ma
             for (int u = 0; u < kBatch; ++u) {
                 if (c[u] == 0u) continue;
                 const int i = i0 + u * kMatchThreads;
+                fd[i] = 0u;
                 const unsigned long long tc = (unsigned)(i / nd), pc = (unsigned)(i % nd);
                 add_pair((tc << prm.L_shift) * (unsigned long long)prm.offset + (pc << prm.L_shift), c[u]);
             }
@@ -986,6 +996,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const Ma
     T.s_cat = (unsigned short *)((double *)t_gslot + kMaxMatched);
     T.max_matched = kMaxMatched;
     match_phases(prm, b, T, m, C);
+    if (tid == 0) prm.entry_n[b] = 0u;      // zero at rest (every thread has read it barriers ago)
     NPB_TL(prm, 4, start);      // slot 4: the accumulation tail (start = matching done)
 
     // state += frame results, frames in order (PanopticQuality.update, pq.py:298-303), by the CTA
@@ -1022,6 +1033,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const Ma
         }
         *dst = acc;
     }
+    if (tid == 0) *prm.done_cnt = 0u;       // zero at rest
     NPB_TL(prm, 4, end);
 }
 
@@ -1545,13 +1557,60 @@ static bool fused_write_supported(int64_t P, int64_t max_instances_per_category,
              (uintptr_t)sem_target) & 3u) == 0;
 }
 
+// The matcher + frame accumulation of an update whose pixel pass has been issued.  `dependent`:
+// launched as a programmatic dependent of the pixel pass (same stream, right behind it); otherwise
+// a plain launch (any stream that is ordered after the pixel pass).
+static int launch_match(void *workspace, int B, int num_categories, int64_t ignored_label,
+                        int64_t max_instances_per_category, int64_t offset, int64_t void_segment_id,
+                        double *iou, double *tp, double *fn, double *fp, double *frame_stats,
+                        int64_t *matches, int match_cap, int32_t *n_matches, int32_t *status,
+                        bool dependent, cudaStream_t s)
+{
+    const PqWorkspace w = pq_workspace(workspace, B);
+    const int nd = pq_dense_side(num_categories, max_instances_per_category);
+    {   // one process may drive several devices: function attributes are per device
+        static std::mutex guard;
+        static bool attr_set_dev[64] = {false};
+        std::lock_guard<std::mutex> lock(guard);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set_dev[dev & 63]) {
+            cudaFuncSetAttribute(match_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)match_smem_bytes());
+            attr_set_dev[dev & 63] = true;
+        }
+    }
+    MatchParams mp = {};
+    mp.entry_keys = w.ekeys; mp.entry_cnts = w.ecnts; mp.entry_n = w.en; mp.entry_cap = w.entry_cap;
+    mp.frame_dense = nd > 0 ? w.fdense : nullptr; mp.nd = nd;
+    mp.num_categories = num_categories;
+    mp.ignored_label = ignored_label; mp.L = max_instances_per_category; mp.offset = offset;
+    mp.void_segment_id = void_segment_id; mp.frame_stats = frame_stats ? frame_stats : w.fstats;
+    mp.L_shift = -1;
+    mp.O_shift = -1;
+    for (int sh = 0; sh < 62; ++sh) {
+        if ((1ll << sh) == max_instances_per_category) mp.L_shift = sh;
+        if ((1ll << sh) == offset) mp.O_shift = sh;
+    }
+    mp.matches = (long long *)matches; mp.match_cap = match_cap; mp.n_matches = n_matches;
+    mp.status = status;
+    mp.done_cnt = w.en + B; mp.iou = iou; mp.tp = tp; mp.fn = fn; mp.fp = fp;
+    NPB_TL_SET(mp);
+    if (dependent)
+        launch_dependent(match_frames_kernel, dim3(B), dim3(kMatchThreads), match_smem_bytes(), s, mp);
+    else
+        match_frames_kernel<<<dim3(B), dim3(kMatchThreads), match_smem_bytes(), s>>>(mp);
+    return record_launch("npb_pq_update (matcher)");
+}
+
 static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64_t *target,
                           const uint8_t *sem_target, int B, int64_t P, int num_categories,
                           int64_t ignored_label, int64_t max_instances_per_category, int64_t offset,
                           int64_t void_segment_id, void *workspace, double *iou, double *tp,
                           double *fn, double *fp, int64_t *confmat, int confmat_n,
                           double *frame_stats, int64_t *matches, int match_cap,
-                          int32_t *n_matches, int32_t *status, bool cleared, void *stream)
+                          int32_t *n_matches, int32_t *status, bool cleared, bool skip_match,
+                          void *stream)
 {
     if ((!pred && !fw) || !target || !workspace || !iou || !tp || !fn || !fp || !status) return NPB_ERR_ARG;
     if (B < 1 || B > 65535 || P < 1 || num_categories < 1 || num_categories > 256 ||
@@ -1566,7 +1625,6 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     const unsigned entry_cap = w.entry_cap;
     unsigned long long *ekeys = w.ekeys;
     unsigned *ecnts = w.ecnts, *en = w.en, *fdense = w.fdense;
-    double *fstats = frame_stats ? frame_stats : w.fstats;
 
     const int nd = pq_dense_side(num_categories, max_instances_per_category);
     if (!cleared) pq_clear_workspace(workspace, B, num_categories, max_instances_per_category, stream);
@@ -1633,8 +1691,6 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     if (!pc_attr_set_dev[dslot]) {
         for (int v = 0; v < kVariants; ++v)
             cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(match_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)match_smem_bytes());
         pc_attr_set_dev[dslot] = true;
     }
     const int n_sm = device_sm_count();
@@ -1678,18 +1734,12 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     }
     launch_dependent(kernel, grid, dim3(kPairThreads), launch_smem, s, pp);
 
-    MatchParams mp = {};
-    mp.entry_keys = ekeys; mp.entry_cnts = ecnts; mp.entry_n = en; mp.entry_cap = entry_cap;
-    mp.frame_dense = pp.frame_dense; mp.nd = nd;
-    mp.num_categories = num_categories;
-    mp.ignored_label = ignored_label; mp.L = max_instances_per_category; mp.offset = offset;
-    mp.void_segment_id = void_segment_id; mp.frame_stats = fstats;
-    mp.L_shift = pp.L_shift; mp.O_shift = pp.O_shift;
-    mp.matches = (long long *)matches; mp.match_cap = match_cap; mp.n_matches = n_matches;
-    mp.status = status;
-    mp.done_cnt = en + B; mp.iou = iou; mp.tp = tp; mp.fn = fn; mp.fp = fp;
-    NPB_TL_SET(mp);
-    launch_dependent(match_frames_kernel, dim3(B), dim3(kMatchThreads), match_smem_bytes(), s, mp);
+    if (skip_match) return record_launch("npb_pq_update (pixel pass)");
+    // the attribute of the matcher is set above
+    const int rc = launch_match(workspace, B, num_categories, ignored_label, max_instances_per_category,
+                                offset, void_segment_id, iou, tp, fn, fp, frame_stats, matches,
+                                match_cap, n_matches, status, true, s);
+    if (rc != NPB_OK) return rc;
     return record_launch("npb_pq_update");
 }
 
@@ -1705,7 +1755,7 @@ extern "C" int npb_pq_update(const int64_t *pred, const int64_t *target, const u
     return pq_update_impl(pred, nullptr, target, sem_target, B, P, num_categories, ignored_label,
                           max_instances_per_category, offset, void_segment_id, workspace, iou, tp,
                           fn, fp, confmat, confmat_n, frame_stats, matches, match_cap, n_matches,
-                          status, false, stream);
+                          status, false, false, stream);
 }
 
 // `fold`: derive the instance tables from the vote histograms inside the fused pass (or, when
@@ -1715,7 +1765,8 @@ int npb::write_panoptic_eval_impl(const uint8_t *sem, const uint8_t *inst, int64
                                   int32_t *inst_class, int B, int C, int H, int W,
                                   const uint8_t *h_thing_lut, int64_t max_instances_per_category,
                                   int64_t *pan_out, uint8_t *pan_sem_out, const npb_eval_args *ev,
-                                  const FinalizeParams *fold, bool cleared, void *stream)
+                                  const FinalizeParams *fold, bool cleared, bool skip_match,
+                                  void *stream)
 {
     if (!sem || !inst || !inst_pan_id || !pan_out || !h_thing_lut || !ev) return NPB_ERR_ARG;
     if (C < 1 || C > 255 || B < 1 || H < 1 || W < 1) return NPB_ERR_ARG;
@@ -1727,7 +1778,7 @@ int npb::write_panoptic_eval_impl(const uint8_t *sem, const uint8_t *inst, int64
                               ev->ignored_label, max_instances_per_category, ev->offset,
                               ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
                               ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches,
-                              ev->match_cap, ev->n_matches, ev->status, cleared, stream);
+                              ev->match_cap, ev->n_matches, ev->status, cleared, skip_match, stream);
     // other id geometries / unaligned maps: the passes one after the other (same results)
     if (fold) {
         const int rc0 = launch_finalize(*fold, B, stream);
@@ -1740,7 +1791,7 @@ int npb::write_panoptic_eval_impl(const uint8_t *sem, const uint8_t *inst, int64
                           ev->ignored_label, max_instances_per_category, ev->offset,
                           ev->void_segment_id, ev->workspace, ev->iou, ev->tp, ev->fn, ev->fp,
                           ev->confmat, ev->confmat_n, ev->frame_stats, ev->matches, ev->match_cap,
-                          ev->n_matches, ev->status, cleared, stream);
+                          ev->n_matches, ev->status, cleared, skip_match, stream);
 }
 
 extern "C" int npb_write_panoptic_eval(const uint8_t *sem, const uint8_t *inst,
@@ -1751,7 +1802,30 @@ extern "C" int npb_write_panoptic_eval(const uint8_t *sem, const uint8_t *inst,
 {
     return write_panoptic_eval_impl(sem, inst, (int64_t *)inst_pan_id, (int32_t *)inst_class, B, C,
                                     H, W, h_thing_lut, max_instances_per_category, pan_out,
-                                    pan_sem_out, ev, nullptr, false, stream);
+                                    pan_sem_out, ev, nullptr, false, false, stream);
+}
+
+// matcher of an update whose pixel pass was issued with `skip_match` (api.cu: pipelined chain),
+// as a programmatic dependent of whatever precedes it on the stream
+int npb::pq_match_impl(const npb_eval_args *ev, int B, int64_t max_instances_per_category,
+                       void *stream)
+{
+    if (!ev || !ev->workspace || !ev->iou || !ev->tp || !ev->fn || !ev->fp || !ev->status)
+        return NPB_ERR_ARG;
+    if (B < 1 || B > 65535 || ev->num_categories < 1 || ev->num_categories > 256 ||
+        max_instances_per_category < 1 || ev->offset < 1)
+        return NPB_ERR_ARG;
+    if (ev->matches && (ev->match_cap < 1 || !ev->n_matches)) return NPB_ERR_ARG;
+    return launch_match(ev->workspace, B, ev->num_categories, ev->ignored_label,
+                        max_instances_per_category, ev->offset, ev->void_segment_id, ev->iou, ev->tp,
+                        ev->fn, ev->fp, ev->frame_stats, ev->matches, ev->match_cap, ev->n_matches,
+                        ev->status, true, (cudaStream_t)stream);
+}
+
+extern "C" int npb_pq_match_pending(const npb_eval_args *pending, int B,
+                                    int64_t max_instances_per_category, void *stream)
+{
+    return pq_match_impl(pending, B, max_instances_per_category, stream);
 }
 
 // ---- fall-back entry point -----------------------------------------------------------------------

@@ -41,4 +41,7 @@ class CapturedStep:
         tables = self.result.get('_panoptic_instance_tables') if isinstance(self.result, dict) else None
         if tables is not None:
             tables.invalidate()
+        remark = self.result.get('_panoptic_evaluation_pipelined') if isinstance(self.result, dict) else None
+        if remark is not None:
+            remark()        # the replayed step leaves the matcher of its batch pending again
         return self.result

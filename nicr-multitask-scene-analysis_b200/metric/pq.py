@@ -24,28 +24,45 @@ def _safe_divide(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return torch.where(torch.abs(y) < _EPSILON, torch.zeros_like(x), x / y)
 
 
+class _ScratchOwner:
+    def __init__(self, scratch):
+        self._scratch = scratch
+
+
 class _PQKernel:
     """Workspace + launch helper shared by PanopticQuality and compare_and_accumulate."""
 
-    _scratch = {}      # (device, stream, B, num_categories) -> reusable workspace
+    _scratch = {}      # workspaces of the function-style entry points (compare_and_accumulate)
 
     @classmethod
-    def _workspace(cls, dev, B, num_categories):
-        # scratch only lives for the duration of one call, so calls issued on the same stream
-        # can share it; calls on different streams get their own
-        key = (dev, torch.cuda.current_stream(dev).cuda_stream, B, num_categories)
+    def _workspace(cls, dev, B, num_categories, scratch=None):
+        """(device, stream, B, num_categories) -> reusable workspace.  `scratch`: the dict of the
+        metric object that owns the update -- a workspace may hold the hand-over of an update
+        whose matcher has not run yet (pipelined matching), so metric objects do not share one."""
+        if scratch is not None:
+            # one workspace per metric object, batch size and device -- NOT per stream: a pending
+            # hand-over must be found again by a call that is issued on another (ordered) stream,
+            # e.g. the capture stream of a CUDA graph behind eager warm-up calls, and a workspace
+            # must never be created (zero-filled) inside a capture
+            cls = _ScratchOwner(scratch)
+            key = (dev, None, B, num_categories)
+        else:
+            key = (dev, torch.cuda.current_stream(dev).cuda_stream, B, num_categories)
         if key not in cls._scratch:
             # the size depends on the SM count of the device the kernels will run on
             with torch.cuda.device(dev):
                 nbytes = _lib.lib().npb_pq_update_workspace_bytes(B, num_categories)
-            cls._scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            # zeroed once: the hand-over tables between pixel pass and matcher are zero at rest
+            # (the matcher cleans up behind itself; npb_panoptic_forward_eval_pipelined relies on it)
+            cls._scratch[key] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         return cls._scratch[key]
 
     @staticmethod
     def prepare(target: torch.Tensor, num_categories: int, ignored_label: int, offset: int,
                 void_segment_id: int, iou, tp, fn, fp, sem_target: Optional[torch.Tensor] = None,
                 confmat: Optional[torch.Tensor] = None, want_matches: bool = False,
-                want_frame_stats: bool = False, status: Optional[torch.Tensor] = None):
+                want_frame_stats: bool = False, status: Optional[torch.Tensor] = None,
+                scratch: Optional[Dict] = None):
         """Everything of an update except the prediction: validated targets, scratch, optional
         outputs.  Returns (`_lib.EvalArgs`, dict of the tensors it points into)."""
         dev = iou.device
@@ -53,7 +70,7 @@ class _PQKernel:
             raise RuntimeError('PanopticQuality.update needs its states on a CUDA device')
         target = _lib.require_cuda(target.to(dev).to(torch.int64), 'targets', ndim=3)
         B = target.shape[0]
-        ws = _PQKernel._workspace(dev, B, num_categories)
+        ws = _PQKernel._workspace(dev, B, num_categories, scratch)
         if status is None or status.numel() < B:
             status = torch.zeros(B, dtype=torch.int32, device=dev)
         matches = n_matches = frame_stats = None
@@ -188,6 +205,10 @@ class PanopticQuality(MetricState):
         # atomicMin) and a capacity overflow stays an error.
         self._status: Dict[int, torch.Tensor] = {}
         self._pending: List[Dict] = []
+        self._scratch: Dict = {}            # kernel workspaces of this metric object
+        # pipelined matching (PanopticPostprocessing.fuse_evaluation(..., pipeline_matching=True)):
+        # the update whose pixel pass has been issued but whose matcher has not run yet
+        self._deferred: Optional[Dict] = None
 
     # ---- update --------------------------------------------------------------------------
     def _status_for(self, B: int) -> Tuple[torch.Tensor, bool]:
@@ -225,8 +246,11 @@ class PanopticQuality(MetricState):
             self._resolve(self._pending.pop(0))
 
     def _resolve(self, entry: Dict) -> None:
-        entry['landed'].synchronize()
-        codes = entry['host'].tolist()
+        if entry.get('host') is None:
+            codes = entry['status'].cpu().tolist()
+        else:
+            entry['landed'].synchronize()
+            codes = entry['host'].tolist()
         big = [b for b, c in enumerate(codes) if c == _lib.ERR_CAPACITY]
         _lib.raise_for_status([c for c in codes if c != _lib.ERR_CAPACITY],
                               type(self).__name__ + '.update')
@@ -240,16 +264,50 @@ class PanopticQuality(MetricState):
                 n_matches_row=None if n is None else n[b:b + 1],
                 where=type(self).__name__ + '.update')
 
+    # ---- pipelined matching ----------------------------------------------------------------
+    def _set_deferred(self, args, keep: Dict, preds: Optional[torch.Tensor], B: int) -> None:
+        """The pixel pass of an update has been issued, its matcher has not (it runs next to
+        the kernels of the next pipelined call, or in `_flush_deferred`)."""
+        self._deferred = dict(args=args, keep=keep, preds=preds, B=int(B))
+
+    def _deferred_matcher_issued(self, captured: bool = False) -> None:
+        """The matcher of the deferred update has just been enqueued: an eager update is followed
+        up from here (its status words are final behind that matcher)."""
+        d, self._deferred = self._deferred, None
+        if d is None or not d['keep'].get('eager'):
+            return
+        k = d['keep']
+        if captured:
+            # handed over to a CUDA graph (the first replay runs its matcher and reports into the
+            # shared status words): only its own words are looked at, at the next check
+            self._pending.append(dict(status=k['status'], host=None, landed=None, preds=d['preds'],
+                                      targets=k['target'], matches=None, n_matches=None))
+        else:
+            self._follow_up(k['status'], d['preds'], k['target'], k['matches'], k['n_matches'])
+
+    def _flush_deferred(self) -> None:
+        """Run the matcher of the deferred update now (current stream)."""
+        d = self._deferred
+        if d is None:
+            return
+        import ctypes
+        dev = self.iou_per_class.device
+        _lib.check(_lib.lib().npb_pq_match_pending(
+            ctypes.byref(d['args']), c_int(d['B']), c_int64(self.max_instances_per_category),
+            _lib.stream_ptr(dev)), 'npb_pq_match_pending')
+        self._deferred_matcher_issued()
+
     def _launch(self, preds, targets, **kw):
         assert preds.ndim == 3
         assert targets.shape == preds.shape
+        self._flush_deferred()      # the stand-alone update shares the hand-over workspace
         self._shared_status(preds.shape[0])
         status, eager = self._status_for(preds.shape[0])
         _, matches, n_matches, frame_stats = _PQKernel.run(
             preds, targets, self.num_categories, self.ignored_label,
             self.max_instances_per_category, self.offset, self.void_segment_id,
             self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
-            status=status, **kw)
+            status=status, scratch=self._scratch, **kw)
         if eager:
             self._follow_up(status, preds, targets, matches, n_matches)
         return matches, n_matches, frame_stats
@@ -264,7 +322,7 @@ class PanopticQuality(MetricState):
         args, keep = _PQKernel.prepare(
             targets, self.num_categories, self.ignored_label, self.offset, self.void_segment_id,
             self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
-            status=status, **kw)
+            status=status, scratch=self._scratch, **kw)
         keep['eager'] = eager
         return args, keep
 
@@ -281,6 +339,7 @@ class PanopticQuality(MetricState):
         self._launch(preds, targets)
 
     def check_status(self) -> None:
+        self._flush_deferred()
         pending, self._pending = self._pending, []
         for entry in pending:
             self._resolve(entry)
@@ -290,6 +349,7 @@ class PanopticQuality(MetricState):
             _lib.raise_for_status(codes, type(self).__name__ + '.update')
 
     def reset(self) -> None:
+        self._flush_deferred()      # its frames belong to the states that are being dropped
         super().reset()
         self._pending = []
         for status in self._status.values():

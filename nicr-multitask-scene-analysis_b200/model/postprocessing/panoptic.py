@@ -69,7 +69,7 @@ class PanopticPostprocessing(DensePostprocessingBase):
         return {**r_sem, **r_ins}
 
     # ------------------------------------------------------------------ fused kernel chain
-    def _forward_kernels(self, logits, heat, offset, orientation, eval_args=None):
+    def _forward_kernels(self, logits, heat, offset, orientation, eval_args=None, pipeline=None):
         post = self._instance_postprocessing
         logits = _lib.require_cuda(logits, 'semantic logits', torch.float32, 4)
         dev = logits.device
@@ -127,22 +127,42 @@ class PanopticPostprocessing(DensePostprocessingBase):
             tables.dptr('inst_area'), tables.dptr('inst_angle'), tables.dptr('status'))
         if eval_args is None:
             _lib.check(L.npb_panoptic_forward(*args, _lib.stream_ptr(dev)), 'npb_panoptic_forward')
-        else:       # the last stage also evaluates the ids it writes
+        elif pipeline is None:       # the last stage also evaluates the ids it writes
             import ctypes
             _lib.check(L.npb_panoptic_forward_eval(*args, ctypes.byref(eval_args),
                                                    _lib.stream_ptr(dev)),
                        'npb_panoptic_forward_eval')
+        else:
+            # ... and leaves its matcher to the next call, which runs it next to its own centre
+            # detection + grouping (`pipeline` = (pending npb_eval_args or None, its batch size))
+            import ctypes
+            pending, pending_B = pipeline
+            _lib.check(L.npb_panoptic_forward_eval_pipelined(
+                *args, ctypes.byref(eval_args),
+                ctypes.byref(pending) if pending is not None else None, c_int(pending_B),
+                _lib.stream_ptr(dev)), 'npb_panoptic_forward_eval_pipelined')
         return sem, inst, pan, pan_sem, tables
 
     # ------------------------------------------------------------------ fused evaluation
-    def fuse_evaluation(self, evaluation) -> None:
+    PIPELINE_MAX_FRAMES = 16    # largest batch whose matcher is pipelined over consecutive calls
+
+    def fuse_evaluation(self, evaluation, pipeline_matching: bool = False) -> None:
         """Attach a `metric.PanopticEvaluation` (or None to detach).  When the batch handed to
         `postprocess` carries the ground truth (`panoptic_fullres`, `semantic_fullres`) at the
         resolution of the network outputs, the kernel that writes the panoptic ids also feeds
         PQ and mIoU (task_helper/panoptic.py:104-126) -- the ids are not read back.  The result
         dict then carries `_panoptic_evaluation_fused` (and `_panoptic_matches` when the batch
-        has orientations) so that the task helper skips its own update."""
+        has orientations) so that the task helper skips its own update.
+
+        `pipeline_matching`: a validation LOOP.  The PQ matcher of a batch (one CTA per frame of
+        pure latency) is left pending and runs next to the centre detection + grouping of the
+        NEXT call, or when anything reads / resets the PQ states (`compute`, `check_status`,
+        `reset`, a stand-alone `update`).  States and results are identical; only batches that
+        need their matches right away (orientation MAAE) are matched in their own call."""
+        if self._fused_evaluation is not None and evaluation is not self._fused_evaluation:
+            self._fused_evaluation.pq._flush_deferred()
         self._fused_evaluation = evaluation
+        self._pipeline_matching = bool(pipeline_matching) and evaluation is not None
 
     def _fused_eval_args(self, batch, logits):
         ev = getattr(self, '_fused_evaluation', None)
@@ -155,7 +175,15 @@ class PanopticPostprocessing(DensePostprocessingBase):
         if tuple(pan_t.shape) != shape or tuple(sem_t.shape) != shape:
             return None         # evaluation happens at dataset resolution: not the same maps
         want_matches = 'orientations_present' in batch and hasattr(ev.pq, 'update_mae')
-        return ev.eval_args(pan_t, sem_t, want_matches=want_matches) + (ev,)
+        # Every matcher CTA owns a whole SM while it works through its latency-bound phases:
+        # next to the (HBM-saturating) grouping kernel of a large batch that costs more than the
+        # matcher's place at the end of the step (measured: 64 frames 530x730, 800 -> 850 us),
+        # for a few frames it removes it from the step (8 frames 480x640, 108 -> 99 us)
+        pipelined = getattr(self, '_pipeline_matching', False) and not want_matches and \
+            shape[0] <= self.PIPELINE_MAX_FRAMES
+        if not pipelined:
+            ev.pq._flush_deferred()         # the call below clears the hand-over workspace
+        return ev.eval_args(pan_t, sem_t, want_matches=want_matches) + (ev, pipelined)
 
     def _thing_mask(self, sem_u8: torch.Tensor) -> torch.Tensor:
         """panoptic.py:123-127 `isin(semantic idx, thing ids)` -> bool (B,H,W)."""
@@ -173,9 +201,26 @@ class PanopticPostprocessing(DensePostprocessingBase):
         orientation = i_output[2] if with_orientation else None
 
         fused = self._fused_eval_args(batch, s_output)
+        pipeline = None
+        if fused and fused[3]:
+            pq = fused[2].pq
+            capturing = torch.cuda.is_current_stream_capturing()
+            B = s_output.shape[0]
+            if capturing and pq._deferred is not None and pq._deferred['B'] != B:
+                raise RuntimeError('a pipelined update of another batch size is pending: call '
+                                   'check_status() / compute() before capturing this step')
+            if capturing and pq._deferred is not None:
+                # every replay runs the matcher of the replay before it: same buffers, same
+                # (shared) status words as this call -- the descriptor of this call itself
+                pipeline = (fused[0], B)
+            elif not capturing:
+                d = pq._deferred
+                pipeline = (d['args'], d['B']) if d is not None else (None, 0)
+            # (a capture that finds nothing pending cannot start a pipeline: it would replay a
+            # pixel pass whose matcher never runs -- that call is matched in place)
         sem, inst, pan, pan_sem, tables = self._forward_kernels(
             s_output, center_heatmap, center_offset, orientation,
-            eval_args=fused[0] if fused else None)
+            eval_args=fused[0] if fused else None, pipeline=pipeline)
 
         # semantic + instance entries (panoptic.py:86-94); the class map is shared
         r = ResultDict(semantic_output=s_output, semantic_side_outputs=s_side_outputs)
@@ -190,9 +235,19 @@ class PanopticPostprocessing(DensePostprocessingBase):
         r.defer('panoptic_segmentation_deeplab_semantic_idx', lambda: widen_u8(pan_sem))
         r['panoptic_segmentation_deeplab_instance_idx'] = inst
         r['_panoptic_instance_tables'] = tables
-        if fused:
+        if fused and pipeline is not None:
+            pq = fused[2].pq
+            captured = torch.cuda.is_current_stream_capturing()
+            pq._deferred_matcher_issued(captured=captured)     # the pending one has been enqueued
+            pq._set_deferred(fused[0], fused[1], pan, s_output.shape[0])
+            # a CUDA-graph replay leaves the same update pending again (graph.CapturedStep)
+            r['_panoptic_evaluation_pipelined'] = \
+                lambda pq=pq, a=fused[0], k=fused[1], B=s_output.shape[0]: pq._set_deferred(a, k, None, B)
+        elif fused:
             fused[2].pq._fused_issued(fused[1], pan)
-            # PQ / mIoU states already hold this batch; a task helper must not add it again
+        if fused:
+            # PQ / mIoU states already hold this batch (or will, before anybody can read them);
+            # a task helper must not add it again
             r['_panoptic_evaluation_fused'] = True
             if fused[1].get('matches') is not None:
                 r['_panoptic_matches'] = (fused[1]['matches'], fused[1]['n_matches'])

@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--config', default='nyuv2')
     ap.add_argument('--frames', type=int, default=0)
     ap.add_argument('--eager', action='store_true')
+    ap.add_argument('--no-pipeline', action='store_true')
     args = ap.parse_args()
     w = dict(bench.WORKLOADS[args.config])
     if args.frames:
@@ -52,7 +53,7 @@ def main():
     raw = ((data['logits'], inst_out), (None, None))
     r0 = post.postprocess(raw, batch, is_training=False)
     tgt_pan, tgt_sem = testing.make_eval_targets(r0['panoptic_segmentation_deeplab'], 1 << 16)
-    post.fuse_evaluation(ev)
+    post.fuse_evaluation(ev, pipeline_matching=not args.no_pipeline)
     batch_gt = dict(batch, panoptic_fullres=tgt_pan, semantic_fullres=tgt_sem)
 
     def eager():

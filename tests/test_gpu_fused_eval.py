@@ -186,3 +186,123 @@ def test_fused_step_with_overflowing_frames(cuda_device):
     assert np.array_equal(got[1:], state[1:])
     np.testing.assert_allclose(got[0], state[0], rtol=1e-14)
     assert np.array_equal(ev.miou.confmat.cpu().numpy(), oracle.confmat(ref['panoptic'] // L, tgt_sem, C + 1))
+
+
+def _gt_batch(pan_ref, B, H, W, dev, shift=5):
+    from nicr_mt_scene_analysis_b200 import testing
+    tgt = np.roll(pan_ref, shift, axis=-1)
+    return dict(testing.make_batch_dict(B, H, W),
+                panoptic_fullres=torch.from_numpy(tgt).to(dev),
+                semantic_fullres=torch.from_numpy((tgt // L).astype(np.uint8)).to(dev))
+
+
+def test_pipelined_matching_equals_in_place_matching(cuda_device):
+    """`fuse_evaluation(..., pipeline_matching=True)`: the matcher of a batch runs during the next
+    call (or when the states are read).  Batches of different sizes and contents, a read of the
+    states in the middle, a stand-alone update in between and a reset: the float64 states and
+    the confusion matrix are bit-identical to matching every batch in its own call."""
+    from nicr_mt_scene_analysis_b200 import testing
+    C, K, H, W = 9, 4, 64, 96
+    post_p, ev_p, is_thing, has_ori = _make(C, cuda_device)
+    post_s, ev_s, _, _ = _make(C, cuda_device)
+    post_p.fuse_evaluation(ev_p, pipeline_matching=True)
+    post_s.fuse_evaluation(ev_s)
+    batches = []
+    for i, B in enumerate((3, 3, 2, 3, 1, 3)):
+        data = testing.make_batch(B, C, H, W, K, seed=60 + i)
+        ref = oracle.panoptic_postprocess(*(data[k].numpy() for k in
+                                            ('logits', 'heat', 'offset', 'orientation')),
+                                          is_thing, has_ori)
+        batches.append((data, _gt_batch(ref['panoptic'], B, H, W, cuda_device, shift=3 + i)))
+
+    def run(post, ev, i):
+        data, gt = batches[i]
+        r = post.postprocess(_raw(data, cuda_device), gt, is_training=False)
+        assert r.get('_panoptic_evaluation_fused') is True
+        return r
+
+    for i in range(3):
+        rp, rs = run(post_p, ev_p, i), run(post_s, ev_s, i)
+        assert torch.equal(rp['panoptic_segmentation_deeplab'], rs['panoptic_segmentation_deeplab'])
+    assert ev_p.pq._deferred is not None            # the last batch is still unmatched ...
+    assert np.array_equal(_states(ev_s), _states(ev_s))
+    ev_p.pq.check_status()                          # ... until somebody needs the states
+    assert ev_p.pq._deferred is None
+    assert np.array_equal(_states(ev_p), _states(ev_s))
+    # a stand-alone update between pipelined calls (it shares the hand-over workspace)
+    run(post_p, ev_p, 3), run(post_s, ev_s, 3)
+    data, gt = batches[0]
+    pan = run(post_s, ev_s, 0)['panoptic_segmentation_deeplab']
+    ev_p.update(pan, gt['panoptic_fullres'], gt['semantic_fullres'])
+    for i in (4, 5):
+        run(post_p, ev_p, i), run(post_s, ev_s, i)
+    res_p, res_s = ev_p.compute(), ev_s.compute()
+    assert np.array_equal(_states(ev_p), _states(ev_s))
+    assert np.array_equal(ev_p.miou.confmat.cpu().numpy(), ev_s.miou.confmat.cpu().numpy())
+    assert float(res_p['all_pq']) == float(res_s['all_pq'])
+    # reset with a batch pending: that batch must not leak into the new states
+    run(post_p, ev_p, 1)
+    ev_p.reset()
+    run(post_p, ev_p, 2)
+    ev_s.reset()
+    run(post_s, ev_s, 2)
+    ev_p.pq.check_status(), ev_s.pq.check_status()
+    assert np.array_equal(_states(ev_p), _states(ev_s))
+
+
+def test_pipelined_matching_in_a_cuda_graph(cuda_device):
+    """The pipelined step captured into a CUDA graph (what bench.py replays): every replay runs
+    the matcher of the replay before it; reading the states flushes the last one; replaying after
+    such a read, and eager calls mixed with replays, stay exact."""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.graph import CapturedStep
+    C, K, B, H, W = 7, 3, 4, 48, 64
+    post_p, ev_p, is_thing, has_ori = _make(C, cuda_device)
+    post_s, ev_s, _, _ = _make(C, cuda_device)
+    post_p.fuse_evaluation(ev_p, pipeline_matching=True)
+    post_s.fuse_evaluation(ev_s)
+    data = testing.make_batch(B, C, H, W, K, seed=71)
+    ref = oracle.panoptic_postprocess(*(data[k].numpy() for k in
+                                        ('logits', 'heat', 'offset', 'orientation')), is_thing, has_ori)
+    gt = _gt_batch(ref['panoptic'], B, H, W, cuda_device)
+    raw = _raw(data, cuda_device)
+    post_p._async_results = True                     # nothing may block inside a capture
+    step = CapturedStep(lambda: post_p.postprocess(raw, gt, is_training=False), warmup=3,
+                        device=cuda_device)
+    n = 3                                            # the warm-up steps count as updates
+    for _ in range(4):
+        step.replay()
+        n += 1
+    ev_p.pq.check_status()
+    for _ in range(2):                               # replays after a flush
+        step.replay()
+        n += 1
+    post_p.postprocess(raw, gt, is_training=False)   # an eager call behind a replay
+    n += 1
+    step.replay()
+    n += 1
+    for _ in range(n):
+        post_s.postprocess(raw, gt, is_training=False)
+    res_p, res_s = ev_p.compute(), ev_s.compute()
+    assert np.array_equal(_states(ev_p), _states(ev_s))
+    assert np.array_equal(ev_p.miou.confmat.cpu().numpy(), ev_s.miou.confmat.cpu().numpy())
+    assert float(res_p['all_pq']) == float(res_s['all_pq']) > 0
+
+
+def test_pipelined_matching_keeps_orientation_batches_in_place(cuda_device):
+    """batches that need their matches right away (orientation MAAE) are not deferred"""
+    from nicr_mt_scene_analysis_b200 import testing
+    C, K, B, H, W = 8, 3, 2, 48, 64
+    post, ev, is_thing, has_ori = _make(C, cuda_device, with_mae=True)
+    post.fuse_evaluation(ev, pipeline_matching=True)
+    data = testing.make_batch(B, C, H, W, K, seed=81)
+    ref = oracle.panoptic_postprocess(*(data[k].numpy() for k in
+                                        ('logits', 'heat', 'offset', 'orientation')), is_thing, has_ori)
+    gt = _gt_batch(ref['panoptic'], B, H, W, cuda_device)
+    post.postprocess(_raw(data, cuda_device), gt, is_training=False)
+    assert ev.pq._deferred is not None
+    gt_o = dict(gt, orientations_present=[{} for _ in range(B)])
+    r = post.postprocess(_raw(data, cuda_device), gt_o, is_training=False)
+    assert ev.pq._deferred is None and '_panoptic_matches' in r
+    ev.pq.check_status()
+    assert float(ev.pq.tp_per_class.sum()) > 0
