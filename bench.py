@@ -572,7 +572,7 @@ def run_ours(args):
                          'for the CPU baseline')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    bound_cores = bind_to_gpu_cores(local_rank) if world > 1 else None
+    bound_cores = bind_to_gpu_cores(local_rank) if world > 1 and not os.environ.get('NPB_BENCH_NO_BIND') else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 

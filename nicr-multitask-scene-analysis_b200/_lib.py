@@ -135,18 +135,83 @@ def lib():
                 raise
             fn.restype = restype
             fn.argtypes = argtypes
-        _lib = handle
+        _lib = _Library(handle)
     return _lib
+
+
+class _Library:
+    """The loaded library.  Every entry point that takes a stream is wrapped so that a device
+    switch made by `stream_ptr` while the arguments were built is undone when the call returns
+    OR raises (e.g. ctypes.ArgumentError during argument conversion)."""
+
+    def __init__(self, handle):
+        self._handle = handle
+        for name, (_, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name, None)
+            if fn is None:
+                continue
+            setattr(self, name, self._guarded(fn) if argtypes and argtypes[-1] is _P and
+                    name.startswith('npb_') and 'workspace_bytes' not in name else fn)
+
+    @staticmethod
+    def _guarded(fn):
+        def call(*args):
+            try:
+                return fn(*args)
+            finally:
+                restore_device()
+        call.__name__ = fn.__name__
+        return call
+
+    def __getattr__(self, name):        # anything not in _SIGNATURES (debug builds: timeline)
+        return getattr(self._handle, name)
+
+
+def raise_for_code(code: int, where: str = '') -> None:
+    """Return code of a library call -> exception."""
+    if code != OK:
+        raise NpbError(code, where)
 
 
 def check(code: int, where: str = '') -> None:
     """Return code of a library call -> exception.  Also undoes the device switch `stream_ptr`
     made for that call (see there)."""
+    restore_device()
+    raise_for_code(code, where)
+
+
+def restore_device() -> None:
+    """Undo the device switches of `stream_ptr` of the current thread (idempotent).  `check`
+    calls it; call sites that may fail between `stream_ptr` and `check` (argument conversion)
+    can call it from a `finally`."""
     stack = getattr(_switched, 'stack', None)
-    if stack:
+    while stack:
         torch.cuda.set_device(stack.pop())
-    if code != OK:
-        raise NpbError(code, where)
+
+
+class on_device:
+    """Context manager: the library launches on the CURRENT device of the calling thread, so the
+    device of the tensors is made current for the call and restored afterwards -- also when the
+    call raises (ctypes.ArgumentError and the like).  With one process per GPU nothing is switched."""
+    __slots__ = ('index', 'previous')
+
+    def __init__(self, device):
+        device = torch.device(device)
+        self.index = device.index
+        self.previous = None
+
+    def __enter__(self):
+        if self.index is not None:
+            current = torch.cuda.current_device()
+            if current != self.index:
+                self.previous = current
+                torch.cuda.set_device(self.index)
+        return self
+
+    def __exit__(self, *exc):
+        if self.previous is not None:
+            torch.cuda.set_device(self.previous)
+        return False
 
 
 def raise_for_status(status, where: str = '') -> None:
@@ -183,8 +248,8 @@ def stream_ptr(device) -> c_void_p:
 
     The kernels launch on the CURRENT device of the calling thread, so for tensors that live on
     another device of the process (one process driving several GPUs) that device is made current
-    here; `check`, which every call site applies to the return code of the same call, switches
-    back.  With one process per GPU (the usual set-up) nothing is switched."""
+    here; the call wrapper of `lib()` switches back when the call returns or raises (`check`
+    does so as well).  With one process per GPU (the usual set-up) nothing is switched."""
     device = torch.device(device)
     current = torch.cuda.current_device()
     index = current if device.index is None else device.index
@@ -205,9 +270,19 @@ def dtype_code(t: torch.Tensor) -> int:
 
 
 def host_lut(flags: Sequence[bool], n: int):
-    """bool sequence -> ctypes uint8 array (host look-up table argument `h_*_lut`)."""
-    arr = (ctypes.c_uint8 * max(n, 1))()
-    for i, f in enumerate(flags):
-        if i < n and f:
-            arr[i] = 1
+    """bool sequence -> ctypes uint8 array (host look-up table argument `h_*_lut`); the arrays
+    are read-only for the library and cached per (flags, n)."""
+    key = (tuple(bool(f) for f in flags), int(n))
+    arr = _LUT_CACHE.get(key)
+    if arr is None:
+        arr = (ctypes.c_uint8 * max(n, 1))()
+        for i, f in enumerate(key[0]):
+            if i < n and f:
+                arr[i] = 1
+        if len(_LUT_CACHE) > 256:
+            _LUT_CACHE.clear()
+        _LUT_CACHE[key] = arr
     return arr
+
+
+_LUT_CACHE = {}

@@ -19,23 +19,42 @@ from . import _lib
 
 
 class _Deferred:
-    __slots__ = ('fn',)
+    """`fn()` -- or `fn(result_dict)` when `wants_dict` -- produces the value on first access.
+    Entries that need the dict itself get it handed in at that moment instead of closing over it:
+    a closure over the dict would make it a reference cycle, and its tensors (tens of megabytes
+    per batch) would stay allocated until the garbage collector gets round to it."""
+    __slots__ = ('fn', 'wants_dict')
 
-    def __init__(self, fn: Callable[[], Any]):
+    def __init__(self, fn: Callable[..., Any], wants_dict: bool = False):
         self.fn = fn
+        self.wants_dict = wants_dict
+
+
+class _Alias:
+    __slots__ = ('source',)
+
+    def __init__(self, source: str):
+        self.source = source
 
 
 class ResultDict(dict):
     def defer(self, key: str, fn: Callable[[], Any]) -> None:
         dict.__setitem__(self, key, _Deferred(fn))
 
+    def defer_with_dict(self, key: str, fn: Callable[['ResultDict'], Any]) -> None:
+        """like `defer`, `fn` receives this dict"""
+        dict.__setitem__(self, key, _Deferred(fn, wants_dict=True))
+
     def alias(self, key: str, source: str) -> None:
         """`key` resolves to whatever `source` resolves to (identity full-res twins)."""
-        dict.__setitem__(self, key, _Deferred(lambda: self[source]))
+        dict.__setitem__(self, key, _Alias(source))
 
     def _resolve(self, key, value):
         if isinstance(value, _Deferred):
-            value = value.fn()
+            value = value.fn(self) if value.wants_dict else value.fn()
+            dict.__setitem__(self, key, value)
+        elif isinstance(value, _Alias):
+            value = self[value.source]
             dict.__setitem__(self, key, value)
         return value
 
@@ -61,7 +80,7 @@ class ResultDict(dict):
         return [self[k] for k in list(dict.keys(self))]
 
     def is_deferred(self, key: str) -> bool:
-        return isinstance(dict.__getitem__(self, key), _Deferred)
+        return isinstance(dict.__getitem__(self, key), (_Deferred, _Alias))
 
     def materialize(self) -> 'ResultDict':
         for k in list(dict.keys(self)):
@@ -81,9 +100,18 @@ class InstanceTables:
               ('inst_class', np.int32, _lib.MAX_INST), ('inst_area', np.int32, _lib.MAX_INST),
               ('inst_angle', np.float32, _lib.MAX_INST), ('inst_pan_id', np.int64, _lib.MAX_INST))
 
+    _layouts: Dict[int, Any] = {}
+
     @classmethod
     def layout(cls, batch_size: int):
         """byte offsets of the fields inside the packed buffer (largest alignment first)"""
+        cached = cls._layouts.get(batch_size)
+        if cached is None:
+            cached = cls._layouts[batch_size] = cls._layout(batch_size)
+        return cached
+
+    @classmethod
+    def _layout(cls, batch_size: int):
         offsets, off = {}, 0
         for name, dt, per_frame in sorted(cls.FIELDS, key=lambda f: -np.dtype(f[1]).itemsize):
             nbytes = np.dtype(dt).itemsize * per_frame * batch_size
@@ -125,13 +153,25 @@ class InstanceTables:
         self._np = None
         return self
 
+    # pinned staging buffers for the synchronous download (cudaHostAlloc costs tens of
+    # microseconds: they are kept); the tables are copied out of them before they are reused
+    _staging: Dict[Any, List[torch.Tensor]] = {}
+
     def wait(self) -> 'InstanceTables':
         if self._np is None:
             if self._host is not None:
                 self._host[1].synchronize()
                 raw = self._host[0].numpy()
             else:
-                raw = self.dev.cpu().numpy()    # blocks until the producing kernels are done
+                pool = self._staging.setdefault((self.nbytes, self.device), [])
+                pinned = pool.pop() if pool else torch.empty(self.nbytes, dtype=torch.uint8,
+                                                             pin_memory=True)
+                pinned.copy_(self.dev, non_blocking=True)
+                # blocks until the producing kernels and this copy are done
+                torch.cuda.current_stream(self.device).synchronize()
+                raw = pinned.numpy().copy()
+                if len(pool) < 4:
+                    pool.append(pinned)
             self._np = {}
             for name, (off, nbytes, dt, per_frame) in self._offsets.items():
                 a = raw[off:off + nbytes].view(dt)
@@ -148,33 +188,45 @@ class InstanceTables:
         self._host = None
 
     # ---- python structures of the reference API ------------------------------------------
+    def _rows(self):
+        """(n per frame as a list, largest n): the python structures only look at the used rows
+        of the 256-row tables"""
+        n = self['n_centers'].tolist()
+        return n, (max(n) if n else 0)
+
     def centers_list(self) -> List[torch.Tensor]:
         """instance.py:163-166: list of (n, 2) int32 tensors (y, x), raster order."""
         n = self['n_centers']
         c = self['centers_yx'].reshape(self.B, _lib.MAX_INST, 2)
         return [torch.from_numpy(c[b, :n[b]].copy()) for b in range(self.B)]
 
-    def meta(self) -> List[Dict[int, Dict[str, Any]]]:
-        """instance.py:253-266: {id: {'center_yx', 'area', 'score'}} for every centre."""
-        n = self['n_centers']
-        c = self['centers_yx'].reshape(self.B, _lib.MAX_INST, 2).tolist()
-        area = self['inst_area'].tolist()
-        score = self['center_score'].tolist()
-        return [{i + 1: {'center_yx': (c[b][i][0], c[b][i][1]), 'area': area[b][i + 1],
-                         'score': score[b][i]} for i in range(n[b])} for b in range(self.B)]
+    def meta(self, with_orientation: bool = False) -> List[Dict[int, Dict[str, Any]]]:
+        """instance.py:253-266: {id: {'center_yx', 'area', 'score'}} for every centre;
+        `with_orientation`: + 'orientation' (NaN for instances without one, panoptic.py:305-314)."""
+        n, m = self._rows()
+        c = self['centers_yx'].reshape(self.B, _lib.MAX_INST, 2)[:, :m].tolist()
+        area = self['inst_area'][:, :m + 1].tolist()
+        score = self['center_score'][:, :m].tolist()
+        if not with_orientation:
+            return [{i + 1: {'center_yx': (cb[i][0], cb[i][1]), 'area': ab[i + 1], 'score': sb[i]}
+                     for i in range(nb)} for nb, cb, ab, sb in zip(n, c, area, score)]
+        ang = self['inst_angle'][:, :m + 1].tolist()
+        return [{i + 1: {'center_yx': (cb[i][0], cb[i][1]), 'area': ab[i + 1], 'score': sb[i],
+                         'orientation': gb[i + 1]}
+                 for i in range(nb)} for nb, cb, ab, sb, gb in zip(n, c, area, score, ang)]
 
     def panoptic_ids(self) -> List[Dict[int, int]]:
         """panoptic_merge.py:209: {panoptic id: raw instance id}, ascending instance id."""
-        n = self['n_centers']
-        cls = self['inst_class']
-        pan = self['inst_pan_id']
-        return [{int(pan[b, i]): i for i in range(1, n[b] + 1) if cls[b, i] >= 0}
-                for b in range(self.B)]
+        n, m = self._rows()
+        cls = self['inst_class'][:, :m + 1].tolist()
+        pan = self['inst_pan_id'][:, :m + 1].tolist()
+        return [{pb[i]: i for i in range(1, nb + 1) if cb[i] >= 0}
+                for nb, cb, pb in zip(n, cls, pan)]
 
     def orientations(self) -> List[Dict[int, float]]:
         """instance.py:301-317: {raw instance id: angle} for instances whose panoptic class
         carries an orientation (angle is NaN-free there by construction)."""
-        n = self['n_centers']
-        ang = self['inst_angle']
-        return [{i: float(ang[b, i]) for i in range(1, n[b] + 1) if not np.isnan(ang[b, i])}
-                for b in range(self.B)]
+        n, m = self._rows()
+        ang = self['inst_angle'][:, :m + 1].tolist()
+        return [{i: ab[i] for i in range(1, nb + 1) if ab[i] == ab[i]}      # NaN != NaN
+                for nb, ab in zip(n, ang)]

@@ -206,6 +206,7 @@ class PanopticQuality(MetricState):
         self._status: Dict[int, torch.Tensor] = {}
         self._pending: List[Dict] = []
         self._scratch: Dict = {}            # kernel workspaces of this metric object
+        self._status_hosts: Dict[int, List[torch.Tensor]] = {}     # pinned status copies, recycled
         # pipelined matching (PanopticPostprocessing.fuse_evaluation(..., pipeline_matching=True)):
         # the update whose pixel pass has been issued but whose matcher has not run yet
         self._deferred: Optional[Dict] = None
@@ -235,7 +236,9 @@ class PanopticQuality(MetricState):
         now (their kernels have long finished, so this does not stall the device)."""
         # the status words travel to pinned memory right behind the update's kernels; waiting for
         # THAT copy later does not wait for anything enqueued after it
-        host = torch.empty(status.shape, dtype=status.dtype, pin_memory=True)
+        pool = self._status_hosts.setdefault(status.numel(), [])
+        # (pinned allocations cost tens of microseconds: the buffers are recycled by _resolve)
+        host = pool.pop() if pool else torch.empty(status.shape, dtype=status.dtype, pin_memory=True)
         host.copy_(status, non_blocking=True)
         landed = torch.cuda.Event()
         landed.record(torch.cuda.current_stream(status.device))
@@ -251,6 +254,9 @@ class PanopticQuality(MetricState):
         else:
             entry['landed'].synchronize()
             codes = entry['host'].tolist()
+            pool = self._status_hosts.setdefault(entry['host'].numel(), [])
+            if len(pool) < 2 * self.FOLLOW_UP_DEPTH:
+                pool.append(entry['host'])
         big = [b for b, c in enumerate(codes) if c == _lib.ERR_CAPACITY]
         _lib.raise_for_status([c for c in codes if c != _lib.ERR_CAPACITY],
                               type(self).__name__ + '.update')

@@ -32,8 +32,8 @@ class DensePostprocessingBase(PostprocessingBase):
         (network resolution == dataset resolution: every BASELINE configuration)."""
         h, w = hw
         sl_h, sl_w = valid_region_slices
-        return (tuple(range(h)[sl_h]) == tuple(range(h)) and
-                tuple(range(w)[sl_w]) == tuple(range(w)) and tuple(shape) == (h, w))
+        return (range(h)[sl_h] == range(h) and range(w)[sl_w] == range(w) and
+                tuple(shape) == (h, w))
 
     @staticmethod
     def _crop_geometry(hw: Tuple[int, int], valid_region_slices):

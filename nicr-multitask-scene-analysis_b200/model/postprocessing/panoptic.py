@@ -69,8 +69,60 @@ class PanopticPostprocessing(DensePostprocessingBase):
         return {**r_sem, **r_ins}
 
     # ------------------------------------------------------------------ fused kernel chain
-    def _forward_kernels(self, logits, heat, offset, orientation, eval_args=None, pipeline=None):
+    def _forward_plan(self, dev, B, C, H, W):
+        """Everything of a `_forward_kernels` call that only depends on (device, stream, shape,
+        configuration): scratch workspace, layout of the output allocation, the constant part of
+        the C argument list.  Built once per shape -- the per-call host work is one allocation,
+        a dozen integer additions and the call."""
         post = self._instance_postprocessing
+        ks = post._heatmap_nms_kernel_size
+        use_thr = post._offset_distance_threshold is not None
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream, B, C, H, W, ks,
+               post._heatmap_threshold, post._top_k_instances, post._heatmap_apply_foreground_mask,
+               self._normalized_offset, post._offset_distance_threshold)
+        plan = self._ws.get(key)
+        if plan is not None:
+            return plan
+        if len(self._is_thing) != C:
+            raise ValueError(f'semantic_classes_is_thing has {len(self._is_thing)} entries, the '
+                             f'logits have {C} classes')
+        L = _lib.lib()
+        # scratch (candidate lists, vote histograms, orientation sums) is reused across calls:
+        # the calls are ordered on the stream, nothing in it outlives a call
+        # (one scratch buffer per stream: calls on different streams may run concurrently)
+        # (npb_panoptic_forward_workspace_init once per buffer and shape: the chain itself contains
+        # no memset and leaves the workspace ready for the next call)
+        ws_bytes = L.npb_panoptic_forward_workspace_bytes(B, C, H, W, ks)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.npb_panoptic_forward_workspace_init(
+            _lib.ptr(ws), c_int(B), c_int(C), c_int(H), c_int(W), c_int(ks),
+            _lib.stream_ptr(dev)), 'npb_panoptic_forward_workspace_init')
+        # all outputs of a call live in ONE fresh allocation: [pan i64 | tables | sem | inst | pan_sem]
+        P = H * W
+        offsets, tab_bytes = InstanceTables.layout(B)
+        pan_bytes = B * P * 8
+        u8_bytes = (B * P + 15) // 16 * 16
+        o = pan_bytes + tab_bytes
+        plan = dict(
+            ws=ws, P=P, pan_bytes=pan_bytes, tab_bytes=tab_bytes, u8_bytes=u8_bytes,
+            total=pan_bytes + tab_bytes + 3 * u8_bytes, sem_off=o, inst_off=o + u8_bytes,
+            pan_sem_off=o + 2 * u8_bytes,
+            table_offs=tuple(pan_bytes + offsets[name][0] for name in (
+                'centers_yx', 'n_centers', 'center_score', 'inst_class', 'inst_pan_id', 'inst_area',
+                'inst_angle', 'status')),
+            shape_args=(c_int(B), c_int(C), c_int(H), c_int(W),
+                        _lib.host_lut(self._is_thing, C), _lib.host_lut(self._has_orientation, C),
+                        c_float(post._heatmap_threshold), c_int(ks), c_int(post._top_k_instances),
+                        c_int(int(post._heatmap_apply_foreground_mask)),
+                        c_int(int(self._normalized_offset)), c_int(int(use_thr)),
+                        c_float(float(post._offset_distance_threshold) if use_thr else 0.0),
+                        c_int64(self._max_instances_per_category), ws.data_ptr()))
+        if len(self._ws) >= 8:      # shapes rarely change; do not hoard scratch if they do
+            self._ws.clear()
+        self._ws[key] = plan
+        return plan
+
+    def _forward_kernels(self, logits, heat, offset, orientation, eval_args=None, pipeline=None):
         logits = _lib.require_cuda(logits, 'semantic logits', torch.float32, 4)
         dev = logits.device
         heat = _lib.require_cuda(heat, 'center_heatmap', torch.float32, 4)
@@ -78,69 +130,44 @@ class PanopticPostprocessing(DensePostprocessingBase):
         if orientation is not None:
             orientation = _lib.require_cuda(orientation, 'orientation', torch.float32, 4)
         B, C, H, W = logits.shape
-        if len(self._is_thing) != C:
-            raise ValueError(f'semantic_classes_is_thing has {len(self._is_thing)} entries, the '
-                             f'logits have {C} classes')
         if heat.shape != (B, 1, H, W) or offset.shape != (B, 2, H, W):
             raise ValueError('instance outputs do not match the semantic logits in shape')
         L = _lib.lib()
-        ks = post._heatmap_nms_kernel_size
-        # scratch (candidate lists, vote histograms, orientation sums) is reused across calls:
-        # the calls are ordered on the stream, nothing in it outlives a call
-        # (one scratch buffer per stream: calls on different streams may run concurrently)
-        # (npb_panoptic_forward_workspace_init once per buffer and shape: the chain itself contains
-        # no memset and leaves the workspace ready for the next call)
-        ws_key = (dev, torch.cuda.current_stream(dev).cuda_stream, B, C, H, W, ks)
-        ws = self._ws.get(ws_key)
-        if ws is None:
-            ws_bytes = L.npb_panoptic_forward_workspace_bytes(B, C, H, W, ks)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            _lib.check(L.npb_panoptic_forward_workspace_init(
-                _lib.ptr(ws), c_int(B), c_int(C), c_int(H), c_int(W), c_int(ks),
-                _lib.stream_ptr(dev)), 'npb_panoptic_forward_workspace_init')
-            if len(self._ws) >= 8:      # shapes rarely change; do not hoard scratch if they do
-                self._ws.clear()
-            self._ws[ws_key] = ws
-        # all outputs of a call live in ONE fresh allocation: [pan i64 | tables | sem | inst | pan_sem]
-        P = H * W
-        _, tab_bytes = InstanceTables.layout(B)
-        pan_bytes = B * P * 8
-        u8_bytes = (B * P + 15) // 16 * 16
-        buf = torch.empty(pan_bytes + tab_bytes + 3 * u8_bytes, dtype=torch.uint8, device=dev)
+        plan = self._forward_plan(dev, B, C, H, W)
+        P, pan_bytes, tab_bytes = plan['P'], plan['pan_bytes'], plan['tab_bytes']
+        buf = torch.empty(plan['total'], dtype=torch.uint8, device=dev)
+        base = buf.data_ptr()
         pan = buf[:pan_bytes].view(torch.int64).view(B, H, W)
         tables = InstanceTables(B, dev, storage=buf[pan_bytes:pan_bytes + tab_bytes])
-        o = pan_bytes + tab_bytes
+        o = plan['sem_off']
         sem = buf[o:o + B * P].view(B, H, W)
-        inst = buf[o + u8_bytes:o + u8_bytes + B * P].view(B, H, W)
-        pan_sem = buf[o + 2 * u8_bytes:o + 2 * u8_bytes + B * P].view(B, H, W)
-        use_thr = post._offset_distance_threshold is not None
-        args = (
-            _lib.ptr(logits), _lib.ptr(heat), _lib.ptr(offset), _lib.ptr(orientation),
-            c_int(B), c_int(C), c_int(H), c_int(W),
-            _lib.host_lut(self._is_thing, C), _lib.host_lut(self._has_orientation, C),
-            c_float(post._heatmap_threshold), c_int(ks), c_int(post._top_k_instances),
-            c_int(int(post._heatmap_apply_foreground_mask)), c_int(int(self._normalized_offset)),
-            c_int(int(use_thr)), c_float(float(post._offset_distance_threshold) if use_thr else 0.0),
-            c_int64(self._max_instances_per_category), _lib.ptr(ws), _lib.ptr(sem), _lib.ptr(inst),
-            _lib.ptr(pan), _lib.ptr(pan_sem), tables.dptr('centers_yx'), tables.dptr('n_centers'),
-            tables.dptr('center_score'), tables.dptr('inst_class'), tables.dptr('inst_pan_id'),
-            tables.dptr('inst_area'), tables.dptr('inst_angle'), tables.dptr('status'))
-        if eval_args is None:
-            _lib.check(L.npb_panoptic_forward(*args, _lib.stream_ptr(dev)), 'npb_panoptic_forward')
-        elif pipeline is None:       # the last stage also evaluates the ids it writes
-            import ctypes
-            _lib.check(L.npb_panoptic_forward_eval(*args, ctypes.byref(eval_args),
-                                                   _lib.stream_ptr(dev)),
-                       'npb_panoptic_forward_eval')
-        else:
-            # ... and leaves its matcher to the next call, which runs it next to its own centre
-            # detection + grouping (`pipeline` = (pending npb_eval_args or None, its batch size))
-            import ctypes
-            pending, pending_B = pipeline
-            _lib.check(L.npb_panoptic_forward_eval_pipelined(
-                *args, ctypes.byref(eval_args),
-                ctypes.byref(pending) if pending is not None else None, c_int(pending_B),
-                _lib.stream_ptr(dev)), 'npb_panoptic_forward_eval_pipelined')
+        o = plan['inst_off']
+        inst = buf[o:o + B * P].view(B, H, W)
+        o = plan['pan_sem_off']
+        pan_sem = buf[o:o + B * P].view(B, H, W)
+        args = (logits.data_ptr(), heat.data_ptr(), offset.data_ptr(),
+                None if orientation is None else orientation.data_ptr()) + plan['shape_args'] + \
+            (base + plan['sem_off'], base + plan['inst_off'], base, base + plan['pan_sem_off']) + \
+            tuple(base + t for t in plan['table_offs'])
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with _lib.on_device(dev):
+            if eval_args is None:
+                rc = L.npb_panoptic_forward(*args, stream)
+                where = 'npb_panoptic_forward'
+            elif pipeline is None:       # the last stage also evaluates the ids it writes
+                import ctypes
+                rc = L.npb_panoptic_forward_eval(*args, ctypes.byref(eval_args), stream)
+                where = 'npb_panoptic_forward_eval'
+            else:
+                # ... and leaves its matcher to the next call, which runs it next to its own centre
+                # detection + grouping (`pipeline` = (pending npb_eval_args or None, its batch size))
+                import ctypes
+                pending, pending_B = pipeline
+                rc = L.npb_panoptic_forward_eval_pipelined(
+                    *args, ctypes.byref(eval_args),
+                    ctypes.byref(pending) if pending is not None else None, c_int(pending_B), stream)
+                where = 'npb_panoptic_forward_eval_pipelined'
+        _lib.raise_for_code(rc, where)
         return sem, inst, pan, pan_sem, tables
 
     # ------------------------------------------------------------------ fused evaluation
@@ -253,10 +280,11 @@ class PanopticPostprocessing(DensePostprocessingBase):
                 r['_panoptic_matches'] = (fused[1]['matches'], fused[1]['n_matches'])
         if self._async_results:
             r.defer('panoptic_segmentation_deeplab_ids', tables.panoptic_ids)
-            r.defer('panoptic_segmentation_deeplab_instance_meta', lambda: self._meta(r, tables))
+            r.defer_with_dict('panoptic_segmentation_deeplab_instance_meta',
+                              lambda r_: self._meta(r_, tables))
         else:
             r['panoptic_segmentation_deeplab_ids'] = tables.panoptic_ids()
-            r['panoptic_segmentation_deeplab_instance_meta'] = tables.meta()
+            r['panoptic_segmentation_deeplab_instance_meta'] = tables.meta(with_orientation)
 
         if self._compute_scores:
             self._add_scores(r, s_output, pan, pan_sem, tables)
@@ -273,31 +301,23 @@ class PanopticPostprocessing(DensePostprocessingBase):
             if identity:
                 r.alias(fullres_key(key), key)
             else:
-                r.defer(fullres_key(key),
-                        lambda key=key: self._crop_to_valid_region_and_resize_prediction(
-                            r[key], crop, shape, mode='nearest'))
+                r.defer_with_dict(
+                    fullres_key(key),
+                    lambda r_, key=key: self._crop_to_valid_region_and_resize_prediction(
+                        r_[key], crop, shape, mode='nearest'))
 
         # orientation (panoptic.py:294-314)
         if with_orientation:
             if self._async_results:
                 r.defer('orientations_panoptic_segmentation_deeplab_instance', tables.orientations)
             else:
-                orientations = tables.orientations()
-                r['orientations_panoptic_segmentation_deeplab_instance'] = orientations
-                for meta_b, ori_b in zip(r['panoptic_segmentation_deeplab_instance_meta'],
-                                         orientations):
-                    for id_, entry in meta_b.items():
-                        entry['orientation'] = ori_b.get(id_, float('nan'))
+                # (the 'orientation' fields of the meta dicts were filled from the same table)
+                r['orientations_panoptic_segmentation_deeplab_instance'] = tables.orientations()
         return r
 
     @staticmethod
     def _meta(r: ResultDict, tables: InstanceTables):
-        meta = tables.meta()
-        if 'orientations_panoptic_segmentation_deeplab_instance' in r:
-            for meta_b, ori_b in zip(meta, tables.orientations()):
-                for id_, entry in meta_b.items():
-                    entry['orientation'] = ori_b.get(id_, float('nan'))
-        return meta
+        return tables.meta('orientations_panoptic_segmentation_deeplab_instance' in r)
 
     # ------------------------------------------------------------------ optional score maps
     def _add_scores(self, r, logits, pan, pan_sem, tables):
@@ -335,6 +355,6 @@ class PanopticPostprocessing(DensePostprocessingBase):
 
         key = 'panoptic_segmentation_deeplab_instance_meta'
         if r.is_deferred(key):
-            r.defer(key, lambda: fill(self._meta(r, tables)))
+            r.defer_with_dict(key, lambda r_: fill(self._meta(r_, tables)))
         else:
             fill(r[key])
