@@ -125,6 +125,7 @@ __device__ void select_centers_frame(const SelectParams &sp, int b)
         const uint2 c = __ldcg(cb + i);
         if (c.x >= kth_bits && (!fgb || fgb[c.y])) {
             const int slot = atomicAdd(&s_n, 1);
+            NPB_ASSERT(slot >= 0 && c.y < (unsigned)P);
             if (slot < kMaxInst) s_idx[slot] = c.y;
         }
     }

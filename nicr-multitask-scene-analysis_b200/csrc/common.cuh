@@ -116,6 +116,25 @@ __device__ __forceinline__ void grid_launch_dependents()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// ---- bounds / overflow asserts of the shared-memory tables (only with -DNPB_DEBUG) ------------
+// compute-sanitizer is not available on the GPU pool, so the histogram / hash-table / queue
+// kernels carry their own checks: an -DNPB_DEBUG build (csrc/build.py -DNPB_DEBUG --out=...,
+// loaded through NPB_LIB_PATH) traps with file:line on the first violated bound, and the GPU test
+// suite is run once against it per round (scripts/round_evidence.sh).
+#ifdef NPB_DEBUG
+#include <stdio.h>
+#define NPB_ASSERT(cond)                                                                      \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            printf("NPB_ASSERT failed: %s  (%s:%d, block %d,%d thread %d)\n", #cond, __FILE__, \
+                   __LINE__, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);              \
+            __trap();                                                                         \
+        }                                                                                     \
+    } while (0)
+#else
+#define NPB_ASSERT(cond) ((void)0)
+#endif
+
 // ---- in-situ timeline (only with -DNPB_TIMELINE: scripts/probes/timeline.py) -----------------
 // Every CTA stamps the global timer at its start, after its grid_dependency_wait() and at its
 // end into slot `id` of a small device buffer (min / max), which shows where the kernels of a

@@ -54,7 +54,9 @@ __device__ __forceinline__ bool table_add(unsigned long long *keys, unsigned *cn
                                           int max_probe, unsigned long long key, unsigned cnt)
 {
     unsigned h = hash64(key) & (unsigned)(slots - 1);
+    NPB_ASSERT((slots & (slots - 1)) == 0 && cnt > 0u);
     for (int probe = 0; probe < max_probe; ++probe) {
+        NPB_ASSERT(h < (unsigned)slots);
         unsigned long long k = keys[h];
         if (k == kEmptyKey) k = atomicCAS(keys + h, kEmptyKey, key);
         if (k == kEmptyKey || k == key) {
@@ -205,7 +207,9 @@ __device__ __forceinline__ void pair_consume_std(const PairTables &t, const Pair
     // instance-free on both sides: pred & 0xffff == 0 and target & 0xffff == 0
     const bool inst_free = ((lo & 0xff00ffffu) | (hi & 255u)) == 0u;
     bool dense = false;
+    NPB_ASSERT(cnt >= 1u && cnt <= 128u);      // a queue entry stands for 1..128 pixels of a warp
     if (inst_free && pc < (unsigned)prm.nd && tc < (unsigned)prm.nd) {
+        NPB_ASSERT(tc * (unsigned)prm.nd + pc < (unsigned)(prm.nd * prm.nd));
         atomicAdd(t.dense + tc * (unsigned)prm.nd + pc, cnt);
         dense = true;
     }
@@ -219,6 +223,7 @@ __device__ __forceinline__ void pair_consume_std(const PairTables &t, const Pair
             set_status(prm.status + b, NPB_ERR_CATEGORY_RANGE);
         } else {
             const unsigned cell = st * (unsigned)prm.n + pc;
+            NPB_ASSERT(cell < (unsigned)(prm.n * prm.n));
             if (cm_smem) atomicAdd(t.cm + cell, cnt);
             else atomicAdd(prm.confmat + cell, (unsigned long long)cnt);
         }
@@ -454,6 +459,7 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
                 sts_entry(q_tail + 8u * (unsigned)(total_minor + __popc(leader_mask & lt_mask)), lk_lo,
                           lk_hi | (total << 24));
             q_len += total_minor + __popc(leader_mask);
+            NPB_ASSERT(q_len <= kQueueCap);
             __syncwarp();
             while (q_len >= 32) {           // consume full warps of entries from the tail
                 q_len -= 32;
@@ -754,6 +760,7 @@ __device__ void match_phases(const MatchParams &prm, int b, const MatchTables<Sl
         const long long p = key - g * prm.offset;
         const int gs = seg_slot(T.g_id, T.seg_slots, (unsigned long long)g);
         const int ps = seg_slot(T.p_id, T.seg_slots, (unsigned long long)p);
+        NPB_ASSERT(gs < T.seg_slots && ps < T.seg_slots && t < T.pair_slots);
         if (gs < 0 || ps < 0) {
             C.fail = 1;
             T.t_key[t] = kEmptyKey;         // phase 2 skips the pair (its frame failed anyway)
@@ -790,6 +797,7 @@ __device__ void match_phases(const MatchParams &prm, int b, const MatchTables<Sl
             T.p_matched[ps] = 1;
             atomicAdd(&C.tp[(int)gcat], 1);
             const int slot = atomicAdd(&C.nm, 1);
+            NPB_ASSERT(slot >= 0);
             if (slot < T.max_matched) {
                 T.m_key[slot] = key;
                 T.m_ia[slot] = (unsigned)ia;
@@ -843,6 +851,7 @@ __device__ void match_phases(const MatchParams &prm, int b, const MatchTables<Sl
         const long long key = T.m_key[i];
         int rank = 0;
         for (int j = 0; j < nm; ++j) rank += T.m_key[j] < key;
+        NPB_ASSERT(rank >= 0 && rank < nm);
         T.s_iou[rank] = (double)T.m_ia[i] / (double)T.m_uni[i];            // pq.py:145
         T.s_cat[rank] = T.m_cat[i];
     }
@@ -918,6 +927,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const Ma
             if (cur == kEmptyKey) {
                 cur = atomicCAS(t_key + h, kEmptyKey, key);
                 if (cur == kEmptyKey) {                      // this thread claimed the slot
+                    NPB_ASSERT(h < (unsigned)kPairSlots);
                     const int idx = atomicAdd(&s_m, 1);
                     if (idx < kMaxPairs) s_idx[idx] = (unsigned short)h;
                     else C.fail = 1;

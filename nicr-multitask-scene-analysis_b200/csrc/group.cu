@@ -199,6 +199,7 @@ group_pixels_kernel(const GroupParams prm)
     if (MODE == kFromLogits) grid_dependency_wait();
     NPB_TL(prm, 1, wait);
     const int n = prm.n_centers[b];
+    NPB_ASSERT(n >= 0 && n < kMaxInst);
     for (int i = tid; i < n; i += NT) {
         const int32_t *c = prm.centers_yx + ((size_t)b * kMaxInst + i) * 2;
         const float cy = (float)c[0], cx = (float)c[1];
@@ -374,6 +375,7 @@ group_pixels_kernel(const GroupParams prm)
         const unsigned peers = __match_any_sync(kFullMask, k0);
         const int total = __reduce_add_sync(peers, cnt0);
         if (k0 >= 0) {
+            NPB_ASSERT(k0 < kMaxInst * CH && total >= 1 && total <= 32 * VEC);
             if (lane == __ffs(peers) - 1) atomicAdd(hist + k0, (uint32_t)total);
 #pragma unroll
             for (int j = 0; j < VEC; ++j)

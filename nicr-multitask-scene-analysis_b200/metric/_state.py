@@ -68,3 +68,25 @@ class MetricState:
                 out[n] = flat[off:off + k].reshape(local[n].shape).clone()
                 off += k
         return out
+
+    def host_states(self) -> Dict[str, torch.Tensor]:
+        """`synced_states()` on the host with ONE device->host copy per dtype (every copy is a
+        synchronisation: four PQ vectors one by one cost more than the kernels of a small batch)."""
+        local = {n: getattr(self, n) for n in self._defaults}
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        out = {}
+        by_dtype: Dict[torch.dtype, List[str]] = {}
+        for n, t in local.items():
+            by_dtype.setdefault(t.dtype, []).append(n)
+        for dtype, names in by_dtype.items():
+            flat = torch.cat([local[n].reshape(-1) for n in names]) if len(names) > 1 or distributed \
+                else local[names[0]].reshape(-1)
+            if distributed:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat = flat.cpu()
+            off = 0
+            for n in names:
+                k = local[n].numel()
+                out[n] = flat[off:off + k].reshape(local[n].shape).clone()
+                off += k
+        return out

@@ -64,7 +64,7 @@ class MeanIntersectionOverUnion(MetricState):
         """miou.py:58-94 on the (rank-summed) confusion matrix; float32 like the reference.
         Results are CPU tensors."""
         self.check_status()
-        cm = self.synced_states()['confmat'].cpu()
+        cm = self.host_states()['confmat']
         tp = torch.diag(cm).float()
         sum_pred = cm.sum(dim=0).float()
         sum_gt = cm.sum(dim=1).float()

@@ -371,7 +371,7 @@ class PanopticQuality(MetricState):
 
     def _host_states(self) -> Dict[str, torch.Tensor]:
         self.check_status()
-        return {k: v.cpu() for k, v in self.synced_states().items()}
+        return self.host_states()
 
     def result_per_category(self, states: Optional[Dict[str, torch.Tensor]] = None) -> Dict:
         s = states if states is not None else self._host_states()

@@ -7,6 +7,11 @@ set -u
 R=${ROUND:-r02}
 mkdir -p gpurun_out
 python -m pytest tests -q -m gpu -x 2>&1 | tail -3 > gpurun_out/${R}_tests.log
+# the same suite against the -DNPB_DEBUG build (bounds / overflow asserts of the shared-memory tables)
+if [ -f build/debug/libnicr_panoptic_b200.so ]; then
+  NPB_LIB_PATH=$PWD/build/debug/libnicr_panoptic_b200.so python -m pytest tests -q -m gpu -x 2>&1 | tail -3 > gpurun_out/${R}_tests_debug_build.log
+  NPB_LIB_PATH=$PWD/build/debug/libnicr_panoptic_b200.so python -c "from nicr_mt_scene_analysis_b200 import _lib; print(_lib.lib().npb_build_info().decode())" >> gpurun_out/${R}_tests_debug_build.log 2>&1
+fi
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${R}_smoke.log
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${R}_bench_reference.json 2>gpurun_out/${R}_bench_reference.err
 python bench.py --steps 20 --warmup 3 > gpurun_out/${R}_bench_steps20.json 2>gpurun_out/${R}_bench.err
