@@ -1,7 +1,10 @@
 """Build libnicr_panoptic_b200.so (hand-written sm_100a CUDA behind a C ABI) in-tree.
 
-    nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared
+    nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -cudart shared
          -Xcompiler -fPIC -I include  csrc/*.cu  -o csrc/libnicr_panoptic_b200.so
+
+(the CUDA runtime is linked dynamically: the process already holds torch's libcudart, and the
+library stays free of the runtime's own entry points)
 
 No fast-math: the grouping distance relies on IEEE sqrtf / explicit rounding intrinsics.
 """
@@ -36,7 +39,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
         return LIB
     os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     cmd = [NVCC, '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-           '-shared', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'), '-I', HERE]
+           '-shared', '-cudart', 'shared', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'),
+           '-I', HERE]
     cmd += ['-D' + d for d in defines]
     if verbose:
         cmd += ['-Xptxas', '-v']

@@ -112,6 +112,7 @@ struct PairParams {
     const long long *target;
     const uint8_t *sem_target;  // nullable
     long long P;
+    int B;                      // frames
     long long offset, L;
     int L_shift;                // >= 0 when L is a power of two
     int O_shift;                // >= 0 when offset is a power of two
@@ -270,42 +271,52 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     t.dense = t.cnts + kSmemSlots;                            // [nd*nd]
     t.cm = t.dense + prm.nd * prm.nd;                         // [n*n] when privatised
 
-    const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = prm.n, nd = prm.nd;
     const bool cm_smem = CONFMAT && n <= kSmemConfmatMaxN;
     unsigned short *q_meta_all = (unsigned short *)(t.cm + (cm_smem ? n * n : 0));
     unsigned long long *q_key = q_key_all + warp * kQueueCap;
     unsigned short *q_meta = q_meta_all + warp * kQueueCap;
+    const long long P = prm.P;
+    const long long chunk = (long long)kPairThreads * VEC;
+    const long long n_chunks = (P + chunk - 1) / chunk;
+    // The grid is ONE wave of persistent CTAs over the chunks of the whole batch: CTA i takes
+    // the i-th equal share of all B * n_chunks chunks, a contiguous range that may cross frame
+    // boundaries -- every CTA has the same amount of work whatever the ratio of CTA slots to
+    // frames is (2 CTAs per frame on 2.3 slots per frame left 14 % of the SMs' slots empty).
+    // Within a frame a CTA's range is a band of rows: a segment then shows up in the tables of
+    // the few CTAs whose band it crosses instead of in all of them -- fewer entries per CTA table
+    // and far fewer duplicates for the matcher to merge.  The tables are flushed (and cleared)
+    // at the end of every frame part.
+    const long long g_total = n_chunks * prm.B;
+    const long long g_begin = g_total * blockIdx.x / gridDim.x;
+    const long long g_end = g_total * (blockIdx.x + 1) / gridDim.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool waited = false;
+  for (long long g_at = g_begin; g_at < g_end;) {
+    const int b = (int)(g_at / n_chunks);
+    const long long ch_begin = g_at - (long long)b * n_chunks;
+    const long long ch_end = (ch_begin + (g_end - g_at) < n_chunks) ? ch_begin + (g_end - g_at) : n_chunks;
+    g_at += ch_end - ch_begin;
     for (int i = tid; i < kSmemSlots; i += kPairThreads) { t.keys[i] = kEmptyKey; t.cnts[i] = 0; }
     for (int i = tid; i < nd * nd; i += kPairThreads) t.dense[i] = 0;
     if (cm_smem)
         for (int i = tid; i < n * n; i += kPairThreads) t.cm[i] = 0;
     // everything above touched shared memory only: it overlaps the tail of the predecessor
-    grid_dependency_wait();
+    if (!waited) { grid_dependency_wait(); waited = true; }
     NPB_TL(prm, 2, wait);
     if (FUSED) {
         // panoptic id of every instance of the frame: from the table, or derived right here from
         // the vote histograms of the grouping kernel (every CTA of the frame repeats the few
         // hundred loads; CTA 0 stores the tables) -- no finalize launch in between
         const long long pan = prm.fold_finalize
-                                  ? finalize_frame(prm.fin, b, tid, s_fin_cls, blockIdx.x == 0)
+                                  ? finalize_frame(prm.fin, b, tid, s_fin_cls, ch_begin == 0)
                                   : prm.inst_pan_id[(size_t)b * kMaxInst + tid];
         s_pan32[tid] = (unsigned)pan;
         s_stuff[tid] = prm.thing.has(tid) ? 0u : ((unsigned)tid + 1u) << 16;
     }
     __syncthreads();
     NPB_TL(prm, 10, wait);      // instance tables of the frame derived
-
-    const long long P = prm.P;
-    const long long chunk = (long long)kPairThreads * VEC;
-    const long long n_chunks = (P + chunk - 1) / chunk;
-    // every CTA takes a CONTIGUOUS range of chunks (a band of rows): a segment then shows up in
-    // the tables of the few CTAs whose band it crosses instead of in all of them -- fewer entries
-    // per CTA table and far fewer duplicates for the matcher to merge
-    const long long ch_begin = n_chunks * blockIdx.x / gridDim.x;
-    const long long ch_end = n_chunks * (blockIdx.x + 1) / gridDim.x;
-    const unsigned lt_mask = (1u << lane) - 1u;
     int q_len = 0;      // warp-uniform
 
     if constexpr (STD && VEC == 4) {
@@ -408,45 +419,42 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
             }
             fetch();
 
-            // lead pixel of the lane: the first one that agrees with another pixel of the lane
-            // (the background segment when an isolated pixel or a boundary cuts the lane); its
-            // agreeing pixels join the warp-wide group of that entry, the others ("minors")
-            // are queued as single pixels.  Branch free: nearly every warp has lanes of each kind.
-            const bool e01 = klo[0] == klo[1] && khi[0] == khi[1];
-            const bool e02 = klo[0] == klo[2] && khi[0] == khi[2];
-            const bool e03 = klo[0] == klo[3] && khi[0] == khi[3];
-            const bool e12 = klo[1] == klo[2] && khi[1] == khi[2];
-            const bool e13 = klo[1] == klo[3] && khi[1] == khi[3];
-            const bool e23 = klo[2] == klo[3] && khi[2] == khi[3];
-            const unsigned m0 = (e01 ? 2u : 0u) | (e02 ? 4u : 0u) | (e03 ? 8u : 0u);
-            const unsigned m1 = (e12 ? 4u : 0u) | (e13 ? 8u : 0u);
-            const bool lead0 = m0 != 0u, lead1 = !lead0 && m1 != 0u, lead2 = !lead0 && !lead1 && e23;
-            // bit j: pixel j agrees with the lead
-            const unsigned member = lead0 ? (m0 | 1u) : lead1 ? (m1 | 2u) : lead2 ? 12u : 1u;
-            const unsigned lk_lo = lead1 ? klo[1] : lead2 ? klo[2] : klo[0];
-            const unsigned lk_hi = lead1 ? khi[1] : lead2 ? khi[2] : khi[0];
+            // Lead pixels of the lane: its first run of >= 2 equal NEIGHBOURS (the background
+            // segment when an isolated pixel or a boundary cuts the lane), else pixel 0.  The run
+            // joins the warp-wide group of that entry, the other pixels ("minors") are queued as
+            // single pixels -- also a pixel that equals the lead but is not adjacent to its run
+            // (A x A A): one more queue entry in a rare pattern buys three compares instead of
+            // six and a table look-up instead of the select chains.  Branch free: nearly every
+            // warp has lanes of each kind.
+            const unsigned d01 = (klo[0] ^ klo[1]) | (khi[0] ^ khi[1]);
+            const unsigned d12 = (klo[1] ^ klo[2]) | (khi[1] ^ khi[2]);
+            const unsigned d23 = (klo[2] ^ klo[3]) | (khi[2] ^ khi[3]);
+            // member mask by (e01, e12, e23): 000 -> 0001, 001 -> 0011, 010 -> 0110, 011 -> 0111,
+            // 100 -> 1100, 101 -> 0011, 110 -> 1110, 111 -> 1111 (bit j: pixel j is in the run)
+            const unsigned sh = (d01 ? 0u : 4u) + (d12 ? 0u : 8u) + (d23 ? 0u : 16u);
+            const unsigned member = (0xFE3C7631u >> sh) & 15u;
+            const unsigned lk_lo = (member & 1u) ? klo[0] : (member & 2u) ? klo[1] : klo[2];
+            const unsigned lk_hi = (member & 1u) ? khi[0] : (member & 2u) ? khi[1] : khi[2];
             const unsigned actm = __ballot_sync(kFullMask, act);
             const unsigned peers =
                 __match_any_sync(kFullMask, ((unsigned long long)lk_hi << 32) | lk_lo) & actm;
-            const int n_minor = 4 - __popc(member);
-            // pixels of the group = 4 * lanes - minors of its lanes (no REDUX: a reduction with
-            // per-group masks would serialise over the groups)
-            const unsigned b1 = __ballot_sync(kFullMask, n_minor == 1) & actm;
-            const unsigned b2 = __ballot_sync(kFullMask, n_minor == 2) & actm;
-            const unsigned b3 = __ballot_sync(kFullMask, n_minor == 3) & actm;
-            const unsigned total = 4 * __popc(peers) - __popc(peers & b1) - 2 * __popc(peers & b2) -
-                                   3 * __popc(peers & b3);
+            const unsigned n_minor = 4u - (unsigned)__popc(member);     // 0..3
+            // pixels of the group = 4 * lanes - minors of its lanes, the minors counted from two
+            // ballots of the bits of n_minor (no REDUX: a reduction with per-group masks would
+            // serialise over the groups)
+            const unsigned n0 = __ballot_sync(kFullMask, (n_minor & 1u) != 0u) & actm;
+            const unsigned n1 = __ballot_sync(kFullMask, (n_minor & 2u) != 0u) & actm;
+            const unsigned total = 4 * __popc(peers) - __popc(peers & n0) - 2 * __popc(peers & n1);
             const bool leader = act && (peers & lt_mask) == 0u;
             const unsigned leader_mask = __ballot_sync(kFullMask, leader);
-            const int total_minor = __popc(b1) + 2 * __popc(b2) + 3 * __popc(b3);
+            const int total_minor = __popc(n0) + 2 * __popc(n1);
 
             // push: minors as single pixels, then one entry per group leader
             const unsigned q_tail = q_base + 8u * (unsigned)q_len;
             if (act && n_minor > 0) {
                 // one address register per store: a store still in flight keeps reading its own
                 const unsigned mm = ~member & 15u;              // bit j: pixel j is a minor
-                const unsigned a0 = q_tail + 8u * (unsigned)(__popc(b1 & lt_mask) + 2 * __popc(b2 & lt_mask) +
-                                                             3 * __popc(b3 & lt_mask));
+                const unsigned a0 = q_tail + 8u * (unsigned)(__popc(n0 & lt_mask) + 2 * __popc(n1 & lt_mask));
                 const unsigned a1 = a0 + 8u * (mm & 1u);
                 const unsigned a2 = a0 + 8u * (unsigned)__popc(mm & 3u);
                 const unsigned a3 = a0 + 8u * (unsigned)__popc(mm & 7u);
@@ -649,6 +657,9 @@ __global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairP
     if (cm_smem)
         for (int i = tid; i < n * n; i += kPairThreads)
             if (t.cm[i]) atomicAdd(prm.confmat + i, (unsigned long long)t.cm[i]);
+    __syncthreads();        // the tables are cleared for the next frame part
+  }
+    if (!waited) grid_dependency_wait();     // (a CTA without work: the chain rule still holds)
     NPB_TL(prm, 2, end);
 }
 
@@ -1471,7 +1482,9 @@ static unsigned pq_entry_cap(int B)
 {
     // every CTA of the pixel pass appends at most its hash table; the rest is head room for
     // single entries of overflowing CTA tables
-    const long long ctas_per_frame = ((long long)device_sm_count() * kMaxPairCtasPerSm + B - 1) / B;
+    // (a frame is touched by at most ceil(slots / B) + 1 CTAs: the equal shares of the batch's
+    // chunks may start and end inside a frame)
+    const long long ctas_per_frame = ((long long)device_sm_count() * kMaxPairCtasPerSm + B - 1) / B + 1;
     return (unsigned)(4 * kMaxPairs + (long long)kSmemSlots * ctas_per_frame);
 }
 
@@ -1652,7 +1665,7 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
         pp.pan_out = (long long *)fw->pan_out; pp.pan_sem_out = fw->pan_sem_out;
         if (fw->fold) { pp.fold_finalize = 1; pp.fin = *fw->fold; }
     }
-    pp.sem_target = sem_target; pp.P = P; pp.offset = offset; pp.L = max_instances_per_category;
+    pp.sem_target = sem_target; pp.P = P; pp.B = B; pp.offset = offset; pp.L = max_instances_per_category;
     pp.L_shift = -1;
     pp.O_shift = -1;
     for (int sh = 0; sh < 62; ++sh) {
@@ -1729,10 +1742,11 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     // few frames: every CTA only gets a handful of chunks, so its fixed cost (table set-up, flush)
     // and the duplicates it hands to the matcher weigh more than the extra residency
     if (B <= 32 && per_sm > 2) per_sm = 2;
-    long long bx = ((long long)n_sm * per_sm) / B;
-    if (bx < 1) bx = 1;
-    if (bx > n_chunks) bx = n_chunks;
-    dim3 grid((unsigned)bx, B);
+    // one wave of CTAs, each with the same share of the B * n_chunks chunks of the batch
+    long long n_ctas = (long long)n_sm * per_sm;
+    if (n_ctas > n_chunks * B) n_ctas = n_chunks * B;
+    if (n_ctas < 1) n_ctas = 1;
+    dim3 grid((unsigned)n_ctas);
     // The grid is one wave of `per_sm` CTAs per SM.  As a programmatic dependent its CTAs are
     // placed while the predecessor drains, SM by SM: with room for more than `per_sm` of them the
     // first free SMs would take four and others none.  Padding the dynamic shared memory makes

@@ -27,6 +27,8 @@ class PanopticEvaluation:
                semantic_targets: torch.Tensor, want_matches: bool = False):
         """(B,H,W) int64, (B,H,W) int64, (B,H,W) uint8.  Returns (matches, n_matches) device
         tensors when `want_matches` (for the MAAE loop), else None."""
+        if panoptic_preds.shape[0] == 0:        # an empty batch adds nothing
+            return (None, None) if want_matches else None
         if semantic_targets.dtype != torch.uint8:
             semantic_targets = semantic_targets.to(torch.uint8)
         matches, n_matches, _ = self.pq._launch(
@@ -57,6 +59,8 @@ class PanopticEvaluation:
         with_mae = orientation_preds is not None and orientation_target is not None
         out = self.update(panoptic_preds, panoptic_target, semantic_target, want_matches=with_mae)
         if not with_mae:
+            return
+        if out[0] is None:
             return
         self.update_mae_from_matches(out, orientation_preds, panoptic_preds_id_dicts,
                                      orientation_target, panoptic_target_id_dicts)

@@ -75,6 +75,8 @@ class PanopticQualityWithOrientationMAE(PanopticQuality, _AngularErrorMixin):
         assert panoptic_preds.ndim == 3
         assert len(panoptic_target) == len(panoptic_preds)
         with_mae = orientation_preds is not None and orientation_target is not None
+        if panoptic_preds.shape[0] == 0:        # an empty batch adds nothing
+            return
         matches, n_matches, _ = self._launch(panoptic_preds, panoptic_target,
                                              want_matches=with_mae)
         if not with_mae:

@@ -225,6 +225,8 @@ class PanopticQuality(MetricState):
 
     def _shared_status(self, B: int) -> None:
         dev = self.iou_per_class.device
+        if torch.cuda.is_current_stream_capturing():
+            return      # never allocated inside a capture (a memset node would clear it per replay)
         status = self._status.get(B)
         if status is None or status.device != dev:
             self._status[B] = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -370,7 +372,25 @@ class PanopticQuality(MetricState):
         return valid
 
     def _host_states(self) -> Dict[str, torch.Tensor]:
-        self.check_status()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # a data error on ONE rank must not leave the others blocked in the all-reduce of the
+            # states: every rank learns whether any rank failed before anybody raises
+            err = None
+            try:
+                self.check_status()
+            except Exception as e:      # noqa: BLE001
+                err = e
+            flag = torch.tensor([0 if err is None else 1], dtype=torch.int32,
+                                device=self.iou_per_class.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if err is not None:
+                raise err
+            if int(flag.item()):
+                raise RuntimeError(type(self).__name__ + '.compute: another rank reported an '
+                                   'error in its updates')
+        else:
+            self.check_status()
         return self.host_states()
 
     def result_per_category(self, states: Optional[Dict[str, torch.Tensor]] = None) -> Dict:

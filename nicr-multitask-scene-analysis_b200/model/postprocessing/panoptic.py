@@ -188,6 +188,15 @@ class PanopticPostprocessing(DensePostprocessingBase):
         need their matches right away (orientation MAAE) are matched in their own call."""
         if self._fused_evaluation is not None and evaluation is not self._fused_evaluation:
             self._fused_evaluation.pq._flush_deferred()
+        if evaluation is not None:
+            # the fused kernels evaluate with THIS object's id geometry and class count
+            if evaluation.pq.max_instances_per_category != self._max_instances_per_category:
+                raise ValueError('fuse_evaluation: the PanopticQuality object uses '
+                                 f'{evaluation.pq.max_instances_per_category} instances per '
+                                 f'category, the post-processing {self._max_instances_per_category}')
+            if evaluation.pq.num_categories != len(self._is_thing) + 1 or \
+                    evaluation.miou._n_classes != len(self._is_thing) + 1:
+                raise ValueError('fuse_evaluation: the metrics must count the network classes + void')
         self._fused_evaluation = evaluation
         self._pipeline_matching = bool(pipeline_matching) and evaluation is not None
 

@@ -21,7 +21,7 @@ from .model.postprocessing.panoptic import PanopticPostprocessing
 
 
 class PanopticHostPipeline:
-    N_SLOTS = 2     # staging slots, used round robin across calls
+    N_SLOTS = 2     # staging slots of `chunk_frames` frames each, used round robin across calls
 
     def __init__(self, postprocessing: PanopticPostprocessing,
                  evaluation: Optional[PanopticEvaluation] = None, chunk_frames: int = 8,
@@ -61,6 +61,8 @@ class PanopticHostPipeline:
         python structures.  Pass pinned tensors (and `out`) to get asynchronous copies."""
         B = inputs['logits'].shape[0]
         H, W = inputs['logits'].shape[-2:]
+        if B == 0:
+            raise ValueError('PanopticHostPipeline.run: empty batch')
         staged = dict(inputs)
         if targets is not None:
             staged['_tgt_pan'] = targets['panoptic']
