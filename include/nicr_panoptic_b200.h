@@ -310,7 +310,11 @@ int npb_confmat_update_nonvoid(const void *preds, int preds_dtype, const void *t
  *           with confmat: MeanIntersectionOverUnion.update of task_helper/panoptic.py:123-126.
  * pred, target (B,P) int64 panoptic ids (>= 0).  sem_target (B,P) u8 or NULL.
  * State (accumulated in place): iou/tp/fn/fp [num_categories] f64, confmat [n][n] i64.
- * Per-frame outputs (nullable): frame_stats [B][4][num_categories] f64,
+ * Per-frame outputs (nullable): frame_stats [B + 1][4][num_categories] f64 -- rows 0..B-1 the
+ *   (iou, tp, fn, fp) of every frame (zero for a frame that reports NPB_ERR_CAPACITY), row B the
+ *   states as they were BEFORE this update: with the result of npb_pq_update_big_frame put in
+ *   place of a failed frame's row, `row B + row 0 + ... + row B-1` (in that order) is the state
+ *   the reference reaches frame by frame (pq.py:298-303), bit for bit;
  *   matches [B][match_cap][2] i64 (gt_id, pred_id), n_matches [B].
  * status [B]: NPB_ERR_ZERO_DIVISION / _CATEGORY_RANGE / _CAPACITY per frame; must be zero on
  *   entry.  A frame that reports NPB_ERR_CAPACITY (more than 4096 distinct (gt, pred) pairs,
@@ -363,7 +367,7 @@ typedef struct npb_eval_args {
     void *workspace;            /* npb_pq_update_workspace_bytes(B, num_categories)         */
     double *iou, *tp, *fn, *fp; /* [num_categories] accumulated states                      */
     int64_t *confmat;           /* [confmat_n][confmat_n] accumulated, nullable             */
-    double *frame_stats;        /* nullable */
+    double *frame_stats;        /* [B + 1][4][num_categories], nullable (see npb_pq_update) */
     int64_t *matches;           /* nullable */
     int match_cap;
     int32_t *n_matches;         /* nullable */

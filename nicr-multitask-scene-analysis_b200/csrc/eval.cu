@@ -31,7 +31,13 @@
 namespace npb {
 
 constexpr int kPairThreads = 256;
-constexpr int kSmemSlots = 2048;       // per-CTA pair hash table (instance pairs; class pairs go dense)
+#ifndef NPB_PAIR_MIN_CTAS
+#define NPB_PAIR_MIN_CTAS 4
+#endif
+#ifndef NPB_PAIR_SLOTS
+#define NPB_PAIR_SLOTS 2048
+#endif
+constexpr int kSmemSlots = NPB_PAIR_SLOTS;       // per-CTA pair hash table (instance pairs; class pairs go dense)
 constexpr int kMaxPairs = 4096;        // distinct pairs per frame handled by the matcher
 constexpr int kMatchThreads = 1024;
 constexpr unsigned long long kEmptyKey = ~0ull;
@@ -251,7 +257,7 @@ __device__ __forceinline__ uint2 lds_entry(unsigned addr)
 // go to a per-warp shared-memory queue and are consumed 32 at a time, one entry per lane, so
 // the table updates (the expensive, divergent part) always run with a full warp.
 template <int VEC, bool CONFMAT, bool STD, bool FUSED = false>
-__global__ void __launch_bounds__(kPairThreads, 4) pair_count_kernel(const PairParams prm)
+__global__ void __launch_bounds__(kPairThreads, NPB_PAIR_MIN_CTAS) pair_count_kernel(const PairParams prm)
 {
     static_assert(!FUSED || (STD && VEC == 4), "the fused variant exists for the standard geometry only");
     // fused variant: panoptic id of an instance / of a stuff class (0 for thing classes: a thing
@@ -674,7 +680,7 @@ struct MatchParams {
     int num_categories;
     long long ignored_label, L, offset, void_segment_id;
     int L_shift, O_shift;  // >= 0 when L / offset are powers of two (shifts instead of 64-bit divisions)
-    double *frame_stats;   // [B][4][num_categories]
+    double *frame_stats;   // [B + 1][4][num_categories]; row B: the states before this update
     unsigned *done_cnt;    // frames matched so far (zero at rest); null: no accumulation
     double *iou, *tp, *fn, *fp;     // running state [num_categories]
     long long *matches;    // [B][match_cap][2] nullable
@@ -1040,6 +1046,11 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_frames_kernel(const Ma
         const int stat = tid / NC, c = tid - stat * NC;
         double *dst = (stat == 0 ? prm.iou : stat == 1 ? prm.tp : stat == 2 ? prm.fn : prm.fp) + c;
         double acc = *dst;
+        // journal: the states as they were before this update (row B).  The host re-accumulates
+        // from it, in frame order, when a frame of this update has to be redone by
+        // npb_pq_update_big_frame (PanopticQuality._replay): the float64 sums then still equal
+        // the reference's frame-by-frame order, pq.py:298-303
+        prm.frame_stats[(size_t)B * row + tid] = acc;
         // batches of independent loads (adjacent threads read adjacent words), added strictly in
         // frame order
         constexpr int kFrames = 8;
@@ -1497,7 +1508,7 @@ static int pq_dense_side(int num_categories, int64_t max_instances_per_category)
     return (pow2 && num_categories <= kSmemConfmatMaxN) ? num_categories : 0;
 }
 
-// workspace: [entry_keys | entry_cnts | (entry_n, frames done | frame_dense: one memset) | frame_stats]
+// workspace: [entry_keys | entry_cnts | (entry_n, frames done | frame_dense: one memset) | frame_stats (B + 1 rows)]
 static size_t pq_counter_bytes(int B) { return align256((size_t)(B + 1) * sizeof(unsigned)); }
 static size_t pq_cleared_bytes(int B)
 {
@@ -1556,7 +1567,7 @@ extern "C" size_t npb_pq_update_workspace_bytes(int B, int num_categories)
     size_t bytes = align256((size_t)B * cap * sizeof(unsigned long long));
     bytes += align256((size_t)B * cap * sizeof(unsigned));
     bytes += pq_cleared_bytes(B);
-    bytes += align256((size_t)B * 4 * num_categories * sizeof(double));
+    bytes += align256((size_t)(B + 1) * 4 * num_categories * sizeof(double));
     return bytes;
 }
 

@@ -78,7 +78,9 @@ class _PQKernel:
             matches = torch.empty((B, MATCH_CAP, 2), dtype=torch.int64, device=dev)
             n_matches = torch.zeros(B, dtype=torch.int32, device=dev)
         if want_frame_stats:
-            frame_stats = torch.empty((B, 4, num_categories), dtype=torch.float64, device=dev)
+            # rows 0..B-1: per-frame results, row B: the states before this update (the journal
+            # `PanopticQuality._replay` re-accumulates from)
+            frame_stats = torch.empty((B + 1, 4, num_categories), dtype=torch.float64, device=dev)
         n_cm = 0
         if confmat is not None:
             sem_target = _lib.require_cuda(sem_target.to(dev), 'semantic target', torch.uint8, 3)
@@ -233,7 +235,8 @@ class PanopticQuality(MetricState):
 
     FOLLOW_UP_DEPTH = 3     # eager updates whose status words have not been read yet
 
-    def _follow_up(self, status, preds, targets, matches=None, n_matches=None) -> None:
+    def _follow_up(self, status, preds, targets, matches=None, n_matches=None,
+                   frame_stats=None) -> None:
         """Remember an eager update until its status has been read; the oldest ones are resolved
         now (their kernels have long finished, so this does not stall the device)."""
         # the status words travel to pinned memory right behind the update's kernels; waiting for
@@ -245,32 +248,87 @@ class PanopticQuality(MetricState):
         landed = torch.cuda.Event()
         landed.record(torch.cuda.current_stream(status.device))
         self._pending.append(dict(status=status, host=host, landed=landed, preds=preds,
-                                  targets=targets, matches=matches, n_matches=n_matches))
+                                  targets=targets, matches=matches, n_matches=n_matches,
+                                  frame_stats=frame_stats))
         # a few updates may be in flight: the host never waits for the batch it has just issued
         while len(self._pending) > self.FOLLOW_UP_DEPTH:
             self._resolve(self._pending.pop(0))
 
-    def _resolve(self, entry: Dict) -> None:
+    def _codes(self, entry: Dict) -> List[int]:
+        """Status words of a pending update (waits for their copy, not for the device)."""
         if entry.get('host') is None:
-            codes = entry['status'].cpu().tolist()
+            return entry['status'].cpu().tolist()
+        entry['landed'].synchronize()
+        codes = entry['host'].tolist()
+        pool = self._status_hosts.setdefault(entry['host'].numel(), [])
+        if len(pool) < 2 * self.FOLLOW_UP_DEPTH:
+            pool.append(entry['host'])
+        entry['host'] = None
+        return codes
+
+    def _resolve(self, entry: Dict) -> None:
+        codes = self._codes(entry)
+        if _lib.ERR_CAPACITY not in codes:
+            _lib.raise_for_status(codes, type(self).__name__ + '.update')
+            return
+        # a frame beyond the capacities of the batched matcher contributed nothing; it is
+        # evaluated again on the large-frame path and put back IN ITS PLACE: the updates issued
+        # since (all still pending) are re-accumulated with it
+        later, self._pending = self._pending, []
+        self._replay([(entry, codes)] + [(e, self._codes(e)) for e in later])
+
+    def _states(self) -> Tuple[torch.Tensor, ...]:
+        return self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class
+
+    def _replay(self, entries: List[Tuple[Dict, List[int]]]) -> None:
+        """Large-frame follow-up with the reference's float64 order (pq.py:298-303).
+
+        `entries`: every update issued since (and including) the oldest one with an
+        over-capacity frame, with their status words.  Each left a journal -- per-frame results
+        + the states before it (`frame_stats`, see npb_pq_update) -- so the states are rebuilt
+        from the oldest journal frame by frame, the large-frame results in the places of the
+        frames that had contributed zeros.  Updates this object does not know about (replays of
+        a CUDA graph on the same metric in between) are detected by rebuilding the CURRENT
+        states first: when that does not reproduce them bit for bit the large-frame results are
+        simply added (exact counts, float64 IoU sums out of frame order)."""
+        where = type(self).__name__ + '.update'
+        errors: List[int] = []
+        redone = {}
+        for k, (entry, codes) in enumerate(entries):
+            errors += [c for c in codes if c != _lib.ERR_CAPACITY]
+            for b, c in enumerate(codes):
+                if c != _lib.ERR_CAPACITY:
+                    continue
+                fs = [torch.zeros_like(s) for s in self._states()]
+                m, n = entry['matches'], entry['n_matches']
+                _evaluate_big_frame(
+                    entry['preds'][b], entry['targets'][b], self.num_categories,
+                    self.ignored_label, self.max_instances_per_category, self.offset,
+                    self.void_segment_id, *fs, matches_row=None if m is None else m[b],
+                    n_matches_row=None if n is None else n[b:b + 1], where=where)
+                redone[(k, b)] = torch.stack(fs)        # 0 + x = x: the frame's own result
+        journals = [e.get('frame_stats') for e, _ in entries]
+        exact = all(j is not None for j in journals)
+        if exact:
+            current = torch.stack(self._states())
+            rebuilt = journals[0][-1].clone()
+            for j in journals:
+                for b in range(j.shape[0] - 1):
+                    rebuilt += j[b]
+            # (bit patterns: NaN-safe and -0.0 != 0.0)
+            exact = bool(torch.equal(rebuilt.view(torch.int64), current.view(torch.int64)))
+        if exact:
+            state = journals[0][-1].clone()
+            for k, j in enumerate(journals):
+                for b in range(j.shape[0] - 1):
+                    state += redone.get((k, b), j[b])
+            for dst, src in zip(self._states(), state):
+                dst.copy_(src)
         else:
-            entry['landed'].synchronize()
-            codes = entry['host'].tolist()
-            pool = self._status_hosts.setdefault(entry['host'].numel(), [])
-            if len(pool) < 2 * self.FOLLOW_UP_DEPTH:
-                pool.append(entry['host'])
-        big = [b for b, c in enumerate(codes) if c == _lib.ERR_CAPACITY]
-        _lib.raise_for_status([c for c in codes if c != _lib.ERR_CAPACITY],
-                              type(self).__name__ + '.update')
-        for b in big:
-            m, n = entry['matches'], entry['n_matches']
-            _evaluate_big_frame(
-                entry['preds'][b], entry['targets'][b], self.num_categories, self.ignored_label,
-                self.max_instances_per_category, self.offset, self.void_segment_id,
-                self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
-                matches_row=None if m is None else m[b],
-                n_matches_row=None if n is None else n[b:b + 1],
-                where=type(self).__name__ + '.update')
+            for fs in redone.values():
+                for dst, src in zip(self._states(), fs):
+                    dst += src
+        _lib.raise_for_status(errors, where)
 
     # ---- pipelined matching ----------------------------------------------------------------
     def _set_deferred(self, args, keep: Dict, preds: Optional[torch.Tensor], B: int) -> None:
@@ -291,7 +349,8 @@ class PanopticQuality(MetricState):
             self._pending.append(dict(status=k['status'], host=None, landed=None, preds=d['preds'],
                                       targets=k['target'], matches=None, n_matches=None))
         else:
-            self._follow_up(k['status'], d['preds'], k['target'], k['matches'], k['n_matches'])
+            self._follow_up(k['status'], d['preds'], k['target'], k['matches'], k['n_matches'],
+                            k['frame_stats'])
 
     def _flush_deferred(self) -> None:
         """Run the matcher of the deferred update now (current stream)."""
@@ -315,9 +374,9 @@ class PanopticQuality(MetricState):
             preds, targets, self.num_categories, self.ignored_label,
             self.max_instances_per_category, self.offset, self.void_segment_id,
             self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
-            status=status, scratch=self._scratch, **kw)
+            status=status, scratch=self._scratch, want_frame_stats=eager, **kw)
         if eager:
-            self._follow_up(status, preds, targets, matches, n_matches)
+            self._follow_up(status, preds, targets, matches, n_matches, frame_stats)
         return matches, n_matches, frame_stats
 
     def _eval_args(self, targets, **kw):
@@ -330,13 +389,14 @@ class PanopticQuality(MetricState):
         args, keep = _PQKernel.prepare(
             targets, self.num_categories, self.ignored_label, self.offset, self.void_segment_id,
             self.iou_per_class, self.tp_per_class, self.fn_per_class, self.fp_per_class,
-            status=status, scratch=self._scratch, **kw)
+            status=status, scratch=self._scratch, want_frame_stats=eager, **kw)
         keep['eager'] = eager
         return args, keep
 
     def _fused_issued(self, keep: Dict, preds: torch.Tensor) -> None:
         if keep.get('eager'):
-            self._follow_up(keep['status'], preds, keep['target'], keep['matches'], keep['n_matches'])
+            self._follow_up(keep['status'], preds, keep['target'], keep['matches'], keep['n_matches'],
+                            keep['frame_stats'])
 
     def update(self, preds: torch.Tensor, targets: torch.Tensor) -> None:
         """preds, targets: (B,H,W) panoptic ids (class * max_instances + instance).
@@ -348,9 +408,8 @@ class PanopticQuality(MetricState):
 
     def check_status(self) -> None:
         self._flush_deferred()
-        pending, self._pending = self._pending, []
-        for entry in pending:
-            self._resolve(entry)
+        while self._pending:        # (a large-frame follow-up takes the later entries with it)
+            self._resolve(self._pending.pop(0))
         for status in self._status.values():
             codes = status.cpu().tolist()
             status.zero_()

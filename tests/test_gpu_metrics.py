@@ -210,8 +210,8 @@ def test_pq_thousands_of_pairs_per_frame(frames, cuda_device):
 def test_pq_large_frame_path(cuda_device):
     """A frame beyond the shared-memory matcher (~6300 distinct pairs, 1499 gt / 1013 pred
     segments) between two ordinary ones: it contributes nothing in the batched pass and is
-    evaluated again with the global-memory tables -- the states equal the oracle's (the IoU sums
-    up to the order in which the frames are added)."""
+    evaluated again with the global-memory tables and put back in its place: the states equal
+    the oracle's bit for bit, the float64 IoU sums included (frame order of pq.py:298-303)."""
     from nicr_mt_scene_analysis_b200.metric import (MeanIntersectionOverUnion, PanopticEvaluation,
                                                     PanopticQuality, compare_and_accumulate)
     L, OFF, NC = 1 << 16, 256 ** 3, 3
@@ -233,8 +233,7 @@ def test_pq_large_frame_path(cuda_device):
             for s, v in zip(state, out[:4]):
                 s += v
     got = np.stack(_states(pq))
-    assert np.array_equal(got[1:], state[1:])                       # tp / fn / fp
-    np.testing.assert_allclose(got[0], state[0], rtol=1e-14)        # IoU sums (frame order differs)
+    assert np.array_equal(got, state)       # tp / fn / fp AND the IoU sums, in frame order
     assert np.array_equal(miou.confmat.cpu().numpy(), oracle.confmat((pred // L).numpy(), sem_t.numpy(), NC))
     # single-frame API: same path, same float64 order as the reference -> bit-exact, with matches
     iou, tp, fn, fp, m = compare_and_accumulate(big[0].to(cuda_device), big[1].to(cuda_device),
@@ -242,6 +241,62 @@ def test_pq_large_frame_path(cuda_device):
     for a, b in zip((iou, tp, fn, fp), frames[1][:4]):
         assert np.array_equal(a.numpy(), b)
     assert m == frames[1][4]
+
+
+def test_pq_large_frames_keep_the_frame_order_over_several_updates(cuda_device):
+    """Seven eager updates of three frames, over-capacity frames in the second, fourth (two of
+    them) and last one: every follow-up rebuilds the states from the journal of the oldest
+    affected update, so the float64 IoU sums equal the frame-by-frame order of the reference
+    (pq.py:298-303) bit for bit -- also when another large frame turns up among the updates that
+    are re-accumulated, and with ordinary updates in between."""
+    from nicr_mt_scene_analysis_b200.metric import PanopticQuality
+    L, OFF, NC = 1 << 16, 256 ** 3, 3
+    def frame(seed, shift, noisy_rows):
+        # 16x16 blocks of alternating classes, the prediction shifted by `shift` px (matches with
+        # IoUs (16 - shift) / (16 + shift) and clipped ones at the border); the upper
+        # `noisy_rows` rows carry a different (gt, pred) pair in every pixel
+        side = 96
+        yy, xx = torch.meshgrid(torch.arange(side), torch.arange(side), indexing='ij')
+        blk = (yy // 16) * 6 + xx // 16
+        tgt = (1 + blk % 2) * L + blk + 1
+        pred = torch.roll(tgt, shifts=(shift, seed % 3), dims=(1, 0))
+        if noisy_rows:
+            g = torch.Generator().manual_seed(seed)
+            n = noisy_rows * side
+            idx = torch.randperm(n, generator=g).reshape(noisy_rows, side)
+            tgt[:noisy_rows] = 1 * L + 100 + idx % 1499
+            pred[:noisy_rows] = 1 * L + 100 + idx % 1013
+        return pred, tgt
+    smalls = [frame(s, s, 0) for s in range(1, 6)]
+    bigs = [frame(7, 2, 64), frame(9, 4, 80)]
+    plan = [(0, 1, 2), (3, 'b0', 4), (1, 1, 0), ('b1', 2, 'b0'), (4, 3, 2), (0, 0, 1), (2, 'b1', 3)]
+    pick = lambda k: bigs[int(k[1])] if isinstance(k, str) else smalls[k]
+    pq = PanopticQuality(NC, 0, L, OFF, [False, True, True], device=cuda_device)
+    state = np.zeros((4, NC))
+    cache = {}
+    for upd in plan:
+        pred = torch.stack([pick(k)[0] for k in upd])
+        tgt = torch.stack([pick(k)[1] for k in upd])
+        pq.update(pred.to(cuda_device), tgt.to(cuda_device))
+        for k in upd:
+            if k not in cache:
+                cache[k] = oracle.pq_compare_and_accumulate(pick(k)[0].numpy(), pick(k)[1].numpy(),
+                                                            NC, 0, L, OFF, 0)[:4]
+            for s, v in zip(state, cache[k]):
+                s += v
+    pq.check_status()
+    assert state[0].sum() != np.floor(state[0].sum())      # (the sums are not trivially exact)
+    assert np.array_equal(np.stack(_states(pq)), state)
+    # and once more on top of the non-zero states
+    for upd in plan[:4]:
+        pred = torch.stack([pick(k)[0] for k in upd])
+        tgt = torch.stack([pick(k)[1] for k in upd])
+        pq.update(pred.to(cuda_device), tgt.to(cuda_device))
+        for k in upd:
+            for s, v in zip(state, cache[k]):
+                s += v
+    pq.check_status()
+    assert np.array_equal(np.stack(_states(pq)), state)
 
 
 def test_pq_capacity_error_inside_a_cuda_graph(cuda_device):
