@@ -36,6 +36,7 @@ extern "C" {
 #endif
 
 #define NPB_MAX_INST 256
+#define NPB_MAX_WIDE_CENTERS 8192   /* centres of a frame kept for npb_overflow_centers */
 
 #define NPB_OK 0
 #define NPB_ERR_ARG (-1)               /* invalid argument / unsupported size            */
@@ -142,6 +143,38 @@ int npb_group_pixels(const float *logits, const uint8_t *sem_in, const uint8_t *
                      const int32_t *n_centers, int normalized_offset, int use_distance_threshold,
                      float distance_threshold, uint8_t *sem_out, uint8_t *inst_out,
                      uint32_t *vote_hist, double *ori_sum, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * More than 255 centres in a frame: the reference's uint8 wrap, on request.
+ * Replaces: the silent wrap of `instance_id = (instance_id + 1).type(torch.uint8)`,
+ *           model/postprocessing/instance.py:231-236, with the meta dict of :253-266 that keeps
+ *           growing past 255 entries (areas of the entries beyond 255 are zero).
+ * A frame whose centre selection finds more than 255 centres (k-th-value ties of a saturated
+ * heat-map) reports NPB_ERR_TOO_MANY_CENTERS and gets no instances.  Its complete centre list
+ * (up to NPB_MAX_WIDE_CENTERS) stays in the `workspace` of that npb_instance_centers /
+ * npb_panoptic_forward call until the next call on it:
+ *   npb_overflow_centers   copies it out: n_out [1] (-1: beyond NPB_MAX_WIDE_CENTERS),
+ *                          centers_yx [cap][2] (y, x) raster order, center_score [cap];
+ *                          `heat` (B,1,H,W), B, H, W, nms_kernel_size as in the call that failed
+ *                          (for npb_panoptic_forward: the head of its workspace);
+ *   npb_group_pixels_wide  redoes the grouping of that ONE frame with all centres,
+ *                          id = (arg-min + 1) mod 256 like the reference: inst_out (H,W) u8,
+ *                          vote_hist [256][C] / ori_sum [256][2] of the frame (zeroed by the
+ *                          call), n_rows_out [1] = min(n, 255) (the `n_centers` entry for
+ *                          npb_finalize_instances), status [1] put back to NPB_OK.
+ *                          sem_in / fg_in / offset / orientation: the frame's planes.
+ * npb_finalize_instances + npb_write_panoptic (B = 1, the frame's rows) complete the frame.
+ * ------------------------------------------------------------------------- */
+int npb_overflow_centers(const void *workspace, const float *heat, int B, int H, int W,
+                         int nms_kernel_size, int frame, int32_t *n_out, int32_t *centers_yx,
+                         float *center_score, int cap, void *stream);
+int npb_group_pixels_wide(const uint8_t *sem_in, const uint8_t *fg_in, const float *offset,
+                          const float *orientation, int C, int H, int W,
+                          const uint8_t *h_thing_lut, const int32_t *centers_yx,
+                          const int32_t *n_centers, int normalized_offset,
+                          int use_distance_threshold, float distance_threshold,
+                          uint8_t *inst_out, uint32_t *vote_hist, double *ori_sum,
+                          int32_t *n_rows_out, int32_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------
  * Per-frame instance table: majority class (smallest class on ties), per-class running

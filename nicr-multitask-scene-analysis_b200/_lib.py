@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('NPB_LIB_PATH') or os.path.join(_HERE, 'csrc', 'libnicr_panoptic_b200.so')
 
 MAX_INST = 256
+MAX_WIDE_CENTERS = 8192     # NPB_MAX_WIDE_CENTERS
 
 OK = 0
 ERR_ARG, ERR_TOO_MANY_CENTERS, ERR_ZERO_DIVISION, ERR_CATEGORY_RANGE, ERR_CAPACITY, ERR_CUDA = \
@@ -63,6 +64,9 @@ _SIGNATURES = {
                                      _P, _P, _P, _P, _P, _P]),
     'npb_group_pixels': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,
                                  c_int, c_int, c_float, _P, _P, _P, _P, _P]),
+    'npb_overflow_centers': (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P]),
+    'npb_group_pixels_wide': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int,
+                                      c_float, _P, _P, _P, _P, _P, _P]),
     'npb_finalize_instances': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, _P, _P,
                                        _P, _P, _P, _P]),
     'npb_write_panoptic': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P,

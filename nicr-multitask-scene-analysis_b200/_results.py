@@ -130,11 +130,21 @@ class InstanceTables:
         self._np = None
         self._host = None           # (pinned copy, event) once prefetch() ran
         self._where = 'panoptic post-processing'
+        # frames redone with more than 255 centres (`on_overflow='wrap'`, instance.py:236):
+        # frame -> (centres (K,2) int32, scores (K,) float32) on the host; their table rows hold
+        # the 255 wrapped instance ids
+        self.wide: Dict[int, Any] = {}
 
     def dptr(self, name: str):
         off, _, _, _ = self._offsets[name]
         import ctypes
         return ctypes.c_void_p(self.dev.data_ptr() + off)
+
+    def dptr_row(self, name: str, b: int):
+        """device pointer of frame `b`'s row of a table"""
+        off, _, dt, per_frame = self._offsets[name]
+        import ctypes
+        return ctypes.c_void_p(self.dev.data_ptr() + off + b * per_frame * np.dtype(dt).itemsize)
 
     def dview(self, name: str) -> torch.Tensor:
         off, nbytes, dt, per_frame = self._offsets[name]
@@ -198,7 +208,8 @@ class InstanceTables:
         """instance.py:163-166: list of (n, 2) int32 tensors (y, x), raster order."""
         n = self['n_centers']
         c = self['centers_yx'].reshape(self.B, _lib.MAX_INST, 2)
-        return [torch.from_numpy(c[b, :n[b]].copy()) for b in range(self.B)]
+        return [torch.from_numpy(self.wide[b][0].copy() if b in self.wide else c[b, :n[b]].copy())
+                for b in range(self.B)]
 
     def meta(self, with_orientation: bool = False) -> List[Dict[int, Dict[str, Any]]]:
         """instance.py:253-266: {id: {'center_yx', 'area', 'score'}} for every centre;
@@ -208,12 +219,32 @@ class InstanceTables:
         area = self['inst_area'][:, :m + 1].tolist()
         score = self['center_score'][:, :m].tolist()
         if not with_orientation:
-            return [{i + 1: {'center_yx': (cb[i][0], cb[i][1]), 'area': ab[i + 1], 'score': sb[i]}
-                     for i in range(nb)} for nb, cb, ab, sb in zip(n, c, area, score)]
-        ang = self['inst_angle'][:, :m + 1].tolist()
-        return [{i + 1: {'center_yx': (cb[i][0], cb[i][1]), 'area': ab[i + 1], 'score': sb[i],
-                         'orientation': gb[i + 1]}
-                 for i in range(nb)} for nb, cb, ab, sb, gb in zip(n, c, area, score, ang)]
+            out = [{i + 1: {'center_yx': (cb[i][0], cb[i][1]), 'area': ab[i + 1], 'score': sb[i]}
+                    for i in range(nb)} for nb, cb, ab, sb in zip(n, c, area, score)]
+        else:
+            ang = self['inst_angle'][:, :m + 1].tolist()
+            out = [{i + 1: {'center_yx': (cb[i][0], cb[i][1]), 'area': ab[i + 1], 'score': sb[i],
+                            'orientation': gb[i + 1]}
+                    for i in range(nb)} for nb, cb, ab, sb, gb in zip(n, c, area, score, ang)]
+        for b in self.wide:
+            out[b] = self._meta_wide(b, with_orientation)
+        return out
+
+    def _meta_wide(self, b: int, with_orientation: bool) -> Dict[int, Dict[str, Any]]:
+        """Meta dict of a frame with K > 255 centres the way the reference builds it
+        (instance.py:253-266): one entry per centre; areas are the bincount of the WRAPPED uint8
+        ids, so entries beyond 255 have area 0 (and no orientation: NaN, panoptic.py:311-314)."""
+        cyx, score = self.wide[b]
+        area = self['inst_area'][b].tolist()
+        ang = self['inst_angle'][b].tolist() if with_orientation else None
+        nan = float('nan')
+        out = {}
+        for i, ((y, x), sc) in enumerate(zip(cyx.tolist(), score.tolist()), start=1):
+            e = {'center_yx': (y, x), 'area': area[i] if i < _lib.MAX_INST else 0, 'score': sc}
+            if with_orientation:
+                e['orientation'] = ang[i] if i < _lib.MAX_INST else nan
+            out[i] = e
+        return out
 
     def panoptic_ids(self) -> List[Dict[int, int]]:
         """panoptic_merge.py:209: {panoptic id: raw instance id}, ascending instance id."""

@@ -49,8 +49,14 @@ struct SelectParams {
     // before this grid has completed): no memset node between the kernels of a step
     uint32_t *clear0, *clear1;
     size_t clear0_words, clear1_words;
+    // a frame with more than 255 centres (NPB_ERR_TOO_MANY_CENTERS) leaves ALL of them here, as
+    // flat pixel indices in raster order, for npb_overflow_centers (the reference's uint8 wrap)
+    int32_t *wide_n;            // [B] centres of the frame, -1: more than NPB_MAX_WIDE_CENTERS
+    unsigned *wide_idx;         // [B][2][NPB_MAX_WIDE_CENTERS]: unsorted | sorted
     NPB_TL_FIELD
 };
+
+constexpr int kWideCap = NPB_MAX_WIDE_CENTERS;
 
 // every CTA of the NMS pass zeroes its share of the downstream scratch
 __device__ __forceinline__ void clear_downstream_scratch(const SelectParams &sp)
@@ -134,6 +140,31 @@ __device__ void select_centers_frame(const SelectParams &sp, int b)
     // the counters of the frame go back to zero: the next call on this workspace needs no memset
     if (tid == 0) { sp.cand_cnt[b] = 0; sp.done_cnt[b] = 0; }
     if (n > kMaxInst - 1) {
+        // Beyond the uint8 instance ids (instance.py:236 wraps them silently): an error for this
+        // call.  The complete centre list stays in the workspace so that a caller who wants the
+        // reference's wrapped result can redo the frame (npb_overflow_centers +
+        // npb_group_pixels_wide).  Rare path: second pass over the candidates, rank sort in
+        // global memory.
+        if (sp.wide_idx) {
+            unsigned *tmp = sp.wide_idx + (size_t)b * 2 * kWideCap, *sorted = tmp + kWideCap;
+            if (n <= kWideCap) {
+                __syncthreads();
+                if (tid == 0) s_n = 0;
+                __syncthreads();
+                for (int i = tid; i < S; i += NT) {
+                    const uint2 c = __ldcg(cb + i);
+                    if (c.x >= kth_bits && (!fgb || fgb[c.y])) tmp[atomicAdd(&s_n, 1)] = c.y;
+                }
+                __syncthreads();
+                for (int i = tid; i < n; i += NT) {
+                    const unsigned my = tmp[i];
+                    int rank = 0;
+                    for (int j = 0; j < n; ++j) rank += (tmp[j] < my);
+                    sorted[rank] = my;
+                }
+            }
+            if (tid == 0) sp.wide_n[b] = n <= kWideCap ? n : -1;
+        }
         if (tid == 0) {
             set_status(sp.status + b, NPB_ERR_TOO_MANY_CENTERS);
             sp.n_centers[b] = 0;
@@ -401,6 +432,7 @@ extern "C" size_t npb_instance_centers_workspace_bytes(int B, int H, int W, int 
     size_t bytes = (size_t)B * cap * sizeof(uint2);
     bytes = (bytes + 255) & ~(size_t)255;
     bytes += npb::centers_counter_bytes(B);
+    bytes += npb::centers_wide_bytes(B);
     return bytes;
 }
 
@@ -432,6 +464,8 @@ int npb::instance_centers_impl(const float *heat, int B, int H, int W, float thr
     int32_t *cand_cnt = (int32_t *)((char *)workspace + off);
 
     int32_t *done_cnt = cand_cnt + B;
+    int32_t *wide_n = (int32_t *)((char *)cand_cnt + centers_counter_bytes(B));
+    unsigned *wide_idx = (unsigned *)((char *)wide_n + align256((size_t)B * sizeof(int32_t)));
     if (!cleared) cudaMemsetAsync(cand_cnt, 0, 2 * (size_t)B * sizeof(int32_t), s);
     SelectParams sp;
     sp.cand = cand; sp.cap = cap; sp.cand_cnt = cand_cnt; sp.done_cnt = done_cnt; sp.heat = heat;
@@ -441,6 +475,7 @@ int npb::instance_centers_impl(const float *heat, int B, int H, int W, float thr
     sp.late_wait = late_wait ? 1 : 0;
     sp.clear0 = sp.clear1 = nullptr;
     sp.clear0_words = sp.clear1_words = 0;
+    sp.wide_n = wide_n; sp.wide_idx = wide_idx;
     if (downstream) {
         sp.clear0 = (uint32_t *)downstream->p0; sp.clear0_words = downstream->bytes0 / 4;
         sp.clear1 = (uint32_t *)downstream->p1; sp.clear1_words = downstream->bytes1 / 4;
@@ -477,4 +512,37 @@ extern "C" int npb_instance_centers(const float *heat, int B, int H, int W, floa
     return instance_centers_impl(heat, B, H, W, threshold, nms_kernel_size, top_k, fg, apply_fg_mask,
                                  workspace, centers_yx, n_centers, center_score, status, false,
                                  false, nullptr, false, stream);
+}
+
+// ---- > 255 centres: the reference's uint8 wrap (instance.py:236) -------------------------------
+__global__ void __launch_bounds__(256)
+overflow_centers_kernel(const int32_t *wide_n, const unsigned *sorted, const float *heat_frame,
+                        int W, int cap, int32_t *n_out, int32_t *centers_yx, float *score)
+{
+    const int n = *wide_n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = n;
+    if (n < 0) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < cap; i += gridDim.x * blockDim.x) {
+        const unsigned idx = sorted[i];
+        centers_yx[2 * i] = (int32_t)(idx / (unsigned)W);
+        centers_yx[2 * i + 1] = (int32_t)(idx % (unsigned)W);
+        score[i] = heat_frame[idx];
+    }
+}
+
+extern "C" int npb_overflow_centers(const void *workspace, const float *heat, int B, int H, int W,
+                                    int nms_kernel_size, int frame, int32_t *n_out,
+                                    int32_t *centers_yx, float *center_score, int cap, void *stream)
+{
+    if (!workspace || !heat || !n_out || !centers_yx || !center_score) return NPB_ERR_ARG;
+    if (B < 1 || frame < 0 || frame >= B || H < 1 || W < 1 || cap < 1) return NPB_ERR_ARG;
+    const int ccap = cand_capacity(H, W, nms_kernel_size);
+    const size_t off = ((size_t)B * ccap * sizeof(uint2) + 255) & ~(size_t)255;
+    const char *counters = (const char *)workspace + off;
+    const int32_t *wide_n = (const int32_t *)(counters + centers_counter_bytes(B));
+    const unsigned *wide_idx = (const unsigned *)((const char *)wide_n + align256((size_t)B * sizeof(int32_t)));
+    overflow_centers_kernel<<<16, 256, 0, (cudaStream_t)stream>>>(
+        wide_n + frame, wide_idx + ((size_t)frame * 2 + 1) * kWideCap,
+        heat + (size_t)frame * H * W, W, cap, n_out, centers_yx, center_score);
+    return record_launch("npb_overflow_centers");
 }

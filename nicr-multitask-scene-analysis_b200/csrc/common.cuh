@@ -52,6 +52,12 @@ int record_launch(const char *what);  // api.cu: cudaGetLastError -> NPB_ERR_CUD
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // counters at the end of the centres workspace: candidates per frame, finished NMS CTAs per frame
 inline size_t centers_counter_bytes(int B) { return align256(2 * (size_t)B * sizeof(int32_t)); }
+// behind them: the complete centre lists of frames with more than 255 centres (centers.cu)
+inline size_t centers_wide_bytes(int B)
+{
+    return align256((size_t)B * sizeof(int32_t)) +
+           align256((size_t)B * 2 * NPB_MAX_WIDE_CENTERS * sizeof(unsigned));
+}
 
 // internal forms of npb_instance_centers / npb_group_pixels for npb_panoptic_forward, which clears
 // the scratch of both stages with ONE memset (centers.cu, group.cu)

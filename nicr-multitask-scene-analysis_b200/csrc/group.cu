@@ -463,6 +463,65 @@ static void launch_group(const GroupParams &prm, int B, bool ori, cudaStream_t s
     else launch_group_nt<VEC, MODE, false>(prm, B, s);
 }
 
+// ---- more than 255 centres: the reference's uint8 wrap ----------------------------------------
+// One frame whose centre list does not fit the uint8 ids (npb_overflow_centers).  The reference
+// goes on regardless (instance.py:231-236): arg-min over ALL centres, id = uint8(arg + 1), so
+// centre 256 becomes "no instance", centre 257 joins instance 1, ...  Correctness path for a
+// pathological regime (hundreds of exactly tied heat-map peaks): one pixel per thread, the
+// centres streamed from global memory, the reference's distance formula as written (one sqrtf
+// per pair, first minimum wins, the oracle's loop), plain atomics for votes / orientation sums.
+struct WideGroupParams {
+    const uint8_t *sem_in, *fg_in;
+    const float *offset, *orientation;
+    const int32_t *centers_yx, *n_centers;
+    int P, W, C, normalized, use_thr;
+    float fH, fW, dist_thr;
+    ClassSet thing;
+    uint8_t *inst_out;
+    uint32_t *vote_hist;
+    double *ori_sum;
+    int32_t *n_rows_out, *status;
+};
+
+__global__ void __launch_bounds__(256) group_pixels_wide_kernel(const WideGroupParams prm)
+{
+    const int n = *prm.n_centers;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *prm.n_rows_out = n < kMaxInst - 1 ? n : kMaxInst - 1;     // rows of the instance tables
+        *prm.status = NPB_OK;                                       // the frame has been redone
+    }
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= prm.P) return;
+    const int cls = prm.sem_in ? prm.sem_in[p] : 0;
+    const bool fg = prm.sem_in ? prm.thing.has(cls) : prm.fg_in[p] != 0;
+    int id = 0;
+    if (fg && n > 0) {
+        const int y = p / prm.W, x = p - y * prm.W;
+        float oy = prm.offset[p], ox = prm.offset[(size_t)prm.P + p];
+        if (prm.normalized) { oy = __fmul_rn(oy, prm.fH); ox = __fmul_rn(ox, prm.fW); }
+        const float ly = __fadd_rn((float)y, oy), lx = __fadd_rn((float)x, ox);
+        float best = 0.0f;
+        int arg = 0;
+        for (int i = 0; i < n; ++i) {
+            const float d0 = __fsub_rn((float)__ldg(prm.centers_yx + 2 * i), ly);
+            const float d1 = __fsub_rn((float)__ldg(prm.centers_yx + 2 * i + 1), lx);
+            const float d = __fsqrt_rn(__fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+            if (i == 0 || d < best) { best = d; arg = i; }
+        }
+        id = (arg + 1) & 255;                                        // instance.py:236
+        if (prm.use_thr && best > prm.dist_thr) id = 0;             // instance.py:246
+    }
+    prm.inst_out[p] = (uint8_t)id;
+    if (id > 0) {
+        const int CH = prm.sem_in ? prm.C : 1;
+        atomicAdd(prm.vote_hist + id * CH + (prm.sem_in ? cls : 0), 1u);
+        if (prm.ori_sum) {
+            atomicAdd(prm.ori_sum + 2 * id, (double)prm.orientation[p]);
+            atomicAdd(prm.ori_sum + 2 * id + 1, (double)prm.orientation[(size_t)prm.P + p]);
+        }
+    }
+}
+
 }  // namespace npb
 
 using namespace npb;
@@ -537,4 +596,36 @@ extern "C" int npb_group_pixels(const float *logits, const uint8_t *sem_in, cons
     return group_pixels_impl(logits, sem_in, fg_in, offset, orientation, B, C, H, W, h_thing_lut,
                              centers_yx, n_centers, normalized_offset, use_distance_threshold,
                              distance_threshold, sem_out, inst_out, vote_hist, ori_sum, false, stream);
+}
+
+extern "C" int npb_group_pixels_wide(const uint8_t *sem_in, const uint8_t *fg_in, const float *offset,
+                                     const float *orientation, int C, int H, int W,
+                                     const uint8_t *h_thing_lut, const int32_t *centers_yx,
+                                     const int32_t *n_centers, int normalized_offset,
+                                     int use_distance_threshold, float distance_threshold,
+                                     uint8_t *inst_out, uint32_t *vote_hist, double *ori_sum,
+                                     int32_t *n_rows_out, int32_t *status, void *stream)
+{
+    if (((sem_in != nullptr) + (fg_in != nullptr)) != 1 || !offset || !centers_yx || !n_centers ||
+        !inst_out || !vote_hist || !n_rows_out || !status)
+        return NPB_ERR_ARG;
+    if (C < 1 || C > 256 || H < 1 || W < 1 || (long long)H * W >= (1ll << 30)) return NPB_ERR_ARG;
+    if (sem_in && !h_thing_lut) return NPB_ERR_ARG;
+    if (fg_in && C != 1) return NPB_ERR_ARG;
+    if ((orientation != nullptr) != (ori_sum != nullptr)) return NPB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    WideGroupParams prm;
+    prm.sem_in = sem_in; prm.fg_in = fg_in; prm.offset = offset; prm.orientation = orientation;
+    prm.centers_yx = centers_yx; prm.n_centers = n_centers;
+    prm.P = H * W; prm.W = W; prm.C = C; prm.normalized = normalized_offset;
+    prm.use_thr = use_distance_threshold; prm.fH = (float)H; prm.fW = (float)W;
+    prm.dist_thr = distance_threshold;
+    prm.thing = make_class_set(h_thing_lut, fg_in ? 0 : C);
+    prm.inst_out = inst_out; prm.vote_hist = vote_hist; prm.ori_sum = ori_sum;
+    prm.n_rows_out = n_rows_out; prm.status = status;
+    const int CH = fg_in ? 1 : C;
+    cudaMemsetAsync(vote_hist, 0, (size_t)kMaxInst * CH * sizeof(uint32_t), s);
+    if (ori_sum) cudaMemsetAsync(ori_sum, 0, (size_t)kMaxInst * 2 * sizeof(double), s);
+    group_pixels_wide_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm);
+    return record_launch("npb_group_pixels_wide");
 }

@@ -39,6 +39,14 @@ class InstancePostprocessing(DensePostprocessingBase):
         self._normalized_offset = normalized_offset
         self._offset_distance_threshold = offset_distance_threshold
         self.debug = kwargs.get('debug', False)
+        # More than 255 centres in a frame (k-th-value ties of a saturated heat-map).  'raise'
+        # (default): NpbError(TOO_MANY_CENTERS) when the results are read.  'wrap': the frame is
+        # redone the way the reference computes it -- uint8 ids that wrap silently
+        # (instance.py:236: centre 256 is "no instance", centre 257 joins instance 1, the meta
+        # dict keeps all centres) -- at the price of one status read-back per call.
+        self._on_overflow = kwargs.get('on_overflow', 'raise')
+        if self._on_overflow not in ('raise', 'wrap'):
+            raise ValueError("on_overflow must be 'raise' or 'wrap'")
 
     # ------------------------------------------------------------------ kernels
     def _run_centers(self, heat: torch.Tensor, fg_u8: Optional[torch.Tensor]) -> InstanceTables:
@@ -61,7 +69,55 @@ class InstancePostprocessing(DensePostprocessingBase):
             tables.dptr('centers_yx'), tables.dptr('n_centers'), tables.dptr('center_score'),
             tables.dptr('status'), _lib.stream_ptr(dev)), 'npb_instance_centers')
         tables._where = 'instance centres'
+        tables._centers_ws = ws         # holds the complete centre list of an overflowing frame
         return tables
+
+    # ------------------------------------------------------------------ > 255 centres
+    def _overflow_frames(self, tables: InstanceTables) -> List[int]:
+        """Frames of the call that reported more than 255 centres (one synchronous read of the
+        status words; only with `on_overflow='wrap'`)."""
+        if self._on_overflow != 'wrap':
+            return []
+        codes = tables.dview('status').cpu().tolist()
+        return [b for b, c in enumerate(codes) if c == _lib.ERR_TOO_MANY_CENTERS]
+
+    def _wide_centers(self, tables: InstanceTables, workspace: torch.Tensor, heat: torch.Tensor,
+                      b: int):
+        """npb_overflow_centers: the complete centre list of frame `b` -> device (count [1],
+        centres (cap,2), scores (cap)); the host copy goes into `tables.wide[b]`."""
+        B, _, H, W = heat.shape
+        dev = heat.device
+        cap = _lib.MAX_WIDE_CENTERS
+        n_dev = torch.empty(1, dtype=torch.int32, device=dev)
+        cyx = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+        score = torch.empty(cap, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().npb_overflow_centers(
+            _lib.ptr(workspace), _lib.ptr(heat), c_int(B), c_int(H), c_int(W),
+            c_int(self._heatmap_nms_kernel_size), c_int(b), _lib.ptr(n_dev), _lib.ptr(cyx),
+            _lib.ptr(score), c_int(cap), _lib.stream_ptr(dev)), 'npb_overflow_centers')
+        n = int(n_dev.item())
+        if n < 0:
+            raise _lib.NpbError(_lib.ERR_TOO_MANY_CENTERS,
+                                f'more than {cap} instance centres in frame {b}')
+        tables.wide[b] = (cyx[:n].cpu().numpy(), score[:n].cpu().numpy())
+        return n_dev, cyx, score
+
+    def _regroup_wide(self, tables: InstanceTables, b: int, centers, sem_b, fg_b, offset_b,
+                      orientation_b, C: int, H: int, W: int, thing_lut, normalized: bool,
+                      inst_b: torch.Tensor, hist: torch.Tensor, ori_sum) -> None:
+        """npb_group_pixels_wide for frame `b`: ids wrapped like instance.py:236; leaves the
+        frame's vote histogram / orientation sums in `hist` / `ori_sum`, puts min(n, 255) into
+        the frame's `n_centers` word and its status word back to OK."""
+        n_dev, cyx, _ = centers
+        use_thr = self._offset_distance_threshold is not None
+        dev = inst_b.device
+        _lib.check(_lib.lib().npb_group_pixels_wide(
+            _lib.ptr(sem_b), _lib.ptr(fg_b), _lib.ptr(offset_b), _lib.ptr(orientation_b),
+            c_int(C), c_int(H), c_int(W), thing_lut, _lib.ptr(cyx), _lib.ptr(n_dev),
+            c_int(int(normalized)), c_int(int(use_thr)),
+            c_float(float(self._offset_distance_threshold) if use_thr else 0.0),
+            _lib.ptr(inst_b), _lib.ptr(hist), _lib.ptr(ori_sum), tables.dptr_row('n_centers', b),
+            tables.dptr_row('status', b), _lib.stream_ptr(dev)), 'npb_group_pixels_wide')
 
     @staticmethod
     def _as_fg_u8(foreground_mask: torch.Tensor, device) -> torch.Tensor:
@@ -85,6 +141,9 @@ class InstancePostprocessing(DensePostprocessingBase):
         if self._heatmap_apply_foreground_mask and foreground_mask is not None:
             fg = self._as_fg_u8(foreground_mask, center_heatmap.device)
         tables = self._run_centers(center_heatmap, fg)
+        for b in self._overflow_frames(tables):         # on_overflow='wrap': all of them
+            self._wide_centers(tables, tables._centers_ws, center_heatmap, b)
+            tables.dview('status')[b] = 0
         centers = tables.centers_list()
         B, _, H, W = center_heatmap.shape
         mask = torch.zeros((B, H, W), dtype=torch.bool)
@@ -94,7 +153,7 @@ class InstancePostprocessing(DensePostprocessingBase):
         return mask.to(center_heatmap.device), centers
 
     def _group(self, tables: InstanceTables, center_offset: torch.Tensor, fg_u8: torch.Tensor,
-               normalized: bool = False):
+               normalized: bool = False, heat: Optional[torch.Tensor] = None):
         """npb_group_pixels with an explicit foreground mask (no classes) +
         npb_finalize_instances for the areas."""
         off = _lib.require_cuda(center_offset, 'center_offset', torch.float32, 4)
@@ -117,6 +176,15 @@ class InstancePostprocessing(DensePostprocessingBase):
             c_int64(1 << 16), c_int64(0), None, tables.dptr('inst_class'), _lib.ptr(pan_dummy),
             tables.dptr('inst_area'), tables.dptr('inst_angle'), _lib.stream_ptr(dev)),
             'npb_finalize_instances')
+        for b in self._overflow_frames(tables):         # on_overflow='wrap'
+            centers = self._wide_centers(tables, tables._centers_ws, heat, b)
+            self._regroup_wide(tables, b, centers, None, fg_u8[b], off[b], None, 1, H, W, None,
+                               normalized, inst[b], hist[b], None)
+            _lib.check(L.npb_finalize_instances(
+                _lib.ptr(hist[b]), None, tables.dptr_row('n_centers', b), c_int(1), c_int(1),
+                c_int(1), c_int64(1 << 16), c_int64(0), None, tables.dptr_row('inst_class', b),
+                _lib.ptr(pan_dummy[b]), tables.dptr_row('inst_area', b),
+                tables.dptr_row('inst_angle', b), _lib.stream_ptr(dev)), 'npb_finalize_instances')
         return inst
 
     def _get_instance_segmentation(
@@ -135,7 +203,8 @@ class InstancePostprocessing(DensePostprocessingBase):
         dev = center_heatmap.device
         fg = self._as_fg_u8(foreground_mask, dev)
         tables = self._run_centers(center_heatmap, fg)
-        inst = self._group(tables, center_offset, fg, normalized)
+        heat = _lib.require_cuda(center_heatmap, 'center_heatmap', torch.float32, 4)
+        inst = self._group(tables, center_offset, fg, normalized, heat)
         return inst, tables.meta()
 
     def _get_instance_orientation(

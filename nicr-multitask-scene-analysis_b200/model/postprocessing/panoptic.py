@@ -12,7 +12,8 @@ Differences to the reference that a caller can observe (all documented in DESIGN
   * dense outputs stay on the CUDA device (the reference moves the panoptic outputs to the
     CPU, panoptic.py:143-152); `.cpu()` in the callers keeps working;
   * a few bulky, rarely read entries are deferred (see _results.ResultDict);
-  * more than 255 centres in a frame raise instead of silently wrapping uint8 ids.
+  * more than 255 centres in a frame raise instead of silently wrapping uint8 ids, unless the
+    instance post-processing was built with `on_overflow='wrap'` (the reference's result).
 Extra keyword arguments (accepted through **kwargs like the reference's):
   * `async_results=True`: do not block on the table download; the dict / list entries are
     built on first access.
@@ -168,7 +169,41 @@ class PanopticPostprocessing(DensePostprocessingBase):
                     ctypes.byref(pending) if pending is not None else None, c_int(pending_B), stream)
                 where = 'npb_panoptic_forward_eval_pipelined'
         _lib.raise_for_code(rc, where)
+        post = self._instance_postprocessing
+        for b in post._overflow_frames(tables):         # on_overflow='wrap' only (one sync)
+            self._redo_wrapped_frame(plan, tables, b, heat, offset, orientation, sem, inst, pan,
+                                     pan_sem, C, H, W)
         return sem, inst, pan, pan_sem, tables
+
+    def _redo_wrapped_frame(self, plan, tables, b, heat, offset, orientation, sem, inst, pan,
+                            pan_sem, C, H, W) -> None:
+        """A frame with more than 255 centres, redone like the reference computes it
+        (instance.py:231-236 wraps the uint8 ids): complete centre list from the workspace of
+        the call, grouping with all centres (ids mod 256), then the ordinary instance table and
+        id writer on the frame's rows."""
+        post = self._instance_postprocessing
+        dev = heat.device
+        L = _lib.lib()
+        centers = post._wide_centers(tables, plan['ws'], heat, b)
+        hist = torch.empty((_lib.MAX_INST, C), dtype=torch.int32, device=dev)
+        ori_sum = None if orientation is None else \
+            torch.empty((_lib.MAX_INST, 2), dtype=torch.float64, device=dev)
+        thing_lut = _lib.host_lut(self._is_thing, C)
+        post._regroup_wide(tables, b, centers, sem[b], None, offset[b],
+                           None if orientation is None else orientation[b], C, H, W, thing_lut,
+                           self._normalized_offset, inst[b], hist, ori_sum)
+        stream = _lib.stream_ptr(dev)
+        _lib.check(L.npb_finalize_instances(
+            _lib.ptr(hist), _lib.ptr(ori_sum), tables.dptr_row('n_centers', b), c_int(1), c_int(C),
+            c_int(1), c_int64(self._max_instances_per_category), c_int64(0),
+            _lib.host_lut(self._has_orientation, C), tables.dptr_row('inst_class', b),
+            tables.dptr_row('inst_pan_id', b), tables.dptr_row('inst_area', b),
+            tables.dptr_row('inst_angle', b), stream), 'npb_finalize_instances')
+        _lib.check(L.npb_write_panoptic(
+            _lib.ptr(sem[b]), _lib.ptr(inst[b]), tables.dptr_row('inst_pan_id', b),
+            tables.dptr_row('inst_class', b), c_int(1), c_int(C), c_int(H), c_int(W), thing_lut,
+            c_int64(self._max_instances_per_category), _lib.ptr(pan[b]), _lib.ptr(pan_sem[b]),
+            _lib.stream_ptr(dev)), 'npb_write_panoptic')
 
     # ------------------------------------------------------------------ fused evaluation
     PIPELINE_MAX_FRAMES = 16    # largest batch whose matcher is pipelined over consecutive calls
@@ -188,6 +223,10 @@ class PanopticPostprocessing(DensePostprocessingBase):
         need their matches right away (orientation MAAE) are matched in their own call."""
         if self._fused_evaluation is not None and evaluation is not self._fused_evaluation:
             self._fused_evaluation.pq._flush_deferred()
+        if evaluation is not None and self._instance_postprocessing._on_overflow == 'wrap':
+            raise ValueError("fuse_evaluation: on_overflow='wrap' redoes frames after the call, "
+                             'when the fused evaluation has already counted them; update the '
+                             'metrics from the result dict instead')
         if evaluation is not None:
             # the fused kernels evaluate with THIS object's id geometry and class count
             if evaluation.pq.max_instances_per_category != self._max_instances_per_category:

@@ -123,6 +123,20 @@ def poison_logits(logits: torch.Tensor, fraction: float, seed: int = 0) -> torch
     return logits
 
 
+def saturate_heat(heat: torch.Tensor, step: int = 4, value: float = 1.0,
+                  frames=None) -> torch.Tensor:
+    """Overwrite the centre heat-maps (B,1,H,W) of `frames` (default: all) in place with a lattice
+    of exactly tied peaks, one every `step` pixels: every peak equals the k-th value, so ALL of
+    them become centres (instance.py:152-155) -- more than 255 for any frame larger than
+    16 * step pixels squared, the regime in which the reference's uint8 ids wrap
+    (instance.py:236)."""
+    B = heat.shape[0]
+    for b in (range(B) if frames is None else frames):
+        heat[b].fill_(0.0)
+        heat[b, 0, step // 2::step, step // 2::step] = value
+    return heat
+
+
 def make_eval_targets(panoptic: torch.Tensor, max_instances_per_category: int = 1 << 16,
                       shift: int = 5):
     """Evaluation targets: panoptic target = prediction rolled

@@ -90,6 +90,17 @@ def instance_centers(heat, threshold=0.1, nms_kernel_size=3, top_k=64, foregroun
     return mask.astype(bool), [centers[b, :n[b]].copy() for b in range(B)]
 
 
+class allow_wrap:
+    """`with oracle.allow_wrap():` -- more than 255 centres wrap like the reference's uint8 ids
+    (instance.py:236) instead of being rejected; pass `cap` >= the number of centres."""
+
+    def __enter__(self):
+        lib().orc_set_allow_wrap(c_int(1))
+
+    def __exit__(self, *exc):
+        lib().orc_set_allow_wrap(c_int(0))
+
+
 def instance_segmentation(heat, offset, foreground, threshold=0.1, nms_kernel_size=3,
                           top_k=64, apply_foreground_mask=False, normalized_offset=True,
                           offset_distance_threshold=None, cap=255):

@@ -232,6 +232,13 @@ int orc_instance_centers(const float *heat, int B, int H, int W, float thr, int 
 /*  :253  areas = bincount(id)                                                */
 /*  :257-265 meta: centre (y, x), area, score = heat[y, x] (un-thresholded)   */
 /* ------------------------------------------------------------------------ */
+/* > 255 centres: rejected by default; with the wrap switch the loop goes on like   */
+/* the reference does (:236 casts to uint8, so centre 256 becomes "no instance",   */
+/* centre 257 joins instance 1, ...; :253 bincount of the uint8 ids, so the areas  */
+/* of the meta entries beyond 255 are zero)                                        */
+static int g_allow_wrap = 0;
+void orc_set_allow_wrap(int on) { g_allow_wrap = on; }
+
 static int frame_grouping(const float *heat, const float *off_y, const float *off_x,
                           const uint8_t *fg, int H, int W, int normalized,
                           int use_dist_thr, float dist_thr,
@@ -241,7 +248,7 @@ static int frame_grouping(const float *heat, const float *off_y, const float *of
     long P = (long)H * W;
     memset(inst, 0, (size_t)P);
     if (n == 0) return ORC_OK;                        /* :214-215            */
-    if (n > 255) return ORC_ERR_TOO_MANY_CENTERS;
+    if (n > 255 && !g_allow_wrap) return ORC_ERR_TOO_MANY_CENTERS;
     const float fh = (float)H, fw = (float)W;
     for (long p = 0; p < P; ++p) {
         if (!fg[p]) continue;

@@ -48,9 +48,14 @@ def meta_to_json(meta):
 
 def run_postprocess(name, B, C, H, W, K, seed, quantize, with_orientation=True, top_k=64,
                     ks=3, thr=0.1, apply_fg=False, normalized=True, dist_thr=None,
-                    compute_scores=False, poison=0.0):
+                    compute_scores=False, poison=0.0, saturate=()):
     data = testing.make_batch(B, C, H, W, K, seed=seed, with_orientation=with_orientation,
                               quantize=quantize)
+    if saturate:    # frames with hundreds of exactly tied peaks: > 255 centres, uint8 ids wrap
+        testing.saturate_heat(data['heat'], step=4, frames=saturate)
+        # the last of them with (nearly) zero offsets: every thing pixel joins the lattice centre
+        # next to it, so all centres own pixels and the wrapped ids collide everywhere
+        data['offset'][saturate[-1]] *= 0.01
     if poison:      # non-finite logits at a fraction of the pixels (semantic.py:52-53 on NaN / Inf)
         testing.poison_logits(data['logits'], poison, seed)
     if not normalized:      # offsets in pixels
@@ -486,7 +491,11 @@ if __name__ == '__main__':
     torch.set_num_threads(1)
     if len(sys.argv) > 1:       # regenerate selected fixtures only: make_golden.py task_helpers pq
         for name in sys.argv[1:]:
-            globals()[f'run_{name}']()
+            if name == 'post_wrap':
+                run_postprocess('wrap', B=3, C=6, H=72, W=96, K=5, seed=7, quantize='q10',
+                                saturate=(1, 2), dist_thr=30)
+            else:
+                globals()[f'run_{name}']()
         sys.exit(0)
     run_postprocess('q10', B=3, C=8, H=96, W=128, K=5, seed=1, quantize='q10')
     run_postprocess('tie', B=3, C=6, H=96, W=128, K=6, seed=2, quantize='tie', top_k=3)
@@ -497,6 +506,8 @@ if __name__ == '__main__':
     run_postprocess('scores', B=2, C=6, H=64, W=96, K=4, seed=5, quantize='q10',
                     compute_scores=True)
     run_postprocess('nonfinite', B=2, C=6, H=48, W=64, K=4, seed=6, quantize='q10', poison=0.05)
+    run_postprocess('wrap', B=3, C=6, H=72, W=96, K=5, seed=7, quantize='q10', saturate=(1, 2),
+                    dist_thr=30)
     run_fullres()
     run_centers()
     run_merge()

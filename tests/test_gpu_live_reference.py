@@ -142,3 +142,72 @@ def test_cuda_path_equals_live_reference(seed, ref, cuda_device):
         assert np.array_equal(getattr(pq, name).cpu().numpy(), w_.numpy()), (name, c)   # bit for bit
     assert np.array_equal(miou.confmat.cpu().numpy(), ref_miou.confmat.numpy()), c
     assert float(miou.compute()) == pytest.approx(float(ref_miou.compute()), rel=1e-6)
+
+
+@pytest.mark.parametrize('seed', range(int(os.environ.get('NPB_LIVE_SEEDS', '0')) or 6))
+def test_wrapped_instance_ids_equal_live_reference(seed, ref, cuda_device):
+    """`on_overflow='wrap'` against the unmodified reference in the regime where its uint8
+    instance ids wrap (instance.py:231-236): lattices of exactly tied heat-map peaks, hundreds of
+    centres per frame (one frame of the batch stays ordinary), random NMS windows, foreground-
+    masked centres, distance thresholds, offset scales."""
+    from nicr_mt_scene_analysis_b200 import testing
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    rng = np.random.default_rng(5300 + seed)
+    B, C = 3, int(rng.integers(3, 12))
+    H, W = int(rng.integers(66, 120)), int(rng.integers(70, 150))
+    ks = int(rng.choice([1, 3, 3, 5]))
+    step = int(rng.choice([3, 4])) if ks <= 3 else 4
+    apply_fg = bool(rng.integers(0, 2))
+    dist_thr = None if rng.integers(0, 2) else int(rng.integers(3, 40))
+    normalized = bool(rng.integers(0, 2))
+    data = testing.make_batch(B, C, H, W, 4, seed=700 + seed, quantize='q10', with_orientation=True)
+    testing.saturate_heat(data['heat'], step=step, value=float(rng.choice([1.0, 0.5])), frames=(0, 2))
+    data['offset'][2] *= float(rng.choice([0.0, 0.01, 0.3]))
+    if not normalized:
+        data['offset'][:, 0] *= H
+        data['offset'][:, 1] *= W
+    is_thing = (True,) * C if apply_fg else tuple(bool(x) for x in rng.integers(0, 2, C))
+    if not any(is_thing):
+        is_thing = (True,) + is_thing[1:]
+    has_ori = tuple(bool(t and rng.integers(0, 2)) for t in is_thing)
+    kw = dict(heatmap_nms_kernel_size=ks, top_k_instances=int(rng.integers(1, 65)),
+              heatmap_apply_foreground_mask=apply_fg, normalized_offset=normalized,
+              offset_distance_threshold=dist_thr)
+
+    def build(get, **extra):
+        return get('panoptic', semantic_postprocessing=get('semantic')(),
+                   instance_postprocessing=get('instance', **kw, **extra)(),
+                   semantic_classes_is_thing=is_thing, semantic_class_has_orientation=has_ori,
+                   normalized_offset=normalized)()
+
+    names = ('heat', 'offset', 'orientation')
+    batch = testing.make_batch_dict(B, H, W)
+    want = build(ref['get_postprocessing_class']).postprocess(
+        ((data['logits'].clone(), tuple(data[k].clone() for k in names)), (None, None)), batch,
+        is_training=False)
+    wmeta = want['panoptic_segmentation_deeplab_instance_meta']
+    assert max(len(m) for m in wmeta) > 255, [len(m) for m in wmeta]
+    raw = ((data['logits'].to(cuda_device), tuple(data[k].to(cuda_device) for k in names)),
+           (None, None))
+    got = build(get_postprocessing_class, on_overflow='wrap').postprocess(raw, batch,
+                                                                         is_training=False)
+    for key in ('semantic_segmentation_idx', 'panoptic_segmentation_deeplab',
+                'panoptic_segmentation_deeplab_instance_idx',
+                'panoptic_segmentation_deeplab_semantic_idx'):
+        assert torch.equal(got[key].cpu(), want[key].cpu()), key
+    assert got['panoptic_segmentation_deeplab_ids'] == \
+        [{int(k): int(v) for k, v in d.items()} for d in want['panoptic_segmentation_deeplab_ids']]
+    for gm, wm in zip(got['panoptic_segmentation_deeplab_instance_meta'], wmeta):
+        assert sorted(gm) == sorted(int(k) for k in wm)
+        for k, v in wm.items():
+            g = gm[int(k)]
+            assert tuple(g['center_yx']) == tuple(int(x) for x in v['center_yx']), k
+            assert g['area'] == int(v['area']), k
+            assert g['score'] == pytest.approx(float(v['score']), rel=1e-6), k
+            wo, go = float(v['orientation']), g['orientation']
+            assert (wo != wo and go != go) or abs(go - wo) <= 1e-5 * max(1.0, abs(wo)), k
+    key = 'orientations_panoptic_segmentation_deeplab_instance'
+    for dg, dw in zip(got[key], want[key]):
+        assert sorted(dg) == sorted(int(k) for k in dw)
+        for k, v in dw.items():
+            assert abs(dg[int(k)] - float(v)) <= 1e-5 * max(1.0, abs(float(v))), k

@@ -103,6 +103,70 @@ def test_golden_postprocess(name, async_results, cuda_device):
                           z['panoptic_segmentation_deeplab'])
 
 
+@pytest.mark.parametrize('async_results', [False, True])
+def test_golden_postprocess_wrapped_instance_ids(async_results, cuda_device):
+    """`post_wrap` (from the unmodified reference): two of three frames have 432 tied centres.
+    Default: the error is explicit.  `on_overflow='wrap'`: the frames are redone with all centres
+    and ids mod 256 -- maps, id dicts, the 432-entry meta dicts (zero areas beyond 255, NaN
+    orientations) and the orientations equal the reference's (instance.py:231-266)."""
+    from nicr_mt_scene_analysis_b200._lib import ERR_TOO_MANY_CENTERS, NpbError
+    from nicr_mt_scene_analysis_b200.model.postprocessing import get_postprocessing_class
+    z = load_golden('post_wrap')
+    cfg = jload(z['cfg'])
+    _, _, pan = _build(cfg, z['is_thing'], z['has_orientation'], async_results=async_results)
+    with pytest.raises(NpbError) as err:
+        r = _run(pan, z['logits'], z['heat'], z['offset'], z.get('orientation'), cuda_device)
+        r['panoptic_segmentation_deeplab_ids']
+    assert err.value.code == ERR_TOO_MANY_CENTERS
+
+    ins = get_postprocessing_class(
+        'instance', heatmap_threshold=cfg['thr'], heatmap_nms_kernel_size=cfg['ks'],
+        top_k_instances=cfg['top_k'], heatmap_apply_foreground_mask=cfg['apply_fg'],
+        normalized_offset=cfg['normalized'], offset_distance_threshold=cfg['dist_thr'],
+        on_overflow='wrap')()
+    pan = get_postprocessing_class(
+        'panoptic', semantic_postprocessing=get_postprocessing_class('semantic')(),
+        instance_postprocessing=ins,
+        semantic_classes_is_thing=tuple(bool(x) for x in z['is_thing']),
+        semantic_class_has_orientation=tuple(bool(x) for x in z['has_orientation']),
+        normalized_offset=cfg['normalized'], async_results=async_results)()
+    for _ in range(2):      # (the second call reuses the workspace of the first)
+        r = _run(pan, z['logits'], z['heat'], z['offset'], z.get('orientation'), cuda_device)
+        g = lambda k: r[k].cpu().numpy()
+        assert np.array_equal(g('panoptic_segmentation_deeplab_instance_idx'),
+                              z['panoptic_segmentation_deeplab_instance_idx'])
+        assert np.array_equal(g('panoptic_segmentation_deeplab'), z['panoptic_segmentation_deeplab'])
+        assert np.array_equal(g('panoptic_segmentation_deeplab_semantic_idx'),
+                              z['panoptic_segmentation_deeplab_semantic_idx'])
+        assert r['panoptic_segmentation_deeplab_ids'] == int_keys(jload(z['ids']))
+        meta = r['panoptic_segmentation_deeplab_instance_meta']
+        assert [len(m) for m in meta] == [5, 432, 432]
+        _check_meta(jload(z['meta']), meta)
+        _check_orient(int_keys(jload(z['orientations'])),
+                      r['orientations_panoptic_segmentation_deeplab_instance'])
+    # the stage functions of the instance post-processing (ground-truth foreground path)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    fg = z['panoptic_foreground_mask']
+    mask, centers = ins._get_instance_centers(t(z['heat']), t(fg))
+    assert np.array_equal(mask.cpu().numpy(), z['center_mask'])
+    assert [c.tolist() for c in centers] == jload(z['centers'])
+    H, W = fg.shape[-2:]
+    off_px = z['offset'] * np.array([H, W], np.float32).reshape(1, 2, 1, 1)
+    seg, meta = ins._get_instance_segmentation(t(z['heat']), t(off_px.astype(np.float32)), t(fg))
+    with oracle.allow_wrap():
+        o_seg, o_meta = oracle.instance_segmentation(
+            z['heat'], off_px.astype(np.float32), fg, cfg['thr'], cfg['ks'], cfg['top_k'],
+            cfg['apply_fg'], False, cfg['dist_thr'], cap=1024)
+    assert np.array_equal(seg.cpu().numpy(), o_seg)
+    assert [len(m) for m in meta] == [5, 432, 432]
+    for gm, om in zip(meta, o_meta):
+        assert {k: (tuple(v['center_yx']), v['area']) for k, v in gm.items()} == \
+            {k: (tuple(v['center_yx']), v['area']) for k, v in om.items()}
+    # the fused evaluation counts a frame before it could be redone: refused up front
+    with pytest.raises(ValueError):
+        pan.fuse_evaluation(object())
+
+
 def test_result_keys_like_reference(cuda_device):
     """tests/test_decoders+postprocessing.py:208-250 of the reference: key presence"""
     z = load_golden('post_scores')

@@ -44,6 +44,35 @@ def test_postprocess_pipeline(name):
                 assert dg[k] == pytest.approx(dr[k], rel=1e-5, abs=1e-6)
 
 
+def test_postprocess_pipeline_with_wrapped_instance_ids():
+    """`post_wrap`: two frames with 432 exactly tied heat-map peaks.  The reference keeps all of
+    them and its uint8 ids wrap (instance.py:236): centre 256 is "no instance", centre 257 joins
+    instance 1, the meta dict has 432 entries (zero areas beyond 255).  The oracle refuses such
+    frames by default and reproduces the reference under `allow_wrap`."""
+    z = load_golden('post_wrap')
+    cfg = jload(z['cfg'])
+    args = (z['logits'], z['heat'], z['offset'], z.get('orientation'), z['is_thing'],
+            z['has_orientation'])
+    kw = dict(threshold=cfg['thr'], nms_kernel_size=cfg['ks'], top_k=cfg['top_k'],
+              apply_foreground_mask=cfg['apply_fg'], normalized_offset=cfg['normalized'],
+              offset_distance_threshold=cfg['dist_thr'])
+    with pytest.raises(oracle.OracleError) as err:
+        oracle.panoptic_postprocess(*args, **kw)
+    assert err.value.code == -2
+    with oracle.allow_wrap():
+        r = oracle.panoptic_postprocess(*args, cap=1024, **kw)
+    assert [len(m) for m in r['meta']] == [5, 432, 432]
+    assert np.array_equal(r['instance_idx'], z['panoptic_segmentation_deeplab_instance_idx'])
+    assert np.array_equal(r['panoptic'], z['panoptic_segmentation_deeplab'])
+    assert r['ids'] == int_keys(jload(z['ids']))
+    _meta_equal(jload(z['meta']), r['meta'])
+    ref = int_keys(jload(z['orientations']))
+    assert [sorted(d) for d in ref] == [sorted(d) for d in r['orientations']]
+    for dr, dg in zip(ref, r['orientations']):
+        for k in dr:
+            assert dg[k] == pytest.approx(dr[k], rel=1e-5, abs=1e-6)
+
+
 @pytest.mark.parametrize('name', POST_CASES)
 def test_stage_functions(name):
     """stage-wise: arg-max, centres, grouping, merge each against the reference."""

@@ -108,6 +108,59 @@ def test_oracle_equals_live_reference(seed, ref):
             for k, v in dr.items():
                 assert abs(dg[int(k)] - float(v)) <= 1e-5 * max(1.0, abs(float(v))), (c, k)
 
+@pytest.mark.parametrize('seed', range(MORE or 4))
+def test_wrapped_instance_ids_equal_live_reference(seed, ref):
+    """More than 255 centres (a lattice of exactly tied peaks): the reference's uint8 ids wrap
+    (instance.py:231-236) and its meta dict keeps every centre (:253-266).  The oracle under
+    `allow_wrap` must give the same maps, id dicts, meta dicts and orientations, for random
+    NMS windows, thresholds, foreground-masked centres and offset scales."""
+    from nicr_mt_scene_analysis_b200 import testing
+    rng = np.random.default_rng(9100 + seed)
+    B, C = 2, int(rng.integers(3, 8))
+    H, W = int(rng.integers(66, 90)), int(rng.integers(70, 110))
+    ks = int(rng.choice([1, 3, 3, 5]))
+    step = int(rng.choice([3, 4])) if ks <= 3 else 4
+    apply_fg = bool(rng.integers(0, 2))
+    dist_thr = None if rng.integers(0, 2) else int(rng.integers(3, 40))
+    data = testing.make_batch(B, C, H, W, 4, seed=500 + seed, quantize='q10', with_orientation=True)
+    testing.saturate_heat(data['heat'], step=step, value=float(rng.choice([1.0, 0.5])))
+    data['offset'][1] *= float(rng.choice([0.0, 0.01, 0.3]))
+    is_thing = tuple(bool(x) for x in rng.integers(0, 2, C))
+    if not any(is_thing):
+        is_thing = (True,) + is_thing[1:]
+    if apply_fg:            # (centres outside the thing mask are dropped: keep enough of them)
+        is_thing = (True,) * C
+    has_ori = tuple(bool(t and rng.integers(0, 2)) for t in is_thing)
+    get = ref['get']
+    pan = get('panoptic', semantic_postprocessing=get('semantic')(),
+              instance_postprocessing=get(
+                  'instance', heatmap_nms_kernel_size=ks, top_k_instances=int(rng.integers(1, 65)),
+                  heatmap_apply_foreground_mask=apply_fg, offset_distance_threshold=dist_thr)(),
+              semantic_classes_is_thing=is_thing, semantic_class_has_orientation=has_ori)()
+    top_k = pan._instance_postprocessing._top_k_instances
+    inst_out = (data['heat'], data['offset'], data['orientation'])
+    r = pan.postprocess(((data['logits'].clone(), tuple(t.clone() for t in inst_out)), (None, None)),
+                        testing.make_batch_dict(B, H, W), is_training=False)
+    rmeta = r['panoptic_segmentation_deeplab_instance_meta']
+    assert max(len(m) for m in rmeta) > 255, [len(m) for m in rmeta]
+    with oracle.allow_wrap():
+        got = oracle.panoptic_postprocess(
+            data['logits'].numpy(), data['heat'].numpy(), data['offset'].numpy(),
+            data['orientation'].numpy(), is_thing, has_ori, nms_kernel_size=ks, top_k=top_k,
+            apply_foreground_mask=apply_fg, offset_distance_threshold=dist_thr, cap=4096)
+    assert np.array_equal(got['instance_idx'], r['panoptic_segmentation_deeplab_instance_idx'].numpy())
+    assert np.array_equal(got['panoptic'], r['panoptic_segmentation_deeplab'].numpy())
+    assert got['ids'] == [{int(k): int(v) for k, v in d.items()}
+                          for d in r['panoptic_segmentation_deeplab_ids']]
+    for gm, rm in zip(got['meta'], rmeta):
+        assert {k: (tuple(v['center_yx']), v['area']) for k, v in gm.items()} == \
+            {int(k): (tuple(int(x) for x in v['center_yx']), int(v['area'])) for k, v in rm.items()}
+    for dg, dr in zip(got['orientations'], r['orientations_panoptic_segmentation_deeplab_instance']):
+        assert sorted(dg) == sorted(int(k) for k in dr)
+        for k, v in dr.items():
+            assert abs(dg[int(k)] - float(v)) <= 1e-5 * max(1.0, abs(float(v))), k
+
+
     # evaluation: the reference's compare_and_accumulate and confusion matrix on the same maps
     L, OFF = 1 << 16, 256 ** 3
     pred = r['panoptic_segmentation_deeplab']
