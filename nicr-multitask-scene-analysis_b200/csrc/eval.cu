@@ -32,7 +32,7 @@ namespace npb {
 
 constexpr int kPairThreads = 256;
 #ifndef NPB_PAIR_MIN_CTAS
-#define NPB_PAIR_MIN_CTAS 4
+#define NPB_PAIR_MIN_CTAS 3
 #endif
 #ifndef NPB_PAIR_SLOTS
 #define NPB_PAIR_SLOTS 2048
