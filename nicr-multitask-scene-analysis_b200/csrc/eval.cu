@@ -297,7 +297,12 @@ __global__ void __launch_bounds__(kPairThreads, NPB_PAIR_MIN_CTAS) pair_count_ke
     const long long g_total = n_chunks * prm.B;
     const long long g_begin = g_total * blockIdx.x / gridDim.x;
     const long long g_end = g_total * (blockIdx.x + 1) / gridDim.x;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned lt_mask = (1u << lane) - 1u;
+#ifndef NPB_PAIR_NO_PIN
+    // (an opaque definition: the compiler keeps the value in a register instead of rebuilding
+    // it from %tid in every iteration of the pixel loop)
+    asm volatile("" : "+r"(lt_mask));
+#endif
     bool waited = false;
   for (long long g_at = g_begin; g_at < g_end;) {
     const int b = (int)(g_at / n_chunks);
@@ -339,29 +344,42 @@ __global__ void __launch_bounds__(kPairThreads, NPB_PAIR_MIN_CTAS) pair_count_ke
         const uint8_t *sem_b = CONFMAT ? prm.sem_target + (size_t)b * P : nullptr;
         const uint8_t *csem_b = FUSED ? prm.sem_map + (size_t)b * P : nullptr;
         const uint8_t *cinst_b = FUSED ? prm.inst_map + (size_t)b * P : nullptr;
-        const unsigned q_base = (unsigned)__cvta_generic_to_shared(q_key);   // this warp's queue
-        uint4 n_p0, n_p1, n_t0, n_t1;
-        unsigned n_sw, n_cw = 0u, n_iw = 0u;
+        unsigned q_base = (unsigned)__cvta_generic_to_shared(q_key);   // this warp's queue
+#ifndef NPB_PAIR_NO_PIN
+        asm volatile("" : "+r"(q_base));      // (kept, not rebuilt from the shared window base)
+#endif
+        // (zero once: a lane beyond the end of its range keeps its last words, which nothing
+        // looks at -- every use below is gated by `act`)
+        uint4 n_p0 = make_uint4(0u, 0u, 0u, 0u), n_p1 = n_p0, n_t0 = n_p0, n_t1 = n_p0;
+        unsigned n_sw = 0u, n_cw = 0u, n_iw = 0u;
         // software pipeline: the loads of the next chunk are issued before the current chunk is
         // processed, so their DRAM latency hides behind the (instruction bound) table updates
+        // running pointers of the lane (advanced by one chunk per fetch: two adds per stream
+        // instead of rebuilding frame base + pixel offset from the parameters every time)
+        const char *pp_at = FUSED ? nullptr : (const char *)(pred_b + q_next);
+        const char *tp_at = (const char *)(target_b + q_next);
+        const char *sp_at = CONFMAT ? (const char *)(sem_b + q_next) : nullptr;
+        const char *cs_at = FUSED ? (const char *)(csem_b + q_next) : nullptr;
+        const char *ci_at = FUSED ? (const char *)(cinst_b + q_next) : nullptr;
         auto fetch = [&]() {
-            n_p0 = n_p1 = n_t0 = n_t1 = make_uint4(0u, 0u, 0u, 0u);
-            n_sw = 0u;
-            n_cw = n_iw = 0u;
             if (q_next < q_end) {
                 if (FUSED) {
                     // class / instance maps were written by the grouping kernel just before: L2
-                    n_cw = *(const unsigned *)(csem_b + q_next);
-                    n_iw = *(const unsigned *)(cinst_b + q_next);
+                    n_cw = *(const unsigned *)cs_at;
+                    n_iw = *(const unsigned *)ci_at;
                 } else {
-                    const uint4 *pp = (const uint4 *)(pred_b + q_next);
+                    const uint4 *pp = (const uint4 *)pp_at;
                     n_p0 = __ldcs(pp); n_p1 = __ldcs(pp + 1);
                 }
-                const uint4 *tp = (const uint4 *)(target_b + q_next);
+                const uint4 *tp = (const uint4 *)tp_at;
                 n_t0 = __ldcs(tp); n_t1 = __ldcs(tp + 1);
-                if (CONFMAT) n_sw = __ldcs((const unsigned *)(sem_b + q_next));
+                if (CONFMAT) n_sw = __ldcs((const unsigned *)sp_at);
             }
             q_next += stride;
+            if (!FUSED) pp_at += stride * 8;
+            tp_at += stride * 8;
+            if (CONFMAT) sp_at += stride;
+            if (FUSED) { cs_at += stride; ci_at += stride; }
         };
         fetch();
         for (long long ch = ch_begin; ch < ch_end; ++ch) {
@@ -391,7 +409,7 @@ __global__ void __launch_bounds__(kPairThreads, NPB_PAIR_MIN_CTAS) pair_count_ke
             const unsigned hi_or = n_p0.y | n_p0.w | n_p1.y | n_p1.w | n_t0.y | n_t0.w | n_t1.y | n_t1.w;
             const unsigned p_or = n_p0.x | n_p0.z | n_p1.x | n_p1.z;
             const unsigned t_or = n_t0.x | n_t0.z | n_t1.x | n_t1.z;
-            if ((hi_or | ((p_or | t_or) >> 24)) != 0u) {
+            if (act && (hi_or | ((p_or | t_or) >> 24)) != 0u) {
                 // rare: the lane's ids fail the 24-bit range check -- an error (pred outside
                 // [0, offset) or a negative target), or a target id >= 2^24 (a category >= 256:
                 // only meaningful as the ignored label) whose pixels are counted one by one
