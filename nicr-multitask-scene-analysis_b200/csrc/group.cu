@@ -30,7 +30,16 @@ namespace npb {
 // finer grained; the launcher picks the variant whose grid fills its waves best.
 constexpr int kGroupThreads = 256;
 constexpr int kGroupThreadsSmall = 128;
-constexpr int kGroupCtasPerSm = 4, kGroupCtasPerSmSmall = 9;
+#ifndef NPB_GROUP_CTAS
+#define NPB_GROUP_CTAS 4
+#endif
+#ifndef NPB_GROUP_CTAS_SMALL
+#define NPB_GROUP_CTAS_SMALL 9
+#endif
+#ifndef NPB_GROUP_U
+#define NPB_GROUP_U 8
+#endif
+constexpr int kGroupCtasPerSm = NPB_GROUP_CTAS, kGroupCtasPerSmSmall = NPB_GROUP_CTAS_SMALL;
 
 enum SemSource { kFromLogits = 0, kFromSemMap = 1, kFromFgMask = 2 };
 
@@ -146,7 +155,7 @@ group_pixels_kernel(const GroupParams prm)
             // compare: the loop is latency bound, bytes in flight are what buys bandwidth.  All
             // C planes go through ceil(C / 8) batches (plane 0 included, the last batch with its
             // loads predicated): every batch is one DRAM latency in the life of the CTA.
-            constexpr int U = 8;
+            constexpr int U = NPB_GROUP_U;
             // Non-finite logits: the reference takes the arg-max of softmax(logits), which is NaN
             // in every class -- index 0 -- as soon as a logit is NaN or +Inf, or all are -Inf
             // (semantic.py:52-53); -Inf next to finite logits just has probability 0.  The

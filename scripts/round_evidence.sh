@@ -31,5 +31,11 @@ done
 ncu --set full --clock-control none --import-source on -k regex:pair_count -s 6 -c 1 -f \
     -o gpurun_out/${R}_pair_count_nyuv2 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-api --no-extra --no-graph > gpurun_out/${R}_ncu_pair.log 2>&1
 ncu -i gpurun_out/${R}_pair_count_nyuv2.ncu-rep --page raw --csv > gpurun_out/${R}_pair_count_nyuv2_ncu_raw.csv 2>/dev/null
+# evaluation-only workload (BASELINE configs[4]): bench line + capture of the stand-alone pixel pass
+python scripts/bench_eval.py > gpurun_out/${R}_bench_eval.json 2>gpurun_out/${R}_bench_eval.err
+ncu --set full --clock-control none --import-source on -k regex:pair_count -s 6 -c 1 -f \
+    -o gpurun_out/${R}_pair_count_eval python scripts/bench_eval.py --frames 2560 > gpurun_out/${R}_ncu_pair_eval.log 2>&1
+ncu -i gpurun_out/${R}_pair_count_eval.ncu-rep --page raw --csv > gpurun_out/${R}_pair_count_eval_ncu_raw.csv 2>/dev/null
+cut -c1-260 gpurun_out/${R}_bench_eval.json
 tail -2 gpurun_out/${R}_tests.log; tail -1 gpurun_out/${R}_smoke.log; cut -c1-330 gpurun_out/${R}_bench_default.json; cut -c1-200 gpurun_out/${R}_bench_reference.json
 tail -9 gpurun_out/${R}_launches_nyuv2.csv | cut -d, -f5,9,15 | cut -c1-120
