@@ -1770,7 +1770,13 @@ static int pq_update_impl(const int64_t *pred, const FusedWrite *fw, const int64
     if (per_sm > kMaxPairCtasPerSm) per_sm = kMaxPairCtasPerSm;     // pq_entry_cap() assumes it
     // few frames: every CTA only gets a handful of chunks, so its fixed cost (table set-up, flush)
     // and the duplicates it hands to the matcher weigh more than the extra residency
-    if (B <= 32 && per_sm > 2) per_sm = 2;
+    static int small_cap = -1;     // NPB_PAIR_SMALL_CTAS=<n>: A/B of that rule
+    if (small_cap < 0) {
+        const char *e = getenv("NPB_PAIR_SMALL_CTAS");
+        small_cap = e ? atoi(e) : 2;
+        if (small_cap < 1) small_cap = 2;
+    }
+    if (B <= 32 && per_sm > small_cap) per_sm = small_cap;
     // one wave of CTAs, each with the same share of the B * n_chunks chunks of the batch
     long long n_ctas = (long long)n_sm * per_sm;
     if (n_ctas > n_chunks * B) n_ctas = n_chunks * B;
