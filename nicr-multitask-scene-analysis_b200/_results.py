@@ -215,17 +215,20 @@ class InstanceTables:
         """instance.py:253-266: {id: {'center_yx', 'area', 'score'}} for every centre;
         `with_orientation`: + 'orientation' (NaN for instances without one, panoptic.py:305-314)."""
         n, m = self._rows()
-        c = self['centers_yx'].reshape(self.B, _lib.MAX_INST, 2)[:, :m].tolist()
+        # columns, not (y, x) pairs: one list per frame and coordinate instead of one per centre
+        # (every container allocated here counts towards the thresholds of python's cyclic GC)
+        c = self['centers_yx'].reshape(self.B, _lib.MAX_INST, 2)
+        ys, xs = c[:, :m, 0].tolist(), c[:, :m, 1].tolist()
         area = self['inst_area'][:, :m + 1].tolist()
         score = self['center_score'][:, :m].tolist()
         if not with_orientation:
-            out = [{i + 1: {'center_yx': (cb[i][0], cb[i][1]), 'area': ab[i + 1], 'score': sb[i]}
-                    for i in range(nb)} for nb, cb, ab, sb in zip(n, c, area, score)]
+            out = [{i + 1: {'center_yx': (yb[i], xb[i]), 'area': ab[i + 1], 'score': sb[i]}
+                    for i in range(nb)} for nb, yb, xb, ab, sb in zip(n, ys, xs, area, score)]
         else:
             ang = self['inst_angle'][:, :m + 1].tolist()
-            out = [{i + 1: {'center_yx': (cb[i][0], cb[i][1]), 'area': ab[i + 1], 'score': sb[i],
+            out = [{i + 1: {'center_yx': (yb[i], xb[i]), 'area': ab[i + 1], 'score': sb[i],
                             'orientation': gb[i + 1]}
-                    for i in range(nb)} for nb, cb, ab, sb, gb in zip(n, c, area, score, ang)]
+                    for i in range(nb)} for nb, yb, xb, ab, sb, gb in zip(n, ys, xs, area, score, ang)]
         for b in self.wide:
             out[b] = self._meta_wide(b, with_orientation)
         return out
