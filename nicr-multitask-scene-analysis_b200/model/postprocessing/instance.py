@@ -78,6 +78,9 @@ class InstancePostprocessing(DensePostprocessingBase):
         status words; only with `on_overflow='wrap'`)."""
         if self._on_overflow != 'wrap':
             return []
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("on_overflow='wrap' reads the status words of every call on the "
+                               'host: such a step cannot be captured into a CUDA graph')
         codes = tables.dview('status').cpu().tolist()
         return [b for b, c in enumerate(codes) if c == _lib.ERR_TOO_MANY_CENTERS]
 
