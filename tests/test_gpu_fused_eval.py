@@ -306,3 +306,51 @@ def test_pipelined_matching_keeps_orientation_batches_in_place(cuda_device):
     assert ev.pq._deferred is None and '_panoptic_matches' in r
     ev.pq.check_status()
     assert float(ev.pq.tp_per_class.sum()) > 0
+
+
+@pytest.mark.parametrize('pipelined', [False, True])
+def test_fused_evaluation_puts_large_frames_back_in_frame_order(pipelined, cuda_device, monkeypatch):
+    """A validation loop through the fused (and pipelined) evaluation in which some frames have
+    thousands of ground-truth segments (per-pixel ids in the upper rows: beyond the 1536
+    segments / 4096 pairs of the batched matcher).  Such a frame is redone on the large-frame
+    path and put back in its place: the float64 states equal the oracle's frame-by-frame sums
+    (pq.py:298-303) bit for bit, the confusion matrix is untouched by the follow-up."""
+    from nicr_mt_scene_analysis_b200 import testing
+    C, K, H, W = 7, 4, 64, 96
+    post, ev, is_thing, has_ori = _make(C, cuda_device)
+    post.fuse_evaluation(ev, pipeline_matching=pipelined)
+    from nicr_mt_scene_analysis_b200.metric import pq as pq_module
+    redone = []
+    real = pq_module._evaluate_big_frame
+    monkeypatch.setattr(pq_module, '_evaluate_big_frame',
+                        lambda *a, **k: (redone.append(1), real(*a, **k))[1])
+    rng = np.random.default_rng(3)
+    state = np.zeros((4, C + 1))
+    cm = np.zeros((C + 1, C + 1), np.int64)
+    noisy = {(1, 1), (3, 0), (3, 2), (4, 1)}        # (batch, frame) with a noisy target
+    for i in range(6):
+        B = 3
+        data = testing.make_batch(B, C, H, W, K, seed=80 + i)
+        ref = oracle.panoptic_postprocess(*(data[k].numpy() for k in
+                                            ('logits', 'heat', 'offset', 'orientation')),
+                                          is_thing, has_ori)
+        tgt = np.roll(ref['panoptic'], 3 + i, axis=-1).copy()
+        for b in range(B):
+            if (i, b) in noisy:     # 40 rows of (nearly) unique thing ids of class 2
+                tgt[b, :40] = 2 * L + 1 + rng.permutation(40 * W).reshape(40, W) % 3000
+        tgt_sem = (tgt // L).astype(np.uint8)
+        gt = dict(testing.make_batch_dict(B, H, W),
+                  panoptic_fullres=torch.from_numpy(tgt).to(cuda_device),
+                  semantic_fullres=torch.from_numpy(tgt_sem).to(cuda_device))
+        r = post.postprocess(_raw(data, cuda_device), gt, is_training=False)
+        assert r.get('_panoptic_evaluation_fused') is True
+        for b in range(B):
+            out = oracle.pq_compare_and_accumulate(ref['panoptic'][b], tgt[b], C + 1, 0, L, OFF, 0)
+            for s, v in zip(state, out[:4]):
+                s += v
+        cm += oracle.confmat(ref['panoptic'] // L, tgt_sem, C + 1)
+    ev.pq.check_status()
+    assert len(redone) == len(noisy)                # every noisy frame took the large-frame path
+    assert state[0].sum() != np.floor(state[0].sum())
+    assert np.array_equal(_states(ev), state)
+    assert np.array_equal(ev.miou.confmat.cpu().numpy(), cm)
