@@ -271,6 +271,19 @@ def test_eval_args_struct_layout_matches_the_header(tmp_path):
     assert out[1:] == [getattr(_lib.EvalArgs, n).offset for n in names]
 
 
+def test_table_constants_match_the_header():
+    """Row lengths the Python layer allocates its tables with, and the error codes it decodes,
+    are the header's."""
+    import re
+    from nicr_mt_scene_analysis_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'nicr_panoptic_b200.h')).read()
+    macro = lambda name: int(re.search(r'#define\s+%s\s+\(?(-?\d+)\)?' % name, text).group(1))
+    assert macro('NPB_MAX_INST') == _lib.MAX_INST
+    assert macro('NPB_MAX_WIDE_CENTERS') == _lib.MAX_WIDE_CENTERS
+    for name in ('ARG', 'TOO_MANY_CENTERS', 'ZERO_DIVISION', 'CATEGORY_RANGE', 'CAPACITY', 'CUDA'):
+        assert macro('NPB_ERR_' + name) == getattr(_lib, 'ERR_' + name), name
+
+
 def test_reference_citations_resolve():
     """Every `file.py:first-last` citation of the C header, the design / integration notes, the
     host package, the kernels and the oracle names a file of the reference that has that many
