@@ -25,16 +25,21 @@
 
 namespace npb {
 
-// CTA sizes of the grouping kernel: 256 threads x 4 resident CTAs per SM, or 128 threads x 9
-// (same 56 registers per thread).  The smaller CTAs make the last, partial wave of a small batch
-// finer grained; the launcher picks the variant whose grid fills its waves best.
+// CTA sizes of the grouping kernel: 256 threads x 4 resident CTAs per SM, or 64 threads x 18
+// (same 56 registers per thread, 1152 instead of 1024 threads per SM).  The smaller CTAs make the
+// ramp and the last, partial wave of a small batch finer grained (8 frames 480x640: 0.865 of the
+// HBM peak with 256-thread CTAs, 0.915 with 128 x 9, 0.936 with 64 x 18); the launcher picks the
+// variant whose grid fills its waves best.
 constexpr int kGroupThreads = 256;
-constexpr int kGroupThreadsSmall = 128;
+#ifndef NPB_GROUP_THREADS_SMALL
+#define NPB_GROUP_THREADS_SMALL 64
+#endif
+constexpr int kGroupThreadsSmall = NPB_GROUP_THREADS_SMALL;
 #ifndef NPB_GROUP_CTAS
 #define NPB_GROUP_CTAS 4
 #endif
 #ifndef NPB_GROUP_CTAS_SMALL
-#define NPB_GROUP_CTAS_SMALL 9
+#define NPB_GROUP_CTAS_SMALL 18
 #endif
 #ifndef NPB_GROUP_U
 #define NPB_GROUP_U 8
@@ -449,8 +454,8 @@ static void launch_group_nt(const GroupParams &prm, int B, cudaStream_t s)
     const long long big = (groups + kGroupThreads - 1) / kGroupThreads * B;
     const long long small = (groups + kGroupThreadsSmall - 1) / kGroupThreadsSmall * B;
     static int n_sm = group_sm_count();
-    // the 128-thread CTAs only pay where the batch is a handful of waves: their last wave is
-    // finer grained (and 9 x 128 threads are resident per SM instead of 4 x 256)
+    // the small CTAs only pay where the batch is a handful of waves: their last wave is
+    // finer grained (and 18 x 64 threads are resident per SM instead of 4 x 256)
     const bool use_small = VEC == 4 && big <= 16ll * n_sm * kGroupCtasPerSm &&
                            wave_fill(small, (long long)n_sm * kGroupCtasPerSmSmall) >
                                wave_fill(big, (long long)n_sm * kGroupCtasPerSm) + 0.02;

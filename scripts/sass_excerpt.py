@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'nicr-multitask-scene-analysis_b200', 'csrc', 'libnicr_panoptic_b200.so')
 KERNELS = [
-    '_ZN3npb19group_pixels_kernelILi4ELi0ELb0ELi128EEEvNS_11GroupParamsE',
+    '_ZN3npb19group_pixels_kernelILi4ELi0ELb0ELi64EEEvNS_11GroupParamsE',
     '_ZN3npb19group_pixels_kernelILi4ELi0ELb1ELi256EEEvNS_11GroupParamsE',
     '_ZN3npb17pair_count_kernelILi4ELb1ELb1ELb1EEEvNS_10PairParamsE',
     '_ZN3npb17pair_count_kernelILi4ELb1ELb1ELb0EEEvNS_10PairParamsE',
