@@ -237,7 +237,13 @@ def require_cuda(t: torch.Tensor, name: str, dtype: Optional[torch.dtype] = None
         raise RuntimeError(f'{name}: expected a CUDA tensor (this implementation has no CPU '
                            f'path); got device {t.device}')
     if dtype is not None and t.dtype != dtype:
-        raise TypeError(f'{name}: expected dtype {dtype}, got {t.dtype}')
+        if dtype == torch.float32 and t.dtype in (torch.float16, torch.bfloat16, torch.float64):
+            # decoder outputs of a network that ran under autocast (or in double precision): the
+            # kernels compute in float32.  Widening half / bfloat16 is exact, so the results are
+            # those of the float32 path on the very same values.
+            t = t.float()
+        else:
+            raise TypeError(f'{name}: expected dtype {dtype}, got {t.dtype}')
     if ndim is not None and t.ndim != ndim:
         raise ValueError(f'{name}: expected {ndim} dims, got shape {tuple(t.shape)}')
     return t.contiguous()

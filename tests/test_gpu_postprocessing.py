@@ -383,6 +383,30 @@ def test_cpu_tensors_are_rejected(cuda_device):
         _run(pan, z['logits'], z['heat'], z['offset'], z['orientation'], torch.device('cpu'))
 
 
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float64])
+def test_half_precision_decoder_outputs_are_widened(dtype, cuda_device):
+    """Decoder outputs of a network that ran under autocast: the kernels compute in float32, and
+    widening is exact -- every result equals the float32 path on the same (rounded) values."""
+    from nicr_mt_scene_analysis_b200 import testing
+    z = load_golden('post_q10')
+    cfg = jload(z['cfg'])
+    _, _, pan = _build(cfg, z['is_thing'], z['has_orientation'])
+    B, _, H, W = z['logits'].shape
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device).to(dtype)
+    raw = (t(z['logits']), (t(z['heat']), t(z['offset']), t(z['orientation'])))
+    wide = (raw[0].float(), tuple(x.float() for x in raw[1]))
+    batch = testing.make_batch_dict(B, H, W)
+    got = pan.postprocess((raw, (None, None)), batch, is_training=False)
+    want = pan.postprocess((wide, (None, None)), batch, is_training=False)
+    for k in ('semantic_segmentation_idx', 'panoptic_segmentation_deeplab',
+              'panoptic_segmentation_deeplab_instance_idx'):
+        assert torch.equal(got[k], want[k]), k
+    assert got['panoptic_segmentation_deeplab_ids'] == want['panoptic_segmentation_deeplab_ids']
+    _check_meta(want['panoptic_segmentation_deeplab_instance_meta'],
+                got['panoptic_segmentation_deeplab_instance_meta'])
+    assert torch.equal(got['semantic_segmentation_score'], want['semantic_segmentation_score'])
+
+
 def test_full_size_properties(cuda_device):
     """BASELINE-size frame (530x730, C=37, 20 centres): size-independent invariants +
     agreement with the oracle on one frame."""
