@@ -380,6 +380,18 @@ int npb_pq_update_big_frame(const int64_t *pred, const int64_t *target, int64_t 
                             int32_t *n_matches, int32_t *status, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Optional stuff-area filter on finished panoptic maps (NOT part of the reference: its merge
+ * keeps every stuff class present in a frame, utils/panoptic_merge.py:213-223; Panoptic-DeepLab's
+ * original merge drops stuff regions below `stuff_area` pixels to void).  A stuff segment is the
+ * pixel set of one id with `pan > 0 && pan % L == 0`; segments with fewer than `stuff_area`
+ * pixels become `void_label` (pan_sem, nullable, becomes `void_label / L`).
+ * pan (B,P) i64 in/out, workspace [B][n_classes] u32 (n_classes counts void, <= 256).
+ * ------------------------------------------------------------------------- */
+int npb_filter_stuff_area(int64_t *pan, uint8_t *pan_sem, int B, int64_t P, int n_classes,
+                          int64_t max_instances_per_category, int64_t stuff_area,
+                          int64_t void_label, uint32_t *workspace, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Fused validation step: panoptic ids written AND evaluated in one pass.
  * Replaces: the tail of PanopticPostprocessing._postprocess_inference (panoptic.py:139-167)
  *           followed by PanopticTaskHelper.validation_step (task_helper/panoptic.py:104-126),

@@ -64,6 +64,7 @@ _SIGNATURES = {
                                      _P, _P, _P, _P, _P, _P]),
     'npb_group_pixels': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,
                                  c_int, c_int, c_float, _P, _P, _P, _P, _P]),
+    'npb_filter_stuff_area': (c_int, [_P, _P, c_int, c_int64, c_int, c_int64, c_int64, c_int64, _P, _P]),
     'npb_overflow_centers': (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P]),
     'npb_group_pixels_wide': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int,
                                       c_float, _P, _P, _P, _P, _P, _P]),

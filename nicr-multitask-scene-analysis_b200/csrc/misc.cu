@@ -3,6 +3,7 @@
 //   * uint8 -> int64 widening           the reference's int64 index outputs (semantic.py:53,
 //                                       panoptic.py:160)
 //   * per-instance orientation for arbitrary instance maps       instance.py:270-319
+//   * optional stuff-area filter on a finished panoptic map (not in the reference: off by default)
 #include <math.h>
 
 #include "common.cuh"
@@ -139,4 +140,86 @@ extern "C" int npb_instance_orientation(const float *orientation, const void *se
                                                  max_id, count, sums, status);
     orientation_angle_kernel<<<(int)((rows + 255) / 256), 256, 0, s>>>(count, sums, rows, angle);
     return record_launch("npb_instance_orientation");
+}
+
+// ---- optional stuff-area filter ---------------------------------------------------------------
+namespace npb {
+
+// The reference's merge gives EVERY stuff class present in a frame its id `class * L`
+// (utils/panoptic_merge.py:213-223); Panoptic-DeepLab's original merge drops stuff regions
+// smaller than `stuff_area` pixels to void.  Offered as an option (default off = the reference):
+// a stuff segment is a pixel set with `pan > 0 && pan % L == 0`; pass 1 counts the pixels of
+// every such segment per frame (privatised shared-memory histogram over the <= 256 classes),
+// pass 2 rewrites the segments below the limit to `void_label`.
+__global__ void __launch_bounds__(256)
+stuff_area_count_kernel(const long long *__restrict__ pan, long long P, int n_classes, long long L,
+                        int L_shift, unsigned *__restrict__ hist)
+{
+    __shared__ unsigned s_hist[256];
+    const int b = blockIdx.y;
+    s_hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const long long *pb = pan + (size_t)b * P;
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += stride) {
+        const long long v = pb[p];
+        if (v <= 0) continue;
+        const long long c = L_shift >= 0 ? (v >> L_shift) : (v / L);
+        if (v - c * L == 0 && c < n_classes) atomicAdd(&s_hist[(int)c], 1u);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n_classes && s_hist[threadIdx.x])
+        atomicAdd(hist + (size_t)b * n_classes + threadIdx.x, s_hist[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+stuff_area_apply_kernel(long long *__restrict__ pan, uint8_t *__restrict__ pan_sem, long long P,
+                        int n_classes, long long L, int L_shift, long long stuff_area,
+                        long long void_label, const unsigned *__restrict__ hist)
+{
+    __shared__ unsigned char s_drop[256];
+    const int b = blockIdx.y;
+    s_drop[threadIdx.x] = ((int)threadIdx.x < n_classes &&
+                           (long long)hist[(size_t)b * n_classes + threadIdx.x] < stuff_area) ? 1 : 0;
+    __syncthreads();
+    long long *pb = pan + (size_t)b * P;
+    uint8_t *sb = pan_sem ? pan_sem + (size_t)b * P : nullptr;
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += stride) {
+        const long long v = pb[p];
+        if (v <= 0) continue;
+        const long long c = L_shift >= 0 ? (v >> L_shift) : (v / L);
+        if (v - c * L == 0 && c < n_classes && s_drop[(int)c]) {
+            pb[p] = void_label;
+            if (sb) sb[p] = (uint8_t)(void_label / L);
+        }
+    }
+}
+
+}  // namespace npb
+
+using namespace npb;
+
+extern "C" int npb_filter_stuff_area(int64_t *pan, uint8_t *pan_sem, int B, int64_t P, int n_classes,
+                                     int64_t max_instances_per_category, int64_t stuff_area,
+                                     int64_t void_label, uint32_t *workspace, void *stream)
+{
+    if (!pan || !workspace) return NPB_ERR_ARG;
+    if (B < 1 || B > 65535 || P < 1 || n_classes < 1 || n_classes > 256 ||
+        max_instances_per_category < 1 || stuff_area < 0 || void_label < 0)
+        return NPB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int L_shift = -1;
+    for (int sh = 0; sh < 62; ++sh)
+        if ((1ll << sh) == max_instances_per_category) L_shift = sh;
+    cudaMemsetAsync(workspace, 0, (size_t)B * n_classes * sizeof(uint32_t), s);
+    long long blocks = (P + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 1024) blocks = 1024;
+    dim3 grid((unsigned)blocks, B);
+    stuff_area_count_kernel<<<grid, 256, 0, s>>>((const long long *)pan, P, n_classes,
+                                                 max_instances_per_category, L_shift, workspace);
+    stuff_area_apply_kernel<<<grid, 256, 0, s>>>((long long *)pan, pan_sem, P, n_classes,
+                                                 max_instances_per_category, L_shift, stuff_area,
+                                                 void_label, workspace);
+    return record_launch("npb_filter_stuff_area");
 }

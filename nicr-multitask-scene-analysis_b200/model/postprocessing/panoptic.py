@@ -17,6 +17,8 @@ Differences to the reference that a caller can observe (all documented in DESIGN
 Extra keyword arguments (accepted through **kwargs like the reference's):
   * `async_results=True`: do not block on the table download; the dict / list entries are
     built on first access.
+  * `stuff_area=n` (default 0 = off = the reference): Panoptic-DeepLab's filter, stuff segments
+    of fewer than n pixels become void.
 """
 from ctypes import c_float, c_int, c_int64
 from typing import Tuple
@@ -56,6 +58,12 @@ class PanopticPostprocessing(DensePostprocessingBase):
         self._compute_scores = compute_scores
         self._max_instances_per_category = 1 << 16
         self._async_results = bool(kwargs.get('async_results', False))
+        # Panoptic-DeepLab's `stuff_area`: stuff segments of fewer pixels become void.  NOT in the
+        # reference (its merge keeps every stuff class present, panoptic_merge.py:213-223), so the
+        # default 0 = off is the reference's result; see npb_filter_stuff_area.
+        self._stuff_area = int(kwargs.get('stuff_area', 0))
+        if self._stuff_area < 0:
+            raise ValueError('stuff_area must be >= 0')
         self._ws = {}
         self._fused_evaluation = None       # see fuse_evaluation()
 
@@ -173,6 +181,12 @@ class PanopticPostprocessing(DensePostprocessingBase):
         for b in post._overflow_frames(tables):         # on_overflow='wrap' only (one sync)
             self._redo_wrapped_frame(plan, tables, b, heat, offset, orientation, sem, inst, pan,
                                      pan_sem, C, H, W)
+        if self._stuff_area > 0:
+            counts = torch.empty((B, C + 1), dtype=torch.int32, device=dev)
+            _lib.check(L.npb_filter_stuff_area(
+                _lib.ptr(pan), _lib.ptr(pan_sem), c_int(B), c_int64(P), c_int(C + 1),
+                c_int64(self._max_instances_per_category), c_int64(self._stuff_area), c_int64(0),
+                _lib.ptr(counts), _lib.stream_ptr(dev)), 'npb_filter_stuff_area')
         return sem, inst, pan, pan_sem, tables
 
     def _redo_wrapped_frame(self, plan, tables, b, heat, offset, orientation, sem, inst, pan,
@@ -227,6 +241,9 @@ class PanopticPostprocessing(DensePostprocessingBase):
             raise ValueError("fuse_evaluation: on_overflow='wrap' redoes frames after the call, "
                              'when the fused evaluation has already counted them; update the '
                              'metrics from the result dict instead')
+        if evaluation is not None and self._stuff_area > 0:
+            raise ValueError('fuse_evaluation: the stuff-area filter rewrites the ids after the '
+                             'kernel that writes (and would evaluate) them')
         if evaluation is not None:
             # the fused kernels evaluate with THIS object's id geometry and class count
             if evaluation.pq.max_instances_per_category != self._max_instances_per_category:

@@ -167,6 +167,45 @@ def test_golden_postprocess_wrapped_instance_ids(async_results, cuda_device):
         pan.fuse_evaluation(object())
 
 
+def test_optional_stuff_area_filter(cuda_device):
+    """`stuff_area=n` (Panoptic-DeepLab's filter; the reference has none, default off): stuff
+    segments (`pan > 0 and pan % L == 0`) of fewer than n pixels become void, everything else --
+    thing instances, id dicts, meta, the raw instance map -- stays as without the filter.  Checked
+    against a numpy restatement of the rule on the golden case."""
+    z = load_golden('post_q10')
+    cfg = jload(z['cfg'])
+    L = 1 << 16
+    _, _, plain = _build(cfg, z['is_thing'], z['has_orientation'])
+    r0 = _run(plain, z['logits'], z['heat'], z['offset'], z.get('orientation'), cuda_device)
+    base = r0['panoptic_segmentation_deeplab'].cpu().numpy()
+    assert np.array_equal(base, z['panoptic_segmentation_deeplab'])
+    sizes = []
+    for b in range(base.shape[0]):
+        ids, cnt = np.unique(base[b], return_counts=True)
+        sizes += [int(c) for i, c in zip(ids, cnt) if i > 0 and i % L == 0]
+    limit = int(np.median(sizes)) + 1           # about half of the stuff segments go
+    _, _, filt = _build(cfg, z['is_thing'], z['has_orientation'], stuff_area=limit)
+    r1 = _run(filt, z['logits'], z['heat'], z['offset'], z.get('orientation'), cuda_device)
+    want = base.copy()
+    dropped = 0
+    for b in range(base.shape[0]):
+        ids, cnt = np.unique(base[b], return_counts=True)
+        for i, c in zip(ids, cnt):
+            if i > 0 and i % L == 0 and c < limit:
+                want[b][base[b] == i] = 0
+                dropped += 1
+    assert 0 < dropped < len(sizes)
+    got = r1['panoptic_segmentation_deeplab'].cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(r1['panoptic_segmentation_deeplab_semantic_idx'].cpu().numpy(), want // L)
+    assert r1['panoptic_segmentation_deeplab_ids'] == r0['panoptic_segmentation_deeplab_ids']
+    assert torch.equal(r1['panoptic_segmentation_deeplab_instance_idx'],
+                       r0['panoptic_segmentation_deeplab_instance_idx'])
+    assert torch.equal(r1['semantic_segmentation_idx'], r0['semantic_segmentation_idx'])
+    with pytest.raises(ValueError):
+        filt.fuse_evaluation(object())
+
+
 def test_result_keys_like_reference(cuda_device):
     """tests/test_decoders+postprocessing.py:208-250 of the reference: key presence"""
     z = load_golden('post_scores')
